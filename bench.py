@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — Mpaths/s of the rayz hot path on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA backend
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+A step is one full render of the workload (one pass of Tracer.render's pixel loop):
+  N = 1 : BASELINE config 2 — RTOW final scene (randomBouncing, scene seed 42, 485 spheres),
+          1200x675, 500 spp, max depth 50;
+  N > 1 : BASELINE config 3 — same scene at 3840x2160, 1000 spp, image rows dealt to the ranks in
+          round-robin bands of 4 rows, slabs gathered to GPU0 over NCCL (strong scaling).
+`value`  : whole-job Mpaths/s with scene and camera resident in HBM, results left in HBM on GPU0.
+`e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
+           (rayz_cuda_upload_scene + rayz_cuda_render: H2D of the scene, D2H of linear float4 + RGB8).
+`roofline`: FP32 (FFMA issue) bound — algorithmic flop of the brute-force search (SURVEY §8d /
+           DESIGN.md) over the CUDA-event duration of the path kernel, against the FFMA peak
+           measured live by the K6 microbenchmark.
+Only the cpu_baseline leg and --impl reference execute oracle/ (the CPU restatement of the Zig
+reference, which cannot be compiled in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpaths/s"
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45: SMs x lanes x 2 flop x max SM clock
+
+
+def workload(n_gpus: int, args) -> dict:
+    if n_gpus <= 1:
+        w = dict(name="config2: RTOW final scene (randomBouncing seed 42), 1200x675, 500 spp, depth 50",
+                 width=1200, spp=500)
+    else:
+        w = dict(name="config3: RTOW final scene (randomBouncing seed 42), 3840x2160, 1000 spp, depth 50, "
+                      "rows dealt to ranks in bands of 4", width=3840, spp=1000)
+    if args.width:
+        w["width"] = args.width
+    if args.spp:
+        w["spp"] = args.spp
+    if args.width or args.spp:
+        w["name"] = f"custom: randomBouncing seed 42, width {w['width']}, {w['spp']} spp, depth 50"
+    w["height"] = int(float(w["width"]) / (16.0 / 9.0))
+    w["depth"] = 50
+    w["scene_seed"] = 42
+    return w
+
+
+# ------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank: int, world: int):
+    """The reference algorithm (oracle port of the Zig renderer) on the box's host cores."""
+    if rank != 0:
+        return
+    import oracle
+    w = workload(args.gpus, args)
+    threads = os.cpu_count() or 1
+    scene = oracle.Scene.random_bouncing(w["scene_seed"])
+    cam, h = oracle.default_camera(w["width"])
+    assert h == w["height"]
+    # bounded sample of the same workload: full resolution, few spp (the rate is spp-independent)
+    # ~5 s of wall time per step at ~0.25 Mpaths/s per core
+    spp = args.ref_spp or max(1, min(16, int(round(0.25e6 * threads * 5.0 / (w["width"] * h)))))
+    paths = w["width"] * h * spp
+    for i in range(args.warmup):
+        scene.render(cam, w["width"], h, spp, w["depth"], seed=100 + i, threads=threads)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        scene.render(cam, w["width"], h, spp, w["depth"], seed=200 + i, threads=threads)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    v = paths / dt / 1e6
+    sample = f"{w['width']}x{h} at {spp} spp of the {w['spp']}-spp workload per step (rate is spp-independent)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "oracle/ C++ restatement of the Zig reference (no zig toolchain in the image); rows "
+                                 "over all host threads with per-row PRNG streams; the reference itself is single-threaded"},
+        "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------- our arm
+def algorithmic_flops_per_path(stats: dict, n_static: int, n_moving: int) -> dict:
+    """F_path = S*F_isect + (S - p_sky)*F_shade + F_cam + p_sky*F_sky."""
+    paths = max(1, stats["paths"])
+    S = stats["segments"] / paths
+    p_sky = stats["ended_sky"] / paths
+    f_isect = n_static * 16 + n_moving * 22
+    f_path = S * f_isect + (S - p_sky) * 70 + 45 + p_sky * 19
+    return {"segments_per_path": S, "p_sky": p_sky, "f_isect": f_isect, "f_path": f_path}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "mega", "bvh", "wavefront"])
+    ap.add_argument("--width", type=int, default=0, help="override workload width (quick checks only)")
+    ap.add_argument("--spp", type=int, default=0, help="override workload spp (quick checks only)")
+    ap.add_argument("--ref-spp", type=int, default=0, help="--impl reference: spp of the bounded sample")
+    ap.add_argument("--rays-per-thread", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # launched without torchrun: re-exec one rank per GPU the way the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr",
+               "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.warmup < 3:
+        args.warmup = 3  # timing rules: W >= 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import rayz_b200
+    from rayz_b200 import Backend
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the backend has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctl = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ctl = dist.new_group(backend="gloo")  # control-plane barriers that do not spin on the GPUs
+
+    w = workload(world, args)
+    W, H, SPP, DEPTH = w["width"], w["height"], w["spp"], w["depth"]
+    tracer = rayz_b200.random_bouncing(W, seed=w["scene_seed"])   # host-side scene author (rayz.zig:45-168)
+    scene = tracer.pool.arrays()
+    cam = tracer.camera.rz
+
+    be = Backend((local_rank,))
+    if args.rays_per_thread or args.chunk:
+        be.set_tuning(args.rays_per_thread, args.chunk)
+    # a dedicated (non-default) torch stream: the library launches on it, torch events time it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    be.set_stream(stream.cuda_stream)
+    be.upload_scene(scene)
+    band = 4
+    p = Backend.params(W, H, SPP, DEPTH, seed=1, variant=args.variant, shard_index=rank, shard_count=world, band_rows=band)
+    rows_of = [int(be.lib.rayz_cuda_shard_rows(H, r, world, band)) for r in range(world)]
+    my_rows = rows_of[rank]
+
+    class DevArray:  # wraps a raw device pointer for torch.as_tensor (no copy)
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr, "version": 3, "strides": None}
+
+    if world > 1 and rank == 0:
+        final_lin = torch.empty((H, W, 4), dtype=torch.float32, device=dev)
+        final_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+        slabs_lin = [torch.empty((rows_of[r], W, 4), dtype=torch.float32, device=dev) for r in range(world)]
+        slabs_rgb = [torch.empty((rows_of[r], W, 3), dtype=torch.uint8, device=dev) for r in range(world)]
+        row_idx = []
+        for r in range(world):
+            idx = [j for j in range(H) if (j // band) % world == r]
+            row_idx.append(torch.tensor(idx, dtype=torch.long, device=dev))
+
+    def step_device():
+        """One render, inputs resident in HBM, result left in HBM on GPU0 (after the NCCL gather for N>1)."""
+        dl, d8, n = be.render_device(cam, p, sync=False)
+        if world == 1:
+            return n
+        lin = torch.as_tensor(DevArray(dl, (my_rows, W, 4), "<f4"), device=dev)
+        rgb = torch.as_tensor(DevArray(d8, (my_rows, W, 3), "|u1"), device=dev)
+        if rank == 0:
+            ops = []
+            for r in range(1, world):
+                ops.append(dist.P2POp(dist.irecv, slabs_lin[r], r))
+                ops.append(dist.P2POp(dist.irecv, slabs_rgb[r], r))
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            final_lin[row_idx[0]] = lin
+            final_rgb[row_idx[0]] = rgb
+            for r in range(1, world):
+                final_lin[row_idx[r]] = slabs_lin[r]
+                final_rgb[row_idx[r]] = slabs_rgb[r]
+        else:
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, lin, 0), dist.P2POp(dist.isend, rgb, 0)]):
+                req.wait()
+        return n
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(group=ctl)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # ---- stats pass (not timed): segments/path for the algorithmic flop count
+    ps = Backend.params(W, H, min(SPP, 8), DEPTH, seed=1, variant=args.variant, shard_index=rank, shard_count=world,
+                        band_rows=band, collect_stats=True)
+    be.render_device(cam, ps, sync=True)
+    stats = be.stats()
+    tinfo = be.timing()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    # ---- timed: exactly K steps, CUDA events on the launching stream, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t_wall0 = time.time()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    paths_step = 0
+    for k in range(args.steps):
+        flush_buf.zero_()
+        ev[k][0].record(stream)
+        paths_step = step_device()
+        ev[k][1].record(stream)
+        ev[k][1].synchronize()
+    barrier()
+    t_wall1 = time.time()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    total_paths = W * H * SPP
+    ms_per_step = total_ms / args.steps
+    value = total_paths / (ms_per_step * 1e-3) / 1e6
+
+    # ---- path-kernel duration per launch (library CUDA events on the same stream), own pass
+    kms = []
+    for _ in range(min(3, args.steps)):
+        flush_buf.zero_()
+        be.render_device(cam, p, sync=True)
+        kms.append(be.timing()["kernel_ms"])
+    kern_ms = torch.tensor([statistics.mean(kms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    kern_ms = float(kern_ms.item())
+    launches_per_step = be.timing()["launches"]
+
+    # ---- e2e: reference-facing call with host buffers (rank 0 drives all N GPUs through the
+    # library's own multi-device context: this is what the single-process Zig host would call)
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        if rank == 0:
+            be2 = Backend(tuple(range(world))) if world > 1 else be
+            if args.rays_per_thread or args.chunk:
+                be2.set_tuning(args.rays_per_thread, args.chunk)
+            pe = Backend.params(W, H, SPP, DEPTH, seed=1, variant=args.variant)
+            lin_h = torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy()
+            rgb_h = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory().numpy()
+            def step_e2e():
+                be2.upload_scene(scene)
+                return be2.render(cam, pe, out_linear=lin_h, out_rgb8=rgb_h)[2]
+            for _ in range(2):
+                step_e2e()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                n = step_e2e()
+            dt = (time.perf_counter() - t0) / args.steps
+            e2e = {"value": n / dt / 1e6, "unit": "Mpaths/s", "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": int(be2.scene_bytes + 152 + 56), "d2h_bytes_per_step": int(lin_h.nbytes + rgb_h.nbytes),
+                   "api": "rayz_cuda_upload_scene + rayz_cuda_render (host buffers)" + (f", one process driving {world} GPUs, P2P gather" if world > 1 else "")}
+            if world > 1:
+                be2.close()
+        barrier()
+
+    if rank == 0:
+        fl = algorithmic_flops_per_path(stats, tinfo["n_static"], tinfo["n_moving"])
+        peak_tf, sms = be.fp32_peak(400)
+        variant_ran = {1: "mega", 2: "wavefront", 3: "bvh"}.get(be.timing()["variant"], "?")
+        per_gpu_paths = total_paths / world
+        achieved = per_gpu_paths * fl["f_path"] / (kern_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32", "kernel": "rz_path_kernel (" + variant_ran + ")", "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                    "peak_source": "measured live: K6 FFMA microbenchmark (MEASURED_PEAKS.json has no FP32 figure)",
+                    "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
+                    "kernel_ms_per_launch": kern_ms, "flop_per_path": fl["f_path"], "segments_per_path": fl["segments_per_path"],
+                    "flop_per_segment_search": fl["f_isect"], "traffic": None,
+                    "hbm_bytes_algorithmic": 35 * W * H // world,
+                    "note": "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test); "
+                            "tensor cores unused by design; framebuffer HBM traffic is 35 B/pixel once per render"}
+        out = {
+            "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "width": W, "height": H, "spp": SPP, "max_depth": DEPTH, "paths_per_step": total_paths,
+                       "variant": variant_ran, "sharding": f"rows in bands of {band}, round-robin over {world} rank(s)",
+                       "l2": "flushed between steps (256 MiB memset, untimed)"},
+            "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline, "stats": {k: stats[k] for k in ("paths", "segments", "ended_sky", "ended_absorbed", "ended_depth")},
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            import oracle
+            sc = oracle.Scene.random_bouncing(w["scene_seed"])
+            ocam, oh = oracle.default_camera(W)
+            spp_cpu = 3
+            t0 = time.perf_counter()
+            sc.render(ocam, W, oh, spp_cpu, DEPTH, seed=5, threads=1)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": W * oh * spp_cpu / dt / 1e6, "unit": "Mpaths/s", "cores": 1, "kind": "port",
+                                   "sample": f"{W}x{oh} at {spp_cpu} spp, 1 thread, one sequential PRNG (the reference's own structure)",
+                                   "seconds": dt}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier(group=ctl)
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

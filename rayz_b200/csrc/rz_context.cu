@@ -1,0 +1,818 @@
+// rz_context.cu — host side of the C ABI (include/rayz_cuda.h): contexts, scene flattening,
+// BVH builds, kernel orchestration, peer gather.  No CPU rendering path exists here: every
+// entry point that produces pixels or ids launches CUDA kernels or fails.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/rayz_cuda.h"
+#include "rz_device.cuh"
+
+// from rz_path.cu / rz_ids.cu / rz_misc.cu / rz_wavefront.cu
+struct RzRefNode { double low[3], high[3]; int32_t left, right, start, end; };
+struct RzIdsArgs {
+    const RzRefNode *nodes; const uint32_t *order; const double4 *c64; const double4 *v64;
+    uint32_t n_spheres, n_nodes; double look_from[3], px_du[3], px_dv[3], px_origin[3];
+    uint32_t width, height; int use_bvh; int32_t *out;
+};
+struct RzResolveArgs {
+    const unsigned long long *accum; float4 *out_linear; uint8_t *out_rgb8;
+    uint32_t n_local_px, width; uint32_t spp; uint32_t dev_index, dev_count, band_rows;
+};
+extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays_per_thread, int collect_stats, int sm_count,
+                                      cudaStream_t stream, int *grid_out);
+extern "C" cudaError_t rz_launch_ids(const RzIdsArgs *a, cudaStream_t stream);
+extern "C" cudaError_t rz_launch_resolve(const RzResolveArgs *a, cudaStream_t stream);
+extern "C" cudaError_t rz_launch_ffma_peak(float *sink, int grid, int iters, int mode, cudaStream_t stream);
+extern "C" cudaError_t rz_wavefront_render(const RzPathArgs *a, int sm_count, cudaStream_t stream, void **scratch,
+                                           size_t *scratch_bytes, uint32_t *launches);
+
+// ------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int rz_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define RZ_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return rz_fail(e_ == cudaErrorMemoryAllocation ? RZ_ERR_OOM : RZ_ERR_CUDA, "%s:%d %s -> %s", \
+                           __FILE__, __LINE__, #call, cudaGetErrorString(e_));                          \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------ device state
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return RZ_OK;
+        release();
+        if (count == 0) count = 1;
+        RZ_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        n = count;
+        return RZ_OK;
+    }
+    int upload(const std::vector<T> &h, cudaStream_t s) {
+        int rc = alloc(h.size());
+        if (rc) return rc;
+        if (!h.empty()) RZ_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+        return RZ_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct SetBufs {
+    DBuf<float4> cr, vel;
+    DBuf<double4> c64, v64;
+    DBuf<uint32_t> mat;
+    DBuf<int32_t> orig;
+    uint32_t n = 0, n_static = 0, n_static_pad = 0, n_pad = 0;
+    RzSphereSet view() const {
+        RzSphereSet s;
+        s.cr = cr.p; s.vel = vel.p; s.c64 = c64.p; s.v64 = v64.p; s.mat = mat.p; s.orig = orig.p;
+        s.n = n; s.n_static = n_static; s.n_static_pad = n_static_pad; s.n_pad = n_pad;
+        return s;
+    }
+    void release() { cr.release(); vel.release(); c64.release(); v64.release(); mat.release(); orig.release(); }
+};
+
+struct Dev {
+    int id = 0, sms = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, path0, path1, resolve1, done
+    SetBufs brute, bvhset;
+    DBuf<RzBvhNode> bvh;
+    uint32_t bvh_nodes = 0;
+    DBuf<RzRefNode> refnodes;
+    DBuf<uint32_t> reforder;
+    DBuf<double4> c64_orig, v64_orig;
+    uint32_t n_refnodes = 0;
+    DBuf<uint32_t> m_kind, m_tex, m_method, t_kind, t_even, t_odd;
+    DBuf<float> m_fuzz, m_ior;
+    DBuf<float4> t_color;
+    DBuf<double> t_inv_scale;
+    DBuf<unsigned long long> accum;
+    DBuf<unsigned int> counter;
+    DBuf<RzStatsDev> stats;
+    DBuf<float4> out_linear;
+    DBuf<uint8_t> out_rgb8;
+    DBuf<int32_t> ids;
+    DBuf<float> sink;
+    void *wf_scratch = nullptr;
+    size_t wf_scratch_bytes = 0;
+};
+
+struct RzContext {
+    std::vector<Dev> devs;
+    bool have_scene = false;
+    uint32_t n_spheres = 0;
+    RzStats stats{};
+    bool stats_valid = false;
+    RzTiming timing{};
+    int rays_per_thread = 2;
+    uint32_t chunk = 16;
+};
+
+// ------------------------------------------------------------------------------ shard rows
+extern "C" uint32_t rayz_cuda_shard_rows(uint32_t height, uint32_t shard_index, uint32_t shard_count, uint32_t band_rows) {
+    if (shard_count <= 1) return height;
+    if (band_rows == 0) band_rows = 4;
+    if (shard_index >= shard_count) return 0;
+    const uint32_t n_bands = (height + band_rows - 1) / band_rows;
+    uint32_t rows = 0;
+    for (uint32_t gb = shard_index; gb < n_bands; gb += shard_count) rows += std::min(band_rows, height - gb * band_rows);
+    return rows;
+}
+
+// ------------------------------------------------------------------------------ host BVH builds
+namespace {
+
+struct Box {
+    double lo[3], hi[3];
+    Box() { for (int a = 0; a < 3; a++) { lo[a] = std::numeric_limits<double>::infinity(); hi[a] = -lo[a]; } }
+    void grow(const Box &b) { for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], b.lo[a]); hi[a] = std::fmax(hi[a], b.hi[a]); } }
+    double area() const {
+        const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0;
+        return 2 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+// Sphere.boundingBox (geom.zig:24-31): union of the boxes at center.at(0) and center.at(1)
+Box sphere_box(const RzScene &sc, uint32_t i) {
+    const double *c = sc.sphere_center + 3 * i, *v = sc.sphere_velocity + 3 * i;
+    const double r = sc.sphere_radius[i];
+    Box b;
+    for (int a = 0; a < 3; a++) {
+        const double o1 = c[a], o2 = c[a] + v[a] * 1.0;
+        const double l1 = std::fmin(o1 - r, o1 + r), h1 = std::fmax(o1 - r, o1 + r);
+        const double l2 = std::fmin(o2 - r, o2 + r), h2 = std::fmax(o2 - r, o2 + r);
+        b.lo[a] = std::fmin(l1, l2);
+        b.hi[a] = std::fmax(h1, h2);
+    }
+    return b;
+}
+
+// BVH.build (hit.zig:130-161), same shape as the reference: enclose, leaf at <= 2, stable sort
+// of the range by bbox.low[longest axis] (amax tie rule vec.zig:150-156), split at n/2.
+struct RefBuilder {
+    struct H { Box b; uint32_t s; };
+    std::vector<H> h;
+    std::vector<RzRefNode> nodes;
+    int build(size_t si, size_t ei) {
+        const int me = (int)nodes.size();
+        nodes.push_back(RzRefNode());
+        Box bb;
+        for (size_t i = si; i < ei; i++) bb.grow(h[i].b);
+        for (int a = 0; a < 3; a++) { nodes[me].low[a] = bb.lo[a]; nodes[me].high[a] = bb.hi[a]; }
+        nodes[me].left = nodes[me].right = -1;
+        nodes[me].start = nodes[me].end = 0;
+        const size_t n = ei - si;
+        if (n <= 2) {
+            nodes[me].start = (int32_t)si;
+            nodes[me].end = (int32_t)ei;
+        } else {
+            const double ex = bb.hi[0] - bb.lo[0], ey = bb.hi[1] - bb.lo[1], ez = bb.hi[2] - bb.lo[2];
+            int axis;
+            if (ex > ey) axis = ex > ez ? 0 : 2; else axis = ey > ez ? 1 : 2;
+            std::stable_sort(h.begin() + si, h.begin() + ei, [axis](const H &a, const H &b) { return a.b.lo[axis] < b.b.lo[axis]; });
+            const size_t mid = n / 2 + si;
+            const int l = build(si, mid);
+            const int r = build(mid, ei);
+            nodes[me].left = l;
+            nodes[me].right = r;
+        }
+        return me;
+    }
+};
+
+// Binned-SAH BVH2 for the FP32 traversal kernel (K3).  Tree shape is ours to choose: closest
+// hit does not depend on it.  Leaves hold <= 4 spheres; child boxes are stored in the parent.
+struct SahBuilder {
+    struct P { Box b; double c[3]; uint32_t s; };
+    std::vector<P> p;
+    std::vector<RzBvhNode> nodes;
+    std::vector<uint32_t> order;  // leaf order of sphere indices
+    static constexpr int BINS = 16, LEAF = 4;
+
+    static float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
+    static float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
+
+    struct Ref { int32_t child; uint32_t cnt; Box b; };
+
+    Ref build(size_t si, size_t ei) {
+        Box bb, cb;
+        for (size_t i = si; i < ei; i++) {
+            bb.grow(p[i].b);
+            for (int a = 0; a < 3; a++) { cb.lo[a] = std::fmin(cb.lo[a], p[i].c[a]); cb.hi[a] = std::fmax(cb.hi[a], p[i].c[a]); }
+        }
+        const size_t n = ei - si;
+        auto make_leaf = [&]() {
+            Ref r; r.child = ~(int32_t)order.size(); r.cnt = (uint32_t)n; r.b = bb;
+            for (size_t i = si; i < ei; i++) order.push_back(p[i].s);
+            return r;
+        };
+        if (n <= 1) return make_leaf();
+        // best binned split over the three axes
+        double best_cost = std::numeric_limits<double>::infinity();
+        int best_axis = -1, best_bin = -1;
+        for (int a = 0; a < 3; a++) {
+            const double ext = cb.hi[a] - cb.lo[a];
+            if (!(ext > 0)) continue;
+            Box bins[BINS]; size_t cnt[BINS] = {0};
+            const double k = BINS / ext;
+            for (size_t i = si; i < ei; i++) {
+                int bi = (int)((p[i].c[a] - cb.lo[a]) * k);
+                bi = std::min(std::max(bi, 0), BINS - 1);
+                bins[bi].grow(p[i].b); cnt[bi]++;
+            }
+            double la[BINS], ra[BINS]; size_t lc[BINS], rc[BINS];
+            Box acc; size_t c = 0;
+            for (int i = 0; i < BINS; i++) { acc.grow(bins[i]); c += cnt[i]; la[i] = acc.area(); lc[i] = c; }
+            acc = Box(); c = 0;
+            for (int i = BINS - 1; i >= 0; i--) { acc.grow(bins[i]); c += cnt[i]; ra[i] = acc.area(); rc[i] = c; }
+            for (int i = 0; i < BINS - 1; i++) {
+                if (lc[i] == 0 || rc[i + 1] == 0) continue;
+                const double cost = la[i] * (double)lc[i] + ra[i + 1] * (double)rc[i + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = i; }
+            }
+        }
+        size_t mid;
+        if (best_axis < 0) {
+            if (n <= (size_t)LEAF) return make_leaf();
+            mid = si + n / 2;  // coincident centroids: split by count
+        } else {
+            const double leaf_cost = bb.area() * (double)n;
+            if (n <= (size_t)LEAF && leaf_cost <= best_cost + bb.area() * 0.5) return make_leaf();
+            const double ext = cb.hi[best_axis] - cb.lo[best_axis];
+            const double k = BINS / ext;
+            const double lo = cb.lo[best_axis];
+            const int a = best_axis, bbin = best_bin;
+            auto it = std::partition(p.begin() + si, p.begin() + ei, [&](const P &q) {
+                int bi = (int)((q.c[a] - lo) * k);
+                bi = std::min(std::max(bi, 0), BINS - 1);
+                return bi <= bbin;
+            });
+            mid = (size_t)(it - p.begin());
+            if (mid == si || mid == ei) mid = si + n / 2;
+        }
+        const int me = (int)nodes.size();
+        nodes.push_back(RzBvhNode());
+        const Ref l = build(si, mid);
+        const Ref r = build(mid, ei);
+        set_child(me, 0, l);
+        set_child(me, 1, r);
+        Ref out; out.child = me; out.cnt = 0; out.b = bb;
+        return out;
+    }
+    void set_child(int node, int c, const Ref &r) {
+        RzBvhNode &n = nodes[node];
+        n.lox[c] = down(r.b.lo[0]); n.hix[c] = up(r.b.hi[0]);
+        n.loy[c] = down(r.b.lo[1]); n.hiy[c] = up(r.b.hi[1]);
+        n.loz[c] = down(r.b.lo[2]); n.hiz[c] = up(r.b.hi[2]);
+        n.child[c] = r.child; n.cnt[c] = r.cnt;
+    }
+    void run() {
+        nodes.clear(); order.clear();
+        if (p.empty()) { nodes.push_back(empty_node()); return; }
+        const Ref root = build(0, p.size());
+        if (root.child < 0) {  // whole scene is one leaf: wrap it
+            nodes.clear();
+            nodes.push_back(empty_node());
+            set_child(0, 0, root);
+        }
+        // build() creates parents before children and the root first => node 0 is the root
+    }
+    static RzBvhNode empty_node() {
+        RzBvhNode n;
+        for (int c = 0; c < 2; c++) {
+            n.lox[c] = n.loy[c] = n.loz[c] = INFINITY;
+            n.hix[c] = n.hiy[c] = n.hiz[c] = -INFINITY;
+            n.child[c] = ~0; n.cnt[c] = 0;
+        }
+        return n;
+    }
+};
+
+struct HostSet {
+    std::vector<float4> cr, vel;
+    std::vector<double4> c64, v64;
+    std::vector<uint32_t> mat;
+    std::vector<int32_t> orig;
+    uint32_t n = 0, n_static = 0, n_static_pad = 0, n_pad = 0;
+    void push(const RzScene &sc, uint32_t i) {
+        const double *c = sc.sphere_center + 3 * i, *v = sc.sphere_velocity + 3 * i;
+        const double r = sc.sphere_radius[i];
+        cr.push_back(make_float4((float)c[0], (float)c[1], (float)c[2], -(float)(r * r)));
+        vel.push_back(make_float4((float)v[0], (float)v[1], (float)v[2], (float)r));
+        c64.push_back(make_double4(c[0], c[1], c[2], r));
+        v64.push_back(make_double4(v[0], v[1], v[2], 0.0));
+        mat.push_back(sc.sphere_material[i]);
+        orig.push_back((int32_t)i);
+    }
+    void pad_to(size_t count) {
+        while (cr.size() < count) {  // -r^2 = +1 => discriminant b^2 - |oc|^2 - 1 < 0: never hit
+            cr.push_back(make_float4(0.f, 0.f, 0.f, 1.0f));
+            vel.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
+};
+
+int upload_set(SetBufs &d, const HostSet &h, cudaStream_t s) {
+    int rc;
+    if ((rc = d.cr.upload(h.cr, s))) return rc;
+    if ((rc = d.vel.upload(h.vel, s))) return rc;
+    if ((rc = d.c64.upload(h.c64, s))) return rc;
+    if ((rc = d.v64.upload(h.v64, s))) return rc;
+    if ((rc = d.mat.upload(h.mat, s))) return rc;
+    if ((rc = d.orig.upload(h.orig, s))) return rc;
+    d.n = h.n; d.n_static = h.n_static; d.n_static_pad = h.n_static_pad; d.n_pad = h.n_pad;
+    return RZ_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ API
+extern "C" uint32_t rayz_cuda_abi_version(void) { return RAYZ_CUDA_ABI_VERSION; }
+extern "C" const char *rayz_cuda_last_error(void) { return g_err; }
+
+extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
+    if (!out) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return rz_fail(RZ_ERR_CUDA, "rayz_cuda_create: no CUDA device (%s); this backend has no CPU path",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int nd = cfg ? cfg->n_devices : 1;
+    if (nd <= 0) nd = 1;
+    if (nd > 8) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_create: n_devices %d > 8", nd);
+    DeviceGuard guard;
+    RzContext *ctx = new RzContext();
+    ctx->devs.resize(nd);
+    for (int d = 0; d < nd; d++) {
+        Dev &D = ctx->devs[d];
+        D.id = cfg ? cfg->device_ids[d] : 0;
+        if (D.id < 0 || D.id >= count) { delete ctx; return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_create: device id %d out of range (have %d)", D.id, count); }
+        for (int q = 0; q < d; q++)
+            if (ctx->devs[q].id == D.id) { delete ctx; return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_create: device id %d listed twice", D.id); }
+    }
+    for (int d = 0; d < nd; d++) {
+        Dev &D = ctx->devs[d];
+        if ((e = cudaSetDevice(D.id)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaSetDevice(%d): %s", D.id, cudaGetErrorString(e)); }
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, D.id)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+        if (prop.major < 10) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", D.id, prop.major, prop.minor); }
+        D.sms = prop.multiProcessorCount;
+        if ((e = cudaStreamCreateWithFlags(&D.own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        D.stream = D.own_stream;
+        for (auto &ev : D.ev)
+            if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+        if (d > 0) {
+            // the resolve kernel of device d stores straight into device 0's buffers (NVLink P2P)
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, D.id, ctx->devs[0].id);
+            if (!can) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_UNSUPPORTED, "device %d cannot access peer %d", D.id, ctx->devs[0].id); }
+            e = cudaDeviceEnablePeerAccess(ctx->devs[0].id, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    }
+    *out = ctx;
+    return RZ_OK;
+}
+
+extern "C" void rayz_cuda_destroy(RzContext *ctx) {
+    if (!ctx) return;
+    DeviceGuard guard;
+    for (Dev &D : ctx->devs) {
+        if (cudaSetDevice(D.id) != cudaSuccess) continue;
+        if (D.own_stream) cudaStreamSynchronize(D.own_stream);
+        D.brute.release(); D.bvhset.release(); D.bvh.release(); D.refnodes.release(); D.reforder.release();
+        D.c64_orig.release(); D.v64_orig.release();
+        D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
+        D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
+        D.accum.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
+        D.ids.release(); D.sink.release();
+        if (D.wf_scratch) cudaFree(D.wf_scratch);
+        for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
+        if (D.own_stream) cudaStreamDestroy(D.own_stream);
+    }
+    delete ctx;
+}
+
+extern "C" int rayz_cuda_set_stream(RzContext *ctx, void *cuda_stream) {
+    if (!ctx) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_set_stream: ctx is NULL");
+    Dev &D = ctx->devs[0];
+    D.stream = cuda_stream ? (cudaStream_t)cuda_stream : D.own_stream;
+    return RZ_OK;
+}
+
+// Tunables for experiments (not part of the reference-facing ABI): rays per thread {1,2} and
+// samples per work unit.
+extern "C" int rayz_cuda_set_tuning(RzContext *ctx, int rays_per_thread, uint32_t chunk) {
+    if (!ctx) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_set_tuning: ctx is NULL");
+    if (rays_per_thread == 1 || rays_per_thread == 2) ctx->rays_per_thread = rays_per_thread;
+    if (chunk >= 1 && chunk <= 4096) ctx->chunk = chunk;
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
+    if (!ctx || !sc) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: NULL argument");
+    const uint32_t n = sc->n_spheres, nm = sc->n_materials, nt = sc->n_textures;
+    if (n == 0) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: empty scene (BVH.build asserts nobjs > 0, hit.zig:132)");
+    if (n >= (1u << 30)) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: too many spheres");
+    if (!sc->sphere_center || !sc->sphere_velocity || !sc->sphere_radius || !sc->sphere_material || !sc->mat_kind ||
+        !sc->mat_fuzz || !sc->mat_ior || !sc->mat_texture || (nt && (!sc->tex_kind || !sc->tex_color || !sc->tex_scale || !sc->tex_even || !sc->tex_odd)))
+        return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: NULL array in RzScene");
+    for (uint32_t i = 0; i < n; i++) {
+        if (sc->sphere_material[i] >= nm) return rz_fail(RZ_ERR_INVALID_ARG, "sphere %u: material %u out of range (%u)", i, sc->sphere_material[i], nm);
+        if (!(sc->sphere_radius[i] > 0) || !std::isfinite(sc->sphere_radius[i])) return rz_fail(RZ_ERR_INVALID_ARG, "sphere %u: radius must be finite and > 0", i);
+    }
+    for (uint32_t i = 0; i < nm; i++) {
+        if (sc->mat_kind[i] > 2) return rz_fail(RZ_ERR_INVALID_ARG, "material %u: kind %u", i, sc->mat_kind[i]);
+        if (sc->mat_kind[i] != RZ_MAT_DIELECTRIC && sc->mat_texture[i] >= nt) return rz_fail(RZ_ERR_INVALID_ARG, "material %u: texture %u out of range (%u)", i, sc->mat_texture[i], nt);
+        if (sc->mat_method && sc->mat_method[i] > 2) return rz_fail(RZ_ERR_INVALID_ARG, "material %u: diffuse method %u", i, sc->mat_method[i]);
+    }
+    for (uint32_t i = 0; i < nt; i++) {
+        if (sc->tex_kind[i] > 1) return rz_fail(RZ_ERR_INVALID_ARG, "texture %u: kind %u", i, sc->tex_kind[i]);
+        if (sc->tex_kind[i] == RZ_TEX_CHECKER && (sc->tex_even[i] >= nt || sc->tex_odd[i] >= nt || !(sc->tex_scale[i] != 0)))
+            return rz_fail(RZ_ERR_INVALID_ARG, "texture %u: bad checker (even %u, odd %u, scale %g)", i, sc->tex_even[i], sc->tex_odd[i], sc->tex_scale[i]);
+    }
+
+    // ---- brute-force set: stationary first (10-instruction test), then moving (13)
+    HostSet bs;
+    for (uint32_t i = 0; i < n; i++) {
+        const double *v = sc->sphere_velocity + 3 * i;
+        if (v[0] == 0 && v[1] == 0 && v[2] == 0) bs.push(*sc, i);
+    }
+    bs.n_static = (uint32_t)bs.cr.size();
+    bs.n_static_pad = (bs.n_static + 3u) & ~3u;
+    bs.pad_to(bs.n_static_pad);
+    // c64/v64/mat/orig are indexed by set position too: keep them aligned with the padding
+    auto pad_aux = [](HostSet &h) {
+        while (h.c64.size() < h.cr.size()) { h.c64.push_back(make_double4(0, 0, 0, 1)); h.v64.push_back(make_double4(0, 0, 0, 0)); h.mat.push_back(0); h.orig.push_back(-1); }
+    };
+    pad_aux(bs);
+    for (uint32_t i = 0; i < n; i++) {
+        const double *v = sc->sphere_velocity + 3 * i;
+        if (!(v[0] == 0 && v[1] == 0 && v[2] == 0)) bs.push(*sc, i);
+    }
+    bs.n = n;
+    bs.n_pad = ((uint32_t)bs.cr.size() + 3u) & ~3u;
+    bs.pad_to(bs.n_pad);
+    pad_aux(bs);
+
+    // ---- reference-shaped BVH (K0)
+    RefBuilder rb;
+    rb.h.resize(n);
+    for (uint32_t i = 0; i < n; i++) { rb.h[i].b = sphere_box(*sc, i); rb.h[i].s = i; }
+    rb.build(0, n);
+    std::vector<uint32_t> reforder(n);
+    for (uint32_t i = 0; i < n; i++) reforder[i] = rb.h[i].s;
+    std::vector<double4> c64o(n), v64o(n);
+    for (uint32_t i = 0; i < n; i++) {
+        c64o[i] = make_double4(sc->sphere_center[3 * i], sc->sphere_center[3 * i + 1], sc->sphere_center[3 * i + 2], sc->sphere_radius[i]);
+        v64o[i] = make_double4(sc->sphere_velocity[3 * i], sc->sphere_velocity[3 * i + 1], sc->sphere_velocity[3 * i + 2], 0.0);
+    }
+
+    // ---- SAH BVH2 + leaf-ordered set (K3)
+    SahBuilder sb;
+    sb.p.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        sb.p[i].b = rb.h[0].b;  // placeholder, overwritten below (rb.h is sorted, so recompute)
+        sb.p[i].b = sphere_box(*sc, i);
+        for (int a = 0; a < 3; a++) sb.p[i].c[a] = 0.5 * (sb.p[i].b.lo[a] + sb.p[i].b.hi[a]);
+        sb.p[i].s = i;
+    }
+    sb.run();
+    HostSet vs;
+    for (uint32_t k = 0; k < (uint32_t)sb.order.size(); k++) vs.push(*sc, sb.order[k]);
+    vs.n = n; vs.n_static = 0; vs.n_static_pad = 0; vs.n_pad = n;
+
+    // ---- materials / textures
+    std::vector<uint32_t> mk(nm), mt(nm), mm(nm), tk(nt), te(nt), to(nt);
+    std::vector<float> mf(nm), mi(nm);
+    std::vector<float4> tc(nt);
+    std::vector<double> ts(nt);
+    for (uint32_t i = 0; i < nm; i++) {
+        mk[i] = sc->mat_kind[i]; mt[i] = sc->mat_kind[i] == RZ_MAT_DIELECTRIC ? 0u : sc->mat_texture[i];
+        mm[i] = sc->mat_method ? sc->mat_method[i] : (uint32_t)RZ_DIFFUSE_HEMISPHERE;
+        mf[i] = (float)sc->mat_fuzz[i]; mi[i] = (float)sc->mat_ior[i];
+    }
+    for (uint32_t i = 0; i < nt; i++) {
+        tk[i] = sc->tex_kind[i]; te[i] = sc->tex_even[i]; to[i] = sc->tex_odd[i];
+        tc[i] = make_float4((float)sc->tex_color[3 * i], (float)sc->tex_color[3 * i + 1], (float)sc->tex_color[3 * i + 2], 0.f);
+        ts[i] = sc->tex_kind[i] == RZ_TEX_CHECKER ? 1.0 / sc->tex_scale[i] : 0.0;
+    }
+
+    DeviceGuard guard;
+    for (Dev &D : ctx->devs) {
+        RZ_CUDA(cudaSetDevice(D.id));
+        int rc;
+        if ((rc = upload_set(D.brute, bs, D.stream))) return rc;
+        if ((rc = upload_set(D.bvhset, vs, D.stream))) return rc;
+        if ((rc = D.bvh.upload(sb.nodes, D.stream))) return rc;
+        D.bvh_nodes = (uint32_t)sb.nodes.size();
+        if ((rc = D.refnodes.upload(rb.nodes, D.stream))) return rc;
+        D.n_refnodes = (uint32_t)rb.nodes.size();
+        if ((rc = D.reforder.upload(reforder, D.stream))) return rc;
+        if ((rc = D.c64_orig.upload(c64o, D.stream))) return rc;
+        if ((rc = D.v64_orig.upload(v64o, D.stream))) return rc;
+        if ((rc = D.m_kind.upload(mk, D.stream)) || (rc = D.m_tex.upload(mt, D.stream)) || (rc = D.m_method.upload(mm, D.stream)) ||
+            (rc = D.m_fuzz.upload(mf, D.stream)) || (rc = D.m_ior.upload(mi, D.stream)) || (rc = D.t_kind.upload(tk, D.stream)) ||
+            (rc = D.t_even.upload(te, D.stream)) || (rc = D.t_odd.upload(to, D.stream)) || (rc = D.t_color.upload(tc, D.stream)) ||
+            (rc = D.t_inv_scale.upload(ts, D.stream)))
+            return rc;
+        RZ_CUDA(cudaStreamSynchronize(D.stream));  // host vectors die at return: copy semantics
+    }
+    ctx->have_scene = true;
+    ctx->n_spheres = n;
+    ctx->timing.n_static = bs.n_static;
+    ctx->timing.n_moving = n - bs.n_static;
+    return RZ_OK;
+}
+
+static RzCamF32 cam_to_f32(const RzCamera *c) {
+    RzCamF32 k;
+    k.look_from = make_float3((float)c->look_from[0], (float)c->look_from[1], (float)c->look_from[2]);
+    k.px_du = make_float3((float)c->px_du[0], (float)c->px_du[1], (float)c->px_du[2]);
+    k.px_dv = make_float3((float)c->px_dv[0], (float)c->px_dv[1], (float)c->px_dv[2]);
+    k.px_origin = make_float3((float)c->px_origin[0], (float)c->px_origin[1], (float)c->px_origin[2]);
+    k.defocus_u = make_float3((float)c->defocus_u[0], (float)c->defocus_u[1], (float)c->defocus_u[2]);
+    k.defocus_v = make_float3((float)c->defocus_v[0], (float)c->defocus_v[1], (float)c->defocus_v[2]);
+    k.defocus = c->defocus;
+    return k;
+}
+
+static const uint32_t RZ_SMEM_BUDGET = 200u * 1024u;  // of 227 KB per CTA on sm_100
+
+static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams *p, bool sync) {
+    if (!ctx || !cam || !p) return rz_fail(RZ_ERR_INVALID_ARG, "render: NULL argument");
+    if (!ctx->have_scene) return rz_fail(RZ_ERR_NO_SCENE, "render: rayz_cuda_upload_scene has not been called");
+    if (p->width == 0 || p->height == 0 || p->spp == 0) return rz_fail(RZ_ERR_INVALID_ARG, "render: width, height and spp must be > 0");
+    if ((uint64_t)p->width * p->height >= (1ull << 31)) return rz_fail(RZ_ERR_INVALID_ARG, "render: image too large");
+    const uint32_t S = p->shard_count <= 1 ? 1 : p->shard_count;
+    const uint32_t s = p->shard_count <= 1 ? 0 : p->shard_index;
+    if (s >= S) return rz_fail(RZ_ERR_INVALID_ARG, "render: shard_index %u >= shard_count %u", s, S);
+    const uint32_t band = p->band_rows ? p->band_rows : 4;
+    const uint32_t ND = (uint32_t)ctx->devs.size();
+    uint32_t variant = p->variant;
+    const uint32_t brute_smem = (ctx->devs[0].brute.n_pad * 2 - ctx->devs[0].brute.n_static_pad) * 16u;
+    if (variant == RZ_VARIANT_AUTO) variant = brute_smem <= RZ_SMEM_BUDGET ? RZ_VARIANT_MEGA : RZ_VARIANT_BVH;
+    if (variant != RZ_VARIANT_MEGA && variant != RZ_VARIANT_BVH && variant != RZ_VARIANT_WAVEFRONT)
+        return rz_fail(RZ_ERR_INVALID_ARG, "render: unknown variant %u", p->variant);
+    if (variant == RZ_VARIANT_MEGA && brute_smem > RZ_SMEM_BUDGET)
+        return rz_fail(RZ_ERR_UNSUPPORTED, "render: scene needs %u B of shared memory for the brute-force kernel (budget %u); use RZ_VARIANT_BVH", brute_smem, RZ_SMEM_BUDGET);
+
+    const auto t_host0 = std::chrono::steady_clock::now();
+    DeviceGuard guard;
+    const uint32_t rows_ctx = [&] { uint32_t r = 0; for (uint32_t d = 0; d < ND; d++) r += rayz_cuda_shard_rows(p->height, s * ND + d, S * ND, band); return r; }();
+    Dev &D0 = ctx->devs[0];
+    RZ_CUDA(cudaSetDevice(D0.id));
+    {
+        int rc;
+        if ((rc = D0.out_linear.alloc((size_t)rows_ctx * p->width))) return rc;
+        if ((rc = D0.out_rgb8.alloc((size_t)rows_ctx * p->width * 3))) return rc;
+    }
+    uint32_t launches = 0;
+    for (uint32_t d = 0; d < ND; d++) {
+        Dev &D = ctx->devs[d];
+        RZ_CUDA(cudaSetDevice(D.id));
+        const uint32_t sh_index = s * ND + d, sh_count = S * ND;
+        const uint32_t rows = rayz_cuda_shard_rows(p->height, sh_index, sh_count, band);
+        const uint32_t n_local = rows * p->width;
+        const uint32_t n_tiles = (n_local + 31u) / 32u;
+        int rc;
+        if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u))) return rc;
+        if ((rc = D.counter.alloc(4))) return rc;
+        if ((rc = D.stats.alloc(1))) return rc;
+        RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
+        RZ_CUDA(cudaMemsetAsync(D.accum.p, 0, (size_t)n_tiles * 32u * 4u * sizeof(unsigned long long), D.stream));
+        RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 4 * sizeof(unsigned int), D.stream));
+        if (p->collect_stats) RZ_CUDA(cudaMemsetAsync(D.stats.p, 0, sizeof(RzStatsDev), D.stream));
+
+        RzPathArgs a;
+        memset(&a, 0, sizeof a);
+        a.set = (variant == RZ_VARIANT_BVH) ? D.bvhset.view() : D.brute.view();
+        a.mats.kind = D.m_kind.p; a.mats.fuzz = D.m_fuzz.p; a.mats.ior = D.m_ior.p; a.mats.tex = D.m_tex.p; a.mats.method = D.m_method.p;
+        a.texs.kind = D.t_kind.p; a.texs.color = D.t_color.p; a.texs.inv_scale = D.t_inv_scale.p; a.texs.even = D.t_even.p; a.texs.odd = D.t_odd.p;
+        a.bvh = D.bvh.p; a.bvh_nodes = D.bvh_nodes;
+        a.cam = cam_to_f32(cam);
+        a.accum = D.accum.p; a.unit_counter = D.counter.p; a.stats = D.stats.p;
+        a.width = p->width; a.height = p->height; a.n_local_px = n_local;
+        a.spp = p->spp; a.sample_offset = p->sample_offset; a.max_depth = p->max_depth;
+        a.chunk = std::min(ctx->chunk, p->spp);
+        a.n_chunks = (p->spp + a.chunk - 1) / a.chunk;
+        if ((uint64_t)n_tiles * a.n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "render: too many work units");
+        a.n_units = n_tiles * a.n_chunks;
+        a.shard_index = sh_index; a.shard_count = sh_count; a.band_rows = band;
+        a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
+        a.t_min = p->t_min > 0 ? p->t_min : 1e-4f;
+
+        RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
+        if (n_local > 0) {
+            if (variant == RZ_VARIANT_WAVEFRONT) {
+                uint32_t l = 0;
+                RZ_CUDA(rz_wavefront_render(&a, D.sms, D.stream, &D.wf_scratch, &D.wf_scratch_bytes, &l));
+                launches += l;
+            } else {
+                RZ_CUDA(rz_launch_path(&a, (int)variant, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
+                launches += 1;
+            }
+        }
+        RZ_CUDA(cudaEventRecord(D.ev[2], D.stream));
+
+        RzResolveArgs r;
+        r.accum = D.accum.p; r.out_linear = D0.out_linear.p; r.out_rgb8 = D0.out_rgb8.p;
+        r.n_local_px = n_local; r.width = p->width; r.spp = p->spp;
+        r.dev_index = d; r.dev_count = ND; r.band_rows = band;
+        RZ_CUDA(rz_launch_resolve(&r, D.stream));
+        if (n_local > 0) launches += 1;
+        RZ_CUDA(cudaEventRecord(D.ev[3], D.stream));
+    }
+    // gather root waits for every peer's resolve (which already wrote into its memory)
+    RZ_CUDA(cudaSetDevice(D0.id));
+    for (uint32_t d = 1; d < ND; d++) RZ_CUDA(cudaStreamWaitEvent(D0.stream, ctx->devs[d].ev[3], 0));
+    RZ_CUDA(cudaEventRecord(D0.ev[4], D0.stream));
+
+    ctx->timing.launches = launches;
+    ctx->timing.variant = variant;
+    ctx->stats_valid = false;
+    if (sync) {
+        for (uint32_t d = 0; d < ND; d++) {
+            RZ_CUDA(cudaSetDevice(ctx->devs[d].id));
+            RZ_CUDA(cudaStreamSynchronize(ctx->devs[d].stream));
+        }
+        float kmax = 0, rmax = 0;
+        for (uint32_t d = 0; d < ND; d++) {
+            float k = 0, r = 0;
+            RZ_CUDA(cudaEventElapsedTime(&k, ctx->devs[d].ev[1], ctx->devs[d].ev[2]));
+            RZ_CUDA(cudaEventElapsedTime(&r, ctx->devs[d].ev[2], ctx->devs[d].ev[3]));
+            kmax = std::max(kmax, k); rmax = std::max(rmax, r);
+        }
+        ctx->timing.kernel_ms = kmax;
+        ctx->timing.resolve_ms = rmax;
+        ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+        if (p->collect_stats) {
+            RzStats tot;
+            memset(&tot, 0, sizeof tot);
+            for (uint32_t d = 0; d < ND; d++) {
+                RzStatsDev h;
+                RZ_CUDA(cudaSetDevice(ctx->devs[d].id));
+                RZ_CUDA(cudaMemcpy(&h, ctx->devs[d].stats.p, sizeof h, cudaMemcpyDeviceToHost));
+                tot.paths += h.v[0]; tot.segments += h.v[1]; tot.sphere_tests += h.v[2]; tot.node_tests += h.v[3];
+                tot.hits_diffuse += h.v[4]; tot.hits_metallic += h.v[5]; tot.hits_dielectric += h.v[6];
+                tot.ended_sky += h.v[7]; tot.ended_absorbed += h.v[8]; tot.ended_depth += h.v[9];
+            }
+            if (variant == RZ_VARIANT_MEGA) tot.sphere_tests = tot.segments * (uint64_t)ctx->n_spheres;  // brute force tests all
+            ctx->stats = tot;
+            ctx->stats_valid = true;
+        }
+    }
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_render_device(RzContext *ctx, const RzCamera *cam, const RzRenderParams *params, void **d_linear_rgba,
+                                       void **d_rgb8, uint64_t *out_paths, int sync) {
+    const int rc = render_impl(ctx, cam, params, sync != 0);
+    if (rc) return rc;
+    if (d_linear_rgba) *d_linear_rgba = ctx->devs[0].out_linear.p;
+    if (d_rgb8) *d_rgb8 = ctx->devs[0].out_rgb8.p;
+    if (out_paths) {
+        const uint32_t S = params->shard_count <= 1 ? 1 : params->shard_count;
+        const uint32_t rows = rayz_cuda_shard_rows(params->height, params->shard_count <= 1 ? 0 : params->shard_index, S, params->band_rows);
+        *out_paths = (uint64_t)rows * params->width * params->spp;
+    }
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_render(RzContext *ctx, const RzCamera *cam, const RzRenderParams *params, float *out_linear_rgba,
+                                uint8_t *out_rgb8, uint64_t *out_paths) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = render_impl(ctx, cam, params, false);
+    if (rc) return rc;
+    DeviceGuard guard;
+    Dev &D0 = ctx->devs[0];
+    const uint32_t S = params->shard_count <= 1 ? 1 : params->shard_count;
+    const uint32_t rows = rayz_cuda_shard_rows(params->height, params->shard_count <= 1 ? 0 : params->shard_index, S, params->band_rows);
+    const size_t npx = (size_t)rows * params->width;
+    RZ_CUDA(cudaSetDevice(D0.id));
+    if (out_linear_rgba) RZ_CUDA(cudaMemcpyAsync(out_linear_rgba, D0.out_linear.p, npx * sizeof(float4), cudaMemcpyDeviceToHost, D0.stream));
+    if (out_rgb8) RZ_CUDA(cudaMemcpyAsync(out_rgb8, D0.out_rgb8.p, npx * 3, cudaMemcpyDeviceToHost, D0.stream));
+    for (Dev &D : ctx->devs) {
+        RZ_CUDA(cudaSetDevice(D.id));
+        RZ_CUDA(cudaStreamSynchronize(D.stream));
+    }
+    // timings + stats (same bookkeeping as the device-resident entry point)
+    float kmax = 0, rmax = 0;
+    for (Dev &D : ctx->devs) {
+        float k = 0, r = 0;
+        RZ_CUDA(cudaEventElapsedTime(&k, D.ev[1], D.ev[2]));
+        RZ_CUDA(cudaEventElapsedTime(&r, D.ev[2], D.ev[3]));
+        kmax = std::max(kmax, k); rmax = std::max(rmax, r);
+    }
+    ctx->timing.kernel_ms = kmax;
+    ctx->timing.resolve_ms = rmax;
+    ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (params->collect_stats) {
+        RzStats tot;
+        memset(&tot, 0, sizeof tot);
+        for (Dev &D : ctx->devs) {
+            RzStatsDev h;
+            RZ_CUDA(cudaSetDevice(D.id));
+            RZ_CUDA(cudaMemcpy(&h, D.stats.p, sizeof h, cudaMemcpyDeviceToHost));
+            tot.paths += h.v[0]; tot.segments += h.v[1]; tot.sphere_tests += h.v[2]; tot.node_tests += h.v[3];
+            tot.hits_diffuse += h.v[4]; tot.hits_metallic += h.v[5]; tot.hits_dielectric += h.v[6];
+            tot.ended_sky += h.v[7]; tot.ended_absorbed += h.v[8]; tot.ended_depth += h.v[9];
+        }
+        if (ctx->timing.variant == RZ_VARIANT_MEGA) tot.sphere_tests = tot.segments * (uint64_t)ctx->n_spheres;
+        ctx->stats = tot;
+        ctx->stats_valid = true;
+    }
+    if (out_paths) *out_paths = (uint64_t)npx * params->spp;
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_primary_ids(RzContext *ctx, const RzCamera *cam, uint32_t width, uint32_t height, int use_bvh,
+                                     int32_t *out_ids) {
+    if (!ctx || !cam || !out_ids) return rz_fail(RZ_ERR_INVALID_ARG, "primary_ids: NULL argument");
+    if (!ctx->have_scene) return rz_fail(RZ_ERR_NO_SCENE, "primary_ids: rayz_cuda_upload_scene has not been called");
+    if (width == 0 || height == 0 || (uint64_t)width * height >= (1ull << 31)) return rz_fail(RZ_ERR_INVALID_ARG, "primary_ids: bad image size");
+    DeviceGuard guard;
+    Dev &D = ctx->devs[0];
+    RZ_CUDA(cudaSetDevice(D.id));
+    int rc;
+    if ((rc = D.ids.alloc((size_t)width * height))) return rc;
+    RzIdsArgs a;
+    a.nodes = D.refnodes.p; a.order = D.reforder.p; a.c64 = D.c64_orig.p; a.v64 = D.v64_orig.p;
+    a.n_spheres = ctx->n_spheres; a.n_nodes = D.n_refnodes;
+    for (int i = 0; i < 3; i++) { a.look_from[i] = cam->look_from[i]; a.px_du[i] = cam->px_du[i]; a.px_dv[i] = cam->px_dv[i]; a.px_origin[i] = cam->px_origin[i]; }
+    a.width = width; a.height = height; a.use_bvh = use_bvh; a.out = D.ids.p;
+    RZ_CUDA(rz_launch_ids(&a, D.stream));
+    RZ_CUDA(cudaMemcpyAsync(out_ids, D.ids.p, (size_t)width * height * sizeof(int32_t), cudaMemcpyDeviceToHost, D.stream));
+    RZ_CUDA(cudaStreamSynchronize(D.stream));
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_stats(RzContext *ctx, RzStats *out) {
+    if (!ctx || !out) return rz_fail(RZ_ERR_INVALID_ARG, "stats: NULL argument");
+    if (!ctx->stats_valid) return rz_fail(RZ_ERR_INVALID_ARG, "stats: last render did not run with collect_stats (or was not synchronised)");
+    *out = ctx->stats;
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_timing(RzContext *ctx, RzTiming *out) {
+    if (!ctx || !out) return rz_fail(RZ_ERR_INVALID_ARG, "timing: NULL argument");
+    *out = ctx->timing;
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_fp32_peak(RzContext *ctx, uint32_t millis, double *out_tflops, int32_t *out_sms) {
+    if (!ctx || !out_tflops) return rz_fail(RZ_ERR_INVALID_ARG, "fp32_peak: NULL argument");
+    DeviceGuard guard;
+    Dev &D = ctx->devs[0];
+    RZ_CUDA(cudaSetDevice(D.id));
+    int rc;
+    if ((rc = D.sink.alloc(4))) return rc;
+    const int grid = D.sms * 8;
+    auto run = [&](int iters, int mode, float *ms) -> int {
+        RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
+        RZ_CUDA(rz_launch_ffma_peak(D.sink.p, grid, iters, mode, D.stream));
+        RZ_CUDA(cudaEventRecord(D.ev[4], D.stream));
+        RZ_CUDA(cudaStreamSynchronize(D.stream));
+        RZ_CUDA(cudaEventElapsedTime(ms, D.ev[0], D.ev[4]));
+        return RZ_OK;
+    };
+    double best = 0;
+    for (int mode = 0; mode < 2; mode++) {   // scalar-operand chains and SGEMM-like 3-register form
+        float ms = 0;
+        if ((rc = run(2000, mode, &ms))) return rc;                 // warm-up
+        if ((rc = run(20000, mode, &ms))) return rc;                // calibration
+        const double per_iter_ms = ms / 20000.0;
+        const int iters = (int)std::min(2.0e9, std::max(1000.0, (millis ? millis : 200) * 0.5 / per_iter_ms));
+        if ((rc = run(iters, mode, &ms))) return rc;
+        const double flops = 2.0 * 128.0 * (double)iters * 256.0 * (double)grid;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *out_tflops = best;
+    if (out_sms) *out_sms = D.sms;
+    return RZ_OK;
+}

@@ -1,0 +1,341 @@
+// rz_device.cuh — device-side types, counter-based RNG and the shading half of the path kernel.
+//
+// Everything here is `RZ_HD` (host+device) so that tests/hostsim can compile the very same
+// FP32 shading code for the CPU and compare its statistics with the f64 oracle in a container
+// that has no GPU.  That host build is test infrastructure; the product only ever launches the
+// CUDA kernels (rz_path.cu etc.) and has no CPU path.
+//
+// Reference functions restated here (paths under /root/reference/src):
+//   Camera.getRay + randomInDefocus   camera.zig:59-90     -> rz_camera_ray
+//   Hit.init                          hit.zig:25-41        -> rz_refine_hit (front face flip)
+//   Sphere.hitInner (accepted root)   geom.zig:38-66       -> rz_refine_hit (f64 re-evaluation)
+//   Texture.value / CheckerTexture    material.zig:19-51   -> rz_texture
+//   Diffuse/Metallic/Dielectric       material.zig:73-160  -> rz_scatter
+//   reflectance/reflect/refract       material.zig:179-194
+//   bounceRay miss branch (sky)       renderer.zig:124-125 -> rz_sky
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define RZ_HD __host__ __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------
+// Device scene: structure-of-arrays, one "sphere set" per kernel family (the brute-force set is
+// ordered static-first, the BVH set in leaf order).  Index k below is the position in the set.
+// ---------------------------------------------------------------------------------------------
+struct RzSphereSet {
+    const float4 *cr;      // [n_pad] (cx, cy, cz, -r^2)           FP32 intersection operand
+    const float4 *vel;     // [n_pad] (vx, vy, vz, r)              Sphere.center.dir (geom.zig:12)
+    const double4 *c64;    // [n]     (cx, cy, cz, r)  f64, for the refinement of the winning hit
+    const double4 *v64;    // [n]     (vx, vy, vz, 0)  f64
+    const uint32_t *mat;   // [n]     material index (MaterialHandle.idx)
+    const int32_t *orig;   // [n]     index in the caller's sphere array (ids, stats)
+    uint32_t n;            // real spheres
+    uint32_t n_static;     // spheres [0, n_static) are stationary            (brute set only)
+    uint32_t n_static_pad; // static part padded to a multiple of 4           (brute set only)
+    uint32_t n_pad;        // total padded count; moving part = [n_static_pad, n_pad)
+};
+
+struct RzMaterials {
+    const uint32_t *kind;   // RZ_MAT_* (material.zig:162-165)
+    const float *fuzz;      // min(fuzz, 1) is applied at scatter time (material.zig:112)
+    const float *ior;
+    const uint32_t *tex;
+    const uint32_t *method; // RZ_DIFFUSE_* (material.zig:67-71)
+};
+
+struct RzTextures {
+    const uint32_t *kind;    // RZ_TEX_* (material.zig:41-43)
+    const float4 *color;     // solid colour (rgb)
+    const double *inv_scale; // 1 / CheckerTexture.scale
+    const uint32_t *even;
+    const uint32_t *odd;
+};
+
+// BVH2 node for the FP32 traversal kernel: both child boxes live in the parent so one 64-byte
+// fetch decides both children.  child < 0 => leaf: first = ~child, count in cnt.
+struct __align__(16) RzBvhNode {
+    float lox[2], hix[2], loy[2], hiy[2], loz[2], hiz[2];
+    int32_t child[2];
+    uint32_t cnt[2];
+};
+
+struct RzCamF32 {
+    float3 look_from, px_du, px_dv, px_origin, defocus_u, defocus_v;
+    int defocus;
+};
+
+struct RzStatsDev {
+    unsigned long long v[10];  // order of RzStats (include/rayz_cuda.h)
+};
+
+// Everything a path kernel needs, passed by value (fits the 4 KB parameter space easily).
+struct RzPathArgs {
+    RzSphereSet set;
+    RzMaterials mats;
+    RzTextures texs;
+    const RzBvhNode *bvh;        // K3 only
+    uint32_t bvh_nodes;
+    RzCamF32 cam;
+    unsigned long long *accum;   // [n_local_px_pad][4] u64 fixed point (2^-32), rgb + pad
+    unsigned int *unit_counter;  // persistent-kernel work counter (zeroed before launch)
+    RzStatsDev *stats;           // STATS builds only
+    uint32_t width, height;      // full image
+    uint32_t n_local_px;         // pixels owned by this device (compact, band-interleaved rows)
+    uint32_t spp, sample_offset, max_depth;
+    uint32_t chunk;              // samples per work unit
+    uint32_t n_chunks, n_units;
+    uint32_t shard_index, shard_count, band_rows;
+    uint32_t seed_lo, seed_hi;
+    float t_min;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  key = 64-bit seed; counter = (global pixel, sample,
+// bounce, lane) so the stream is a pure function of WHAT is sampled, never of where it runs:
+// any row sharding across GPUs reproduces the full-frame image bit for bit.
+// ---------------------------------------------------------------------------------------------
+RZ_HD void rz_mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+#ifdef __CUDA_ARCH__
+    hi = __umulhi(a, b);
+    lo = a * b;
+#else
+    const uint64_t p = (uint64_t)a * (uint64_t)b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
+
+RZ_HD uint4 rz_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        uint32_t h0, l0, h1, l1;
+        rz_mulhilo(0xD2511F53u, c0, h0, l0);
+        rz_mulhilo(0xCD9E8D57u, c2, h1, l1);
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// 24 random bits -> [0,1)
+RZ_HD float rz_u01(uint32_t bits24) { return (float)bits24 * 5.9604644775390625e-8f; }
+
+// ---------------------------------------------------------------------------------------------
+// small float3 algebra
+// ---------------------------------------------------------------------------------------------
+RZ_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+RZ_HD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RZ_HD float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RZ_HD float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+RZ_HD float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RZ_HD float dot3(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+RZ_HD float rz_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+RZ_HD float3 normalize3(float3 a) { return a * rz_rsqrt(dot3(a, a)); }
+RZ_HD void rz_sincos2pi(float u, float &s, float &c) {
+    // u in [0,1) -> angle in [-pi, pi): keeps the fast-path argument small
+    const float a = (u - 0.5f) * 6.283185307179586f;
+#ifdef __CUDA_ARCH__
+    __sincosf(a, &s, &c);
+#else
+    s = sinf(a);
+    c = cosf(a);
+#endif
+}
+
+// Uniform direction on the unit sphere from two uniforms.  Same DISTRIBUTION as the
+// reference's normalised rejection sample randomUnit (material.zig:196-206); the reference's
+// sequential PRNG cannot be matched draw for draw anyway.
+RZ_HD float3 rz_uniform_sphere(float u1, float u2) {
+    const float z = 1.0f - 2.0f * u1;
+    const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    rz_sincos2pi(u2, s, c);
+    return f3(r * c, r * s, z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-path state
+// ---------------------------------------------------------------------------------------------
+struct RzRay {
+    float3 o, d;   // d is unit length (the reference leaves it un-normalised; geometry is
+                   // scale-invariant in d and every consumer normalises or only needs signs)
+    float time;
+    int self_k;    // sphere (set index) the ray starts on, -1 for camera rays.  Self
+                   // re-intersection is resolved analytically instead of by an epsilon:
+                   // leaving outward -> cannot re-hit a convex sphere; inward -> far root.
+};
+
+// Camera.getRay with rng (camera.zig:59-77): jittered pixel position, thin-lens origin on the
+// defocus disk, time in [0,1).  Disk sample is polar instead of rejection (same distribution).
+// One Philox block gives the five uniforms: 4 x 24 high bits + 3 x 8 low bits.
+RZ_HD RzRay rz_camera_ray(const RzCamF32 &cam, uint32_t px, uint32_t py, uint32_t gpix, uint32_t sample,
+                          uint32_t k0, uint32_t k1) {
+    const uint4 r = rz_philox(gpix, sample, 0u, 0u, k0, k1);
+    const float ux = rz_u01(r.x >> 8), uy = rz_u01(r.y >> 8), ut = rz_u01(r.z >> 8), ur = rz_u01(r.w >> 8);
+    const float ua = rz_u01(((r.x & 0xffu) << 16) | ((r.y & 0xffu) << 8) | (r.z & 0xffu));
+    const float x = (float)px + (ux - 0.5f);
+    const float y = (float)py + (uy - 0.5f);
+    RzRay ray;
+    ray.o = cam.look_from;
+    if (cam.defocus) {
+        const float rad = sqrtf(ur);
+        float s, c;
+        rz_sincos2pi(ua, s, c);
+        ray.o = ray.o + cam.defocus_u * (rad * c) + cam.defocus_v * (rad * s);
+    }
+    const float3 dir = cam.px_du * x + cam.px_dv * y + cam.px_origin - ray.o;
+    ray.d = normalize3(dir);
+    ray.time = ut;
+    ray.self_k = -1;
+    return ray;
+}
+
+// Sky of bounceRay's miss branch (renderer.zig:124-125): ((1-t)*1 + (0.5,0.7,1.0)) * t — not a lerp.
+RZ_HD float3 rz_sky(float3 d_unit) {
+    const float t = 0.5f * (d_unit.y + 1.0f);
+    const float a = 1.0f - t;
+    return f3((a + 0.5f) * t, (a + 0.7f) * t, (a + 1.0f) * t);
+}
+
+// Texture.value (material.zig:44-50) with CheckerTexture's handle recursion (:32-38) unrolled
+// into a bounded loop.  The lattice test runs in f64 on the f64-refined hit point: on the
+// r=1000 ground sphere |y| is ~1e-8 near the origin, far below FP32 resolution at 1000.
+RZ_HD float3 rz_texture(const RzTextures &T, uint32_t tex, double px, double py, double pz) {
+#pragma unroll 1
+    for (int level = 0; level < 8; level++) {
+        if (T.kind[tex] != 0u) break;  // solid
+        const double s = T.inv_scale[tex];
+        const long long ix = (long long)floor(px * s);
+        const long long iy = (long long)floor(py * s);
+        const long long iz = (long long)floor(pz * s);
+        const long long m = (ix + iy + iz) & 1ll;  // floor-mod 2 (two's complement)
+        tex = (m == 0) ? T.even[tex] : T.odd[tex];
+    }
+    const float4 c = T.color[tex];
+    return f3(c.x, c.y, c.z);
+}
+
+struct RzHit {
+    double px, py, pz;  // hit point, f64
+    float3 p;           // same, rounded: next ray origin
+    float3 n;           // shading normal, flipped against the ray (Hit.init, hit.zig:33-37)
+    bool front;
+};
+
+// Re-evaluate the winning sphere in f64 from the FP32 ray (Sphere.hitInner, geom.zig:38-66, with
+// the root the FP32 search selected).  ~40 DFMA-class ops once per segment vs ~6000 FP32
+// instructions of brute-force search; it makes point/normal self-consistent to 1e-13 so the
+// self-intersection rule and the checker lattice are exact.
+RZ_HD RzHit rz_refine_hit(const RzSphereSet &S, const RzRay &ray, int k, bool far_root) {
+    const double4 c = S.c64[k];
+    const double4 v = S.v64[k];
+    const double tm = (double)ray.time;
+    const double cx = fma(v.x, tm, c.x), cy = fma(v.y, tm, c.y), cz = fma(v.z, tm, c.z);
+    const double ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
+    const double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+    const double ocx = cx - ox, ocy = cy - oy, ocz = cz - oz;
+    const double a = dx * dx + dy * dy + dz * dz;
+    const double hb = dx * ocx + dy * ocy + dz * ocz;
+    const double cc = (ocx * ocx + ocy * ocy + ocz * ocz) - c.w * c.w;
+    double disc = hb * hb - a * cc;
+    if (!(disc > 0.0)) disc = 0.0;  // FP32 said "grazing hit"; f64 says tangent/miss: clamp
+    const double rt = sqrt(disc);
+    const double inv_a = 1.0 / a;
+    const double t = (far_root ? (hb + rt) : (hb - rt)) * inv_a;
+    RzHit h;
+    h.px = fma(dx, t, ox);
+    h.py = fma(dy, t, oy);
+    h.pz = fma(dz, t, oz);
+    const double inv_r = 1.0 / c.w;
+    double nx = (h.px - cx) * inv_r, ny = (h.py - cy) * inv_r, nz = (h.pz - cz) * inv_r;
+    h.front = (nx * dx + ny * dy + nz * dz) < 0.0;
+    if (!h.front) { nx = -nx; ny = -ny; nz = -nz; }
+    h.n = f3((float)nx, (float)ny, (float)nz);
+    h.p = f3((float)h.px, (float)h.py, (float)h.pz);
+    return h;
+}
+
+// material.zig:179-183; pow(1-cos,5) as repeated multiplication
+RZ_HD float rz_reflectance(float cosv, float ri) {
+    float r0 = (1.0f - ri) / (1.0f + ri);
+    r0 *= r0;
+    const float m = 1.0f - cosv;
+    const float m2 = m * m;
+    return r0 + (1.0f - r0) * (m2 * m2 * m);
+}
+
+// Material.scatter (material.zig:167-176).  Returns false when the path is absorbed
+// (MetallicMaterial.scatter -> null, :116-117).  `ray` is replaced by the scattered ray,
+// `att` receives the attenuation.  u = four uniforms of this bounce's Philox block.
+RZ_HD bool rz_scatter(const RzMaterials &M, const RzTextures &T, uint32_t mat, uint32_t kind, const RzHit &h, int k,
+                      float4 u, RzRay &ray, float3 &att) {
+    float3 nd;
+    if (kind == 0u) {
+        // DiffuseMaterial.scatter (:77-101).  HEMISPHERE (default, :74): direction of a uniform
+        // ball sample flipped into the normal's hemisphere == uniform over the hemisphere,
+        // no cosine weighting, attenuation = albedo.
+        const uint32_t method = M.method[mat];
+        const float3 s = rz_uniform_sphere(u.x, u.y);
+        if (method == 2u) {
+            nd = dot3(s, h.n) > 0.0f ? s : s * -1.0f;
+        } else {
+            // UNIT_SPHERE: normal + point in ball; UNIT_SPHERE_SURFACE: normal + unit vector (:78-82)
+            const float rad = (method == 0u) ? cbrtf(u.z) : 1.0f;
+            float3 t = h.n + s * rad;
+            if (dot3(t, t) < 1e-12f) t = h.n;
+            nd = normalize3(t);
+        }
+        att = rz_texture(T, M.tex[mat], h.px, h.py, h.pz);
+    } else if (kind == 1u) {
+        // MetallicMaterial.scatter (:108-131): unit mirror direction + min(fuzz,1) * unit vector
+        const float dn = dot3(ray.d, h.n);
+        float3 r = ray.d - h.n * (2.0f * dn);
+        const float fuzz = M.fuzz[mat];
+        if (fuzz > 0.0f) r = r + rz_uniform_sphere(u.x, u.y) * fminf(fuzz, 1.0f);
+        if (!(dot3(r, h.n) > 0.0f)) return false;
+        nd = normalize3(r);
+        att = rz_texture(T, M.tex[mat], h.px, h.py, h.pz);
+    } else {
+        // DielectricMaterial.scatter (:137-159).  The reference leaves cos/sin/sqrt unclamped
+        // (NaN on rounding, mapped to 0 at output by V3.sqrt); FP32 clamps to stay NaN-free.
+        const float ior = M.ior[mat];
+        const float eta = h.front ? 1.0f / ior : ior;
+        const float cos_t = fminf(-dot3(ray.d, h.n), 1.0f);
+        const float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
+        if (eta * sin_t > 1.0f || rz_reflectance(cos_t, eta) > u.x) {
+            nd = ray.d - h.n * (2.0f * dot3(ray.d, h.n));       // reflect (:185-187)
+        } else {
+            const float3 perp = (ray.d + h.n * cos_t) * eta;    // refract (:189-194)
+            const float par = -sqrtf(fmaxf(0.0f, 1.0f - dot3(perp, perp)));
+            nd = perp + h.n * par;
+        }
+        nd = normalize3(nd);
+        att = f3(1.0f, 1.0f, 1.0f);
+    }
+    ray.o = h.p;
+    ray.d = nd;
+    ray.self_k = k;   // time is kept (material.zig:92,122,155)
+    return true;
+}
+
+// local (compact, band-interleaved) pixel index -> global pixel coordinates
+RZ_HD void rz_local_to_global(uint32_t lp, uint32_t width, uint32_t shard_index, uint32_t shard_count,
+                              uint32_t band_rows, uint32_t &i, uint32_t &j) {
+    const uint32_t lr = lp / width;
+    i = lp - lr * width;
+    if (shard_count <= 1u) { j = lr; return; }
+    const uint32_t lb = lr / band_rows;
+    const uint32_t within = lr - lb * band_rows;
+    j = (lb * shard_count + shard_index) * band_rows + within;
+}

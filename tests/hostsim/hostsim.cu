@@ -1,0 +1,122 @@
+// hostsim.cu — TEST INFRASTRUCTURE ONLY (never linked into librayz_cuda.so).
+//
+// Compiles the product's FP32 device shading code (rayz_b200/csrc/rz_device.cuh: Philox, camera
+// ray, f64 hit refinement, scatter, sky, texture) as HOST code and drives it with a scalar
+// restatement of the kernel's search/shade loop (rz_path.cu), so the FP32 algorithm's statistics
+// can be compared with the f64 oracle in a container without a GPU.  The GPU tests compare the
+// real kernels with the oracle; this only de-risks them.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <atomic>
+
+#include "../../include/rayz_cuda.h"
+#include "../../rayz_b200/csrc/rz_device.cuh"
+
+#define RZ_FAR_BIT 0x40000000
+
+static inline void consider(int k, float b, float disc, int self_k, float t_min, float &bt, int &bk) {
+    const float sq = sqrtf(disc);
+    float t = b - sq;
+    int tag = k;
+    if (k == self_k) { t = (b > 0.0f) ? b + sq : -1.0f; tag = k | RZ_FAR_BIT; }
+    else if (t < t_min) { t = b + sq; tag = k | RZ_FAR_BIT; }
+    if (t > t_min && t < bt) { bt = t; bk = tag; }
+}
+
+extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth,
+                              uint64_t seed, float t_min, uint32_t threads, double *out_rgb, uint64_t *counters) {
+    const uint32_t n = sc->n_spheres;
+    std::vector<float4> cr(n), vel(n);
+    std::vector<double4> c64(n), v64(n);
+    std::vector<uint32_t> smat(n);
+    std::vector<int32_t> orig(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const double *c = sc->sphere_center + 3 * i, *v = sc->sphere_velocity + 3 * i; const double r = sc->sphere_radius[i];
+        cr[i] = make_float4((float)c[0], (float)c[1], (float)c[2], -(float)(r * r));
+        vel[i] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)r);
+        c64[i] = make_double4(c[0], c[1], c[2], r); v64[i] = make_double4(v[0], v[1], v[2], 0);
+        smat[i] = sc->sphere_material[i]; orig[i] = (int32_t)i;
+    }
+    const uint32_t nm = sc->n_materials, nt = sc->n_textures;
+    std::vector<uint32_t> mk(nm), mt(nm), mm(nm), tk(nt), te(nt), to(nt);
+    std::vector<float> mf(nm), mi(nm); std::vector<float4> tc(nt); std::vector<double> ts(nt);
+    for (uint32_t i = 0; i < nm; i++) { mk[i] = sc->mat_kind[i]; mt[i] = sc->mat_kind[i] == 2 ? 0 : sc->mat_texture[i]; mm[i] = sc->mat_method ? sc->mat_method[i] : 2; mf[i] = (float)sc->mat_fuzz[i]; mi[i] = (float)sc->mat_ior[i]; }
+    for (uint32_t i = 0; i < nt; i++) { tk[i] = sc->tex_kind[i]; te[i] = sc->tex_even[i]; to[i] = sc->tex_odd[i];
+        tc[i] = make_float4((float)sc->tex_color[3*i], (float)sc->tex_color[3*i+1], (float)sc->tex_color[3*i+2], 0); ts[i] = sc->tex_kind[i] == 0 ? 1.0 / sc->tex_scale[i] : 0; }
+    RzSphereSet S; S.cr = cr.data(); S.vel = vel.data(); S.c64 = c64.data(); S.v64 = v64.data(); S.mat = smat.data(); S.orig = orig.data(); S.n = n; S.n_static = 0; S.n_static_pad = 0; S.n_pad = n;
+    RzMaterials M; M.kind = mk.data(); M.fuzz = mf.data(); M.ior = mi.data(); M.tex = mt.data(); M.method = mm.data();
+    RzTextures T; T.kind = tk.data(); T.color = tc.data(); T.inv_scale = ts.data(); T.even = te.data(); T.odd = to.data();
+    RzCamF32 C;
+    C.look_from = make_float3((float)cam->look_from[0], (float)cam->look_from[1], (float)cam->look_from[2]);
+    C.px_du = make_float3((float)cam->px_du[0], (float)cam->px_du[1], (float)cam->px_du[2]);
+    C.px_dv = make_float3((float)cam->px_dv[0], (float)cam->px_dv[1], (float)cam->px_dv[2]);
+    C.px_origin = make_float3((float)cam->px_origin[0], (float)cam->px_origin[1], (float)cam->px_origin[2]);
+    C.defocus_u = make_float3((float)cam->defocus_u[0], (float)cam->defocus_u[1], (float)cam->defocus_u[2]);
+    C.defocus_v = make_float3((float)cam->defocus_v[0], (float)cam->defocus_v[1], (float)cam->defocus_v[2]);
+    C.defocus = cam->defocus;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    if (!(t_min > 0)) t_min = 1e-4f;
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<uint32_t> next(0);
+    std::vector<std::vector<uint64_t>> cnt(threads, std::vector<uint64_t>(10, 0));
+    auto work = [&](uint32_t tid) {
+        uint64_t *ct = cnt[tid].data();
+        while (true) {
+            const uint32_t j = next.fetch_add(1);
+            if (j >= h) break;
+            for (uint32_t i = 0; i < w; i++) {
+                unsigned long long acc[3] = {0, 0, 0};
+                const uint32_t gpix = j * w + i;
+                for (uint32_t s = 0; s < spp; s++) {
+                    RzRay ray = rz_camera_ray(C, i, j, gpix, s, k0, k1);
+                    float3 thr = f3(1, 1, 1);
+                    uint32_t seg = 0;
+                    bool alive = max_depth > 0;
+                    ct[0]++;
+                    if (!alive) ct[9]++;
+                    while (alive) {
+                        float bt = 3.0e38f; int bk = -1;
+                        for (uint32_t k = 0; k < n; k++) {
+                            const float4 sp = cr[k], v = vel[k];
+                            const float ocx = fmaf(v.x, ray.time, sp.x) - ray.o.x, ocy = fmaf(v.y, ray.time, sp.y) - ray.o.y, ocz = fmaf(v.z, ray.time, sp.z) - ray.o.z;
+                            const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
+                            const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, sp.w)));
+                            const float disc = fmaf(b, b, -c);
+                            if (disc > 0.0f) consider((int)k, b, disc, ray.self_k, t_min, bt, bk);
+                        }
+                        ct[1]++;
+                        if (bk < 0) {
+                            const float3 L = thr * rz_sky(ray.d);
+                            acc[0] += (unsigned long long)llrintf(fminf(fmaxf(L.x, 0.f), 1048576.f) * 4294967296.f);
+                            acc[1] += (unsigned long long)llrintf(fminf(fmaxf(L.y, 0.f), 1048576.f) * 4294967296.f);
+                            acc[2] += (unsigned long long)llrintf(fminf(fmaxf(L.z, 0.f), 1048576.f) * 4294967296.f);
+                            ct[7]++;
+                            break;
+                        }
+                        const int k = bk & ~RZ_FAR_BIT;
+                        const RzHit hit = rz_refine_hit(S, ray, k, (bk & RZ_FAR_BIT) != 0);
+                        const uint32_t mat = S.mat[k], kind = M.kind[mat];
+                        ct[4 + kind]++;
+                        seg++;
+                        const uint4 rb = rz_philox(gpix, s, seg, 0u, k0, k1);
+                        const float4 u = make_float4(rz_u01(rb.x >> 8), rz_u01(rb.y >> 8), rz_u01(rb.z >> 8), rz_u01(rb.w >> 8));
+                        float3 att;
+                        if (!rz_scatter(M, T, mat, kind, hit, k, u, ray, att)) { ct[8]++; break; }
+                        thr = thr * att;
+                        if (seg >= max_depth) { ct[9]++; break; }
+                    }
+                }
+                const double inv = 1.0 / (double)spp, sc32 = 2.3283064365386962890625e-10;
+                for (int c = 0; c < 3; c++) out_rgb[((size_t)j * w + i) * 3 + c] = (double)acc[c] * sc32 * inv;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < threads; t++) pool.emplace_back(work, t);
+    for (auto &t : pool) t.join();
+    if (counters) { for (int i = 0; i < 10; i++) { counters[i] = 0; for (auto &c : cnt) counters[i] += c[i]; } counters[2] = counters[1] * n; }
+    return 0;
+}
