@@ -28,7 +28,7 @@ UNITS = {
     "rz_ids.cu": ["--fmad=false"],
     "rz_context.cu": [],
 }
-HEADERS = ["rz_device.cuh", os.path.join("..", "..", "include", "rayz_cuda.h")]
+HEADERS = ["rz_device.cuh", "rz_search.cuh", os.path.join("..", "..", "include", "rayz_cuda.h")]
 
 
 def _nvcc() -> str:

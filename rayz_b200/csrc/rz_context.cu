@@ -30,8 +30,9 @@ extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays
 extern "C" cudaError_t rz_launch_ids(const RzIdsArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_resolve(const RzResolveArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_ffma_peak(float *sink, int grid, int iters, int mode, cudaStream_t stream);
-extern "C" cudaError_t rz_wavefront_render(const RzPathArgs *a, int sm_count, cudaStream_t stream, void **scratch,
-                                           size_t *scratch_bytes, uint32_t *launches);
+extern "C" cudaError_t rz_wavefront_render(const RzPathArgs *a, int sm_count, int collect_stats, cudaStream_t stream,
+                                           void **scratch, size_t *scratch_bytes, uint32_t *launches);
+extern "C" void rz_wavefront_free(void *scratch);
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -411,7 +412,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
         D.accum.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
         D.ids.release(); D.sink.release();
-        if (D.wf_scratch) cudaFree(D.wf_scratch);
+        if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
         for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
         if (D.own_stream) cudaStreamDestroy(D.own_stream);
     }
@@ -631,7 +632,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         if (n_local > 0) {
             if (variant == RZ_VARIANT_WAVEFRONT) {
                 uint32_t l = 0;
-                RZ_CUDA(rz_wavefront_render(&a, D.sms, D.stream, &D.wf_scratch, &D.wf_scratch_bytes, &l));
+                RZ_CUDA(rz_wavefront_render(&a, D.sms, (int)p->collect_stats, D.stream, &D.wf_scratch, &D.wf_scratch_bytes, &l));
                 launches += l;
             } else {
                 RZ_CUDA(rz_launch_path(&a, (int)variant, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));

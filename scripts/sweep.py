@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--glass", action="store_true")
     ap.add_argument("--grid", type=int, default=11)
-    ap.add_argument("--configs", default="mega:1:16,mega:2:16,mega:2:8,mega:2:32,mega:1:32,bvh:1:16")
+    ap.add_argument("--configs", default="mega:1:16,mega:2:16,mega:2:8,mega:2:32,mega:1:32,bvh:1:16,wavefront:2:16")
     args = ap.parse_args()
     t = rayz_b200.random_bouncing(args.width, seed=42, glass_heavy=args.glass, grid_lo=-args.grid, grid_hi=args.grid)
     be = Backend((0,))

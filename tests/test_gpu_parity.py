@@ -356,3 +356,25 @@ def test_tracer_render_is_a_drop_in(orc):
 def test_fp32_peak_microbenchmark_is_sane(be):
     tf, sms = be.fp32_peak(100)
     assert sms >= 100 and 30.0 < tf < 90.0, (tf, sms)
+
+
+def test_wavefront_matches_megakernel_bitwise(be, scene42):
+    """K2 (staged kernels, ballot compaction, CUDA graph) runs the same search/shade functions with the
+    same RNG keys as K1, and accumulation is integer: the images must be bit-identical."""
+    w, spp = 200, 12
+    cam, h = cam_for(w)
+    be.upload_scene(scene42)
+    a, a8, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=21, variant="mega", collect_stats=True))
+    sa = be.stats()
+    b, b8, n = be.render(cam, Backend.params(w, h, spp, 50, seed=21, variant="wavefront", collect_stats=True))
+    sb = be.stats()
+    assert n == w * h * spp
+    assert np.array_equal(a, b) and np.array_equal(a8, b8)
+    for k in ("paths", "segments", "hits_diffuse", "hits_metallic", "hits_dielectric", "ended_sky", "ended_absorbed", "ended_depth"):
+        assert sa[k] == sb[k], k
+    # edge: sizes that leave padding pixels and a depth-0 render
+    for (ww, hh, s, d) in ((33, 19, 3, 50), (16, 9, 2, 0)):
+        c2 = rayz_b200.Camera.init(20.0, 10.0, 0.6, (13, 2, 3), (0, 0, 0), (0, 1, 0), hh, ww).rz
+        x, _, _ = be.render(c2, Backend.params(ww, hh, s, d, seed=3, variant="mega"))
+        y, _, _ = be.render(c2, Backend.params(ww, hh, s, d, seed=3, variant="wavefront"))
+        assert np.array_equal(x, y)
