@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,15 +223,9 @@ def main():
         def __init__(self, ptr, shape, typestr):
             self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr, "version": 3, "strides": None}
 
-    if world > 1 and rank == 0:
-        final_lin = torch.empty((H, W, 4), dtype=torch.float32, device=dev)
-        final_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
-        slabs_lin = [torch.empty((rows_of[r], W, 4), dtype=torch.float32, device=dev) for r in range(world)]
-        slabs_rgb = [torch.empty((rows_of[r], W, 3), dtype=torch.uint8, device=dev) for r in range(world)]
-        row_idx = []
-        for r in range(world):
-            idx = [j for j in range(H) if (j // band) % world == r]
-            row_idx.append(torch.tensor(idx, dtype=torch.long, device=dev))
+    from rayz_b200.dist import SlabGather
+    gather_lin = SlabGather(H, (W, 4), torch.float32, dev, band) if world > 1 else None
+    gather_rgb = SlabGather(H, (W, 3), torch.uint8, dev, band) if world > 1 else None
 
     def step_device():
         """One render, inputs resident in HBM, result left in HBM on GPU0 (after the NCCL gather for N>1)."""
@@ -239,21 +234,8 @@ def main():
             return n
         lin = torch.as_tensor(DevArray(dl, (my_rows, W, 4), "<f4"), device=dev)
         rgb = torch.as_tensor(DevArray(d8, (my_rows, W, 3), "|u1"), device=dev)
-        if rank == 0:
-            ops = []
-            for r in range(1, world):
-                ops.append(dist.P2POp(dist.irecv, slabs_lin[r], r))
-                ops.append(dist.P2POp(dist.irecv, slabs_rgb[r], r))
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-            final_lin[row_idx[0]] = lin
-            final_rgb[row_idx[0]] = rgb
-            for r in range(1, world):
-                final_lin[row_idx[r]] = slabs_lin[r]
-                final_rgb[row_idx[r]] = slabs_rgb[r]
-        else:
-            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, lin, 0), dist.P2POp(dist.isend, rgb, 0)]):
-                req.wait()
+        gather_lin.run(lin)      # slabs -> GPU0 over NCCL, interleaved into the full frame there
+        gather_rgb.run(rgb)
         return n
 
     def barrier():
@@ -342,6 +324,17 @@ def main():
                 be2.close()
         barrier()
 
+    # ---- the other kernel variants on the same workload (one timed render each; informational)
+    variants = {}
+    if world == 1 and not args.no_variants:
+        for v in ("mega", "bvh", "wavefront"):
+            pv = Backend.params(W, H, SPP, DEPTH, seed=1, variant=v)
+            be.render_device(cam, pv, sync=True)
+            flush_buf.zero_()
+            be.render_device(cam, pv, sync=True)
+            t = be.timing()
+            variants[v] = {"mpaths_s": total_paths / (t["kernel_ms"] * 1e-3) / 1e6, "kernel_ms": t["kernel_ms"], "launches": t["launches"]}
+
     if rank == 0:
         fl = algorithmic_flops_per_path(stats, tinfo["n_static"], tinfo["n_moving"])
         peak_tf, sms = be.fp32_peak(400)
@@ -369,6 +362,8 @@ def main():
         }
         if e2e:
             out["e2e"] = e2e
+        if variants:
+            out["variants"] = variants
         if not args.no_cpu_baseline and world == 1:
             import oracle
             sc = oracle.Scene.random_bouncing(w["scene_seed"])

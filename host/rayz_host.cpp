@@ -1,0 +1,80 @@
+// rayz_host — stand-in for the reference executable (src/rayz.zig:12-43):
+//
+//     rayz_host <img_w> [out.ppm] [--spp N] [--depth N] [--seed S] [--render-seed S]
+//               [--variant auto|mega|wavefront|bvh] [--gpus N] [--grid G]
+//
+// Same argv contract (img_w required, optional output path, else stdout), same report line
+// ("Finished render (…s): … rps and … us per ray", rays = primary samples), same ASCII P3 output.
+// The pixel loop runs in librayz_cuda.so; the timed region covers what the reference's covers
+// (hittables + BVH build == scene upload, and the render).
+#include <chrono>
+#include <cstdlib>
+#include <random>
+#include <string>
+
+#include "rayz_host.hpp"
+
+using namespace rayz;
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        std::fprintf(stderr, "usage: %s <img_w> [out.ppm] [--spp N] [--depth N] [--seed S] [--variant V] [--gpus N]\n", argv[0]);
+        return 2;  // the reference panics on a missing argv[1] (`args.next().?`, rayz.zig:16)
+    }
+    char *end = nullptr;
+    const unsigned long long img_w = std::strtoull(argv[1], &end, 10);
+    if (!end || *end || img_w == 0) { std::fprintf(stderr, "error: InvalidCharacter\n"); return 1; }
+    const char *out_fname = nullptr;
+    uint64_t seed = 0, render_seed = 1;
+    bool have_seed = false;
+    size_t spp = 10, depth = 50;
+    int gpus = 1, grid = 11;
+    uint32_t variant = RZ_VARIANT_AUTO;
+    for (int i = 2; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&]() -> const char * { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", a.c_str()); std::exit(2); } return argv[++i]; };
+        if (a == "--spp") spp = std::strtoull(val(), nullptr, 10);
+        else if (a == "--depth") depth = std::strtoull(val(), nullptr, 10);
+        else if (a == "--seed") { seed = std::strtoull(val(), nullptr, 10); have_seed = true; }
+        else if (a == "--render-seed") render_seed = std::strtoull(val(), nullptr, 10);
+        else if (a == "--gpus") gpus = std::atoi(val());
+        else if (a == "--grid") grid = std::atoi(val());
+        else if (a == "--variant") {
+            const std::string v = val();
+            variant = v == "mega" ? RZ_VARIANT_MEGA : v == "wavefront" ? RZ_VARIANT_WAVEFRONT : v == "bvh" ? RZ_VARIANT_BVH : RZ_VARIANT_AUTO;
+        } else if (!out_fname && a.rfind("--", 0) != 0) out_fname = argv[i];
+        else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    if (!have_seed) { std::random_device rd; seed = ((uint64_t)rd() << 32) ^ rd(); }  // renderer.zig:55-59: seeded from the OS
+
+    try {
+        Tracer tracer((size_t)img_w, 20.0, 10.0, 0.6, {13, 2, 3}, {}, V3::y_hat(), seed);  // rayz.zig:46-55
+        tracer.samples_per_px = spp;
+        tracer.max_bounces = depth;
+        tracer.render_seed = render_seed;
+        tracer.variant = variant;
+        tracer.devices.clear();
+        for (int g = 0; g < gpus; g++) tracer.devices.push_back(g);
+        randomBouncing(tracer, -grid, grid);
+
+        const auto st = std::chrono::steady_clock::now();
+        const double rays_traced = (double)tracer.render();
+        const double durr = std::chrono::duration<double>(std::chrono::steady_clock::now() - st).count();
+        std::fprintf(stderr, "Finished render (%.2fs): %.2f rps and %.2f us per ray\n", durr, rays_traced / durr, 1e6 * durr / rays_traced);
+        std::fprintf(stderr, "  [rayz_cuda] path kernel %.3f ms, resolve %.3f ms, %u launches, %u static + %u moving spheres, variant %u, %d GPU(s)\n",
+                     tracer.timing.kernel_ms, tracer.timing.resolve_ms, tracer.timing.launches, tracer.timing.n_static, tracer.timing.n_moving,
+                     tracer.timing.variant, gpus);
+        if (out_fname) {
+            FILE *f = std::fopen(out_fname, "wb");
+            if (!f) { std::perror(out_fname); return 1; }
+            tracer.img.writePPM(f);
+            std::fclose(f);
+        } else {
+            tracer.img.writePPM(stdout);
+        }
+    } catch (const CudaBackendError &e) {
+        std::fprintf(stderr, "error: CudaBackend (%d): %s\n", e.code, e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -378,3 +378,38 @@ def test_wavefront_matches_megakernel_bitwise(be, scene42):
         x, _, _ = be.render(c2, Backend.params(ww, hh, s, d, seed=3, variant="mega"))
         y, _, _ = be.render(c2, Backend.params(ww, hh, s, d, seed=3, variant="wavefront"))
         assert np.array_equal(x, y)
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_n_gpus() < 2")
+def test_multi_device_context_matches_single_device_bitwise(scene42):
+    """One process driving N GPUs (RzConfig.n_devices): rows are dealt in bands, each device's resolve
+    kernel writes straight into GPU0's framebuffer over NVLink P2P.  Must equal the 1-GPU render bit for bit."""
+    n = min(_n_gpus(), 4)
+    w, spp = 320, 16
+    cam, h = cam_for(w)
+    one = Backend((0,))
+    one.upload_scene(scene42)
+    a, a8, na = one.render(cam, Backend.params(w, h, spp, 50, seed=31, variant="mega"))
+    many = Backend(tuple(range(n)))
+    many.upload_scene(scene42)
+    for variant in ("mega", "bvh"):
+        b, b8, nb = many.render(cam, Backend.params(w, h, spp, 50, seed=31, variant=variant, collect_stats=True))
+        assert na == nb == w * h * spp == many.stats()["paths"]
+        assert np.array_equal(a8, b8)
+        if variant == "mega":
+            assert np.array_equal(a, b)
+    # a multi-device context that is itself one shard of a larger job
+    full = np.empty_like(a)
+    for s in range(2):
+        l, _, _ = many.render(cam, Backend.params(w, h, spp, 50, seed=31, variant="mega", shard_index=s, shard_count=2, band_rows=4))
+        # context shard s of 2 with n devices == shards s*n..s*n+n-1 of 2n
+        rows = sorted(j for d in range(n) for j in range(h) if (j // 4) % (2 * n) == s * n + d)
+        assert l.shape[0] == len(rows)
+        full[rows] = l
+    assert np.array_equal(full, a)
+    one.close(); many.close()
