@@ -72,6 +72,22 @@ __global__ void __launch_bounds__(256) rz_ffma_peak_kernel(float *sink, float a,
                 for (int i = 0; i < 16; i++) x[i] = fmaf(x[i], a, b);
             }
         }
+    } else if (MODE == 2) {
+        // packed FP32x2 (fma.rn.f32x2 -> SASS FFMA2): 8 chains of float2 = the same 16 FMAs per step
+        float2 p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = make_float2(x[2 * i], x[2 * i + 1]);
+        const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], a2, b2);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { x[2 * i] = p[i].x; x[2 * i + 1] = p[i].y; }
     } else {
         // acc[i][j] += y[i]*z[j] : SGEMM-like outer product, three distinct registers per FFMA
         float y[4], z[4];
@@ -99,6 +115,7 @@ __global__ void __launch_bounds__(256) rz_ffma_peak_kernel(float *sink, float a,
 // FFMAs per thread per `iters` unit = 8 * 16 = 128
 extern "C" cudaError_t rz_launch_ffma_peak(float *sink, int grid, int iters, int mode, cudaStream_t stream) {
     if (mode == 0) rz_ffma_peak_kernel<0><<<grid, 256, 0, stream>>>(sink, 0.999f, 1e-3f, iters);
+    else if (mode == 2) rz_ffma_peak_kernel<2><<<grid, 256, 0, stream>>>(sink, 0.999f, 1e-3f, iters);
     else rz_ffma_peak_kernel<1><<<grid, 256, 0, stream>>>(sink, 0.999f, 1e-3f, iters);
     return cudaGetLastError();
 }
