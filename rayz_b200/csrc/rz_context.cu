@@ -80,18 +80,18 @@ struct DBuf {
 };
 
 struct SetBufs {
-    DBuf<float4> cr, vel;
+    DBuf<float4> cr, vel, pk;
     DBuf<double4> c64, v64;
     DBuf<uint32_t> mat;
     DBuf<int32_t> orig;
     uint32_t n = 0, n_static = 0, n_static_pad = 0, n_pad = 0;
     RzSphereSet view() const {
         RzSphereSet s;
-        s.cr = cr.p; s.vel = vel.p; s.c64 = c64.p; s.v64 = v64.p; s.mat = mat.p; s.orig = orig.p;
+        s.cr = cr.p; s.vel = vel.p; s.pk = pk.p; s.c64 = c64.p; s.v64 = v64.p; s.mat = mat.p; s.orig = orig.p;
         s.n = n; s.n_static = n_static; s.n_static_pad = n_static_pad; s.n_pad = n_pad;
         return s;
     }
-    void release() { cr.release(); vel.release(); c64.release(); v64.release(); mat.release(); orig.release(); }
+    void release() { cr.release(); vel.release(); pk.release(); c64.release(); v64.release(); mat.release(); orig.release(); }
 };
 
 struct Dev {
@@ -313,7 +313,7 @@ struct SahBuilder {
 };
 
 struct HostSet {
-    std::vector<float4> cr, vel;
+    std::vector<float4> cr, vel, pkv;
     std::vector<double4> c64, v64;
     std::vector<uint32_t> mat;
     std::vector<int32_t> orig;
@@ -328,6 +328,22 @@ struct HostSet {
         mat.push_back(sc.sphere_material[i]);
         orig.push_back((int32_t)i);
     }
+    // pair-interleaved copy of cr/vel for the packed FP32x2 search (layout: RzSphereSet::pk)
+    std::vector<float4> packed() const {
+        std::vector<float4> pk;
+        if (n_pad == 0 || (n_static_pad & 1u) || (n_pad & 1u)) return pk;
+        for (uint32_t k = 0; k < n_pad; k += 2) {
+            const float4 a = cr[k], b = cr[k + 1];
+            pk.push_back(make_float4(a.x, b.x, a.y, b.y));
+            pk.push_back(make_float4(a.z, b.z, a.w, b.w));
+            if (k >= n_static_pad) {
+                const float4 va = vel[k], vb = vel[k + 1];
+                pk.push_back(make_float4(va.x, vb.x, va.y, vb.y));
+                pk.push_back(make_float4(va.z, vb.z, 0.f, 0.f));
+            }
+        }
+        return pk;
+    }
     void pad_to(size_t count) {
         while (cr.size() < count) {  // -r^2 = +1 => discriminant b^2 - |oc|^2 - 1 < 0: never hit
             cr.push_back(make_float4(0.f, 0.f, 0.f, 1.0f));
@@ -340,6 +356,7 @@ int upload_set(SetBufs &d, const HostSet &h, cudaStream_t s) {
     int rc;
     if ((rc = d.cr.upload(h.cr, s))) return rc;
     if ((rc = d.vel.upload(h.vel, s))) return rc;
+    if (!h.pkv.empty() && (rc = d.pk.upload(h.pkv, s))) return rc;
     if ((rc = d.c64.upload(h.c64, s))) return rc;
     if ((rc = d.v64.upload(h.v64, s))) return rc;
     if ((rc = d.mat.upload(h.mat, s))) return rc;
@@ -480,6 +497,7 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     bs.n_pad = ((uint32_t)bs.cr.size() + 3u) & ~3u;
     bs.pad_to(bs.n_pad);
     pad_aux(bs);
+    bs.pkv = bs.packed();
 
     // ---- reference-shaped BVH (K0)
     RefBuilder rb;
@@ -803,7 +821,7 @@ extern "C" int rayz_cuda_fp32_peak(RzContext *ctx, uint32_t millis, double *out_
         return RZ_OK;
     };
     double best = 0;
-    for (int mode = 0; mode < 2; mode++) {   // scalar-operand chains and SGEMM-like 3-register form
+    for (int mode = 0; mode < 3; mode++) {   // scalar-operand chains, SGEMM-like 3-register form, packed FFMA2
         float ms = 0;
         if ((rc = run(2000, mode, &ms))) return rc;                 // warm-up
         if ((rc = run(20000, mode, &ms))) return rc;                // calibration

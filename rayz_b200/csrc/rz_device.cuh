@@ -27,6 +27,10 @@
 struct RzSphereSet {
     const float4 *cr;      // [n_pad] (cx, cy, cz, -r^2)           FP32 intersection operand
     const float4 *vel;     // [n_pad] (vx, vy, vz, r)              Sphere.center.dir (geom.zig:12)
+    const float4 *pk;      // brute set only: the same numbers pair-interleaved for the packed FP32x2
+                           // search (rz_search_brute2): stationary pair p = spheres (2p, 2p+1) ->
+                           // (cx0,cx1,cy0,cy1)(cz0,cz1,w0,w1), w = -r^2; moving pairs follow, each with
+                           // two more float4 (vx0,vx1,vy0,vy1)(vz0,vz1,0,0).  n_static_pad + 2*n_moving_pad float4.
     const double4 *c64;    // [n]     (cx, cy, cz, r)  f64, for the refinement of the winning hit
     const double4 *v64;    // [n]     (vx, vy, vz, 0)  f64
     const uint32_t *mat;   // [n]     material index (MaterialHandle.idx)

@@ -16,8 +16,9 @@
 //     any multi-GPU row sharding;
 //   * K1: the whole sphere set is staged once per CTA into shared memory with a 1-D bulk
 //     async copy (cp.async.bulk + mbarrier, SASS UBLKCP) and searched by brute force with
-//     warp-uniform (broadcast) LDS.128 operands: 10 FP32 instructions per stationary
-//     sphere-ray pair, 13 per moving one, FFMA dominated;
+//     warp-uniform (broadcast) LDS.128 operands and Blackwell packed FP32x2 arithmetic
+//     (FFMA2/FADD2/FMUL2, two spheres per instruction): 11 issue slots per stationary
+//     sphere PAIR and ray, 14 per moving pair (rz_search_brute2);
 //   * K3: large scenes traverse a BVH2 through the read-only path (ld.global.nc).
 #include "rz_search.cuh"
 
@@ -32,14 +33,14 @@ struct RzStream {
     bool alive;
 };
 
+// G = sphere PAIRS per search-loop iteration
 template <int R, int G, bool STATS, bool BVH>
 __global__ void __launch_bounds__(128) rz_path_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
-    float4 *s_cr = reinterpret_cast<float4 *>(rz_smem);
-    float4 *s_vel = s_cr + a.set.n_pad;
+    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
 
-    if (!BVH) rz_stage_scene(a.set, s_cr, s_vel, &s_bar);
+    if (!BVH) rz_stage_scene_pk(a.set, s_pk, &s_bar);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(128) rz_path_kernel(const RzPathArgs a) {
             for (int r = 0; r < R; r++)
                 if (st[r].alive) rz_search_bvh(a, rays[r], a.t_min, bt[r], bk[r], c_nodes, c_sph);
         } else {
-            rz_search_brute<R, G>(s_cr, s_vel, (int)a.set.n_static_pad, (int)a.set.n_pad, rays, a.t_min, bt, bk);
+            rz_search_brute2<R, G>(s_pk, (int)a.set.n_static_pad, (int)a.set.n_pad, rays, a.t_min, bt, bk);
         }
 
         // ---------------------------------------------------------------- shade
@@ -181,9 +182,9 @@ extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays
     }
     const size_t smem = (size_t)(a->set.n_pad + (a->set.n_pad - a->set.n_static_pad)) * 16u;
     if (rays_per_thread == 1) {
-        return stats ? rz_launch_one<1, 4, true, false>(*a, sm_count, smem, stream, grid_out)
-                     : rz_launch_one<1, 4, false, false>(*a, sm_count, smem, stream, grid_out);
+        return stats ? rz_launch_one<1, 2, true, false>(*a, sm_count, smem, stream, grid_out)
+                     : rz_launch_one<1, 2, false, false>(*a, sm_count, smem, stream, grid_out);
     }
-    return stats ? rz_launch_one<2, 4, true, false>(*a, sm_count, smem, stream, grid_out)
-                 : rz_launch_one<2, 4, false, false>(*a, sm_count, smem, stream, grid_out);
+    return stats ? rz_launch_one<2, 2, true, false>(*a, sm_count, smem, stream, grid_out)
+                 : rz_launch_one<2, 2, false, false>(*a, sm_count, smem, stream, grid_out);
 }

@@ -107,10 +107,10 @@ __device__ __forceinline__ void rz_search_brute(const float4 *__restrict__ s_cr,
         for (int r = 0; r < R; r++) {
 #pragma unroll
             for (int j = 0; j < G; j++) {
-                // centre(t) = center.origin + center.dir * ray.time (geom.zig:40)
-                const float ocx = fmaf(v[j].x, ray[r].time, s[j].x) - ray[r].o.x;
-                const float ocy = fmaf(v[j].y, ray[r].time, s[j].y) - ray[r].o.y;
-                const float ocz = fmaf(v[j].z, ray[r].time, s[j].z) - ray[r].o.z;
+                // oc = (c0 - o) + v * time; centre(t) = center.origin + center.dir * ray.time (geom.zig:40)
+                const float ocx = fmaf(v[j].x, ray[r].time, s[j].x - ray[r].o.x);
+                const float ocy = fmaf(v[j].y, ray[r].time, s[j].y - ray[r].o.y);
+                const float ocz = fmaf(v[j].z, ray[r].time, s[j].z - ray[r].o.z);
                 b[r][j] = fmaf(ocz, ray[r].d.z, fmaf(ocy, ray[r].d.y, ocx * ray[r].d.x));
                 const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, s[j].w)));
                 disc[r][j] = fmaf(b[r][j], b[r][j], -c);
@@ -123,6 +123,182 @@ __device__ __forceinline__ void rz_search_brute(const float4 *__restrict__ s_cr,
 #pragma unroll
                 for (int j = 0; j < G; j++)
                     if (disc[r][j] > 0.0f) rz_consider(i + j, b[r][j], disc[r][j], ray[r].self_k, t_min, bt[r], bk[r]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ K1 search, packed
+// The same arithmetic issued as Blackwell packed-FP32 instructions (PTX add/mul/fma.rn.f32x2 ->
+// SASS FADD2 / FMUL2 / FFMA2): one instruction works on TWO SPHERES (the .x/.y halves of a 64-bit
+// register pair) against one ray, whose operands enter as 32-bit broadcast registers
+// (`R.F32` in SASS), so rays cost no extra registers.  Per ray and sphere PAIR:
+//   stationary: 3 FADD2 + FMUL2 + 2 FFMA2 (b) + 3 FFMA2 (c) + 2 FFMA (disc, needs a negation the
+//               packed forms do not have)                       = 11 issue slots for 2 tests
+//   moving    : + 3 FFMA2 for centre(t) = c0 + v * time (geom.zig:40)  = 14 issue slots
+// versus 20 / 26 scalar instructions.  Every half follows the operation order of
+// rz_search_brute exactly (IEEE rn, FTZ), so both searches return bit-identical (t, k).
+// s_pk: pair-interleaved sphere set in shared memory (layout: RzSphereSet::pk).
+// G2 = sphere pairs per loop iteration (2 => 4 spheres share one max/branch, as before).
+__device__ __forceinline__ float2 rz_f2(float x, float y) { return make_float2(x, y); }
+
+template <int R, int G2>
+__device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk, int n_static_pad, int n_pad,
+                                                 const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
+    float nox[R], noy[R], noz[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { nox[r] = -ray[r].o.x; noy[r] = -ray[r].o.y; noz[r] = -ray[r].o.z; }
+    const float4 *q = s_pk;
+    int k = 0;
+#pragma unroll 1
+    for (; k < n_static_pad; k += 2 * G2, q += 2 * G2) {
+        float4 A[G2], B[G2];
+#pragma unroll
+        for (int j = 0; j < G2; j++) { A[j] = q[2 * j]; B[j] = q[2 * j + 1]; }
+        float2 b[R][G2], disc[R][G2];
+        float m = -1.0f;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+#pragma unroll
+            for (int j = 0; j < G2; j++) {
+                const float2 ocx = __fadd2_rn(rz_f2(A[j].x, A[j].y), rz_f2(nox[r], nox[r]));
+                const float2 ocy = __fadd2_rn(rz_f2(A[j].z, A[j].w), rz_f2(noy[r], noy[r]));
+                const float2 ocz = __fadd2_rn(rz_f2(B[j].x, B[j].y), rz_f2(noz[r], noz[r]));
+                b[r][j] = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
+                                     __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
+                const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B[j].z, B[j].w))));
+                disc[r][j] = rz_f2(fmaf(b[r][j].x, b[r][j].x, -c.x), fmaf(b[r][j].y, b[r][j].y, -c.y));
+                m = fmaxf(m, fmaxf(disc[r][j].x, disc[r][j].y));
+            }
+        }
+        if (m > 0.0f) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int j = 0; j < G2; j++) {
+                    if (disc[r][j].x > 0.0f) rz_consider(k + 2 * j, b[r][j].x, disc[r][j].x, ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (disc[r][j].y > 0.0f) rz_consider(k + 2 * j + 1, b[r][j].y, disc[r][j].y, ray[r].self_k, t_min, bt[r], bk[r]);
+                }
+        }
+    }
+#pragma unroll 1
+    for (; k < n_pad; k += 2 * G2, q += 4 * G2) {
+        float4 A[G2], B[G2], VA[G2], VB[G2];
+#pragma unroll
+        for (int j = 0; j < G2; j++) { A[j] = q[4 * j]; B[j] = q[4 * j + 1]; VA[j] = q[4 * j + 2]; VB[j] = q[4 * j + 3]; }
+        float2 b[R][G2], disc[R][G2];
+        float m = -1.0f;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float2 tm = rz_f2(ray[r].time, ray[r].time);
+#pragma unroll
+            for (int j = 0; j < G2; j++) {
+                // centre(t) = center.origin + center.dir * ray.time (geom.zig:40)
+                // oc = (c0 - o) + v * time: each instruction reads ONE register pair that came from
+                // shared memory (two "cold" 64-bit sources cost an FFMA2 ~3.3 cycles instead of 2)
+                const float2 ocx = __ffma2_rn(rz_f2(VA[j].x, VA[j].y), tm, __fadd2_rn(rz_f2(A[j].x, A[j].y), rz_f2(nox[r], nox[r])));
+                const float2 ocy = __ffma2_rn(rz_f2(VA[j].z, VA[j].w), tm, __fadd2_rn(rz_f2(A[j].z, A[j].w), rz_f2(noy[r], noy[r])));
+                const float2 ocz = __ffma2_rn(rz_f2(VB[j].x, VB[j].y), tm, __fadd2_rn(rz_f2(B[j].x, B[j].y), rz_f2(noz[r], noz[r])));
+                b[r][j] = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
+                                     __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
+                const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B[j].z, B[j].w))));
+                disc[r][j] = rz_f2(fmaf(b[r][j].x, b[r][j].x, -c.x), fmaf(b[r][j].y, b[r][j].y, -c.y));
+                m = fmaxf(m, fmaxf(disc[r][j].x, disc[r][j].y));
+            }
+        }
+        if (m > 0.0f) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int j = 0; j < G2; j++) {
+                    if (disc[r][j].x > 0.0f) rz_consider(k + 2 * j, b[r][j].x, disc[r][j].x, ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (disc[r][j].y > 0.0f) rz_consider(k + 2 * j + 1, b[r][j].y, disc[r][j].y, ray[r].self_k, t_min, bt[r], bk[r]);
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ K1 search, ray-paired
+// Transposed packing: one packed instruction works on TWO RAYS (.x/.y halves) against one sphere,
+// whose numbers enter as 32-bit broadcast operands straight from the LDS destination registers.
+// The 64-bit operands are then the long-lived ray registers (-o, d, time as pairs), which G
+// consecutive instructions share through the operand-reuse cache.  Sphere record in shared memory
+// = 2 x float4: (cx, cy, cz, vx) (vy, vz, w, w), w = -r^2 (stationary: v = 0 and not read).
+// Same operation order per half as rz_search_brute2 => bit-identical results.
+template <int R, int G>
+__device__ __forceinline__ void rz_search_brute_rp(const float4 *__restrict__ s_rp, int n_static_pad, int n_pad,
+                                                   const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
+    static_assert(R % 2 == 0, "ray-paired search needs an even number of rays per thread");
+    constexpr int P = R / 2;
+    float2 nox[P], noy[P], noz[P], dx[P], dy[P], dz[P], tm[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        nox[p] = rz_f2(-ray[2 * p].o.x, -ray[2 * p + 1].o.x); noy[p] = rz_f2(-ray[2 * p].o.y, -ray[2 * p + 1].o.y);
+        noz[p] = rz_f2(-ray[2 * p].o.z, -ray[2 * p + 1].o.z);
+        dx[p] = rz_f2(ray[2 * p].d.x, ray[2 * p + 1].d.x); dy[p] = rz_f2(ray[2 * p].d.y, ray[2 * p + 1].d.y);
+        dz[p] = rz_f2(ray[2 * p].d.z, ray[2 * p + 1].d.z); tm[p] = rz_f2(ray[2 * p].time, ray[2 * p + 1].time);
+    }
+    const float4 *q = s_rp;
+    int k = 0;
+#pragma unroll 1
+    for (; k < n_static_pad; k += G, q += 2 * G) {
+        float4 A[G];
+        float2 W[G];
+#pragma unroll
+        for (int j = 0; j < G; j++) { A[j] = q[2 * j]; W[j] = *reinterpret_cast<const float2 *>(&q[2 * j + 1].z); }
+        float2 b[P][G], disc[P][G];
+        float m = -1.0f;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                const float2 ocx = __fadd2_rn(nox[p], rz_f2(A[j].x, A[j].x));
+                const float2 ocy = __fadd2_rn(noy[p], rz_f2(A[j].y, A[j].y));
+                const float2 ocz = __fadd2_rn(noz[p], rz_f2(A[j].z, A[j].z));
+                b[p][j] = __ffma2_rn(ocz, dz[p], __ffma2_rn(ocy, dy[p], __fmul2_rn(ocx, dx[p])));
+                const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, W[j])));
+                disc[p][j] = rz_f2(fmaf(b[p][j].x, b[p][j].x, -c.x), fmaf(b[p][j].y, b[p][j].y, -c.y));
+                m = fmaxf(m, fmaxf(disc[p][j].x, disc[p][j].y));
+            }
+        }
+        if (m > 0.0f) {
+#pragma unroll
+            for (int p = 0; p < P; p++)
+#pragma unroll
+                for (int j = 0; j < G; j++) {
+                    if (disc[p][j].x > 0.0f) rz_consider(k + j, b[p][j].x, disc[p][j].x, ray[2 * p].self_k, t_min, bt[2 * p], bk[2 * p]);
+                    if (disc[p][j].y > 0.0f) rz_consider(k + j, b[p][j].y, disc[p][j].y, ray[2 * p + 1].self_k, t_min, bt[2 * p + 1], bk[2 * p + 1]);
+                }
+        }
+    }
+#pragma unroll 1
+    for (; k < n_pad; k += G, q += 2 * G) {
+        float4 A[G], B[G];
+#pragma unroll
+        for (int j = 0; j < G; j++) { A[j] = q[2 * j]; B[j] = q[2 * j + 1]; }
+        float2 b[P][G], disc[P][G];
+        float m = -1.0f;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                // oc = (c0 - o) + v * time   (centre(t) = center.origin + center.dir * ray.time, geom.zig:40)
+                const float2 ocx = __ffma2_rn(tm[p], rz_f2(A[j].w, A[j].w), __fadd2_rn(nox[p], rz_f2(A[j].x, A[j].x)));
+                const float2 ocy = __ffma2_rn(tm[p], rz_f2(B[j].x, B[j].x), __fadd2_rn(noy[p], rz_f2(A[j].y, A[j].y)));
+                const float2 ocz = __ffma2_rn(tm[p], rz_f2(B[j].y, B[j].y), __fadd2_rn(noz[p], rz_f2(A[j].z, A[j].z)));
+                b[p][j] = __ffma2_rn(ocz, dz[p], __ffma2_rn(ocy, dy[p], __fmul2_rn(ocx, dx[p])));
+                const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B[j].z, B[j].w))));
+                disc[p][j] = rz_f2(fmaf(b[p][j].x, b[p][j].x, -c.x), fmaf(b[p][j].y, b[p][j].y, -c.y));
+                m = fmaxf(m, fmaxf(disc[p][j].x, disc[p][j].y));
+            }
+        }
+        if (m > 0.0f) {
+#pragma unroll
+            for (int p = 0; p < P; p++)
+#pragma unroll
+                for (int j = 0; j < G; j++) {
+                    if (disc[p][j].x > 0.0f) rz_consider(k + j, b[p][j].x, disc[p][j].x, ray[2 * p].self_k, t_min, bt[2 * p], bk[2 * p]);
+                    if (disc[p][j].y > 0.0f) rz_consider(k + j, b[p][j].y, disc[p][j].y, ray[2 * p + 1].self_k, t_min, bt[2 * p + 1], bk[2 * p + 1]);
+                }
         }
     }
 }
@@ -175,9 +351,9 @@ __device__ __forceinline__ void rz_search_bvh(const RzPathArgs &a, const RzRay &
                         const float4 s = __ldg(a.set.cr + k);
                         const float4 v = __ldg(a.set.vel + k);
                         n_sph++;
-                        const float ocx = fmaf(v.x, ray.time, s.x) - ox;
-                        const float ocy = fmaf(v.y, ray.time, s.y) - oy;
-                        const float ocz = fmaf(v.z, ray.time, s.z) - oz;
+                        const float ocx = fmaf(v.x, ray.time, s.x - ox);   // same order as the packed searches
+                        const float ocy = fmaf(v.y, ray.time, s.y - oy);
+                        const float ocz = fmaf(v.z, ray.time, s.z - oz);
                         const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
                         const float cc = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, s.w)));
                         const float disc = fmaf(b, b, -cc);
@@ -218,6 +394,18 @@ __device__ __forceinline__ void rz_stage_scene(const RzSphereSet &set, float4 *s
         rz_mbar_expect_tx(bar, bytes_cr + bytes_vel);
         rz_bulk_g2s(s_cr, set.cr, bytes_cr, bar);
         if (bytes_vel) rz_bulk_g2s(s_vel, set.vel + set.n_static_pad, bytes_vel, bar);
+    }
+    rz_mbar_wait(bar, 0);
+}
+
+// Same for the pair-interleaved set of rz_search_brute2: one bulk copy of the whole array.
+__device__ __forceinline__ void rz_stage_scene_pk(const RzSphereSet &set, float4 *s_pk, uint64_t *bar) {
+    const uint32_t bytes = (set.n_static_pad + 2u * (set.n_pad - set.n_static_pad)) * 16u;
+    if (threadIdx.x == 0) rz_mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rz_mbar_expect_tx(bar, bytes);
+        rz_bulk_g2s(s_pk, set.pk, bytes, bar);
     }
     rz_mbar_wait(bar, 0);
 }

@@ -136,9 +136,8 @@ template <int R>
 __global__ void __launch_bounds__(128) wf_intersect(const RzPathArgs a, WfState s) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
-    float4 *s_cr = reinterpret_cast<float4 *>(rz_smem);
-    float4 *s_vel = s_cr + a.set.n_pad;
-    rz_stage_scene(a.set, s_cr, s_vel, &s_bar);
+    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
+    rz_stage_scene_pk(a.set, s_pk, &s_bar);
     const WfCounters c = *s.ctr;
     const unsigned int n = c.n_live;
     const unsigned int *live = s.live[c.cur];
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(128) wf_intersect(const RzPathArgs a, WfState 
             rays[r].d = f3(B.x, B.y, B.z); rays[r].self_k = __float_as_int(B.w);
             bt[r] = 3.0e38f; bk[r] = -1;
         }
-        rz_search_brute<R, 4>(s_cr, s_vel, (int)a.set.n_static_pad, (int)a.set.n_pad, rays, a.t_min, bt, bk);
+        rz_search_brute2<R, 2>(s_pk, (int)a.set.n_static_pad, (int)a.set.n_pad, rays, a.t_min, bt, bk);
 #pragma unroll
         for (int r = 0; r < R; r++) {
             unsigned int q = 4u;

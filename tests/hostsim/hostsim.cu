@@ -81,7 +81,7 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
                         float bt = 3.0e38f; int bk = -1;
                         for (uint32_t k = 0; k < n; k++) {
                             const float4 sp = cr[k], v = vel[k];
-                            const float ocx = fmaf(v.x, ray.time, sp.x) - ray.o.x, ocy = fmaf(v.y, ray.time, sp.y) - ray.o.y, ocz = fmaf(v.z, ray.time, sp.z) - ray.o.z;
+                            const float ocx = fmaf(v.x, ray.time, sp.x - ray.o.x), ocy = fmaf(v.y, ray.time, sp.y - ray.o.y), ocz = fmaf(v.z, ray.time, sp.z - ray.o.z);
                             const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
                             const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, sp.w)));
                             const float disc = fmaf(b, b, -c);
