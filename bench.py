@@ -153,6 +153,17 @@ def algorithmic_flops_per_path(stats: dict, n_static: int, n_moving: int) -> dic
     return {"segments_per_path": S, "p_sky": p_sky, "f_isect": f_isect, "f_path": f_path}
 
 
+def ncu_traffic(variant: str):
+    """dram__bytes_read + dram__bytes_write of the path kernel per launch, from the committed ncu --set full
+    capture (profiles/traffic.json; the capture ran the config-2 image at 40 spp — the accumulators and the
+    scene are the only DRAM traffic and do not grow with spp)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(variant, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -295,6 +306,7 @@ def main():
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     kern_ms = float(kern_ms.item())
     launches_per_step = be.timing()["launches"]
+    variant_ran = {1: "mega", 2: "wavefront", 3: "bvh"}.get(be.timing()["variant"], "?")
 
     # ---- e2e: reference-facing call with host buffers (rank 0 drives all N GPUs through the
     # library's own multi-device context: this is what the single-process Zig host would call)
@@ -338,7 +350,6 @@ def main():
     if rank == 0:
         fl = algorithmic_flops_per_path(stats, tinfo["n_static"], tinfo["n_moving"])
         peak_tf, sms = be.fp32_peak(400)
-        variant_ran = {1: "mega", 2: "wavefront", 3: "bvh"}.get(be.timing()["variant"], "?")
         per_gpu_paths = total_paths / world
         achieved = per_gpu_paths * fl["f_path"] / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "fp32", "kernel": "rz_path_kernel (" + variant_ran + ")", "achieved": achieved, "peak": peak_tf,
@@ -346,7 +357,7 @@ def main():
                     "peak_source": "measured live: K6 FFMA microbenchmark (MEASURED_PEAKS.json has no FP32 figure)",
                     "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
                     "kernel_ms_per_launch": kern_ms, "flop_per_path": fl["f_path"], "segments_per_path": fl["segments_per_path"],
-                    "flop_per_segment_search": fl["f_isect"], "traffic": None,
+                    "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran),
                     "hbm_bytes_algorithmic": 35 * W * H // world,
                     "note": "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test); "
                             "tensor cores unused by design; framebuffer HBM traffic is 35 B/pixel once per render"}

@@ -56,6 +56,7 @@ int main(int argc, char **argv) {
         tracer.devices.clear();
         for (int g = 0; g < gpus; g++) tracer.devices.push_back(g);
         randomBouncing(tracer, -grid, grid);
+        tracer.initBackend();  // like Tracer.init's allocations: before the timer (rayz.zig:22-24)
 
         const auto st = std::chrono::steady_clock::now();
         const double rays_traced = (double)tracer.render();

@@ -235,14 +235,19 @@ struct Tracer {
     static void check(int rc) { if (rc != RZ_OK) throw CudaBackendError(rc, rayz_cuda_last_error()); }
 
     // renderer.zig:72-101.  Returns the number of primary rays traced (`!usize`).
+    // Device selection, CUDA context and kernel loading: the counterpart of the allocations
+    // Tracer.init does before main starts its timer (renderer.zig:29-64, rayz.zig:22-24).
+    void initBackend() {
+        if (ctx) return;
+        RzConfig cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.n_devices = (int32_t)devices.size();
+        for (size_t i = 0; i < devices.size() && i < 8; i++) cfg.device_ids[i] = devices[i];
+        check(rayz_cuda_create(&cfg, &ctx));
+    }
+
     size_t render() {
-        if (!ctx) {
-            RzConfig cfg;
-            std::memset(&cfg, 0, sizeof cfg);
-            cfg.n_devices = (int32_t)devices.size();
-            for (size_t i = 0; i < devices.size() && i < 8; i++) cfg.device_ids[i] = devices[i];
-            check(rayz_cuda_create(&cfg, &ctx));
-        }
+        initBackend();
         // pool.initHittables + bvh.build (:76-78) -> flatten + upload
         const size_t ns = pool.spheres.size(), nm = pool.materials.size(), nt = pool.textures.size();
         std::vector<double> sc(3 * ns), sv(3 * ns), sr(ns), mf(nm), mi(nm), tcol(3 * nt), ts(nt);

@@ -27,6 +27,7 @@ struct RzResolveArgs {
 };
 extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays_per_thread, int collect_stats, int sm_count,
                                       cudaStream_t stream, int *grid_out);
+extern "C" cudaError_t rz_path_warm(void);
 extern "C" cudaError_t rz_launch_ids(const RzIdsArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_resolve(const RzResolveArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_ffma_peak(float *sink, int grid, int iters, int mode, cudaStream_t stream);
@@ -403,6 +404,7 @@ extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
         D.stream = D.own_stream;
         for (auto &ev : D.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+        if ((e = rz_path_warm()) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "loading the path kernels: %s", cudaGetErrorString(e)); }
         if (d > 0) {
             // the resolve kernel of device d stores straight into device 0's buffers (NVLink P2P)
             int can = 0;

@@ -172,6 +172,15 @@ static cudaError_t rz_launch_one(const RzPathArgs &a, int sm_count, size_t smem,
     return cudaGetLastError();
 }
 
+// Forces the lazily loaded path kernels into the context (called once from rayz_cuda_create so that
+// the first render does not pay module loading).
+extern "C" cudaError_t rz_path_warm(void) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, rz_path_kernel<2, 2, false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_path_kernel<1, 1, false, true>);
+    return e;
+}
+
 // variant: 1 = brute (K1), 3 = BVH (K3).  rays_per_thread in {1,2}.
 extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays_per_thread, int collect_stats, int sm_count,
                                       cudaStream_t stream, int *grid_out) {

@@ -141,19 +141,38 @@ __device__ __forceinline__ void rz_search_brute(const float4 *__restrict__ s_cr,
 // G2 = sphere pairs per loop iteration (2 => 4 spheres share one max/branch, as before).
 __device__ __forceinline__ float2 rz_f2(float x, float y) { return make_float2(x, y); }
 
-template <int R, int G2>
-__device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk, int n_static_pad, int n_pad,
+// Operand sources for the packed search.  The sphere operands are WARP-UNIFORM (every lane tests
+// the same spheres), so besides shared memory (LDS.128 broadcasts into vector registers) they can
+// come from the constant bank through the uniform datapath: LDCU.64 into uniform registers, which
+// FFMA2/FADD2 take directly as `UR.F32x2` operands.  That removes the LDS register-file write-back
+// and the "cold" vector-register operand reads that hold the FMA pipe at ~67 % in the LDS form
+// (measured: scripts/searchbench.cu mix_kernel, 67 % -> 80 % FMA-pipe utilisation).
+#ifndef RZ_CONST_PK_FLOAT4
+#define RZ_CONST_PK_FLOAT4 4000   // 64,000 B of the 64 KB constant bank: 2000 moving or 4000 stationary spheres
+#endif
+static __constant__ float4 rz_c_pk[RZ_CONST_PK_FLOAT4];   // one instance per translation unit that includes this header
+
+struct RzSrcShared {
+    const float4 *p;
+    __device__ __forceinline__ float4 operator[](int i) const { return p[i]; }
+};
+struct RzSrcConst {
+    __device__ __forceinline__ float4 operator[](int i) const { return rz_c_pk[i]; }
+};
+
+template <int R, int G2, class SRC>
+__device__ __forceinline__ void rz_search_brute2(const SRC src, int n_static_pad, int n_pad,
                                                  const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
     float nox[R], noy[R], noz[R];
 #pragma unroll
     for (int r = 0; r < R; r++) { nox[r] = -ray[r].o.x; noy[r] = -ray[r].o.y; noz[r] = -ray[r].o.z; }
-    const float4 *q = s_pk;
+    int q = 0;   // float4 index into the pair-interleaved set
     int k = 0;
 #pragma unroll 1
     for (; k < n_static_pad; k += 2 * G2, q += 2 * G2) {
         float4 A[G2], B[G2];
 #pragma unroll
-        for (int j = 0; j < G2; j++) { A[j] = q[2 * j]; B[j] = q[2 * j + 1]; }
+        for (int j = 0; j < G2; j++) { A[j] = src[q + 2 * j]; B[j] = src[q + 2 * j + 1]; }
         float2 b[R][G2], disc[R][G2];
         float m = -1.0f;
 #pragma unroll
@@ -184,7 +203,7 @@ __device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk
     for (; k < n_pad; k += 2 * G2, q += 4 * G2) {
         float4 A[G2], B[G2], VA[G2], VB[G2];
 #pragma unroll
-        for (int j = 0; j < G2; j++) { A[j] = q[4 * j]; B[j] = q[4 * j + 1]; VA[j] = q[4 * j + 2]; VB[j] = q[4 * j + 3]; }
+        for (int j = 0; j < G2; j++) { A[j] = src[q + 4 * j]; B[j] = src[q + 4 * j + 1]; VA[j] = src[q + 4 * j + 2]; VB[j] = src[q + 4 * j + 3]; }
         float2 b[R][G2], disc[R][G2];
         float m = -1.0f;
 #pragma unroll
@@ -215,6 +234,12 @@ __device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk
                 }
         }
     }
+}
+
+template <int R, int G2>
+__device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk, int n_static_pad, int n_pad,
+                                                 const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
+    rz_search_brute2<R, G2, RzSrcShared>(RzSrcShared{s_pk}, n_static_pad, n_pad, ray, t_min, bt, bk);
 }
 
 // ------------------------------------------------------------------------------ K1 search, ray-paired

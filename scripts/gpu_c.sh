@@ -1,0 +1,15 @@
+#!/bin/bash
+# Validation run after a kernel change: parity tests, N=1 bench (both arms), host stand-in, ncu launch list + full capture.
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/e_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/e_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/e_bench_n1.json 2> gpurun_out/e_bench_n1.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/e_bench_ref.json 2> gpurun_out/e_bench_ref.err
+( time host/_build/rayz_host 1200 gpurun_out/e_out_1200.ppm --spp 500 --seed 42 ) > gpurun_out/e_host_1gpu.log 2>&1
+md5sum gpurun_out/e_out_1200.ppm >> gpurun_out/e_host_1gpu.log; rm -f gpurun_out/e_out_1200.ppm
+CMD="python bench.py --steps 2 --warmup 3 --spp 40 --no-cpu-baseline --no-e2e --no-variants"
+$CMD > gpurun_out/e_ncu_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/e_launches.csv $CMD > gpurun_out/e_ncu_launches.log 2>&1
+$CMD > gpurun_out/e_ncu_plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:rz_path_kernel -s 2 -c 1 -o gpurun_out/e_prof_path $CMD > gpurun_out/e_ncu_full.log 2>&1
+tail -3 gpurun_out/e_pytest.log gpurun_out/e_host_1gpu.log; cut -c1-600 gpurun_out/e_bench_n1.json

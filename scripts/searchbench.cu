@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) sb_kernel(const SbArgs a) {
     float4 *s_vel = s0 + a.set.n_pad;
     if (MODE == 0) rz_stage_scene(a.set, s0, s_vel, &s_bar);
     else if (MODE == 1) rz_stage_scene_pk(a.set, s0, &s_bar);
-    else {
+    else if (MODE == 2) {
         for (unsigned i = threadIdx.x; i < 2u * a.set.n_pad; i += blockDim.x) s0[i] = a.rp[i];
         __syncthreads();
     }
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(128) sb_kernel(const SbArgs a) {
         for (int r = 0; r < R; r++) { bt[r] = 3.0e38f; bk[r] = -1; }
         if (MODE == 0) rz_search_brute<R, G>(s0, s_vel, (int)a.set.n_static_pad, (int)a.set.n_pad, ray, a.t_min, bt, bk);
         else if (MODE == 1) rz_search_brute2<R, G>(s0, (int)a.set.n_static_pad, (int)a.set.n_pad, ray, a.t_min, bt, bk);
+        else if (MODE == 3) rz_search_brute2<R, G, RzSrcConst>(RzSrcConst{}, (int)a.set.n_static_pad, (int)a.set.n_pad, ray, a.t_min, bt, bk);
         else rz_search_brute_rp<(R % 2 ? R + 1 : R), G>(s0, (int)a.set.n_static_pad, (int)a.set.n_pad, reinterpret_cast<const RzRay (&)[(R % 2 ? R + 1 : R)]>(ray), a.t_min, reinterpret_cast<float (&)[(R % 2 ? R + 1 : R)]>(bt), reinterpret_cast<int (&)[(R % 2 ? R + 1 : R)]>(bk));
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(128) sb_kernel(const SbArgs a) {
 // OP: 0 FFMA2 r,r,r   1 FFMA2 with a 32-bit broadcast operand   2 FADD2 (broadcast)   3 FMUL2 (broadcast)
 //     4 the search's own mix (per pair: 3 FFMA2 centre, 3 FADD2, FMUL2 + 2 FFMA2, 3 FFMA2, 2 FFMA, 1 FMNMX3), data in registers
 //     5 = 4 with the operands re-read from shared memory every iteration (LDS.128 broadcast)
+__constant__ float4 c_sph[64];
+
 template <int OP>
 __global__ void __launch_bounds__(128) mix_kernel(float *sink, float a, float b, int iters, const float4 *gsrc) {
     __shared__ float4 sm[64];
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(128) mix_kernel(float *sink, float a, float b,
 #pragma unroll
     for (int i = 0; i < 8; i++) p[i] = make_float2(1.0f + 0.001f * (threadIdx.x + i), 0.5f + 0.002f * i);
     const float2 a2 = make_float2(a, a * 1.0001f), b2 = make_float2(b, b * 0.999f);
-    float ox = -13.f - 1e-3f * threadIdx.x, oy = -2.f, oz = -3.f, dx = 0.6f, dy = -0.1f, dz = 0.79f, tm = 0.3f, m = -1.f;
+    float ox = -13.f - 1e-3f * threadIdx.x, oy = -2.f + a, oz = -3.f + b, dx = 0.6f * a, dy = -0.1f * a, dz = 0.79f * a, tm = 0.3f, m = -1.f;
     float2 m2 = make_float2(0.f, 0.f);
     float4 rg[16];
 #pragma unroll
@@ -115,18 +118,21 @@ __global__ void __launch_bounds__(128) mix_kernel(float *sink, float a, float b,
 #pragma unroll
             for (int j = 0; j < 4; j++) {   // 4 sphere pairs = 8 tests for this one ray
                 float4 A, B, VA, VB;
-                if (F & 1) { A = q[2 * j]; B = q[2 * j + 1]; VA = q[32 + 2 * j]; VB = q[32 + 2 * j + 1]; }
+                if (F & 32) { const float4 *cq = c_sph + ((it & 3) << 3); A = cq[2 * j]; B = cq[2 * j + 1]; VA = cq[32 + 2 * j]; VB = cq[32 + 2 * j + 1]; }
+                else if (F & 1) { A = q[2 * j]; B = q[2 * j + 1]; VA = q[32 + 2 * j]; VB = q[32 + 2 * j + 1]; }
                 else { A = rg[4 * j]; B = rg[4 * j + 1]; VA = rg[4 * j + 2]; VB = rg[4 * j + 3]; }
                 const float2 t2 = make_float2(tm, tm);
                 float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y);
-                if (!(F & 8)) { cx = __ffma2_rn(make_float2(VA.x, VA.y), t2, cx); cy = __ffma2_rn(make_float2(VA.z, VA.w), t2, cy); cz = __ffma2_rn(make_float2(VB.x, VB.y), t2, cz); }
-                const float2 ocx = __fadd2_rn(cx, make_float2(ox, ox));
-                const float2 ocy = __fadd2_rn(cy, make_float2(oy, oy));
-                const float2 ocz = __fadd2_rn(cz, make_float2(oz, oz));
+                if (!(F & 8) && !(F & 16)) { cx = __ffma2_rn(make_float2(VA.x, VA.y), t2, cx); cy = __ffma2_rn(make_float2(VA.z, VA.w), t2, cy); cz = __ffma2_rn(make_float2(VB.x, VB.y), t2, cz); }
+                float2 ocx = __fadd2_rn(cx, make_float2(ox, ox));
+                float2 ocy = __fadd2_rn(cy, make_float2(oy, oy));
+                float2 ocz = __fadd2_rn(cz, make_float2(oz, oz));
+                if (!(F & 8) && (F & 16)) { ocx = __ffma2_rn(make_float2(VA.x, VA.y), t2, ocx); ocy = __ffma2_rn(make_float2(VA.z, VA.w), t2, ocy); ocz = __ffma2_rn(make_float2(VB.x, VB.y), t2, ocz); }
                 const float2 bb = __ffma2_rn(ocz, make_float2(dz, dz), __ffma2_rn(ocy, make_float2(dy, dy), __fmul2_rn(ocx, make_float2(dx, dx))));
                 const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, make_float2(B.z, B.w))));
                 float2 disc;
-                if (F & 2) disc = __ffma2_rn(bb, bb, c);
+                if (F & 64) disc = __ffma2_rn(bb, bb, make_float2(__int_as_float(__float_as_int(c.x) ^ 0x80000000), __int_as_float(__float_as_int(c.y) ^ 0x80000000)));
+                else if (F & 2) disc = __ffma2_rn(bb, bb, c);
                 else disc = make_float2(fmaf(bb.x, bb.x, -c.x), fmaf(bb.y, bb.y, -c.y));
                 if (F & 4) m2 = __fadd2_rn(m2, disc);
                 else m = fmaxf(m, fmaxf(disc.x, disc.y));
@@ -155,7 +161,7 @@ static void run_mix(float *sink, const float4 *gsrc, int sms, int ctas, double p
     CK(cudaEventElapsedTime(&ms, e0, e1));
     // per iteration and thread: OP<=3: 64 packed instructions; OP>=4: 4 pairs x (13 packed + 2 FFMA)
     const int F = OP - 4;
-    const double packed = OP <= 3 ? 64.0 : 4.0 * (10 + ((F & 8) ? 0 : 3) + ((F & 2) ? 1 : 0) + ((F & 4) ? 1 : 0)), scalar = OP <= 3 ? 0.0 : ((F & 2) ? 0.0 : 8.0);
+    const double packed = OP <= 3 ? 64.0 : 4.0 * (9 + ((F & 8) ? 0 : 3) + ((F & 66) ? 1 : 0) + ((F & 4) ? 1 : 0)), scalar = OP <= 3 ? 0.0 : ((F & 66) ? 0.0 : 8.0);
     const double pipe_cycles = (packed * 2 + scalar) * iters;                 // FMA-pipe cycles per warp if FFMA2 = 2 cycles
     const double cyc = ms * 1e-3 * 1.965e9;                                   // at 1965 MHz
     const double warps_per_smsp = ctas * 4 / 4.0;
@@ -291,11 +297,12 @@ int main(int argc, char **argv) {
         float4 *gsrc;
         CK(cudaMalloc(&gsrc, 64 * 16));
         CK(cudaMemcpy(gsrc, src.data(), 64 * 16, cudaMemcpyHostToDevice));
-        for (int ctas : {4}) {
+        CK(cudaMemcpyToSymbol(c_sph, src.data(), 64 * 16));
+        for (int ctas : {4, 8}) {
             run_mix<0>(sink, gsrc, sms, ctas, peak); run_mix<1>(sink, gsrc, sms, ctas, peak); run_mix<2>(sink, gsrc, sms, ctas, peak);
             run_mix<3>(sink, gsrc, sms, ctas, peak); run_mix<4>(sink, gsrc, sms, ctas, peak); run_mix<5>(sink, gsrc, sms, ctas, peak);
-            run_mix<4 + 2>(sink, gsrc, sms, ctas, peak); run_mix<4 + 4>(sink, gsrc, sms, ctas, peak); run_mix<4 + 6>(sink, gsrc, sms, ctas, peak);
-            run_mix<4 + 8>(sink, gsrc, sms, ctas, peak); run_mix<4 + 14>(sink, gsrc, sms, ctas, peak); run_mix<4 + 7>(sink, gsrc, sms, ctas, peak);
+            run_mix<4 + 16>(sink, gsrc, sms, ctas, peak); run_mix<4 + 17>(sink, gsrc, sms, ctas, peak); run_mix<4 + 16 + 64>(sink, gsrc, sms, ctas, peak); run_mix<4 + 17 + 64>(sink, gsrc, sms, ctas, peak); run_mix<4 + 16 + 2>(sink, gsrc, sms, ctas, peak); run_mix<4 + 16 + 6>(sink, gsrc, sms, ctas, peak);
+            run_mix<4 + 8>(sink, gsrc, sms, ctas, peak); run_mix<4 + 9>(sink, gsrc, sms, ctas, peak);
         }
     }
     if (argc > 2 && atoi(argv[2]) == 2) {
@@ -377,6 +384,7 @@ int main(int argc, char **argv) {
     float4 *d_rp;
     CK(cudaMalloc(&d_rp, rp.size() * 16));
     CK(cudaMemcpy(d_rp, rp.data(), rp.size() * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyToSymbol(rz_c_pk, pk.data(), pk.size() * 16));
     float4 *d_cr, *d_vel, *d_pk, *d_ro, *d_rd;
     int *d_k; float *d_t;
     CK(cudaMalloc(&d_cr, cr.size() * 16)); CK(cudaMalloc(&d_vel, vel.size() * 16)); CK(cudaMalloc(&d_pk, pk.size() * 16));
@@ -407,16 +415,19 @@ int main(int argc, char **argv) {
     }
     RUN(0, 2, 4, 0)
     RUN(1, 2, 2, 0)
-    RUN(2, 2, 2, 0)
-    RUN(2, 2, 4, 0)
-    RUN(2, 2, 8, 0)
-    RUN(2, 4, 2, 0)
-    RUN(2, 4, 4, 0)
-    RUN(2, 2, 4, 4)
-    RUN(2, 4, 4, 2)
-    RUN(2, 4, 2, 3)
+    RUN(3, 2, 2, 0)
+    RUN(3, 2, 1, 0)
+    RUN(3, 1, 2, 0)
+    RUN(3, 3, 2, 0)
+    RUN(3, 4, 2, 0)
+    RUN(3, 4, 1, 0)
+    RUN(3, 2, 2, 5)
+    RUN(3, 2, 2, 4)
+    RUN(3, 2, 2, 3)
+    RUN(3, 4, 2, 3)
+    RUN(3, 4, 2, 2)
     {   // the packed search must return bit-identical (t, k) to the scalar one
-        Result r0 = run<2, 2, 4>(a, sms, 2, 50, smem), r1 = run<1, 2, 2>(a, sms, 2, 50, smem), r2 = run<1, 4, 2>(a, sms, 2, 50, smem);
+        Result r0 = run<3, 2, 2>(a, sms, 2, 50, smem), r1 = run<1, 2, 2>(a, sms, 2, 50, smem), r2 = run<1, 4, 2>(a, sms, 2, 50, smem);
         Result r3 = run<0, 1, 4>(a, sms, 2, 50, smem), r4 = run<1, 1, 4>(a, sms, 2, 50, smem);
         size_t bad = 0, bad2 = 0;
         for (size_t i = 0; i < r0.hk.size(); i++) bad += (r0.hk[i] != r1.hk[i]) || (r0.ht[i] != r1.ht[i]);
