@@ -188,6 +188,12 @@ int rayz_cuda_render_device(RzContext *ctx, const RzCamera *cam, const RzRenderP
 uint32_t rayz_cuda_shard_rows(uint32_t height, uint32_t shard_index, uint32_t shard_count,
                               uint32_t band_rows);
 
+/* Rows a CONTEXT renders (= rows of the out_* buffers of rayz_cuda_render) when it is shard
+ * `shard_index` of `shard_count`: a context with n devices deals its share to them as shards
+ * shard_index*n .. shard_index*n + n-1 of shard_count*n.  Equals rayz_cuda_shard_rows for n = 1. */
+uint32_t rayz_cuda_context_rows(const RzContext *ctx, uint32_t height, uint32_t shard_index,
+                                uint32_t shard_count, uint32_t band_rows);
+
 /* K0: f64, FMA-free closest-hit sphere index of the deterministic pixel-centre ray
  * getRay(i, j, null) (camera.zig:59-77) through the reference's BVH order
  * (hit.zig:181-216).  out_ids: width*height int32, -1 = miss.  use_bvh = 0 => brute force. */

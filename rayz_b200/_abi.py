@@ -75,6 +75,7 @@ SYMBOLS = {
     "rayz_cuda_render_device": (C.c_int, [C.c_void_p, C.POINTER(RzCamera), C.POINTER(RzRenderParams), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]),
     "rayz_cuda_shard_rows": (C.c_uint32, [C.c_uint32] * 4),
+    "rayz_cuda_context_rows": (C.c_uint32, [C.c_void_p] + [C.c_uint32] * 4),
     "rayz_cuda_primary_ids": (C.c_int, [C.c_void_p, C.POINTER(RzCamera), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
     "rayz_cuda_stats": (C.c_int, [C.c_void_p, C.POINTER(RzStats)]),
     "rayz_cuda_timing": (C.c_int, [C.c_void_p, C.POINTER(RzTiming)]),

@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose and out:
                 print(out)
     if force or jobs or _stale(SO, objs):
-        run([nvcc] + ARCH + ["-shared", "-o", SO] + objs + ["-cudart", "static"])
+        run([nvcc] + ARCH + ["-shared", "-o", SO] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined"])
     return SO
 
 

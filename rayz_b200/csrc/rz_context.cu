@@ -143,6 +143,15 @@ extern "C" uint32_t rayz_cuda_shard_rows(uint32_t height, uint32_t shard_index, 
     return rows;
 }
 
+extern "C" uint32_t rayz_cuda_context_rows(const RzContext *ctx, uint32_t height, uint32_t shard_index, uint32_t shard_count,
+                                           uint32_t band_rows) {
+    const uint32_t S = shard_count <= 1 ? 1 : shard_count, s = shard_count <= 1 ? 0 : shard_index;
+    const uint32_t nd = ctx ? (uint32_t)ctx->devs.size() : 1u;
+    uint32_t rows = 0;
+    for (uint32_t d = 0; d < nd; d++) rows += rayz_cuda_shard_rows(height, s * nd + d, S * nd, band_rows ? band_rows : 4);
+    return rows;
+}
+
 // ------------------------------------------------------------------------------ host BVH builds
 namespace {
 
@@ -718,8 +727,7 @@ extern "C" int rayz_cuda_render_device(RzContext *ctx, const RzCamera *cam, cons
     if (d_linear_rgba) *d_linear_rgba = ctx->devs[0].out_linear.p;
     if (d_rgb8) *d_rgb8 = ctx->devs[0].out_rgb8.p;
     if (out_paths) {
-        const uint32_t S = params->shard_count <= 1 ? 1 : params->shard_count;
-        const uint32_t rows = rayz_cuda_shard_rows(params->height, params->shard_count <= 1 ? 0 : params->shard_index, S, params->band_rows);
+        const uint32_t rows = rayz_cuda_context_rows(ctx, params->height, params->shard_index, params->shard_count, params->band_rows);
         *out_paths = (uint64_t)rows * params->width * params->spp;
     }
     return RZ_OK;
@@ -732,8 +740,7 @@ extern "C" int rayz_cuda_render(RzContext *ctx, const RzCamera *cam, const RzRen
     if (rc) return rc;
     DeviceGuard guard;
     Dev &D0 = ctx->devs[0];
-    const uint32_t S = params->shard_count <= 1 ? 1 : params->shard_count;
-    const uint32_t rows = rayz_cuda_shard_rows(params->height, params->shard_count <= 1 ? 0 : params->shard_index, S, params->band_rows);
+    const uint32_t rows = rayz_cuda_context_rows(ctx, params->height, params->shard_index, params->shard_count, params->band_rows);
     const size_t npx = (size_t)rows * params->width;
     RZ_CUDA(cudaSetDevice(D0.id));
     if (out_linear_rgba) RZ_CUDA(cudaMemcpyAsync(out_linear_rgba, D0.out_linear.p, npx * sizeof(float4), cudaMemcpyDeviceToHost, D0.stream));

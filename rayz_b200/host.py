@@ -258,7 +258,7 @@ class Backend:
         return p
 
     def shard_rows(self, p: abi.RzRenderParams) -> int:
-        return int(self.lib.rayz_cuda_shard_rows(p.height, p.shard_index, max(1, p.shard_count), p.band_rows))
+        return int(self.lib.rayz_cuda_context_rows(self._h, p.height, p.shard_index, p.shard_count, p.band_rows))
 
     def render(self, cam: abi.RzCamera, p: abi.RzRenderParams, want_linear=True, want_rgb8=True,
                out_linear: np.ndarray | None = None, out_rgb8: np.ndarray | None = None):
