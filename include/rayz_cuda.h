@@ -124,8 +124,14 @@ typedef struct RzRenderParams {
 typedef struct RzConfig {
     int32_t n_devices;     /* 0 => 1 */
     int32_t device_ids[8]; /* CUDA ordinals; device_ids[0] is the gather root   */
-    uint32_t flags;        /* reserved, 0 */
+    uint32_t flags;        /* RZ_CFG_* bits, 0 = defaults */
 } RzConfig;
+
+/* RzConfig.flags: who builds the BVH of the K3 traversal kernel at rayz_cuda_upload_scene (the
+ * counterpart of bvh.build, renderer.zig:78 / hit.zig:130-161).  Default: binned-SAH on the host for
+ * scenes below 8192 spheres (best tree, negligible time), LBVH on the device above. */
+#define RZ_CFG_BVH_BUILD_HOST 1u   /* always the host binned-SAH builder                */
+#define RZ_CFG_BVH_BUILD_DEVICE 2u /* always the device LBVH builder (rz_bvh_build.cu)  */
 
 /* Counters of the last render with collect_stats != 0 (summed over devices). */
 typedef struct RzStats {
@@ -150,7 +156,8 @@ typedef struct RzTiming {
     uint32_t n_static;  /* stationary spheres in the device layout                  */
     uint32_t n_moving;  /* moving spheres in the device layout                      */
     uint32_t variant;   /* variant that actually ran (AUTO resolved)                */
-    uint32_t reserved0;
+    uint32_t bvh_build_us; /* K3 BVH build inside the last rayz_cuda_upload_scene, microseconds:
+                            * host SAH wall time, or device LBVH by CUDA events (max over devices) */
 } RzTiming;
 
 typedef struct RzContext RzContext;

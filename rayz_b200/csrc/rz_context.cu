@@ -28,6 +28,10 @@ struct RzResolveArgs {
 extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays_per_thread, int collect_stats, int sm_count,
                                       cudaStream_t stream, int *grid_out);
 extern "C" cudaError_t rz_path_warm(void);
+extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n);
+extern "C" cudaError_t rz_lbvh_build(uint32_t n, const double4 *c64, const double4 *v64, const uint32_t *mat, void *scratch,
+                                     size_t scratch_bytes, RzBvhNode *nodes, float4 *o_cr, float4 *o_vel, double4 *o_c64,
+                                     double4 *o_v64, uint32_t *o_mat, int32_t *o_orig, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_ids(const RzIdsArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_resolve(const RzResolveArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_ffma_peak(float *sink, int grid, int iters, int mode, cudaStream_t stream);
@@ -105,6 +109,8 @@ struct Dev {
     DBuf<RzRefNode> refnodes;
     DBuf<uint32_t> reforder;
     DBuf<double4> c64_orig, v64_orig;
+    DBuf<uint32_t> mat_orig;
+    DBuf<unsigned char> lbvh_scratch;
     uint32_t n_refnodes = 0;
     DBuf<uint32_t> m_kind, m_tex, m_method, t_kind, t_even, t_odd;
     DBuf<float> m_fuzz, m_ior;
@@ -130,6 +136,10 @@ struct RzContext {
     RzTiming timing{};
     int rays_per_thread = 2;
     uint32_t chunk = 16;
+    uint32_t flags = 0;
+    // host copy of the sphere boxes: the reference-shaped BVH of K0 is built on first use
+    std::vector<double> ref_lo, ref_hi;
+    bool ref_built = false;
 };
 
 // ------------------------------------------------------------------------------ shard rows
@@ -394,6 +404,7 @@ extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
     if (nd > 8) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_create: n_devices %d > 8", nd);
     DeviceGuard guard;
     RzContext *ctx = new RzContext();
+    ctx->flags = cfg ? cfg->flags : 0u;
     ctx->devs.resize(nd);
     for (int d = 0; d < nd; d++) {
         Dev &D = ctx->devs[d];
@@ -435,7 +446,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         if (cudaSetDevice(D.id) != cudaSuccess) continue;
         if (D.own_stream) cudaStreamSynchronize(D.own_stream);
         D.brute.release(); D.bvhset.release(); D.bvh.release(); D.refnodes.release(); D.reforder.release();
-        D.c64_orig.release(); D.v64_orig.release();
+        D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
         D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
         D.accum.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
@@ -462,6 +473,8 @@ extern "C" int rayz_cuda_set_tuning(RzContext *ctx, int rays_per_thread, uint32_
     if (chunk >= 1 && chunk <= 4096) ctx->chunk = chunk;
     return RZ_OK;
 }
+
+static const uint32_t RZ_SMEM_BUDGET = 200u * 1024u;  // of 227 KB per CTA on sm_100
 
 extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     if (!ctx || !sc) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: NULL argument");
@@ -510,32 +523,39 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     pad_aux(bs);
     bs.pkv = bs.packed();
 
-    // ---- reference-shaped BVH (K0)
-    RefBuilder rb;
-    rb.h.resize(n);
-    for (uint32_t i = 0; i < n; i++) { rb.h[i].b = sphere_box(*sc, i); rb.h[i].s = i; }
-    rb.build(0, n);
-    std::vector<uint32_t> reforder(n);
-    for (uint32_t i = 0; i < n; i++) reforder[i] = rb.h[i].s;
+    // ---- spheres in caller order, f64 (K0, LBVH input); boxes kept on the host for the lazy K0 tree
     std::vector<double4> c64o(n), v64o(n);
+    std::vector<uint32_t> mato(n);
+    ctx->ref_lo.resize(3 * (size_t)n); ctx->ref_hi.resize(3 * (size_t)n);
+    ctx->ref_built = false;
     for (uint32_t i = 0; i < n; i++) {
         c64o[i] = make_double4(sc->sphere_center[3 * i], sc->sphere_center[3 * i + 1], sc->sphere_center[3 * i + 2], sc->sphere_radius[i]);
         v64o[i] = make_double4(sc->sphere_velocity[3 * i], sc->sphere_velocity[3 * i + 1], sc->sphere_velocity[3 * i + 2], 0.0);
+        mato[i] = sc->sphere_material[i];
+        const Box bx = sphere_box(*sc, i);
+        for (int a = 0; a < 3; a++) { ctx->ref_lo[3 * (size_t)i + a] = bx.lo[a]; ctx->ref_hi[3 * (size_t)i + a] = bx.hi[a]; }
     }
 
-    // ---- SAH BVH2 + leaf-ordered set (K3)
+    // ---- K3 tree: binned SAH on the host (small scenes) or LBVH on the device (rz_bvh_build.cu)
+    const bool device_build = (ctx->flags & RZ_CFG_BVH_BUILD_DEVICE) || (!(ctx->flags & RZ_CFG_BVH_BUILD_HOST) && n >= 8192u);
     SahBuilder sb;
-    sb.p.resize(n);
-    for (uint32_t i = 0; i < n; i++) {
-        sb.p[i].b = rb.h[0].b;  // placeholder, overwritten below (rb.h is sorted, so recompute)
-        sb.p[i].b = sphere_box(*sc, i);
-        for (int a = 0; a < 3; a++) sb.p[i].c[a] = 0.5 * (sb.p[i].b.lo[a] + sb.p[i].b.hi[a]);
-        sb.p[i].s = i;
-    }
-    sb.run();
     HostSet vs;
-    for (uint32_t k = 0; k < (uint32_t)sb.order.size(); k++) vs.push(*sc, sb.order[k]);
-    vs.n = n; vs.n_static = 0; vs.n_static_pad = 0; vs.n_pad = n;
+    double host_build_us = 0;
+    if (!device_build) {
+        const auto t0 = std::chrono::steady_clock::now();
+        sb.p.resize(n);
+        for (uint32_t i = 0; i < n; i++) {
+            sb.p[i].b = sphere_box(*sc, i);
+            for (int a = 0; a < 3; a++) sb.p[i].c[a] = 0.5 * (sb.p[i].b.lo[a] + sb.p[i].b.hi[a]);
+            sb.p[i].s = i;
+        }
+        sb.run();
+        for (uint32_t k = 0; k < (uint32_t)sb.order.size(); k++) vs.push(*sc, sb.order[k]);
+        vs.n = n; vs.n_static = 0; vs.n_static_pad = 0; vs.n_pad = n;
+        host_build_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    }
+    const uint32_t brute_smem = (bs.n_pad * 2 - bs.n_static_pad) * 16u;
+    const bool upload_brute = brute_smem <= RZ_SMEM_BUDGET;   // larger scenes can only run the BVH variant
 
     // ---- materials / textures
     std::vector<uint32_t> mk(nm), mt(nm), mm(nm), tk(nt), te(nt), to(nt);
@@ -557,22 +577,43 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     for (Dev &D : ctx->devs) {
         RZ_CUDA(cudaSetDevice(D.id));
         int rc;
-        if ((rc = upload_set(D.brute, bs, D.stream))) return rc;
-        if ((rc = upload_set(D.bvhset, vs, D.stream))) return rc;
-        if ((rc = D.bvh.upload(sb.nodes, D.stream))) return rc;
-        D.bvh_nodes = (uint32_t)sb.nodes.size();
-        if ((rc = D.refnodes.upload(rb.nodes, D.stream))) return rc;
-        D.n_refnodes = (uint32_t)rb.nodes.size();
-        if ((rc = D.reforder.upload(reforder, D.stream))) return rc;
+        if (upload_brute) { if ((rc = upload_set(D.brute, bs, D.stream))) return rc; }
+        else { D.brute.release(); D.brute.n = bs.n; D.brute.n_static = bs.n_static; D.brute.n_static_pad = bs.n_static_pad; D.brute.n_pad = bs.n_pad; }
         if ((rc = D.c64_orig.upload(c64o, D.stream))) return rc;
         if ((rc = D.v64_orig.upload(v64o, D.stream))) return rc;
+        if ((rc = D.mat_orig.upload(mato, D.stream))) return rc;
+        if (!device_build) {
+            if ((rc = upload_set(D.bvhset, vs, D.stream))) return rc;
+            if ((rc = D.bvh.upload(sb.nodes, D.stream))) return rc;
+            D.bvh_nodes = (uint32_t)sb.nodes.size();
+        } else {
+            const size_t scratch = rz_lbvh_scratch_bytes(n);
+            if ((rc = D.lbvh_scratch.alloc(scratch))) return rc;
+            SetBufs &V = D.bvhset;
+            if ((rc = V.cr.alloc(n)) || (rc = V.vel.alloc(n)) || (rc = V.c64.alloc(n)) || (rc = V.v64.alloc(n)) || (rc = V.mat.alloc(n)) ||
+                (rc = V.orig.alloc(n)))
+                return rc;
+            V.n = n; V.n_static = 0; V.n_static_pad = 0; V.n_pad = n;
+            D.bvh_nodes = n > 1 ? n - 1 : 1;
+            if ((rc = D.bvh.alloc(D.bvh_nodes))) return rc;
+            RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
+            RZ_CUDA(rz_lbvh_build(n, D.c64_orig.p, D.v64_orig.p, D.mat_orig.p, D.lbvh_scratch.p, D.lbvh_scratch.n, D.bvh.p, V.cr.p, V.vel.p,
+                                  V.c64.p, V.v64.p, V.mat.p, V.orig.p, D.stream));
+            RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
+        }
         if ((rc = D.m_kind.upload(mk, D.stream)) || (rc = D.m_tex.upload(mt, D.stream)) || (rc = D.m_method.upload(mm, D.stream)) ||
             (rc = D.m_fuzz.upload(mf, D.stream)) || (rc = D.m_ior.upload(mi, D.stream)) || (rc = D.t_kind.upload(tk, D.stream)) ||
             (rc = D.t_even.upload(te, D.stream)) || (rc = D.t_odd.upload(to, D.stream)) || (rc = D.t_color.upload(tc, D.stream)) ||
             (rc = D.t_inv_scale.upload(ts, D.stream)))
             return rc;
         RZ_CUDA(cudaStreamSynchronize(D.stream));  // host vectors die at return: copy semantics
+        if (device_build) {
+            float ms = 0;
+            RZ_CUDA(cudaEventElapsedTime(&ms, D.ev[0], D.ev[1]));
+            host_build_us = std::max(host_build_us, (double)ms * 1e3);
+        }
     }
+    ctx->timing.bvh_build_us = (uint32_t)std::min(host_build_us, 4.0e9);
     ctx->have_scene = true;
     ctx->n_spheres = n;
     ctx->timing.n_static = bs.n_static;
@@ -592,7 +633,6 @@ static RzCamF32 cam_to_f32(const RzCamera *c) {
     return k;
 }
 
-static const uint32_t RZ_SMEM_BUDGET = 200u * 1024u;  // of 227 KB per CTA on sm_100
 
 static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams *p, bool sync) {
     if (!ctx || !cam || !p) return rz_fail(RZ_ERR_INVALID_ARG, "render: NULL argument");
@@ -788,6 +828,24 @@ extern "C" int rayz_cuda_primary_ids(RzContext *ctx, const RzCamera *cam, uint32
     Dev &D = ctx->devs[0];
     RZ_CUDA(cudaSetDevice(D.id));
     int rc;
+    if (use_bvh && !ctx->ref_built) {
+        // reference-shaped BVH (hit.zig:130-161), built on first use: O(N log^2 N) on the host
+        const uint32_t n = ctx->n_spheres;
+        RefBuilder rb;
+        rb.h.resize(n);
+        for (uint32_t i = 0; i < n; i++) {
+            for (int a = 0; a < 3; a++) { rb.h[i].b.lo[a] = ctx->ref_lo[3 * (size_t)i + a]; rb.h[i].b.hi[a] = ctx->ref_hi[3 * (size_t)i + a]; }
+            rb.h[i].s = i;
+        }
+        rb.build(0, n);
+        std::vector<uint32_t> reforder(n);
+        for (uint32_t i = 0; i < n; i++) reforder[i] = rb.h[i].s;
+        if ((rc = D.refnodes.upload(rb.nodes, D.stream))) return rc;
+        D.n_refnodes = (uint32_t)rb.nodes.size();
+        if ((rc = D.reforder.upload(reforder, D.stream))) return rc;
+        RZ_CUDA(cudaStreamSynchronize(D.stream));
+        ctx->ref_built = true;
+    }
     if ((rc = D.ids.alloc((size_t)width * height))) return rc;
     RzIdsArgs a;
     a.nodes = D.refnodes.p; a.order = D.reforder.p; a.c64 = D.c64_orig.p; a.v64 = D.v64_orig.p;

@@ -342,7 +342,9 @@ __device__ __forceinline__ void rz_search_bvh(const RzPathArgs &a, const RzRay &
                                               unsigned long long &n_nodes, unsigned long long &n_sph) {
     const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
     const float ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
-    int stack[48];
+    // depth bound: the host SAH tree is shallow; a Karras LBVH over 63-bit codes + 32-bit index tie-break is < 96 deep,
+    // and near-child-first traversal pushes at most one entry per level
+    int stack[96];
     int sp = 0;
     int node = 0;
     const float4 *nodes = reinterpret_cast<const float4 *>(a.bvh);
@@ -401,7 +403,7 @@ __device__ __forceinline__ void rz_search_bvh(const RzPathArgs &a, const RzRay &
             const bool swap = nt[1] < nt[0];
             const int nearc = swap ? next[1] : next[0];
             const int farc = swap ? next[0] : next[1];
-            if (sp < 48) stack[sp++] = farc;
+            if (sp < 96) stack[sp++] = farc;
             node = nearc;
         } else if (nn == 1) {
             node = next[0];

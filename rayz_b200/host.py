@@ -212,9 +212,12 @@ def scene_struct(arrays: dict):
 class Backend:
     """Owns one RzContext (include/rayz_cuda.h)."""
 
-    def __init__(self, devices=(0,)):
+    BVH_BUILD = {"auto": 0, "host": 1, "device": 2}   # RZ_CFG_BVH_BUILD_* (include/rayz_cuda.h)
+
+    def __init__(self, devices=(0,), bvh_build: str = "auto"):
         self.lib = abi.load()
         cfg = abi.RzConfig()
+        cfg.flags = self.BVH_BUILD[bvh_build]
         cfg.n_devices = len(devices)
         for i, d in enumerate(devices):
             cfg.device_ids[i] = int(d)

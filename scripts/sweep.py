@@ -16,11 +16,13 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--glass", action="store_true")
     ap.add_argument("--grid", type=int, default=11)
+    ap.add_argument("--bvh-build", default="auto", choices=["auto", "host", "device"])
     ap.add_argument("--configs", default="mega:1:16,mega:2:16,mega:2:8,mega:2:32,mega:1:32,bvh:1:16,wavefront:2:16")
     args = ap.parse_args()
     t = rayz_b200.random_bouncing(args.width, seed=42, glass_heavy=args.glass, grid_lo=-args.grid, grid_hi=args.grid)
-    be = Backend((0,))
+    be = Backend((0,), bvh_build=args.bvh_build)
     be.upload_scene(t.pool.arrays())
+    print(json.dumps({"bvh_build": args.bvh_build, "bvh_build_us": be.timing()["bvh_build_us"]}))
     W, H = t.img.w, t.img.h
     peak, sms = be.fp32_peak(300)
     print(json.dumps({"fp32_peak_tflops": peak, "sms": sms}))
