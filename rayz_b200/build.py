@@ -27,6 +27,7 @@ UNITS = {
     "rz_misc.cu": [],
     "rz_ids.cu": ["--fmad=false"],
     "rz_bvh_build.cu": [],
+    "rz_bvh_trace.cu": ["--use_fast_math"],
     "rz_context.cu": [],
 }
 HEADERS = ["rz_device.cuh", "rz_search.cuh", os.path.join("..", "..", "include", "rayz_cuda.h")]

@@ -1,0 +1,214 @@
+// rz_bvh_trace.cu — K3: persistent BVH path kernel for scenes that do not fit the brute-force kernel
+// (and the fastest variant in paths/s on small ones).
+//
+// Restates the role of BVH.findHit + AABB.hit (reference src/hit.zig:70-98, 181-216) inside the path
+// loop of renderer.zig:85-126.  The reference recurses per ray, left child first; here every lane of
+// a persistent warp walks its own ray through a flattened BVH2 (both child boxes in the parent, 64 B,
+// read through ld.global.nc), near child first, with an explicit per-lane stack.
+//
+// What shapes the kernel is SIMT divergence, not arithmetic: the first version (per-lane
+// `while (stack)` with the leaf tests nested inside, rays replaced only between segments) ran with
+// 7.4-9.4 of 32 lanes active per instruction at 80 % issue utilisation (ncu, profiles/).  Hence:
+//   * while-while traversal (Aila & Laine, HPG 2009): an inner loop that only descends through
+//     internal nodes, then a leaf phase that all lanes holding a leaf execute together;
+//   * ray replacement INSIDE the traversal loop: as soon as fewer than ACTIVE_MIN lanes are still
+//     traversing, the finished lanes shade their hit, scatter or start the next (pixel, sample) of
+//     the warp's work unit, and rejoin — instead of idling until the slowest ray of the warp ends;
+//   * leaves are pushed on the stack like nodes (encoded negative), so a popped leaf is handled by the
+//     same leaf phase.
+// Sphere tests, hit refinement, shading, RNG keys and accumulation are the shared device functions of
+// rz_search.cuh / rz_device.cuh: images equal the brute-force kernel's bit for bit.
+#include <cstdlib>
+
+#include "rz_search.cuh"
+
+namespace {
+
+constexpr int RZ_SENTINEL = 0x7fffffff;
+constexpr int RZ_STACK = 96;   // LBVH depth bound: 63 Morton bits + 32 index tie-break bits
+
+// leaf reference: ~((count - 1) << 29 | first); first < 2^29, count <= 4
+__device__ __forceinline__ int rz_leaf_ref(int child, uint32_t cnt) { return ~((int)((cnt - 1u) << 29) | ~child); }
+
+template <bool STATS>
+__global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float4 *__restrict__ nodes = reinterpret_cast<const float4 *>(a.bvh);
+
+    // warp-uniform work-unit state (as in rz_path_kernel)
+    bool have_unit = true;
+    uint32_t unit_lp0 = 0, unit_s0 = 0, unit_paths = 0, k_next = 0;
+
+    // per-lane path state
+    RzRay ray;
+    ray.o = f3(0.f, 0.f, 0.f); ray.d = f3(0.f, 1.f, 0.f); ray.time = 0.f; ray.self_k = -1;
+    float3 thr = f3(0.f, 0.f, 0.f);
+    uint32_t lp = 0, gpix = 0, sample = 0, seg = 0;
+    bool alive = false;
+    // per-lane traversal state
+    int cur = RZ_SENTINEL, sp = 0, bk = -1;
+    float bt = 3.0e38f, ix = 0.f, iy = 0.f, iz = 0.f;
+    int stack[RZ_STACK];
+
+    unsigned long long c_paths = 0, c_segs = 0, c_nodes = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
+
+    auto start_traversal = [&]() {
+        ix = 1.0f / ray.d.x; iy = 1.0f / ray.d.y; iz = 1.0f / ray.d.z;
+        bt = 3.0e38f; bk = -1; sp = 0; cur = 0;
+    };
+
+    while (true) {
+        // ------------------------------------------------------------ shade finished traversals
+        if (alive && cur == RZ_SENTINEL) {
+            if (STATS) c_segs++;
+            uint32_t kind;
+            const int res = rz_shade_segment(a, ray, thr, seg, lp, gpix, sample, bk, kind);
+            if (STATS) {
+                if (kind < 3u) c_hit[kind]++;
+                if (res == RZ_END_SKY) c_sky++;
+                if (res == RZ_END_ABSORBED) c_abs++;
+                if (res == RZ_END_DEPTH) c_depth++;
+            }
+            if (res != RZ_CONT) alive = false; else start_traversal();
+        }
+        // ------------------------------------------------------------ regenerate dead lanes
+        {
+            bool need = !alive;
+            while (true) {
+                const unsigned mask = __ballot_sync(0xffffffffu, need);
+                if (mask == 0u || !have_unit) break;
+                const uint32_t avail = unit_paths - k_next;
+                if (avail == 0u) {
+                    unsigned u = 0;
+                    if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= a.n_units) { have_unit = false; break; }
+                    const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
+                    unit_lp0 = tile * 32u;
+                    unit_s0 = chunk * a.chunk;
+                    unit_paths = 32u * min(a.chunk, a.spp - unit_s0);
+                    k_next = 0;
+                    continue;
+                }
+                const uint32_t rank = __popc(mask & lt_mask);
+                if (need && rank < avail) {
+                    const uint32_t k = k_next + rank;
+                    const uint32_t nlp = unit_lp0 + (k & 31u);
+                    if (nlp < a.n_local_px) {
+                        uint32_t pi, pj;
+                        rz_local_to_global(nlp, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
+                        lp = nlp;
+                        gpix = pj * a.width + pi;
+                        sample = a.sample_offset + unit_s0 + (k >> 5);
+                        ray = rz_camera_ray(a.cam, pi, pj, gpix, sample, a.seed_lo, a.seed_hi);
+                        thr = f3(1.f, 1.f, 1.f);
+                        seg = 0;
+                        alive = a.max_depth > 0u;
+                        if (STATS) { c_paths++; if (!alive) c_depth++; }
+                        if (alive) start_traversal();
+                        need = !alive;
+                    }
+                }
+                k_next += min((uint32_t)__popc(mask), avail);
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+
+        // ------------------------------------------------------------ traversal burst
+        // keep stepping while enough lanes are busy; once work has run out, drain completely
+        const int active_min = have_unit ? (int)a.bvh_active_min : 1;
+        while (__popc(__ballot_sync(0xffffffffu, cur != RZ_SENTINEL)) >= active_min) {
+            // (1) descend through internal nodes until this lane holds a leaf or runs dry
+            while ((unsigned)cur < (unsigned)RZ_SENTINEL) {
+                const float4 q0 = __ldg(nodes + cur * 4 + 0);  // lox0 lox1 hix0 hix1
+                const float4 q1 = __ldg(nodes + cur * 4 + 1);  // loy0 loy1 hiy0 hiy1
+                const float4 q2 = __ldg(nodes + cur * 4 + 2);  // loz0 loz1 hiz0 hiz1
+                const int4 q3 = __ldg(reinterpret_cast<const int4 *>(nodes + cur * 4 + 3));
+                if (STATS) c_nodes += 2;
+                const float ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
+                // slab test of AABB.hit (hit.zig:70-98) with multiply-by-inverse; boxes are padded outward at build time
+                const float ax0 = (q0.x - ox) * ix, bx0 = (q0.z - ox) * ix, ax1 = (q0.y - ox) * ix, bx1 = (q0.w - ox) * ix;
+                const float ay0 = (q1.x - oy) * iy, by0 = (q1.z - oy) * iy, ay1 = (q1.y - oy) * iy, by1 = (q1.w - oy) * iy;
+                const float az0 = (q2.x - oz) * iz, bz0 = (q2.z - oz) * iz, az1 = (q2.y - oz) * iz, bz1 = (q2.w - oz) * iz;
+                const float tn0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), a.t_min));
+                const float tf0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), bt));
+                const float tn1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), a.t_min));
+                const float tf1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), bt));
+                const bool h0 = (tn0 <= tf0 * 1.0000004f) && (q3.x >= 0 || q3.z != 0);   // an unused slot is a leaf of 0 spheres
+                const bool h1 = (tn1 <= tf1 * 1.0000004f) && (q3.y >= 0 || q3.w != 0);
+                // child references: internal index >= 0, or a leaf (encoded negative, carries its count)
+                const int c0 = q3.x >= 0 ? q3.x : rz_leaf_ref(q3.x, (uint32_t)q3.z);
+                const int c1 = q3.y >= 0 ? q3.y : rz_leaf_ref(q3.y, (uint32_t)q3.w);
+                if (h0 && h1) {
+                    const bool swap = tn1 < tn0;
+                    if (sp < RZ_STACK) stack[sp++] = swap ? c0 : c1;
+                    cur = swap ? c1 : c0;
+                } else if (h0) {
+                    cur = c0;
+                } else if (h1) {
+                    cur = c1;
+                } else {
+                    cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
+                }
+            }
+            // (2) leaf phase
+            if (cur < 0) {
+                const int code = ~cur;
+                const int first = code & 0x1fffffff;
+                const int cnt = (code >> 29) + 1;
+                for (int e = 0; e < cnt; e++) {
+                    const int k = first + e;
+                    const float4 s = __ldg(a.set.cr + k);
+                    const float4 v = __ldg(a.set.vel + k);
+                    if (STATS) c_sph++;
+                    const float ocx = fmaf(v.x, ray.time, s.x - ray.o.x);   // same order as the packed searches
+                    const float ocy = fmaf(v.y, ray.time, s.y - ray.o.y);
+                    const float ocz = fmaf(v.z, ray.time, s.z - ray.o.z);
+                    const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
+                    const float cc = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, s.w)));
+                    const float disc = fmaf(b, b, -cc);
+                    if (disc > 0.0f) rz_consider(k, b, disc, ray.self_k, a.t_min, bt, bk);
+                }
+                cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
+            }
+        }
+    }
+
+    if (STATS) {
+        unsigned long long v[10] = {c_paths, c_segs, c_sph, c_nodes, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            unsigned long long s = v[i];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && s) atomicAdd(&a.stats->v[i], s);
+        }
+    }
+}
+
+template <bool STATS>
+cudaError_t launch(const RzPathArgs &a, int sm_count, cudaStream_t stream) {
+    auto kern = rz_bvh_kernel<STATS>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    kern<<<sm_count * per_sm, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" cudaError_t rz_bvh_warm(void) {
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, rz_bvh_kernel<false>);
+}
+
+extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
+    RzPathArgs b = *a;
+    const char *env = getenv("RZ_BVH_ACTIVE_MIN");   // tuning experiment
+    b.bvh_active_min = env ? (uint32_t)atoi(env) : 8u;
+    if (b.bvh_active_min < 1u) b.bvh_active_min = 1u;
+    if (b.bvh_active_min > 32u) b.bvh_active_min = 32u;
+    return collect_stats ? launch<true>(b, sm_count, stream) : launch<false>(b, sm_count, stream);
+}

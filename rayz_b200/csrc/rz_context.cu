@@ -25,9 +25,11 @@ struct RzResolveArgs {
     const unsigned long long *accum; float4 *out_linear; uint8_t *out_rgb8;
     uint32_t n_local_px, width; uint32_t spp; uint32_t dev_index, dev_count, band_rows;
 };
-extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays_per_thread, int collect_stats, int sm_count,
+extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int rays_per_thread, int collect_stats, int sm_count,
                                       cudaStream_t stream, int *grid_out);
 extern "C" cudaError_t rz_path_warm(void);
+extern "C" cudaError_t rz_bvh_warm(void);
+extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n);
 extern "C" cudaError_t rz_lbvh_build(uint32_t n, const double4 *c64, const double4 *v64, const uint32_t *mat, void *scratch,
                                      size_t scratch_bytes, RzBvhNode *nodes, float4 *o_cr, float4 *o_vel, double4 *o_c64,
@@ -424,7 +426,7 @@ extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
         D.stream = D.own_stream;
         for (auto &ev : D.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
-        if ((e = rz_path_warm()) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "loading the path kernels: %s", cudaGetErrorString(e)); }
+        if ((e = rz_path_warm()) != cudaSuccess || (e = rz_bvh_warm()) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "loading the path kernels: %s", cudaGetErrorString(e)); }
         if (d > 0) {
             // the resolve kernel of device d stores straight into device 0's buffers (NVLink P2P)
             int can = 0;
@@ -704,7 +706,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                 RZ_CUDA(rz_wavefront_render(&a, D.sms, (int)p->collect_stats, D.stream, &D.wf_scratch, &D.wf_scratch_bytes, &l));
                 launches += l;
             } else {
-                RZ_CUDA(rz_launch_path(&a, (int)variant, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
+                if (variant == RZ_VARIANT_BVH) RZ_CUDA(rz_launch_bvh(&a, (int)p->collect_stats, D.sms, D.stream));
+                else RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
                 launches += 1;
             }
         }

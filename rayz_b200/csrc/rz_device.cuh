@@ -93,6 +93,7 @@ struct RzPathArgs {
     uint32_t shard_index, shard_count, band_rows;
     uint32_t seed_lo, seed_hi;
     float t_min;
+    uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-// rz_path.cu — K1/K3: the persistent FP32 path-tracing megakernel for sm_100a.
+// rz_path.cu — K1: the persistent FP32 brute-force path-tracing megakernel for sm_100a.
 //
 // Replaces the body of Tracer.render's pixel loop and everything under it
 // (reference src/renderer.zig:85-96, bounceRay :103-126, BVH.findHit hit.zig:181-216,
@@ -19,7 +19,7 @@
 //     warp-uniform (broadcast) LDS.128 operands and Blackwell packed FP32x2 arithmetic
 //     (FFMA2/FADD2/FMUL2, two spheres per instruction): 11 issue slots per stationary
 //     sphere PAIR and ray, 14 per moving pair (rz_search_brute2);
-//   * K3: large scenes traverse a BVH2 through the read-only path (ld.global.nc).
+//   * large scenes use the BVH kernel of rz_bvh_trace.cu (K3) instead.
 #include <cstdlib>
 
 #include "rz_search.cuh"
@@ -36,13 +36,13 @@ struct RzStream {
 };
 
 // G = sphere PAIRS per search-loop iteration
-template <int R, int G, bool STATS, bool BVH, int MB>
+template <int R, int G, bool STATS, int MB>
 __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
     float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
 
-    if (!BVH) rz_stage_scene_pk(a.set, s_pk, &s_bar);
+    rz_stage_scene_pk(a.set, s_pk, &s_bar);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -122,13 +122,7 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
             bk[r] = -1;
             rays[r] = st[r].ray;
         }
-        if (BVH) {
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                if (st[r].alive) rz_search_bvh(a, rays[r], a.t_min, bt[r], bk[r], c_nodes, c_sph);
-        } else {
-            rz_search_brute2<R, G>(s_pk, (int)a.set.n_static_pad, (int)a.set.n_pad, rays, a.t_min, bt, bk);
-        }
+        rz_search_brute2<R, G>(s_pk, (int)a.set.n_static_pad, (int)a.set.n_pad, rays, a.t_min, bt, bk);
 
         // ---------------------------------------------------------------- shade
 #pragma unroll
@@ -159,9 +153,9 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
 }
 
 // ------------------------------------------------------------------------------ launcher
-template <int R, int G, bool STATS, bool BVH, int MB = 5>
+template <int R, int G, bool STATS, int MB = 5>
 static cudaError_t rz_launch_one(const RzPathArgs &a, int sm_count, size_t smem, cudaStream_t stream, int *grid_out) {
-    auto kern = rz_path_kernel<R, G, STATS, BVH, MB>;
+    auto kern = rz_path_kernel<R, G, STATS, MB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -178,27 +172,20 @@ static cudaError_t rz_launch_one(const RzPathArgs &a, int sm_count, size_t smem,
 // the first render does not pay module loading).
 extern "C" cudaError_t rz_path_warm(void) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, rz_path_kernel<2, 2, false, false, 8>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_path_kernel<1, 1, false, true, 8>);
-    return e;
+    return cudaFuncGetAttributes(&fa, rz_path_kernel<2, 2, false, 8>);
 }
 
-// variant: 1 = brute (K1), 3 = BVH (K3).  rays_per_thread in {1,2}.
-extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int variant, int rays_per_thread, int collect_stats, int sm_count,
-                                      cudaStream_t stream, int *grid_out) {
+// rays_per_thread in {1,2}.
+extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int rays_per_thread, int collect_stats, int sm_count, cudaStream_t stream,
+                                      int *grid_out) {
     const bool stats = collect_stats != 0;
-    if (variant == 3) {
-        return stats ? rz_launch_one<1, 1, true, true, 8>(*a, sm_count, 0, stream, grid_out)
-                     : rz_launch_one<1, 1, false, true, 8>(*a, sm_count, 0, stream, grid_out);
-    }
     const size_t smem = (size_t)(a->set.n_pad + (a->set.n_pad - a->set.n_static_pad)) * 16u;
     if (rays_per_thread == 1) {
-        return stats ? rz_launch_one<1, 2, true, false>(*a, sm_count, smem, stream, grid_out)
-                     : rz_launch_one<1, 2, false, false>(*a, sm_count, smem, stream, grid_out);
+        return stats ? rz_launch_one<1, 2, true>(*a, sm_count, smem, stream, grid_out)
+                     : rz_launch_one<1, 2, false>(*a, sm_count, smem, stream, grid_out);
     }
     // 8 resident CTAs per SM (64 registers, 232 B of spills outside the search loop) measured 3 % faster than
     // the 5 CTAs the unconstrained 88-register build gets: 1522 vs 1472 Mpaths/s at config 2 / 100 spp.
-    if (!stats) return rz_launch_one<2, 2, false, false, 8>(*a, sm_count, smem, stream, grid_out);
-    return stats ? rz_launch_one<2, 2, true, false>(*a, sm_count, smem, stream, grid_out)
-                 : rz_launch_one<2, 2, false, false>(*a, sm_count, smem, stream, grid_out);
+    return stats ? rz_launch_one<2, 2, true>(*a, sm_count, smem, stream, grid_out)
+                 : rz_launch_one<2, 2, false, 8>(*a, sm_count, smem, stream, grid_out);
 }

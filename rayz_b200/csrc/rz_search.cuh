@@ -334,87 +334,6 @@ __device__ __forceinline__ void rz_search_brute_rp(const float4 *__restrict__ s_
     }
 }
 
-// ------------------------------------------------------------------------------ K3 search
-// BVH2 traversal, ordered (near child first), per-thread stack.  Restates the role of
-// BVH.findHit + AABB.hit (hit.zig:70-98,181-216) on a flattened, SAH-built tree; closest-hit
-// results do not depend on tree shape.
-__device__ __forceinline__ void rz_search_bvh(const RzPathArgs &a, const RzRay &ray, float t_min, float &bt, int &bk,
-                                              unsigned long long &n_nodes, unsigned long long &n_sph) {
-    const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
-    const float ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
-    // depth bound: the host SAH tree is shallow; a Karras LBVH over 63-bit codes + 32-bit index tie-break is < 96 deep,
-    // and near-child-first traversal pushes at most one entry per level
-    int stack[96];
-    int sp = 0;
-    int node = 0;
-    const float4 *nodes = reinterpret_cast<const float4 *>(a.bvh);
-    while (true) {
-        const float4 q0 = __ldg(nodes + node * 4 + 0);  // lox0 lox1 hix0 hix1
-        const float4 q1 = __ldg(nodes + node * 4 + 1);  // loy0 loy1 hiy0 hiy1
-        const float4 q2 = __ldg(nodes + node * 4 + 2);  // loz0 loz1 hiz0 hiz1
-        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(nodes + node * 4 + 3));
-        n_nodes += 2;
-        float tn[2], tf[2];
-        {
-            const float lox[2] = {q0.x, q0.y}, hix[2] = {q0.z, q0.w};
-            const float loy[2] = {q1.x, q1.y}, hiy[2] = {q1.z, q1.w};
-            const float loz[2] = {q2.x, q2.y}, hiz[2] = {q2.z, q2.w};
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const float ax = (lox[c] - ox) * ix, bx = (hix[c] - ox) * ix;
-                const float ay = (loy[c] - oy) * iy, by = (hiy[c] - oy) * iy;
-                const float az = (loz[c] - oz) * iz, bz = (hiz[c] - oz) * iz;
-                tn[c] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_min));
-                tf[c] = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), bt));
-            }
-        }
-        const int child[2] = {q3.x, q3.y};
-        const int cnt[2] = {q3.z, q3.w};
-        int next[2];
-        float nt[2];
-        int nn = 0;
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            // slack of 2 ulp-ish on the box test; boxes are already padded outward at build time
-            if (tn[c] <= tf[c] * 1.0000004f) {
-                if (child[c] < 0) {
-                    const int first = ~child[c];
-                    for (int e = 0; e < cnt[c]; e++) {
-                        const int k = first + e;
-                        const float4 s = __ldg(a.set.cr + k);
-                        const float4 v = __ldg(a.set.vel + k);
-                        n_sph++;
-                        const float ocx = fmaf(v.x, ray.time, s.x - ox);   // same order as the packed searches
-                        const float ocy = fmaf(v.y, ray.time, s.y - oy);
-                        const float ocz = fmaf(v.z, ray.time, s.z - oz);
-                        const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
-                        const float cc = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, s.w)));
-                        const float disc = fmaf(b, b, -cc);
-                        if (disc > 0.0f) rz_consider(k, b, disc, ray.self_k, t_min, bt, bk);
-                    }
-                } else {
-                    next[nn] = child[c];
-                    nt[nn] = tn[c];
-                    nn++;
-                }
-            }
-        }
-        if (nn == 2) {
-            const bool swap = nt[1] < nt[0];
-            const int nearc = swap ? next[1] : next[0];
-            const int farc = swap ? next[0] : next[1];
-            if (sp < 96) stack[sp++] = farc;
-            node = nearc;
-        } else if (nn == 1) {
-            node = next[0];
-        } else {
-            if (sp == 0) break;
-            node = stack[--sp];
-        }
-    }
-}
-
-
 // ------------------------------------------------------------------------------ stage scene
 // Stage the brute-force sphere set global -> shared with the bulk async-copy engine
 // (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP).  All threads of the CTA must call.
