@@ -94,6 +94,7 @@ struct RzPathArgs {
     uint32_t seed_lo, seed_hi;
     float t_min;
     uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)
+    uint32_t bvh_descend_min;    // K3: a descend round ends once fewer lanes than this are still descending
 };
 
 // ---------------------------------------------------------------------------------------------
