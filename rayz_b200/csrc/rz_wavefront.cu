@@ -18,6 +18,7 @@
 // The same search/shade device functions as the megakernel are used (rz_search.cuh) and the
 // RNG is keyed by (pixel, sample, bounce), so both variants produce bit-identical images.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "rz_search.cuh"
@@ -279,7 +280,9 @@ extern "C" cudaError_t rz_wavefront_render(const RzPathArgs *a, int sm_count, in
     cudaError_t e;
     const unsigned long long n_tiles = (a->n_local_px + 31u) / 32u;
     const unsigned long long total_paths = n_tiles * 32ull * a->spp;   // padding pixels are dead on arrival
-    const size_t M = (size_t)std::min<unsigned long long>(total_paths, 1ull << 21);
+    const char *pool_env = getenv("RZ_WF_POOL_LOG2");   // tuning experiment
+    const int pool_log2 = pool_env ? std::min(26, std::max(16, atoi(pool_env))) : 21;
+    const size_t M = (size_t)std::min<unsigned long long>(total_paths, 1ull << pool_log2);
     WfScratch *ws = reinterpret_cast<WfScratch *>(*scratch);
     if (!ws || ws->M < M) {
         if (ws) {
