@@ -163,6 +163,9 @@ struct RzSrcConst {
 // Entry into the rare path.  A warp-uniform form (__any_sync, no BSSY/BSYNC pair per iteration) was
 // measured with scripts/searchbench.cu: no difference (53.2 % vs 53.1 % of FP32 peak), so the plain
 // per-lane branch stays.
+#ifndef RZ_MOVING_UNROLL
+#define RZ_MOVING_UNROLL 1
+#endif
 #ifndef RZ_TRIGGER
 #define RZ_TRIGGER(c) (c)
 #endif
@@ -205,7 +208,8 @@ __device__ __forceinline__ void rz_search_brute2(const SRC src, int n_static_pad
                 }
         }
     }
-#pragma unroll 1
+    constexpr int kMovingUnroll = RZ_MOVING_UNROLL;
+#pragma unroll kMovingUnroll
     for (; k < n_pad; k += 2 * G2, q += 4 * G2) {
         float4 A[G2], B[G2], VA[G2], VB[G2];
 #pragma unroll
