@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RAYZ_CUDA_ABI_VERSION 1
+#define RAYZ_CUDA_ABI_VERSION 2
 
 enum {
     RZ_OK = 0,
@@ -158,6 +158,8 @@ typedef struct RzTiming {
     uint32_t variant;   /* variant that actually ran (AUTO resolved)                */
     uint32_t bvh_build_us; /* K3 BVH build inside the last rayz_cuda_upload_scene, microseconds:
                             * host SAH wall time, or device LBVH by CUDA events (max over devices) */
+    float primary_ms;      /* two-stage K1: the primary (camera-segment) kernels' share of kernel_ms   */
+    uint32_t passes;       /* two-stage K1: primary+secondary launch pairs of the render, else 0      */
 } RzTiming;
 
 typedef struct RzContext RzContext;

@@ -57,7 +57,7 @@ class RzStats(C.Structure):
 
 class RzTiming(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("resolve_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32),
-                ("n_static", C.c_uint32), ("n_moving", C.c_uint32), ("variant", C.c_uint32), ("bvh_build_us", C.c_uint32)]
+                ("n_static", C.c_uint32), ("n_moving", C.c_uint32), ("variant", C.c_uint32), ("bvh_build_us", C.c_uint32), ("primary_ms", C.c_float), ("passes", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ }
@@ -110,7 +110,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-    if lib.rayz_cuda_abi_version() != 1:
+    if lib.rayz_cuda_abi_version() != 2:
         raise ImportError("librayz_cuda.so ABI version mismatch")
     _lib = lib
     return lib

@@ -33,8 +33,8 @@ namespace {
 constexpr int RZ_SENTINEL = 0x7fffffff;
 constexpr int RZ_STACK = 96;   // LBVH depth bound: 63 Morton bits + 32 index tie-break bits
 
-// leaf reference: ~((count - 1) << 29 | first); first < 2^29, count <= 4
-__device__ __forceinline__ int rz_leaf_ref(int child, uint32_t cnt) { return ~((int)((cnt - 1u) << 29) | ~child); }
+// leaf reference: ~((count - 1) << 28 | first); first < 2^28, count <= 8
+__device__ __forceinline__ int rz_leaf_ref(int child, uint32_t cnt) { return ~((int)((cnt - 1u) << 28) | ~child); }
 
 template <bool STATS>
 __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
             // (2) leaf phase
             if (cur < 0) {
                 const int code = ~cur;
-                const int first = code & 0x1fffffff;
-                const int cnt = (code >> 29) + 1;
+                const int first = code & 0x0fffffff;
+                const int cnt = (code >> 28) + 1;
                 for (int e = 0; e < cnt; e++) {
                     const int k = first + e;
                     const float4 s = __ldg(a.set.cr + k);

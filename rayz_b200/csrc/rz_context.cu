@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -28,6 +29,8 @@ struct RzResolveArgs {
 extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int rays_per_thread, int collect_stats, int sm_count,
                                       cudaStream_t stream, int *grid_out);
 extern "C" cudaError_t rz_path_warm(void);
+extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a);
+extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_bvh_warm(void);
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n);
@@ -119,6 +122,7 @@ struct Dev {
     DBuf<float4> t_color;
     DBuf<double> t_inv_scale;
     DBuf<unsigned long long> accum;
+    DBuf<float4> queue;   // two-stage K1: paths that survived their camera segment (4 x float4 each)
     DBuf<unsigned int> counter;
     DBuf<RzStatsDev> stats;
     DBuf<float4> out_linear;
@@ -127,6 +131,8 @@ struct Dev {
     DBuf<float> sink;
     void *wf_scratch = nullptr;
     size_t wf_scratch_bytes = 0;
+    std::vector<cudaEvent_t> pass_ev;   // two-stage K1: [2i] after the primary kernel of pass i, [2i+1] after the secondary
+    uint32_t passes = 0;                // passes of the last render (0 = not the two-stage form)
 };
 
 struct RzContext {
@@ -233,7 +239,9 @@ struct SahBuilder {
     std::vector<P> p;
     std::vector<RzBvhNode> nodes;
     std::vector<uint32_t> order;  // leaf order of sphere indices
-    static constexpr int BINS = 16, LEAF = 4;
+    static constexpr int BINS = 16;
+    int LEAF = 4;          // max spheres per leaf (K3 encodes up to 8)
+    double node_cost = 0.5; // SAH: cost of one more node visit relative to one sphere test
 
     static float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
     static float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
@@ -283,7 +291,7 @@ struct SahBuilder {
             mid = si + n / 2;  // coincident centroids: split by count
         } else {
             const double leaf_cost = bb.area() * (double)n;
-            if (n <= (size_t)LEAF && leaf_cost <= best_cost + bb.area() * 0.5) return make_leaf();
+            if (n <= (size_t)LEAF && leaf_cost <= best_cost + bb.area() * node_cost) return make_leaf();
             const double ext = cb.hi[best_axis] - cb.lo[best_axis];
             const double k = BINS / ext;
             const double lo = cb.lo[best_axis];
@@ -451,10 +459,11 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
         D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
-        D.accum.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
+        D.accum.release(); D.queue.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
         D.ids.release(); D.sink.release();
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
         for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : D.pass_ev) if (ev) cudaEventDestroy(ev);
         if (D.own_stream) cudaStreamDestroy(D.own_stream);
     }
     delete ctx;
@@ -476,13 +485,13 @@ extern "C" int rayz_cuda_set_tuning(RzContext *ctx, int rays_per_thread, uint32_
     return RZ_OK;
 }
 
-static const uint32_t RZ_SMEM_BUDGET = 200u * 1024u;  // of 227 KB per CTA on sm_100
+static const uint32_t RZ_SMEM_BUDGET = 180u * 1024u;  // of 227 KB per CTA on sm_100: the set, + 25 % for the primary kernel's pair lists
 
 extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     if (!ctx || !sc) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: NULL argument");
     const uint32_t n = sc->n_spheres, nm = sc->n_materials, nt = sc->n_textures;
     if (n == 0) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: empty scene (BVH.build asserts nobjs > 0, hit.zig:132)");
-    if (n >= (1u << 30)) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: too many spheres");
+    if (n >= (1u << 28)) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: too many spheres (K3 leaf references hold 28 bits)");
     if (!sc->sphere_center || !sc->sphere_velocity || !sc->sphere_radius || !sc->sphere_material || !sc->mat_kind ||
         !sc->mat_fuzz || !sc->mat_ior || !sc->mat_texture || (nt && (!sc->tex_kind || !sc->tex_color || !sc->tex_scale || !sc->tex_even || !sc->tex_odd)))
         return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_upload_scene: NULL array in RzScene");
@@ -545,6 +554,8 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     double host_build_us = 0;
     if (!device_build) {
         const auto t0 = std::chrono::steady_clock::now();
+        if (const char *e = getenv("RZ_SAH_LEAF")) sb.LEAF = std::min(8, std::max(1, atoi(e)));     // tuning experiments
+        if (const char *e = getenv("RZ_SAH_NODE_COST")) sb.node_cost = atof(e);
         sb.p.resize(n);
         for (uint32_t i = 0; i < n; i++) {
             sb.p[i].b = sphere_box(*sc, i);
@@ -636,6 +647,44 @@ static RzCamF32 cam_to_f32(const RzCamera *c) {
 }
 
 
+// Device timings (CUDA events) and, if asked for, the counters of the render that just finished on every stream.
+static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
+    float kmax = 0, rmax = 0, pmax = 0;
+    uint32_t passes = 0;
+    for (Dev &D : ctx->devs) {
+        float k = 0, r = 0, pr = 0;
+        RZ_CUDA(cudaSetDevice(D.id));
+        RZ_CUDA(cudaEventElapsedTime(&k, D.ev[1], D.ev[2]));
+        RZ_CUDA(cudaEventElapsedTime(&r, D.ev[2], D.ev[3]));
+        for (uint32_t i = 0; i < D.passes; i++) {
+            float ms = 0;
+            RZ_CUDA(cudaEventElapsedTime(&ms, i == 0 ? D.ev[1] : D.pass_ev[2 * i - 1], D.pass_ev[2 * i]));
+            pr += ms;
+        }
+        kmax = std::max(kmax, k); rmax = std::max(rmax, r); pmax = std::max(pmax, pr);
+        passes = std::max(passes, D.passes);
+    }
+    ctx->timing.kernel_ms = kmax;
+    ctx->timing.resolve_ms = rmax;
+    ctx->timing.primary_ms = pmax;
+    ctx->timing.passes = passes;
+    if (collect_stats) {
+        RzStats tot;
+        memset(&tot, 0, sizeof tot);
+        for (Dev &D : ctx->devs) {
+            RzStatsDev h;
+            RZ_CUDA(cudaSetDevice(D.id));
+            RZ_CUDA(cudaMemcpy(&h, D.stats.p, sizeof h, cudaMemcpyDeviceToHost));
+            tot.paths += h.v[0]; tot.segments += h.v[1]; tot.sphere_tests += h.v[2]; tot.node_tests += h.v[3];
+            tot.hits_diffuse += h.v[4]; tot.hits_metallic += h.v[5]; tot.hits_dielectric += h.v[6];
+            tot.ended_sky += h.v[7]; tot.ended_absorbed += h.v[8]; tot.ended_depth += h.v[9];
+        }
+        ctx->stats = tot;
+        ctx->stats_valid = true;
+    }
+    return RZ_OK;
+}
+
 static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams *p, bool sync) {
     if (!ctx || !cam || !p) return rz_fail(RZ_ERR_INVALID_ARG, "render: NULL argument");
     if (!ctx->have_scene) return rz_fail(RZ_ERR_NO_SCENE, "render: rayz_cuda_upload_scene has not been called");
@@ -700,15 +749,57 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         a.t_min = p->t_min > 0 ? p->t_min : 1e-4f;
 
         RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
+        D.passes = 0;
         if (n_local > 0) {
             if (variant == RZ_VARIANT_WAVEFRONT) {
                 uint32_t l = 0;
                 RZ_CUDA(rz_wavefront_render(&a, D.sms, (int)p->collect_stats, D.stream, &D.wf_scratch, &D.wf_scratch_bytes, &l));
                 launches += l;
             } else {
-                if (variant == RZ_VARIANT_BVH) RZ_CUDA(rz_launch_bvh(&a, (int)p->collect_stats, D.sms, D.stream));
-                else RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
-                launches += 1;
+                if (variant == RZ_VARIANT_BVH) {
+                    RZ_CUDA(rz_launch_bvh(&a, (int)p->collect_stats, D.sms, D.stream));
+                    launches += 1;
+                } else if (getenv("RZ_MEGA_SINGLE") || rz_primary_smem_bytes(&a) > 227u * 1024u) {
+                    // single-stage form (development A/B, or a set whose pair lists do not fit beside it)
+                    RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
+                    launches += 1;
+                } else {
+                    // two-stage K1: primary kernel (tile-culled camera segments) -> HBM queue -> persistent megakernel.
+                    // Passes are sized by the queue (<= 2^25 entries of 64 B = 2 GB of the 180 GB HBM).
+                    const uint64_t unit_paths = 32ull * a.chunk;
+                    const uint64_t cap = std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << 25);
+                    const uint32_t units_per_pass = (uint32_t)std::max<uint64_t>(1, cap / unit_paths);
+                    if ((rc = D.queue.alloc((size_t)std::max<uint64_t>(cap, unit_paths) * 4u))) return rc;
+                    const double pcx = cam->px_origin[0] + 0.5 * (p->width - 1) * cam->px_du[0] + 0.5 * (p->height - 1) * cam->px_dv[0] - cam->look_from[0];
+                    const double pcy = cam->px_origin[1] + 0.5 * (p->width - 1) * cam->px_du[1] + 0.5 * (p->height - 1) * cam->px_dv[1] - cam->look_from[1];
+                    const double pcz = cam->px_origin[2] + 0.5 * (p->width - 1) * cam->px_du[2] + 0.5 * (p->height - 1) * cam->px_dv[2] - cam->look_from[2];
+                    a.focus_dist = (float)std::sqrt(pcx * pcx + pcy * pcy + pcz * pcz);   // look_from -> centre of the focus plane
+                    const double lu = std::sqrt(cam->defocus_u[0] * cam->defocus_u[0] + cam->defocus_u[1] * cam->defocus_u[1] + cam->defocus_u[2] * cam->defocus_u[2]);
+                    const double lv = std::sqrt(cam->defocus_v[0] * cam->defocus_v[0] + cam->defocus_v[1] * cam->defocus_v[1] + cam->defocus_v[2] * cam->defocus_v[2]);
+                    a.lens_radius = cam->defocus ? (float)(std::max(lu, lv) * 1.001) : 0.f;
+                    a.queue = D.queue.p; a.queue_count = D.counter.p + 2; a.queue_cap = (uint32_t)std::max<uint64_t>(cap, unit_paths);
+                    const uint32_t total_units = a.n_units;
+                    const uint32_t n_pass = (total_units + units_per_pass - 1) / units_per_pass;
+                    while (D.pass_ev.size() < 2 * (size_t)n_pass) {
+                        cudaEvent_t e = nullptr;
+                        RZ_CUDA(cudaEventCreate(&e));
+                        D.pass_ev.push_back(e);
+                    }
+                    D.passes = n_pass;
+                    uint32_t pass = 0;
+                    for (uint32_t u0 = 0; u0 < total_units; u0 += units_per_pass, pass++) {
+                        if (u0 > 0) RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 4 * sizeof(unsigned int), D.stream));
+                        RzPathArgs a1 = a;
+                        a1.unit_base = u0; a1.n_units = std::min(units_per_pass, total_units - u0); a1.unit_counter = D.counter.p;
+                        RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, D.stream));
+                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass], D.stream));
+                        RzPathArgs a2 = a;
+                        a2.unit_counter = D.counter.p + 1;
+                        RZ_CUDA(rz_launch_path(&a2, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
+                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass + 1], D.stream));
+                        launches += 2;
+                    }
+                }
             }
         }
         RZ_CUDA(cudaEventRecord(D.ev[2], D.stream));
@@ -734,31 +825,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
             RZ_CUDA(cudaSetDevice(ctx->devs[d].id));
             RZ_CUDA(cudaStreamSynchronize(ctx->devs[d].stream));
         }
-        float kmax = 0, rmax = 0;
-        for (uint32_t d = 0; d < ND; d++) {
-            float k = 0, r = 0;
-            RZ_CUDA(cudaEventElapsedTime(&k, ctx->devs[d].ev[1], ctx->devs[d].ev[2]));
-            RZ_CUDA(cudaEventElapsedTime(&r, ctx->devs[d].ev[2], ctx->devs[d].ev[3]));
-            kmax = std::max(kmax, k); rmax = std::max(rmax, r);
-        }
-        ctx->timing.kernel_ms = kmax;
-        ctx->timing.resolve_ms = rmax;
+        { const int rc = collect_timing_and_stats(ctx, p->collect_stats != 0); if (rc) return rc; }
         ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
-        if (p->collect_stats) {
-            RzStats tot;
-            memset(&tot, 0, sizeof tot);
-            for (uint32_t d = 0; d < ND; d++) {
-                RzStatsDev h;
-                RZ_CUDA(cudaSetDevice(ctx->devs[d].id));
-                RZ_CUDA(cudaMemcpy(&h, ctx->devs[d].stats.p, sizeof h, cudaMemcpyDeviceToHost));
-                tot.paths += h.v[0]; tot.segments += h.v[1]; tot.sphere_tests += h.v[2]; tot.node_tests += h.v[3];
-                tot.hits_diffuse += h.v[4]; tot.hits_metallic += h.v[5]; tot.hits_dielectric += h.v[6];
-                tot.ended_sky += h.v[7]; tot.ended_absorbed += h.v[8]; tot.ended_depth += h.v[9];
-            }
-            if (variant == RZ_VARIANT_MEGA) tot.sphere_tests = tot.segments * (uint64_t)ctx->n_spheres;  // brute force tests all
-            ctx->stats = tot;
-            ctx->stats_valid = true;
-        }
     }
     return RZ_OK;
 }
@@ -792,32 +860,8 @@ extern "C" int rayz_cuda_render(RzContext *ctx, const RzCamera *cam, const RzRen
         RZ_CUDA(cudaSetDevice(D.id));
         RZ_CUDA(cudaStreamSynchronize(D.stream));
     }
-    // timings + stats (same bookkeeping as the device-resident entry point)
-    float kmax = 0, rmax = 0;
-    for (Dev &D : ctx->devs) {
-        float k = 0, r = 0;
-        RZ_CUDA(cudaEventElapsedTime(&k, D.ev[1], D.ev[2]));
-        RZ_CUDA(cudaEventElapsedTime(&r, D.ev[2], D.ev[3]));
-        kmax = std::max(kmax, k); rmax = std::max(rmax, r);
-    }
-    ctx->timing.kernel_ms = kmax;
-    ctx->timing.resolve_ms = rmax;
+    { const int rc2 = collect_timing_and_stats(ctx, params->collect_stats != 0); if (rc2) return rc2; }
     ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (params->collect_stats) {
-        RzStats tot;
-        memset(&tot, 0, sizeof tot);
-        for (Dev &D : ctx->devs) {
-            RzStatsDev h;
-            RZ_CUDA(cudaSetDevice(D.id));
-            RZ_CUDA(cudaMemcpy(&h, D.stats.p, sizeof h, cudaMemcpyDeviceToHost));
-            tot.paths += h.v[0]; tot.segments += h.v[1]; tot.sphere_tests += h.v[2]; tot.node_tests += h.v[3];
-            tot.hits_diffuse += h.v[4]; tot.hits_metallic += h.v[5]; tot.hits_dielectric += h.v[6];
-            tot.ended_sky += h.v[7]; tot.ended_absorbed += h.v[8]; tot.ended_depth += h.v[9];
-        }
-        if (ctx->timing.variant == RZ_VARIANT_MEGA) tot.sphere_tests = tot.segments * (uint64_t)ctx->n_spheres;
-        ctx->stats = tot;
-        ctx->stats_valid = true;
-    }
     if (out_paths) *out_paths = (uint64_t)npx * params->spp;
     return RZ_OK;
 }

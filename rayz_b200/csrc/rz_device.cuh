@@ -93,6 +93,13 @@ struct RzPathArgs {
     uint32_t shard_index, shard_count, band_rows;
     uint32_t seed_lo, seed_hi;
     float t_min;
+    // K1 two-stage form: the primary kernel appends the paths that survive their camera segment to `queue`
+    // (4 x float4 per entry: o+time, d+self_k, thr+seg, lp/gpix/sample), the secondary kernel starts its paths from it
+    float4 *queue;
+    unsigned int *queue_count;   // entries appended so far (device counter)
+    uint32_t queue_cap;          // entries the buffer holds
+    uint32_t unit_base;          // first work unit of this pass (primary kernel)
+    float focus_dist, lens_radius;   // thin-lens numbers for the tile-frustum cull (derived from the camera)
     uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)
     uint32_t bvh_descend_min;    // K3: a descend round ends once fewer lanes than this are still descending
 };

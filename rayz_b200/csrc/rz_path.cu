@@ -20,6 +20,7 @@
 //     (FFMA2/FADD2/FMUL2, two spheres per instruction): 11 issue slots per stationary
 //     sphere PAIR and ray, 14 per moving pair (rz_search_brute2);
 //   * large scenes use the BVH kernel of rz_bvh_trace.cu (K3) instead.
+#include <algorithm>
 #include <cstdlib>
 
 #include "rz_search.cuh"
@@ -36,7 +37,7 @@ struct RzStream {
 };
 
 // G = sphere PAIRS per search-loop iteration
-template <int R, int G, bool STATS, int MB>
+template <int R, int G, bool STATS, int MB, bool QUEUE>
 __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -50,6 +51,9 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
     // warp-uniform unit state
     bool have_unit = true;
     uint32_t unit_lp0 = 0, unit_s0 = 0, unit_paths = 0, k_next = 0;
+    // QUEUE: paths start from the entries the primary kernel appended (512 per work unit)
+    const uint32_t n_entries = QUEUE ? min(*a.queue_count, a.queue_cap) : 0u;
+    const uint32_t n_units = QUEUE ? (n_entries + 511u) / 512u : a.n_units;
 
     RzStream st[R];
 #pragma unroll
@@ -78,30 +82,46 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
                     unsigned u = 0;
                     if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
                     u = __shfl_sync(0xffffffffu, u, 0);
-                    if (u >= a.n_units) { have_unit = false; break; }
-                    const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
-                    unit_lp0 = tile * 32u;
-                    unit_s0 = chunk * a.chunk;
-                    unit_paths = 32u * min(a.chunk, a.spp - unit_s0);
+                    if (u >= n_units) { have_unit = false; break; }
+                    if (QUEUE) {
+                        unit_lp0 = u * 512u;                       // first queue entry of the unit
+                        unit_paths = min(512u, n_entries - unit_lp0);
+                    } else {
+                        const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
+                        unit_lp0 = tile * 32u;
+                        unit_s0 = chunk * a.chunk;
+                        unit_paths = 32u * min(a.chunk, a.spp - unit_s0);
+                    }
                     k_next = 0;
                     continue;
                 }
                 const uint32_t rank = __popc(mask & lt_mask);
                 if (need && rank < avail) {
                     const uint32_t k = k_next + rank;
-                    const uint32_t lp = unit_lp0 + (k & 31u);
-                    if (lp < a.n_local_px) {
-                        uint32_t pi, pj;
-                        rz_local_to_global(lp, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
-                        st[r].lp = lp;
-                        st[r].gpix = pj * a.width + pi;
-                        st[r].sample = a.sample_offset + unit_s0 + (k >> 5);
-                        st[r].ray = rz_camera_ray(a.cam, pi, pj, st[r].gpix, st[r].sample, a.seed_lo, a.seed_hi);
-                        st[r].thr = f3(1.f, 1.f, 1.f);
-                        st[r].seg = 0;
-                        st[r].alive = a.max_depth > 0u;
-                        if (STATS) { c_paths++; if (!st[r].alive) c_depth++; }
-                        need = !st[r].alive;
+                    if (QUEUE) {
+                        const float4 *e = a.queue + (size_t)(unit_lp0 + k) * 4u;
+                        const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
+                        st[r].ray.o = f3(qa.x, qa.y, qa.z); st[r].ray.time = qa.w;
+                        st[r].ray.d = f3(qb.x, qb.y, qb.z); st[r].ray.self_k = __float_as_int(qb.w);
+                        st[r].thr = f3(qc.x, qc.y, qc.z); st[r].seg = __float_as_uint(qc.w);
+                        st[r].lp = __float_as_uint(qd.x); st[r].gpix = __float_as_uint(qd.y); st[r].sample = __float_as_uint(qd.z);
+                        st[r].alive = true;
+                        need = false;
+                    } else {
+                        const uint32_t lp = unit_lp0 + (k & 31u);
+                        if (lp < a.n_local_px) {
+                            uint32_t pi, pj;
+                            rz_local_to_global(lp, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
+                            st[r].lp = lp;
+                            st[r].gpix = pj * a.width + pi;
+                            st[r].sample = a.sample_offset + unit_s0 + (k >> 5);
+                            st[r].ray = rz_camera_ray(a.cam, pi, pj, st[r].gpix, st[r].sample, a.seed_lo, a.seed_hi);
+                            st[r].thr = f3(1.f, 1.f, 1.f);
+                            st[r].seg = 0;
+                            st[r].alive = a.max_depth > 0u;
+                            if (STATS) { c_paths++; if (!st[r].alive) c_depth++; }
+                            need = !st[r].alive;
+                        }
                     }
                 }
                 k_next += min((uint32_t)__popc(mask), avail);
@@ -128,7 +148,7 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (!st[r].alive) continue;
-            if (STATS) c_segs++;
+            if (STATS) { c_segs++; c_sph += a.set.n; }   // brute force: every sphere of the set
             uint32_t kind;
             const int res = rz_shade_segment(a, st[r].ray, st[r].thr, st[r].seg, st[r].lp, st[r].gpix, st[r].sample, bk[r], kind);
             if (STATS) {
@@ -152,10 +172,174 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------ launcher
-template <int R, int G, bool STATS, int MB = 5>
+// ------------------------------------------------------------------------------ primary kernel
+// Stage 1 of the two-stage K1: the camera segment of every path (Camera.getRay camera.zig:59-77 + the first
+// bounceRay level renderer.zig:103-126).  Camera rays of a 32-pixel tile are coherent, so the warp first
+// culls the sphere set against the tile's frustum — a cone around the tile's mean direction, widened by the
+// pixel footprint, the thin-lens blur and each sphere's motion — and the packed search then runs over the
+// surviving handful of sphere pairs instead of all of them (rz_search_list2: same arithmetic, same (t, k)).
+// Paths that scatter are appended, ballot-compacted, to the HBM queue the secondary kernel starts from; paths
+// that leave the scene or are absorbed accumulate here.  36 % of all segments are camera segments.
+template <bool STATS>
+__global__ void __launch_bounds__(128) rz_primary_kernel(const RzPathArgs a) {
+    extern __shared__ __align__(16) unsigned char rz_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
+    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1;   // sphere pairs
+    const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
+    unsigned short *ls = reinterpret_cast<unsigned short *>(s_pk + pk_f4) + (threadIdx.x >> 5) * (n_sp + n_mp);
+    unsigned short *lm = ls + n_sp;
+
+    rz_stage_scene_pk(a.set, s_pk, &s_bar);
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float3 apex = a.cam.look_from;
+    unsigned long long c_paths = 0, c_segs = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
+
+    while (true) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= a.n_units) break;
+        u += a.unit_base;
+        const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
+        const uint32_t lp = tile * 32u + lane;
+        const bool valid = lp < a.n_local_px;
+        uint32_t pi = 0, pj = 0;
+        if (valid) rz_local_to_global(lp, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
+        const uint32_t gpix = pj * a.width + pi;
+
+        // ---- cone around the tile's camera rays: axis = mean pixel direction, half-angle from the pixel corners
+        const float3 pc = a.cam.px_origin + a.cam.px_du * (float)pi + a.cam.px_dv * (float)pj - apex;
+        float3 ax = valid ? normalize3(pc) : f3(0.f, 0.f, 0.f);
+        for (int o = 16; o > 0; o >>= 1) {
+            ax.x += __shfl_xor_sync(0xffffffffu, ax.x, o); ax.y += __shfl_xor_sync(0xffffffffu, ax.y, o); ax.z += __shfl_xor_sync(0xffffffffu, ax.z, o);
+        }
+        const float al = dot3(ax, ax);
+        ax = al > 1e-12f ? ax * rz_rsqrt(al) : f3(0.f, 0.f, 1.f);
+        float cmin = 1.0f;
+        if (valid) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float3 q = pc + a.cam.px_du * ((c & 1) ? 0.5f : -0.5f) + a.cam.px_dv * ((c & 2) ? 0.5f : -0.5f);
+                cmin = fminf(cmin, dot3(ax, normalize3(q)));
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        const bool cull = cmin > 0.2f && al > 1e-12f;   // very wide tiles (tiny images): test everything
+        const float tan_t = cull ? sqrtf(fmaxf(0.f, 1.f - cmin * cmin)) / cmin * 1.05f + 1e-4f : 0.f;
+        const float inv_f = 1.0f / fmaxf(0.9f * a.focus_dist, 1e-6f);
+        auto keep = [&](float cx, float cy, float cz, float vx, float vy, float vz, float w) -> bool {
+            if (!(w < 0.f)) return false;                         // padding entry (-r^2 = +1)
+            if (!cull) return true;
+            const float vl = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float re = sqrtf(-w) + 0.5f * vl;               // sphere swept over time in [0,1): midpoint + half the travel
+            const float3 vv = f3(fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)) - apex;
+            const float h = dot3(vv, ax), d2 = dot3(vv, vv);
+            const float smax = fmaxf(h + re, 0.f);                // farthest along-axis extent of the sphere
+            // cone radius there + thin-lens blur (grows beyond the focus plane) + margins for FP32 and the 1.05 above
+            const float rad = re * 1.02f + 0.02f + a.lens_radius * (1.f + smax * inv_f) + smax * tan_t;
+            if (d2 <= rad * rad) return true;                     // apex inside / next to the sphere
+            if (h + re < 0.f) return false;                       // entirely behind the camera
+            return fmaxf(d2 - h * h, 0.f) <= rad * rad;
+        };
+        int n_ls = 0, n_lm = 0;
+        for (uint32_t p0 = 0; p0 < n_sp; p0 += 32u) {
+            const uint32_t p = p0 + lane;
+            bool k = false;
+            if (p < n_sp) {
+                const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
+                k = keep(A.x, A.z, B.x, 0.f, 0.f, 0.f, B.z) || keep(A.y, A.w, B.y, 0.f, 0.f, 0.f, B.w);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, k);
+            if (k) ls[n_ls + __popc(m & lt_mask)] = (unsigned short)p;
+            n_ls += __popc(m);
+        }
+        const float4 *mv = s_pk + a.set.n_static_pad;
+        for (uint32_t p0 = 0; p0 < n_mp; p0 += 32u) {
+            const uint32_t p = p0 + lane;
+            bool k = false;
+            if (p < n_mp) {
+                const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
+                k = keep(A.x, A.z, B.x, VA.x, VA.z, VB.x, B.z) || keep(A.y, A.w, B.y, VA.y, VA.w, VB.y, B.w);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, k);
+            if (k) lm[n_lm + __popc(m & lt_mask)] = (unsigned short)p;
+            n_lm += __popc(m);
+        }
+        __syncwarp();
+
+        // ---- the tile's samples of this chunk, two per lane and iteration
+        const uint32_t s0 = chunk * a.chunk, ns = min(a.chunk, a.spp - s0);
+        for (uint32_t s = 0; s < ns; s += 2u) {
+            RzRay rays[2];
+            bool live[2];
+            uint32_t smp[2];
+            float bt[2];
+            int bk[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                smp[r] = a.sample_offset + s0 + s + (uint32_t)r;
+                const bool have = valid && (s + (uint32_t)r < ns);
+                live[r] = have && a.max_depth > 0u;
+                if (STATS && have) { c_paths++; if (!live[r]) c_depth++; }
+                if (live[r]) rays[r] = rz_camera_ray(a.cam, pi, pj, gpix, smp[r], a.seed_lo, a.seed_hi);
+                else { rays[r].o = f3(0.f, 0.f, 0.f); rays[r].d = f3(0.f, 1.f, 0.f); rays[r].time = 0.f; rays[r].self_k = -1; }
+                bt[r] = 3.0e38f; bk[r] = -1;
+            }
+            rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
+            if (STATS) c_sph += (unsigned long long)(2 * (n_ls + n_lm)) * (live[0] ? 1u : 0u) + (unsigned long long)(2 * (n_ls + n_lm)) * (live[1] ? 1u : 0u);
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                float3 thr = f3(1.f, 1.f, 1.f);
+                uint32_t seg = 0, kind = 3u;
+                bool cont = false;
+                if (live[r]) {
+                    if (STATS) c_segs++;
+                    const int res = rz_shade_segment(a, rays[r], thr, seg, lp, gpix, smp[r], bk[r], kind);
+                    if (STATS) {
+                        if (kind < 3u) c_hit[kind]++;
+                        if (res == RZ_END_SKY) c_sky++;
+                        if (res == RZ_END_ABSORBED) c_abs++;
+                        if (res == RZ_END_DEPTH) c_depth++;
+                    }
+                    cont = res == RZ_CONT;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, cont);
+                if (m) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(a.queue_count, (unsigned)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned e = base + __popc(m & lt_mask);
+                    if (cont && e < a.queue_cap) {
+                        float4 *q = a.queue + (size_t)e * 4u;
+                        __stcs(q + 0, make_float4(rays[r].o.x, rays[r].o.y, rays[r].o.z, rays[r].time));
+                        __stcs(q + 1, make_float4(rays[r].d.x, rays[r].d.y, rays[r].d.z, __int_as_float(rays[r].self_k)));
+                        __stcs(q + 2, make_float4(thr.x, thr.y, thr.z, __uint_as_float(seg)));
+                        __stcs(q + 3, make_float4(__uint_as_float(lp), __uint_as_float(gpix), __uint_as_float(smp[r]), 0.f));
+                    }
+                }
+            }
+        }
+        __syncwarp();   // the lists are rewritten for the next unit
+    }
+
+    if (STATS) {
+        unsigned long long v[10] = {c_paths, c_segs, c_sph, 0ull, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            unsigned long long sum = v[i];
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0 && sum) atomicAdd(&a.stats->v[i], sum);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ launchers
+template <int R, int G, bool STATS, int MB, bool QUEUE>
 static cudaError_t rz_launch_one(const RzPathArgs &a, int sm_count, size_t smem, cudaStream_t stream, int *grid_out) {
-    auto kern = rz_path_kernel<R, G, STATS, MB>;
+    auto kern = rz_path_kernel<R, G, STATS, MB, QUEUE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -168,24 +352,59 @@ static cudaError_t rz_launch_one(const RzPathArgs &a, int sm_count, size_t smem,
     return cudaGetLastError();
 }
 
+static size_t rz_pk_bytes(const RzPathArgs &a) { return (size_t)(a.set.n_pad + (a.set.n_pad - a.set.n_static_pad)) * 16u; }
+
 // Forces the lazily loaded path kernels into the context (called once from rayz_cuda_create so that
 // the first render does not pay module loading).
 extern "C" cudaError_t rz_path_warm(void) {
     cudaFuncAttributes fa;
-    return cudaFuncGetAttributes(&fa, rz_path_kernel<2, 2, false, 8>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, rz_path_kernel<2, 2, false, 8, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_primary_kernel<false>);
+    return e;
 }
 
-// rays_per_thread in {1,2}.
+// Shared memory the primary kernel needs: the pair-interleaved set + one pair list per warp.
+extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a) {
+    const size_t pairs = a->set.n_pad / 2u;
+    return rz_pk_bytes(*a) + ((4u * pairs * sizeof(unsigned short) + 15u) & ~size_t(15));
+}
+
+// Stage 1: camera segments of the work units [unit_base, unit_base + n_units) -> queue.
+extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
+    const size_t smem = rz_primary_smem_bytes(a);
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const unsigned want = (a->n_units + 3u) / 4u;   // 4 warps per CTA, one unit per warp at a time
+        const unsigned grid = (unsigned)std::max(1u, std::min((unsigned)(sm_count * per_sm), want));
+        kern<<<grid, 128, smem, stream>>>(*a);
+        return cudaGetLastError();
+    };
+    return collect_stats ? launch(rz_primary_kernel<true>) : launch(rz_primary_kernel<false>);
+}
+
+// Stage 2 (queue != nullptr): the persistent megakernel started from the queue; or the single-stage form
+// (queue == nullptr) that generates its own camera rays.  rays_per_thread in {1,2}.
 extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int rays_per_thread, int collect_stats, int sm_count, cudaStream_t stream,
                                       int *grid_out) {
     const bool stats = collect_stats != 0;
-    const size_t smem = (size_t)(a->set.n_pad + (a->set.n_pad - a->set.n_static_pad)) * 16u;
-    if (rays_per_thread == 1) {
-        return stats ? rz_launch_one<1, 2, true>(*a, sm_count, smem, stream, grid_out)
-                     : rz_launch_one<1, 2, false>(*a, sm_count, smem, stream, grid_out);
+    const size_t smem = rz_pk_bytes(*a);
+    if (a->queue) {
+        if (rays_per_thread == 1)
+            return stats ? rz_launch_one<1, 2, true, 5, true>(*a, sm_count, smem, stream, grid_out)
+                         : rz_launch_one<1, 2, false, 5, true>(*a, sm_count, smem, stream, grid_out);
+        return stats ? rz_launch_one<2, 2, true, 5, true>(*a, sm_count, smem, stream, grid_out)
+                     : rz_launch_one<2, 2, false, 8, true>(*a, sm_count, smem, stream, grid_out);
     }
+    if (rays_per_thread == 1)
+        return stats ? rz_launch_one<1, 2, true, 5, false>(*a, sm_count, smem, stream, grid_out)
+                     : rz_launch_one<1, 2, false, 5, false>(*a, sm_count, smem, stream, grid_out);
     // 8 resident CTAs per SM (64 registers, 232 B of spills outside the search loop) measured 3 % faster than
     // the 5 CTAs the unconstrained 88-register build gets: 1522 vs 1472 Mpaths/s at config 2 / 100 spp.
-    return stats ? rz_launch_one<2, 2, true>(*a, sm_count, smem, stream, grid_out)
-                 : rz_launch_one<2, 2, false, 8>(*a, sm_count, smem, stream, grid_out);
+    return stats ? rz_launch_one<2, 2, true, 5, false>(*a, sm_count, smem, stream, grid_out)
+                 : rz_launch_one<2, 2, false, 8, false>(*a, sm_count, smem, stream, grid_out);
 }

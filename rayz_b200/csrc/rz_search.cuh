@@ -252,6 +252,58 @@ __device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk
     rz_search_brute2<R, G2, RzSrcShared>(RzSrcShared{s_pk}, n_static_pad, n_pad, ray, t_min, bt, bk);
 }
 
+// ------------------------------------------------------------------------------ K1 search over a culled list
+// Same packed arithmetic (and therefore the same (t, k), bit for bit) over a LIST of sphere pairs:
+// the primary-visibility kernel culls the set against the frustum of its 32-pixel tile first, so
+// camera rays test a handful of pairs instead of all of them.  ls / lm: pair indices into the
+// stationary / moving part of the pair-interleaved set (layout: RzSphereSet::pk).
+template <int R>
+__device__ __forceinline__ void rz_search_list2(const float4 *__restrict__ s_pk, const unsigned short *__restrict__ ls, int n_ls,
+                                                const unsigned short *__restrict__ lm, int n_lm, int n_static_pad,
+                                                const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
+    float nox[R], noy[R], noz[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { nox[r] = -ray[r].o.x; noy[r] = -ray[r].o.y; noz[r] = -ray[r].o.z; }
+#pragma unroll 1
+    for (int i = 0; i < n_ls; i++) {
+        const int p = ls[i];
+        const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
+        const int k = 2 * p;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float2 ocx = __fadd2_rn(rz_f2(A.x, A.y), rz_f2(nox[r], nox[r]));
+            const float2 ocy = __fadd2_rn(rz_f2(A.z, A.w), rz_f2(noy[r], noy[r]));
+            const float2 ocz = __fadd2_rn(rz_f2(B.x, B.y), rz_f2(noz[r], noz[r]));
+            const float2 b = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
+                                        __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
+            const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B.z, B.w))));
+            const float dx = fmaf(b.x, b.x, -c.x), dy = fmaf(b.y, b.y, -c.y);
+            if (dx > 0.0f) rz_consider(k, b.x, dx, ray[r].self_k, t_min, bt[r], bk[r]);
+            if (dy > 0.0f) rz_consider(k + 1, b.y, dy, ray[r].self_k, t_min, bt[r], bk[r]);
+        }
+    }
+    const float4 *__restrict__ mv = s_pk + n_static_pad;
+#pragma unroll 1
+    for (int i = 0; i < n_lm; i++) {
+        const int p = lm[i];
+        const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
+        const int k = n_static_pad + 2 * p;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float2 tm = rz_f2(ray[r].time, ray[r].time);
+            const float2 ocx = __ffma2_rn(rz_f2(VA.x, VA.y), tm, __fadd2_rn(rz_f2(A.x, A.y), rz_f2(nox[r], nox[r])));
+            const float2 ocy = __ffma2_rn(rz_f2(VA.z, VA.w), tm, __fadd2_rn(rz_f2(A.z, A.w), rz_f2(noy[r], noy[r])));
+            const float2 ocz = __ffma2_rn(rz_f2(VB.x, VB.y), tm, __fadd2_rn(rz_f2(B.x, B.y), rz_f2(noz[r], noz[r])));
+            const float2 b = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
+                                        __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
+            const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B.z, B.w))));
+            const float dx = fmaf(b.x, b.x, -c.x), dy = fmaf(b.y, b.y, -c.y);
+            if (dx > 0.0f) rz_consider(k, b.x, dx, ray[r].self_k, t_min, bt[r], bk[r]);
+            if (dy > 0.0f) rz_consider(k + 1, b.y, dy, ray[r].self_k, t_min, bt[r], bk[r]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ K1 search, ray-paired
 // Transposed packing: one packed instruction works on TWO RAYS (.x/.y halves) against one sphere,
 // whose numbers enter as 32-bit broadcast operands straight from the LDS destination registers.

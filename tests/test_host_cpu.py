@@ -20,7 +20,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(abi.SYMBOLS), (declared ^ set(abi.SYMBOLS))
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rayz_cuda_abi_version() == 1
+    assert lib.rayz_cuda_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.RzRenderParams) == 56
     assert C.sizeof(abi.RzScene) == 16 + 14 * 8
     assert C.sizeof(abi.RzStats) == 80
-    assert C.sizeof(abi.RzTiming) == 32
+    assert C.sizeof(abi.RzTiming) == 40
     assert C.sizeof(abi.RzConfig) == 40
 
 
