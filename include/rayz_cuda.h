@@ -118,8 +118,13 @@ typedef struct RzRenderParams {
     uint32_t shard_count;
     uint32_t band_rows;     /* 0 => 4 */
     uint32_t collect_stats; /* !=0: run the counter-instrumented kernel build    */
-    uint32_t reserved0;
+    uint32_t flags;         /* RZ_RENDER_* bits, 0 = defaults                    */
 } RzRenderParams;
+
+/* RzRenderParams.flags */
+#define RZ_RENDER_SERIAL_PASSES 1u /* two-stage K1: run the passes back to back on one stream instead of
+                                    * overlapping them on two, so that RzTiming.primary_ms and
+                                    * kernel_ms - primary_ms are clean per-kernel durations (profiling) */
 
 typedef struct RzConfig {
     int32_t n_devices;     /* 0 => 1 */
@@ -158,7 +163,8 @@ typedef struct RzTiming {
     uint32_t variant;   /* variant that actually ran (AUTO resolved)                */
     uint32_t bvh_build_us; /* K3 BVH build inside the last rayz_cuda_upload_scene, microseconds:
                             * host SAH wall time, or device LBVH by CUDA events (max over devices) */
-    float primary_ms;      /* two-stage K1: the primary (camera-segment) kernels' share of kernel_ms   */
+    float primary_ms;      /* two-stage K1: sum of the primary (camera-segment) kernels' durations; a clean
+                            * share of kernel_ms only with RZ_RENDER_SERIAL_PASSES (passes overlap otherwise) */
     uint32_t passes;       /* two-stage K1: primary+secondary launch pairs of the render, else 0      */
 } RzTiming;
 

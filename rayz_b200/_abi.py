@@ -40,7 +40,7 @@ class RzRenderParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("max_depth", C.c_uint32),
                 ("seed", C.c_uint64), ("sample_offset", C.c_uint32), ("variant", C.c_uint32), ("t_min", C.c_float),
                 ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("band_rows", C.c_uint32),
-                ("collect_stats", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("collect_stats", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class RzConfig(C.Structure):

@@ -107,6 +107,8 @@ struct SetBufs {
 struct Dev {
     int id = 0, sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // two-stage K1: odd passes run here so that a pass fills the tail of the previous one
+    cudaEvent_t ev_s2 = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, path0, path1, resolve1, done
     SetBufs brute, bvhset;
     DBuf<RzBvhNode> bvh;
@@ -122,7 +124,7 @@ struct Dev {
     DBuf<float4> t_color;
     DBuf<double> t_inv_scale;
     DBuf<unsigned long long> accum;
-    DBuf<float4> queue;   // two-stage K1: paths that survived their camera segment (4 x float4 each)
+    DBuf<float4> queue, queue2;   // two-stage K1: paths that survived their camera segment (4 x float4 each), double buffered
     DBuf<unsigned int> counter;
     DBuf<RzStatsDev> stats;
     DBuf<float4> out_linear;
@@ -133,6 +135,7 @@ struct Dev {
     size_t wf_scratch_bytes = 0;
     std::vector<cudaEvent_t> pass_ev;   // two-stage K1: [2i] after the primary kernel of pass i, [2i+1] after the secondary
     uint32_t passes = 0;                // passes of the last render (0 = not the two-stage form)
+    bool serial_passes = false;
 };
 
 struct RzContext {
@@ -432,6 +435,7 @@ extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
         D.sms = prop.multiProcessorCount;
         if ((e = cudaStreamCreateWithFlags(&D.own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         D.stream = D.own_stream;
+        if ((e = cudaStreamCreateWithFlags(&D.stream2, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreateWithFlags(&D.ev_s2, cudaEventDisableTiming)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         for (auto &ev : D.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
         if ((e = rz_path_warm()) != cudaSuccess || (e = rz_bvh_warm()) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "loading the path kernels: %s", cudaGetErrorString(e)); }
@@ -459,11 +463,13 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
         D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
-        D.accum.release(); D.queue.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
+        D.accum.release(); D.queue.release(); D.queue2.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
         D.ids.release(); D.sink.release();
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
         for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
         for (auto &ev : D.pass_ev) if (ev) cudaEventDestroy(ev);
+        if (D.ev_s2) cudaEventDestroy(D.ev_s2);
+        if (D.stream2) { cudaStreamSynchronize(D.stream2); cudaStreamDestroy(D.stream2); }
         if (D.own_stream) cudaStreamDestroy(D.own_stream);
     }
     delete ctx;
@@ -658,7 +664,9 @@ static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
         RZ_CUDA(cudaEventElapsedTime(&r, D.ev[2], D.ev[3]));
         for (uint32_t i = 0; i < D.passes; i++) {
             float ms = 0;
-            RZ_CUDA(cudaEventElapsedTime(&ms, i == 0 ? D.ev[1] : D.pass_ev[2 * i - 1], D.pass_ev[2 * i]));
+            // overlapped: pass i runs on stream i & 1 after pass i-2 of that stream (the first two start at ev[1]); serial: after pass i-1
+            const uint32_t back = D.serial_passes ? 1u : 2u;
+            RZ_CUDA(cudaEventElapsedTime(&ms, i < back ? D.ev[1] : D.pass_ev[2 * (i - back) + 1], D.pass_ev[2 * i]));
             pr += ms;
         }
         kmax = std::max(kmax, k); rmax = std::max(rmax, r); pmax = std::max(pmax, pr);
@@ -723,11 +731,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         const uint32_t n_tiles = (n_local + 31u) / 32u;
         int rc;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u))) return rc;
-        if ((rc = D.counter.alloc(4))) return rc;
+        if ((rc = D.counter.alloc(8))) return rc;
         if ((rc = D.stats.alloc(1))) return rc;
         RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
         RZ_CUDA(cudaMemsetAsync(D.accum.p, 0, (size_t)n_tiles * 32u * 4u * sizeof(unsigned long long), D.stream));
-        RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 4 * sizeof(unsigned int), D.stream));
+        RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 8 * sizeof(unsigned int), D.stream));
         if (p->collect_stats) RZ_CUDA(cudaMemsetAsync(D.stats.p, 0, sizeof(RzStatsDev), D.stream));
 
         RzPathArgs a;
@@ -767,9 +775,14 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     // two-stage K1: primary kernel (tile-culled camera segments) -> HBM queue -> persistent megakernel.
                     // Passes are sized by the queue (<= 2^25 entries of 64 B = 2 GB of the 180 GB HBM).
                     const uint64_t unit_paths = 32ull * a.chunk;
-                    const uint64_t cap = std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << 25);
+                    const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiment
+                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 26;
+                    const uint64_t cap = std::max<uint64_t>(unit_paths, std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << qlog));
                     const uint32_t units_per_pass = (uint32_t)std::max<uint64_t>(1, cap / unit_paths);
-                    if ((rc = D.queue.alloc((size_t)std::max<uint64_t>(cap, unit_paths) * 4u))) return rc;
+                    const uint32_t total_units = a.n_units;
+                    const uint32_t n_pass = (total_units + units_per_pass - 1) / units_per_pass;
+                    if ((rc = D.queue.alloc((size_t)cap * 4u))) return rc;
+                    if (n_pass > 1 && (rc = D.queue2.alloc((size_t)cap * 4u))) return rc;
                     const double pcx = cam->px_origin[0] + 0.5 * (p->width - 1) * cam->px_du[0] + 0.5 * (p->height - 1) * cam->px_dv[0] - cam->look_from[0];
                     const double pcy = cam->px_origin[1] + 0.5 * (p->width - 1) * cam->px_du[1] + 0.5 * (p->height - 1) * cam->px_dv[1] - cam->look_from[1];
                     const double pcz = cam->px_origin[2] + 0.5 * (p->width - 1) * cam->px_du[2] + 0.5 * (p->height - 1) * cam->px_dv[2] - cam->look_from[2];
@@ -777,27 +790,37 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const double lu = std::sqrt(cam->defocus_u[0] * cam->defocus_u[0] + cam->defocus_u[1] * cam->defocus_u[1] + cam->defocus_u[2] * cam->defocus_u[2]);
                     const double lv = std::sqrt(cam->defocus_v[0] * cam->defocus_v[0] + cam->defocus_v[1] * cam->defocus_v[1] + cam->defocus_v[2] * cam->defocus_v[2]);
                     a.lens_radius = cam->defocus ? (float)(std::max(lu, lv) * 1.001) : 0.f;
-                    a.queue = D.queue.p; a.queue_count = D.counter.p + 2; a.queue_cap = (uint32_t)std::max<uint64_t>(cap, unit_paths);
-                    const uint32_t total_units = a.n_units;
-                    const uint32_t n_pass = (total_units + units_per_pass - 1) / units_per_pass;
+                    a.queue_cap = (uint32_t)cap;
                     while (D.pass_ev.size() < 2 * (size_t)n_pass) {
                         cudaEvent_t e = nullptr;
                         RZ_CUDA(cudaEventCreate(&e));
                         D.pass_ev.push_back(e);
                     }
                     D.passes = n_pass;
+                    D.serial_passes = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
+                    // Passes alternate between two streams and two queue buffers: the persistent secondary kernel ends with a
+                    // tail of a few long paths (measured ~2 ms per pass), which the next pass's kernels fill.
+                    if (n_pass > 1) RZ_CUDA(cudaStreamWaitEvent(D.stream2, D.ev[1], 0));
                     uint32_t pass = 0;
                     for (uint32_t u0 = 0; u0 < total_units; u0 += units_per_pass, pass++) {
-                        if (u0 > 0) RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 4 * sizeof(unsigned int), D.stream));
+                        const int side = (p->flags & RZ_RENDER_SERIAL_PASSES) ? 0 : (int)(pass & 1u);
+                        cudaStream_t st = side ? D.stream2 : D.stream;
+                        unsigned int *ctr = D.counter.p + 4 * side;
+                        if (pass >= 2 || (pass == 1 && side == 0)) RZ_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st));
                         RzPathArgs a1 = a;
-                        a1.unit_base = u0; a1.n_units = std::min(units_per_pass, total_units - u0); a1.unit_counter = D.counter.p;
-                        RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, D.stream));
-                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass], D.stream));
-                        RzPathArgs a2 = a;
-                        a2.unit_counter = D.counter.p + 1;
-                        RZ_CUDA(rz_launch_path(&a2, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
-                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass + 1], D.stream));
+                        a1.queue = side ? D.queue2.p : D.queue.p; a1.queue_count = ctr + 2;
+                        a1.unit_base = u0; a1.n_units = std::min(units_per_pass, total_units - u0); a1.unit_counter = ctr;
+                        RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, st));
+                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass], st));
+                        RzPathArgs a2 = a1;
+                        a2.unit_counter = ctr + 1;
+                        RZ_CUDA(rz_launch_path(&a2, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
+                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass + 1], st));
                         launches += 2;
+                    }
+                    if (n_pass > 1) {   // join the second stream before the resolve
+                        RZ_CUDA(cudaEventRecord(D.ev_s2, D.stream2));
+                        RZ_CUDA(cudaStreamWaitEvent(D.stream, D.ev_s2, 0));
                     }
                 }
             }

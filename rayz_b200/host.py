@@ -250,7 +250,7 @@ class Backend:
 
     @staticmethod
     def params(width, height, spp, max_depth=50, seed=1, sample_offset=0, variant="auto", t_min=0.0, shard_index=0,
-               shard_count=1, band_rows=0, collect_stats=False) -> abi.RzRenderParams:
+               shard_count=1, band_rows=0, collect_stats=False, serial_passes=False) -> abi.RzRenderParams:
         p = abi.RzRenderParams()
         p.width, p.height, p.spp, p.max_depth = width, height, spp, max_depth
         p.seed, p.sample_offset = seed, sample_offset
@@ -258,6 +258,7 @@ class Backend:
         p.t_min = t_min
         p.shard_index, p.shard_count, p.band_rows = shard_index, shard_count, band_rows
         p.collect_stats = 1 if collect_stats else 0
+        p.flags = 1 if serial_passes else 0   # RZ_RENDER_SERIAL_PASSES
         return p
 
     def shard_rows(self, p: abi.RzRenderParams) -> int:

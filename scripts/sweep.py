@@ -41,7 +41,9 @@ def main():
         paths = W * H * args.spp
         S = st["segments"] / st["paths"]
         f_isect = ti["n_static"] * 16 + ti["n_moving"] * 22
-        f_path = S * f_isect + (S - st["ended_sky"] / st["paths"]) * 70 + 45 + 19 * st["ended_sky"] / st["paths"]
+        n_sph = max(1, ti["n_static"] + ti["n_moving"])
+        tests = st["sphere_tests"] / st["paths"] if variant != "bvh" and st["sphere_tests"] else S * n_sph   # bvh: brute-force EQUIVALENT flop
+        f_path = f_isect * tests / n_sph + (S - st["ended_sky"] / st["paths"]) * 70 + 45 + 19 * st["ended_sky"] / st["paths"]
         tf = paths * f_path / (best * 1e-3) / 1e12
         print(json.dumps({"cfg": cfg, "kernel_ms": best, "mpaths_s": paths / best / 1e3, "seg_per_path": S,
                           "brute_equiv_tflops": tf, "frac_of_measured_peak": tf / peak,

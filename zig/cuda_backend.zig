@@ -62,7 +62,7 @@ pub const RzRenderParams = extern struct {
     shard_count: u32 = 1,
     band_rows: u32 = 0,
     collect_stats: u32 = 0,
-    reserved0: u32 = 0,
+    flags: u32 = 0, // RZ_RENDER_* bits
 };
 
 pub const RzConfig = extern struct {
