@@ -406,7 +406,7 @@ def main():
                        "variant": variant_ran, "sharding": f"rows in bands of {band}, round-robin over {world} rank(s)",
                        "l2": "flushed between steps (256 MiB memset, untimed)"},
             "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roofline, "stats": {k: stats[k] for k in ("paths", "segments", "ended_sky", "ended_absorbed", "ended_depth")},
+            "roofline": roofline, "stats": {k: stats[k] for k in ("paths", "segments", "sphere_tests", "ended_sky", "ended_absorbed", "ended_depth")},
         }
         if e2e:
             out["e2e"] = e2e

@@ -773,10 +773,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     launches += 1;
                 } else {
                     // two-stage K1: primary kernel (tile-culled camera segments) -> HBM queue -> persistent megakernel.
-                    // Passes are sized by the queue (<= 2^25 entries of 64 B = 2 GB of the 180 GB HBM).
+                    // Passes are sized by the queue: <= 2^27 entries of 64 B = 8.6 GB per buffer, two buffers, of the 180 GB of HBM
+                    // (measured at config 2: 2^25 -> 196 ms, 2^26 -> 190 ms, 2^27 -> 187 ms, 2^28 -> 187 ms per render).
                     const uint64_t unit_paths = 32ull * a.chunk;
                     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiment
-                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 26;
+                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
                     const uint64_t cap = std::max<uint64_t>(unit_paths, std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << qlog));
                     const uint32_t units_per_pass = (uint32_t)std::max<uint64_t>(1, cap / unit_paths);
                     const uint32_t total_units = a.n_units;
