@@ -162,13 +162,14 @@ def algorithmic_flops_per_path(stats: dict, n_static: int, n_moving: int) -> dic
             "f_secondary": max(0.0, S - 1.0) * f_isect}
 
 
-def ncu_traffic(variant: str):
-    """dram__bytes_read + dram__bytes_write of the path kernel per launch, from the committed ncu --set full
-    capture (profiles/traffic.json; the capture ran the config-2 image at 40 spp — the accumulators and the
-    scene are the only DRAM traffic and do not grow with spp)."""
+def ncu_traffic(variant: str, paths_per_launch: float):
+    """dram__bytes_read + dram__bytes_write of the dominant kernel per launch, scaled from the committed ncu --set full
+    capture (profiles/traffic.json: bytes per path of a 40-spp config-2 render; the traffic is the primary->secondary
+    queue, 64 B per surviving path, plus the first touch of the accumulators)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(variant, {}).get("dram_bytes_per_launch")
+            per_path = json.load(f).get(variant, {}).get("dram_bytes_per_path_secondary_kernel")
+        return None if per_path is None else per_path * paths_per_launch
     except Exception:
         return None
 
@@ -393,7 +394,7 @@ def main():
                     "whole_step_achieved": step_flops, "whole_step_frac": step_flops / peak_tf if peak_tf else None,
                     "flop_per_path": fl["f_path"], "flop_per_path_dominant_kernel": fl["f_secondary"] if two_stage else fl["f_path"],
                     "segments_per_path": fl["segments_per_path"], "sphere_tests_per_path": fl["tests_per_path"],
-                    "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran),
+                    "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran, per_gpu_paths / max(1, passes_per_step)),
                     "hbm_bytes_algorithmic": (35 * W * H + (128 * total_paths if two_stage else 0)) // world,
                     "note": "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test); "
                             "tensor cores unused by design; HBM traffic = 35 B/pixel of framebuffer once per render, plus, in the "

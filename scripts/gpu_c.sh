@@ -12,4 +12,5 @@ $CMD > gpurun_out/e_ncu_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/e_launches.csv $CMD > gpurun_out/e_ncu_launches.log 2>&1
 $CMD > gpurun_out/e_ncu_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:rz_path_kernel -s 2 -c 1 -o gpurun_out/e_prof_path $CMD > gpurun_out/e_ncu_full.log 2>&1
-tail -3 gpurun_out/e_pytest.log gpurun_out/e_host_1gpu.log; cut -c1-600 gpurun_out/e_bench_n1.json
+ncu --set full --clock-control none --import-source on -k regex:rz_primary_kernel -s 2 -c 1 -o gpurun_out/e_prof_primary $CMD > gpurun_out/e_ncu_full2.log 2>&1
+tail -n 3 gpurun_out/e_pytest.log gpurun_out/e_host_1gpu.log; cut -c1-300 gpurun_out/e_bench_n1.json
