@@ -163,9 +163,11 @@ typedef struct RzTiming {
     uint32_t variant;   /* variant that actually ran (AUTO resolved)                */
     uint32_t bvh_build_us; /* K3 BVH build inside the last rayz_cuda_upload_scene, microseconds:
                             * host SAH wall time, or device LBVH by CUDA events (max over devices) */
-    float primary_ms;      /* two-stage K1: sum of the primary (camera-segment) kernels' durations; a clean
+    float primary_ms;      /* staged K1: sum of the primary (camera-segment) kernels' durations; a clean
                             * share of kernel_ms only with RZ_RENDER_SERIAL_PASSES (passes overlap otherwise) */
-    uint32_t passes;       /* two-stage K1: primary+secondary launch pairs of the render, else 0      */
+    uint32_t passes;       /* staged K1: passes (primary / sort + second / megakernel) of the render, else 0 */
+    float second_ms;       /* staged K1: sum of the sort + second-segment kernel durations (clean with serial passes) */
+    uint32_t reserved0;
 } RzTiming;
 
 typedef struct RzContext RzContext;

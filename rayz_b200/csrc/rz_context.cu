@@ -30,6 +30,11 @@ extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int rays_per_thread, 
                                       cudaStream_t stream, int *grid_out);
 extern "C" cudaError_t rz_path_warm(void);
 extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a);
+extern "C" cudaError_t rz_launch_second(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
+extern "C" size_t rz_sort_temp_bytes(uint32_t n);
+extern "C" cudaError_t rz_sort_keys(const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *iota, uint32_t *idx_out, uint32_t n,
+                                    void *temp, size_t temp_bytes, cudaStream_t stream);
+extern "C" cudaError_t rz_iota(uint32_t *p, uint32_t n, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_bvh_warm(void);
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
@@ -124,7 +129,11 @@ struct Dev {
     DBuf<float4> t_color;
     DBuf<double> t_inv_scale;
     DBuf<unsigned long long> accum;
-    DBuf<float4> queue, queue2;   // two-stage K1: paths that survived their camera segment (4 x float4 each), double buffered
+    // staged K1, one set per side (passes alternate between two streams): q1 = after the camera segment, q2 = after the second
+    DBuf<float4> q1[2], q2[2];
+    DBuf<uint32_t> keys[2], keys_sorted[2], idx_sorted[2], iota;
+    DBuf<unsigned char> sort_temp[2];
+    uint32_t iota_n = 0;
     DBuf<unsigned int> counter;
     DBuf<RzStatsDev> stats;
     DBuf<float4> out_linear;
@@ -148,6 +157,7 @@ struct RzContext {
     int rays_per_thread = 2;
     uint32_t chunk = 16;
     uint32_t flags = 0;
+    float sb_lo[3] = {0, 0, 0}, sb_hi[3] = {0, 0, 0}, huge_radius = 3.0e38f;   // box of the non-huge spheres (staged K1 sort key / cull)
     // host copy of the sphere boxes: the reference-shaped BVH of K0 is built on first use
     std::vector<double> ref_lo, ref_hi;
     bool ref_built = false;
@@ -463,7 +473,8 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
         D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
-        D.accum.release(); D.queue.release(); D.queue2.release(); D.counter.release(); D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
+        D.accum.release(); D.counter.release(); D.iota.release();
+        for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.sort_temp[sd].release(); } D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
         D.ids.release(); D.sink.release();
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
         for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
@@ -551,6 +562,26 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
         mato[i] = sc->sphere_material[i];
         const Box bx = sphere_box(*sc, i);
         for (int a = 0; a < 3; a++) { ctx->ref_lo[3 * (size_t)i + a] = bx.lo[a]; ctx->ref_hi[3 * (size_t)i + a] = bx.hi[a]; }
+    }
+
+    // ---- box of the "non-huge" spheres (staged K1): a ray that has left it can only hit a huge sphere (the r = 1000 ground)
+    {
+        std::vector<double> rad(sc->sphere_radius, sc->sphere_radius + n);
+        std::nth_element(rad.begin(), rad.begin() + n / 2, rad.end());
+        const double huge = 8.0 * rad[n / 2];
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        bool any = false;
+        for (uint32_t i = 0; i < n; i++) {
+            if (sc->sphere_radius[i] > huge) continue;
+            any = true;
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], ctx->ref_lo[3 * (size_t)i + a]); hi[a] = std::max(hi[a], ctx->ref_hi[3 * (size_t)i + a]); }
+        }
+        for (int a = 0; a < 3; a++) {
+            const double pad = any ? 1e-3 * (hi[a] - lo[a]) + 1e-3 : 0.0;
+            ctx->sb_lo[a] = any ? SahBuilder::down(lo[a] - pad) : -3.0e38f;
+            ctx->sb_hi[a] = any ? SahBuilder::up(hi[a] + pad) : 3.0e38f;
+        }
+        ctx->huge_radius = (float)huge;
     }
 
     // ---- K3 tree: binned SAH on the host (small scenes) or LBVH on the device (rz_bvh_build.cu)
@@ -655,26 +686,29 @@ static RzCamF32 cam_to_f32(const RzCamera *c) {
 
 // Device timings (CUDA events) and, if asked for, the counters of the render that just finished on every stream.
 static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
-    float kmax = 0, rmax = 0, pmax = 0;
+    float kmax = 0, rmax = 0, pmax = 0, smax = 0;
     uint32_t passes = 0;
     for (Dev &D : ctx->devs) {
-        float k = 0, r = 0, pr = 0;
+        float k = 0, r = 0, pr = 0, se = 0;
         RZ_CUDA(cudaSetDevice(D.id));
         RZ_CUDA(cudaEventElapsedTime(&k, D.ev[1], D.ev[2]));
         RZ_CUDA(cudaEventElapsedTime(&r, D.ev[2], D.ev[3]));
         for (uint32_t i = 0; i < D.passes; i++) {
-            float ms = 0;
             // overlapped: pass i runs on stream i & 1 after pass i-2 of that stream (the first two start at ev[1]); serial: after pass i-1
             const uint32_t back = D.serial_passes ? 1u : 2u;
-            RZ_CUDA(cudaEventElapsedTime(&ms, i < back ? D.ev[1] : D.pass_ev[2 * (i - back) + 1], D.pass_ev[2 * i]));
+            float ms = 0;
+            RZ_CUDA(cudaEventElapsedTime(&ms, i < back ? D.ev[1] : D.pass_ev[3 * (i - back) + 2], D.pass_ev[3 * i]));
             pr += ms;
+            RZ_CUDA(cudaEventElapsedTime(&ms, D.pass_ev[3 * i], D.pass_ev[3 * i + 1]));
+            se += ms;
         }
-        kmax = std::max(kmax, k); rmax = std::max(rmax, r); pmax = std::max(pmax, pr);
+        kmax = std::max(kmax, k); rmax = std::max(rmax, r); pmax = std::max(pmax, pr); smax = std::max(smax, se);
         passes = std::max(passes, D.passes);
     }
     ctx->timing.kernel_ms = kmax;
     ctx->timing.resolve_ms = rmax;
     ctx->timing.primary_ms = pmax;
+    ctx->timing.second_ms = smax;
     ctx->timing.passes = passes;
     if (collect_stats) {
         RzStats tot;
@@ -731,11 +765,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         const uint32_t n_tiles = (n_local + 31u) / 32u;
         int rc;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u))) return rc;
-        if ((rc = D.counter.alloc(8))) return rc;
+        if ((rc = D.counter.alloc(16))) return rc;
         if ((rc = D.stats.alloc(1))) return rc;
         RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
         RZ_CUDA(cudaMemsetAsync(D.accum.p, 0, (size_t)n_tiles * 32u * 4u * sizeof(unsigned long long), D.stream));
-        RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 8 * sizeof(unsigned int), D.stream));
+        RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 16 * sizeof(unsigned int), D.stream));
         if (p->collect_stats) RZ_CUDA(cudaMemsetAsync(D.stats.p, 0, sizeof(RzStatsDev), D.stream));
 
         RzPathArgs a;
@@ -772,18 +806,33 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
                     launches += 1;
                 } else {
-                    // two-stage K1: primary kernel (tile-culled camera segments) -> HBM queue -> persistent megakernel.
-                    // Passes are sized by the queue: <= 2^27 entries of 64 B = 8.6 GB per buffer, two buffers, of the 180 GB of HBM
-                    // (measured at config 2: 2^25 -> 196 ms, 2^26 -> 190 ms, 2^27 -> 187 ms, 2^28 -> 187 ms per render).
+                    // staged K1: primary kernel (tile-culled camera segments) -> queue -> sort -> second-segment kernel (culled per
+                    // sorted unit) -> queue -> persistent megakernel.  Passes are sized by the queues: <= 2^26 entries of 64 B
+                    // (4.3 GB per buffer; two buffers per side, two sides: 17 GB + 3 GB of keys/indices of the 180 GB of HBM).
                     const uint64_t unit_paths = 32ull * a.chunk;
-                    const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiment
-                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
+                    const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
+                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 26;
+                    const bool second_stage = !getenv("RZ_NO_SECOND") && ctx->n_spheres >= 64u;
                     const uint64_t cap = std::max<uint64_t>(unit_paths, std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << qlog));
                     const uint32_t units_per_pass = (uint32_t)std::max<uint64_t>(1, cap / unit_paths);
                     const uint32_t total_units = a.n_units;
                     const uint32_t n_pass = (total_units + units_per_pass - 1) / units_per_pass;
-                    if ((rc = D.queue.alloc((size_t)cap * 4u))) return rc;
-                    if (n_pass > 1 && (rc = D.queue2.alloc((size_t)cap * 4u))) return rc;
+                    const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
+                    const int n_sides = (n_pass > 1 && !serial) ? 2 : 1;
+                    for (int sd = 0; sd < n_sides; sd++) {
+                        if ((rc = D.q1[sd].alloc((size_t)cap * 4u))) return rc;
+                        if (second_stage) {
+                            if ((rc = D.q2[sd].alloc((size_t)cap * 4u)) || (rc = D.keys[sd].alloc((size_t)cap)) || (rc = D.keys_sorted[sd].alloc((size_t)cap)) ||
+                                (rc = D.idx_sorted[sd].alloc((size_t)cap)) || (rc = D.sort_temp[sd].alloc(rz_sort_temp_bytes((uint32_t)cap) + 256)))
+                                return rc;
+                        }
+                    }
+                    if (second_stage && D.iota_n < cap) {
+                        if ((rc = D.iota.alloc((size_t)cap))) return rc;
+                        RZ_CUDA(rz_iota(D.iota.p, (uint32_t)cap, D.stream));
+                        D.iota_n = (uint32_t)cap;
+                        RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));   // the second stream must see it too
+                    }
                     const double pcx = cam->px_origin[0] + 0.5 * (p->width - 1) * cam->px_du[0] + 0.5 * (p->height - 1) * cam->px_dv[0] - cam->look_from[0];
                     const double pcy = cam->px_origin[1] + 0.5 * (p->width - 1) * cam->px_du[1] + 0.5 * (p->height - 1) * cam->px_dv[1] - cam->look_from[1];
                     const double pcz = cam->px_origin[2] + 0.5 * (p->width - 1) * cam->px_du[2] + 0.5 * (p->height - 1) * cam->px_dv[2] - cam->look_from[2];
@@ -792,34 +841,59 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const double lv = std::sqrt(cam->defocus_v[0] * cam->defocus_v[0] + cam->defocus_v[1] * cam->defocus_v[1] + cam->defocus_v[2] * cam->defocus_v[2]);
                     a.lens_radius = cam->defocus ? (float)(std::max(lu, lv) * 1.001) : 0.f;
                     a.queue_cap = (uint32_t)cap;
-                    while (D.pass_ev.size() < 2 * (size_t)n_pass) {
+                    float ext = 0.f;
+                    for (int ax = 0; ax < 3; ax++) {
+                        a.sb_lo[ax] = ctx->sb_lo[ax]; a.sb_hi[ax] = ctx->sb_hi[ax];
+                        const float e = ctx->sb_hi[ax] - ctx->sb_lo[ax];
+                        a.sb_inv_cell[ax] = (e > 0.f && e < 1.0e30f) ? 8.0f / e : 0.f;
+                        if (e < 1.0e30f) ext = std::max(ext, e);
+                    }
+                    a.huge_radius = ctx->huge_radius;
+                    a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;
+                    while (D.pass_ev.size() < 3 * (size_t)n_pass) {
                         cudaEvent_t e = nullptr;
                         RZ_CUDA(cudaEventCreate(&e));
                         D.pass_ev.push_back(e);
                     }
                     D.passes = n_pass;
-                    D.serial_passes = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
-                    // Passes alternate between two streams and two queue buffers: the persistent secondary kernel ends with a
-                    // tail of a few long paths (measured ~2 ms per pass), which the next pass's kernels fill.
-                    if (n_pass > 1) RZ_CUDA(cudaStreamWaitEvent(D.stream2, D.ev[1], 0));
+                    D.serial_passes = serial;
+                    // Passes alternate between two streams and two sets of buffers: the persistent kernel ends with a tail of a
+                    // few long paths (measured ~2 ms per pass), which the next pass's kernels fill.
+                    if (n_sides > 1) RZ_CUDA(cudaStreamWaitEvent(D.stream2, D.ev[1], 0));
                     uint32_t pass = 0;
                     for (uint32_t u0 = 0; u0 < total_units; u0 += units_per_pass, pass++) {
-                        const int side = (p->flags & RZ_RENDER_SERIAL_PASSES) ? 0 : (int)(pass & 1u);
+                        const int side = n_sides > 1 ? (int)(pass & 1u) : 0;
                         cudaStream_t st = side ? D.stream2 : D.stream;
-                        unsigned int *ctr = D.counter.p + 4 * side;
-                        if (pass >= 2 || (pass == 1 && side == 0)) RZ_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st));
+                        unsigned int *ctr = D.counter.p + 8 * side;   // [0..2] unit counters of K1a/K1c/K1b, [3] entries in q1, [4] entries in q2
+                        if (pass >= (uint32_t)n_sides) RZ_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned int), st));
+                        const uint32_t pass_units = std::min(units_per_pass, total_units - u0);
+                        const uint32_t pass_paths = (uint32_t)std::min<uint64_t>(cap, (uint64_t)pass_units * unit_paths);
                         RzPathArgs a1 = a;
-                        a1.queue = side ? D.queue2.p : D.queue.p; a1.queue_count = ctr + 2;
-                        a1.unit_base = u0; a1.n_units = std::min(units_per_pass, total_units - u0); a1.unit_counter = ctr;
+                        a1.q_out = D.q1[side].p; a1.q_out_count = ctr + 3; a1.q_out_keys = second_stage ? D.keys[side].p : nullptr;
+                        a1.unit_base = u0; a1.n_units = pass_units; a1.unit_counter = ctr;
+                        if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(uint32_t), st));
                         RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, st));
-                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass], st));
-                        RzPathArgs a2 = a1;
-                        a2.unit_counter = ctr + 1;
-                        RZ_CUDA(rz_launch_path(&a2, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
-                        RZ_CUDA(cudaEventRecord(D.pass_ev[2 * pass + 1], st));
-                        launches += 2;
+                        RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass], st));
+                        launches += 1;
+                        RzPathArgs a3 = a;
+                        a3.q_in = D.q1[side].p; a3.q_in_count = ctr + 3;
+                        if (second_stage) {
+                            RZ_CUDA(rz_sort_keys(D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, pass_paths, D.sort_temp[side].p,
+                                                 D.sort_temp[side].n, st));
+                            RzPathArgs a2 = a;
+                            a2.q_in = D.q1[side].p; a2.q_in_count = ctr + 3; a2.q_in_idx = D.idx_sorted[side].p;
+                            a2.q_out = D.q2[side].p; a2.q_out_count = ctr + 4; a2.q_out_keys = nullptr; a2.unit_counter = ctr + 1;
+                            RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
+                            launches += 4;   // sort = histogram + 2 passes (cub), + the second-segment kernel
+                            a3.q_in = D.q2[side].p; a3.q_in_count = ctr + 4;
+                        }
+                        RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 1], st));
+                        a3.unit_counter = ctr + 2;
+                        RZ_CUDA(rz_launch_path(&a3, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
+                        RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 2], st));
+                        launches += 1;
                     }
-                    if (n_pass > 1) {   // join the second stream before the resolve
+                    if (n_sides > 1) {   // join the second stream before the resolve
                         RZ_CUDA(cudaEventRecord(D.ev_s2, D.stream2));
                         RZ_CUDA(cudaStreamWaitEvent(D.stream, D.ev_s2, 0));
                     }

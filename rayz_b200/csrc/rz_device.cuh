@@ -93,13 +93,23 @@ struct RzPathArgs {
     uint32_t shard_index, shard_count, band_rows;
     uint32_t seed_lo, seed_hi;
     float t_min;
-    // K1 two-stage form: the primary kernel appends the paths that survive their camera segment to `queue`
-    // (4 x float4 per entry: o+time, d+self_k, thr+seg, lp/gpix/sample), the secondary kernel starts its paths from it
-    float4 *queue;
-    unsigned int *queue_count;   // entries appended so far (device counter)
-    uint32_t queue_cap;          // entries the buffer holds
-    uint32_t unit_base;          // first work unit of this pass (primary kernel)
-    float focus_dist, lens_radius;   // thin-lens numbers for the tile-frustum cull (derived from the camera)
+    // K1 staged form.  Queue entries are 4 x float4 (o+time, d+self_k, thr+seg, lp/gpix/sample).
+    //   K1a (primary)  : camera segments   -> q_out (+ q_out_keys, the sort key of each surviving ray)
+    //   K1c (second)   : q_in through q_in_idx (entries sorted by key) -> second segments -> q_out
+    //   K1b (megakern.): q_in -> every later segment, paths regenerated in place
+    const float4 *q_in;
+    const unsigned int *q_in_count;   // entries in q_in (device counter written by the producing kernel)
+    const uint32_t *q_in_idx;         // K1c: entry indices in key order
+    float4 *q_out;
+    unsigned int *q_out_count;
+    uint32_t *q_out_keys;             // K1a only
+    uint32_t queue_cap;               // entries each queue buffer holds
+    uint32_t unit_base;               // first work unit of this pass (primary kernel)
+    float focus_dist, lens_radius;    // thin-lens numbers for the tile-frustum cull (derived from the camera)
+    float sb_lo[3], sb_hi[3];         // box around every sphere that is not "huge" (radius <= huge_radius), motion included
+    float sb_inv_cell[3];             // 8 / extent per axis (sort-key cells)
+    float huge_radius;                // spheres above this radius are never culled (the r = 1000 ground)
+    float reach_unit;                 // max extent of the box / 32: classes of the sort key's reach field
     uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)
     uint32_t bvh_descend_min;    // K3: a descend round ends once fewer lanes than this are still descending
 };

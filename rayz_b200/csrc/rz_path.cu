@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
     bool have_unit = true;
     uint32_t unit_lp0 = 0, unit_s0 = 0, unit_paths = 0, k_next = 0;
     // QUEUE: paths start from the entries the primary kernel appended (512 per work unit)
-    const uint32_t n_entries = QUEUE ? min(*a.queue_count, a.queue_cap) : 0u;
+    const uint32_t n_entries = QUEUE ? min(*a.q_in_count, a.queue_cap) : 0u;
     const uint32_t n_units = QUEUE ? (n_entries + 511u) / 512u : a.n_units;
 
     RzStream st[R];
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
                 if (need && rank < avail) {
                     const uint32_t k = k_next + rank;
                     if (QUEUE) {
-                        const float4 *e = a.queue + (size_t)(unit_lp0 + k) * 4u;
+                        const float4 *e = a.q_in + (size_t)(unit_lp0 + k) * 4u;
                         const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
                         st[r].ray.o = f3(qa.x, qa.y, qa.z); st[r].ray.time = qa.w;
                         st[r].ray.d = f3(qb.x, qb.y, qb.z); st[r].ray.self_k = __float_as_int(qb.w);
@@ -169,6 +169,52 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0 && s) atomicAdd(&a.stats->v[i], s);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------ queue helpers
+// When does a ray leave the box around all non-huge spheres for good?  (<= 0: it never enters it.)
+__device__ __forceinline__ float rz_box_exit(const RzPathArgs &a, const RzRay &ray) {
+    float t = 3.0e38f;
+    const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        if (d[ax] > 0.f) t = fminf(t, (a.sb_hi[ax] - o[ax]) / d[ax]);
+        else if (d[ax] < 0.f) t = fminf(t, (a.sb_lo[ax] - o[ax]) / d[ax]);
+        else if (o[ax] < a.sb_lo[ax] || o[ax] > a.sb_hi[ax]) t = 0.f;
+    }
+    return t;
+}
+
+// Sort key of a scattered ray: [origin cell 3x3 bits][direction octant 3 bits][reach class 2 bits].  Rays with
+// equal keys start in the same eighth-per-axis cell of the scene, head into the same octant and stay inside the
+// sphere box for a similar distance — which is what the second-segment kernel's per-unit cull feeds on.
+__device__ __forceinline__ uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
+    const int cx = min(7, max(0, (int)((ray.o.x - a.sb_lo[0]) * a.sb_inv_cell[0])));
+    const int cy = min(7, max(0, (int)((ray.o.y - a.sb_lo[1]) * a.sb_inv_cell[1])));
+    const int cz = min(7, max(0, (int)((ray.o.z - a.sb_lo[2]) * a.sb_inv_cell[2])));
+    const uint32_t oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
+    const float te = rz_box_exit(a, ray);
+    const uint32_t reach = te < a.reach_unit ? 0u : te < 3.2f * a.reach_unit ? 1u : te < 10.f * a.reach_unit ? 2u : 3u;
+    return ((uint32_t)((cx << 6) | (cy << 3) | cz) << 5) | (oct << 2) | reach;
+}
+
+// Ballot-compacted append of the warp's surviving paths (one atomic per warp).
+__device__ __forceinline__ void rz_queue_push(const RzPathArgs &a, bool cont, unsigned lane, unsigned lt_mask, const RzRay &ray, float3 thr,
+                                              uint32_t seg, uint32_t lp, uint32_t gpix, uint32_t sample) {
+    const unsigned m = __ballot_sync(0xffffffffu, cont);
+    if (!m) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned e = base + __popc(m & lt_mask);
+    if (cont && e < a.queue_cap) {
+        float4 *q = a.q_out + (size_t)e * 4u;
+        __stcs(q + 0, make_float4(ray.o.x, ray.o.y, ray.o.z, ray.time));
+        __stcs(q + 1, make_float4(ray.d.x, ray.d.y, ray.d.z, __int_as_float(ray.self_k)));
+        __stcs(q + 2, make_float4(thr.x, thr.y, thr.z, __uint_as_float(seg)));
+        __stcs(q + 3, make_float4(__uint_as_float(lp), __uint_as_float(gpix), __uint_as_float(sample), 0.f));
+        if (a.q_out_keys) a.q_out_keys[e] = rz_sort_key(a, ray);
     }
 }
 
@@ -306,20 +352,7 @@ __global__ void __launch_bounds__(128) rz_primary_kernel(const RzPathArgs a) {
                     }
                     cont = res == RZ_CONT;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, cont);
-                if (m) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(a.queue_count, (unsigned)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const unsigned e = base + __popc(m & lt_mask);
-                    if (cont && e < a.queue_cap) {
-                        float4 *q = a.queue + (size_t)e * 4u;
-                        __stcs(q + 0, make_float4(rays[r].o.x, rays[r].o.y, rays[r].o.z, rays[r].time));
-                        __stcs(q + 1, make_float4(rays[r].d.x, rays[r].d.y, rays[r].d.z, __int_as_float(rays[r].self_k)));
-                        __stcs(q + 2, make_float4(thr.x, thr.y, thr.z, __uint_as_float(seg)));
-                        __stcs(q + 3, make_float4(__uint_as_float(lp), __uint_as_float(gpix), __uint_as_float(smp[r]), 0.f));
-                    }
-                }
+                rz_queue_push(a, cont, lane, lt_mask, rays[r], thr, seg, lp, gpix, smp[r]);
             }
         }
         __syncwarp();   // the lists are rewritten for the next unit
@@ -327,6 +360,168 @@ __global__ void __launch_bounds__(128) rz_primary_kernel(const RzPathArgs a) {
 
     if (STATS) {
         unsigned long long v[10] = {c_paths, c_segs, c_sph, 0ull, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            unsigned long long sum = v[i];
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0 && sum) atomicAdd(&a.stats->v[i], sum);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ second-segment kernel
+// Stage 2 of the staged K1: the segment after the camera segment (48 % of what would otherwise be the persistent
+// kernel's searches).  Scattered rays are incoherent, but their queue entries have been SORTED by
+// (origin cell, direction octant, reach class) (rz_sort_key + cub radix sort), so 512 consecutive entries start
+// close together, head the same way and leave the sphere layer after a similar distance.  Per unit the warp
+// derives from the ACTUAL rays: the box of their origins, the axes on which all of them move the same way, and
+// the longest stay T inside the box around the non-huge spheres; a sphere can then only be hit if it is not
+// behind the origin box on such an axis and lies within T + r of the box.  The packed search runs over that
+// list (15 % of the spheres on the RTOW scene) with the same arithmetic per sphere, so (t, k) is unchanged.
+template <bool STATS>
+__global__ void __launch_bounds__(128) rz_second_kernel(const RzPathArgs a) {
+    extern __shared__ __align__(16) unsigned char rz_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
+    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1;
+    const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
+    unsigned short *ls = reinterpret_cast<unsigned short *>(s_pk + pk_f4) + (threadIdx.x >> 5) * (n_sp + n_mp);
+    unsigned short *lm = ls + n_sp;
+
+    rz_stage_scene_pk(a.set, s_pk, &s_bar);
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t n_in = min(*a.q_in_count, a.queue_cap);
+    const uint32_t n_units = (n_in + 511u) / 512u;
+    unsigned long long c_segs = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
+
+    while (true) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const uint32_t e0 = u * 512u, ne = min(512u, n_in - e0);
+
+        // ---- what the unit's rays have in common
+        float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, T = 0.f;
+        unsigned all_pos = 7u, all_neg = 7u;
+        for (uint32_t i = lane; i < ne; i += 32u) {
+            const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + i] * 4u;
+            const float4 qa = __ldg(e), qb = __ldg(e + 1);
+            RzRay r;
+            r.o = f3(qa.x, qa.y, qa.z); r.d = f3(qb.x, qb.y, qb.z); r.time = qa.w; r.self_k = -1;
+            blo[0] = fminf(blo[0], qa.x); blo[1] = fminf(blo[1], qa.y); blo[2] = fminf(blo[2], qa.z);
+            bhi[0] = fmaxf(bhi[0], qa.x); bhi[1] = fmaxf(bhi[1], qa.y); bhi[2] = fmaxf(bhi[2], qa.z);
+            if (qb.x < 0.f) all_pos &= ~1u; if (qb.x > 0.f) all_neg &= ~1u;
+            if (qb.y < 0.f) all_pos &= ~2u; if (qb.y > 0.f) all_neg &= ~2u;
+            if (qb.z < 0.f) all_pos &= ~4u; if (qb.z > 0.f) all_neg &= ~4u;
+            T = fmaxf(T, rz_box_exit(a, r));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++) {
+                blo[ax] = fminf(blo[ax], __shfl_xor_sync(0xffffffffu, blo[ax], o));
+                bhi[ax] = fmaxf(bhi[ax], __shfl_xor_sync(0xffffffffu, bhi[ax], o));
+            }
+            T = fmaxf(T, __shfl_xor_sync(0xffffffffu, T, o));
+            all_pos &= __shfl_xor_sync(0xffffffffu, all_pos, o);
+            all_neg &= __shfl_xor_sync(0xffffffffu, all_neg, o);
+        }
+        T = fminf(T, 1.0e30f) * 1.001f;   // +inf-safe; margin for the FP32 evaluation of the exits
+        auto keep = [&](float cx, float cy, float cz, float vx, float vy, float vz, float w) -> bool {
+            if (!(w < 0.f)) return false;                                  // padding entry
+            const float r = sqrtf(-w);
+            if (r > a.huge_radius) return true;                            // outside the sphere box: never culled
+            const float re = (r + 0.5f * sqrtf(vx * vx + vy * vy + vz * vz)) * 1.02f + 0.02f;   // swept over the shutter + margin
+            const float c[3] = {fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)};
+            float d2 = 0.f;
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++) {
+                if (((all_pos >> ax) & 1u) && c[ax] + re < blo[ax]) return false;   // every ray moves up this axis: sphere is behind
+                if (((all_neg >> ax) & 1u) && c[ax] - re > bhi[ax]) return false;
+                const float dd = fmaxf(0.f, fmaxf(blo[ax] - c[ax], c[ax] - bhi[ax]));
+                d2 = fmaf(dd, dd, d2);
+            }
+            const float rad = T + re;
+            return d2 <= rad * rad;                                        // within reach of some ray of the unit
+        };
+        int n_ls = 0, n_lm = 0;
+        for (uint32_t p0 = 0; p0 < n_sp; p0 += 32u) {
+            const uint32_t p = p0 + lane;
+            bool k = false;
+            if (p < n_sp) {
+                const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
+                k = keep(A.x, A.z, B.x, 0.f, 0.f, 0.f, B.z) || keep(A.y, A.w, B.y, 0.f, 0.f, 0.f, B.w);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, k);
+            if (k) ls[n_ls + __popc(m & lt_mask)] = (unsigned short)p;
+            n_ls += __popc(m);
+        }
+        const float4 *mv = s_pk + a.set.n_static_pad;
+        for (uint32_t p0 = 0; p0 < n_mp; p0 += 32u) {
+            const uint32_t p = p0 + lane;
+            bool k = false;
+            if (p < n_mp) {
+                const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
+                k = keep(A.x, A.z, B.x, VA.x, VA.z, VB.x, B.z) || keep(A.y, A.w, B.y, VA.y, VA.w, VB.y, B.w);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, k);
+            if (k) lm[n_lm + __popc(m & lt_mask)] = (unsigned short)p;
+            n_lm += __popc(m);
+        }
+        __syncwarp();
+
+        // ---- the unit's rays, two per lane and iteration
+        for (uint32_t b0 = 0; b0 < ne; b0 += 64u) {
+            RzRay rays[2];
+            float3 thr[2];
+            uint32_t seg[2], lp[2], gpix[2], smp[2];
+            bool live[2];
+            float bt[2];
+            int bk[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const uint32_t i = b0 + lane + 32u * (uint32_t)r;
+                live[r] = i < ne;
+                if (live[r]) {
+                    const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + i] * 4u;
+                    const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
+                    rays[r].o = f3(qa.x, qa.y, qa.z); rays[r].time = qa.w;
+                    rays[r].d = f3(qb.x, qb.y, qb.z); rays[r].self_k = __float_as_int(qb.w);
+                    thr[r] = f3(qc.x, qc.y, qc.z); seg[r] = __float_as_uint(qc.w);
+                    lp[r] = __float_as_uint(qd.x); gpix[r] = __float_as_uint(qd.y); smp[r] = __float_as_uint(qd.z);
+                } else {
+                    rays[r].o = f3(0.f, 0.f, 0.f); rays[r].d = f3(0.f, 1.f, 0.f); rays[r].time = 0.f; rays[r].self_k = -1;
+                    thr[r] = f3(0.f, 0.f, 0.f); seg[r] = 0; lp[r] = 0; gpix[r] = 0; smp[r] = 0;
+                }
+                bt[r] = 3.0e38f; bk[r] = -1;
+            }
+            rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
+            if (STATS) c_sph += (unsigned long long)(2 * (n_ls + n_lm)) * ((live[0] ? 1u : 0u) + (live[1] ? 1u : 0u));
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                bool cont = false;
+                if (live[r]) {
+                    if (STATS) c_segs++;
+                    uint32_t kind;
+                    const int res = rz_shade_segment(a, rays[r], thr[r], seg[r], lp[r], gpix[r], smp[r], bk[r], kind);
+                    if (STATS) {
+                        if (kind < 3u) c_hit[kind]++;
+                        if (res == RZ_END_SKY) c_sky++;
+                        if (res == RZ_END_ABSORBED) c_abs++;
+                        if (res == RZ_END_DEPTH) c_depth++;
+                    }
+                    cont = res == RZ_CONT;
+                }
+                rz_queue_push(a, cont, lane, lt_mask, rays[r], thr[r], seg[r], lp[r], gpix[r], smp[r]);
+            }
+        }
+        __syncwarp();
+    }
+
+    if (STATS) {
+        unsigned long long v[10] = {0ull, c_segs, c_sph, 0ull, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
 #pragma unroll
         for (int i = 0; i < 10; i++) {
             unsigned long long sum = v[i];
@@ -360,6 +555,7 @@ extern "C" cudaError_t rz_path_warm(void) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, rz_path_kernel<2, 2, false, 8, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_primary_kernel<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_second_kernel<false>);
     return e;
 }
 
@@ -387,13 +583,29 @@ extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats,
     return collect_stats ? launch(rz_primary_kernel<true>) : launch(rz_primary_kernel<false>);
 }
 
-// Stage 2 (queue != nullptr): the persistent megakernel started from the queue; or the single-stage form
-// (queue == nullptr) that generates its own camera rays.  rays_per_thread in {1,2}.
+// Stage 2: second segments of the sorted queue (q_in through q_in_idx) -> q_out.
+extern "C" cudaError_t rz_launch_second(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
+    const size_t smem = rz_primary_smem_bytes(a);
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        kern<<<sm_count * per_sm, 128, smem, stream>>>(*a);
+        return cudaGetLastError();
+    };
+    return collect_stats ? launch(rz_second_kernel<true>) : launch(rz_second_kernel<false>);
+}
+
+// Last stage (q_in != nullptr): the persistent megakernel started from a queue; or the single-stage form
+// (q_in == nullptr) that generates its own camera rays.  rays_per_thread in {1,2}.
 extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int rays_per_thread, int collect_stats, int sm_count, cudaStream_t stream,
                                       int *grid_out) {
     const bool stats = collect_stats != 0;
     const size_t smem = rz_pk_bytes(*a);
-    if (a->queue) {
+    if (a->q_in) {
         if (rays_per_thread == 1)
             return stats ? rz_launch_one<1, 2, true, 5, true>(*a, sm_count, smem, stream, grid_out)
                          : rz_launch_one<1, 2, false, 5, true>(*a, sm_count, smem, stream, grid_out);
