@@ -812,7 +812,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const uint64_t unit_paths = 32ull * a.chunk;
                     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
                     const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 26;
-                    const bool second_stage = !getenv("RZ_NO_SECOND") && ctx->n_spheres >= 64u;
+                    // sorted stages after the camera segment: measured at config 2 (Mpaths/s): 0 -> 2141, 1 -> 2824, 2 -> 3127, 3 -> 3248,
+                    // 4 -> 3222, 6 -> 3077 (each stage re-sorts the pass; later segments are few)
+                    const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
+                    const int n_second = ctx->n_spheres >= 64u ? (senv ? std::min(8, std::max(0, atoi(senv))) : 3) : 0;
+                    const bool second_stage = n_second > 0;
                     const uint64_t cap = std::max<uint64_t>(unit_paths, std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << qlog));
                     const uint32_t units_per_pass = (uint32_t)std::max<uint64_t>(1, cap / unit_paths);
                     const uint32_t total_units = a.n_units;
@@ -877,16 +881,25 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         launches += 1;
                         RzPathArgs a3 = a;
                         a3.q_in = D.q1[side].p; a3.q_in_count = ctr + 3;
-                        if (second_stage) {
+                        // sorted, culled stages for the next `n_second` segments: q1 -> q2 -> q1 -> ...
+                        float4 *qa = D.q1[side].p, *qb = second_stage ? D.q2[side].p : nullptr;
+                        unsigned int *ca = ctr + 3, *cb = ctr + 4;
+                        for (int stg = 0; stg < n_second; stg++) {
+                            const bool more = stg + 1 < n_second;
+                            // cub sorts every slot of the pass (the live count is only known on the device); unused slots carry key 0xffffffff
                             RZ_CUDA(rz_sort_keys(D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, pass_paths, D.sort_temp[side].p,
                                                  D.sort_temp[side].n, st));
+                            if (stg > 0) RZ_CUDA(cudaMemsetAsync(cb, 0, sizeof(unsigned int), st));           // recycled output counter
+                            if (stg > 0) RZ_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned int), st));      // the stage's unit counter
+                            if (more) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(uint32_t), st));   // keys of the next stage
                             RzPathArgs a2 = a;
-                            a2.q_in = D.q1[side].p; a2.q_in_count = ctr + 3; a2.q_in_idx = D.idx_sorted[side].p;
-                            a2.q_out = D.q2[side].p; a2.q_out_count = ctr + 4; a2.q_out_keys = nullptr; a2.unit_counter = ctr + 1;
+                            a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p;
+                            a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
                             RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
-                            launches += 4;   // sort = histogram + 2 passes (cub), + the second-segment kernel
-                            a3.q_in = D.q2[side].p; a3.q_in_count = ctr + 4;
+                            launches += 4;   // sort = histogram + 2 passes (cub), + the sorted-segment kernel
+                            std::swap(qa, qb); std::swap(ca, cb);
                         }
+                        a3.q_in = qa; a3.q_in_count = ca;
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 1], st));
                         a3.unit_counter = ctr + 2;
                         RZ_CUDA(rz_launch_path(&a3, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
