@@ -271,6 +271,7 @@ def main():
                         band_rows=band, collect_stats=True)
     be.render_device(cam, ps, sync=True)
     stats = be.stats()
+    stage_stats = [be.stage_stats(k) for k in range(3)]
     tinfo = be.timing()
 
     # ---- warm-up
@@ -311,16 +312,17 @@ def main():
     # persistent secondary kernel (the dominant one).
     p_serial = Backend.params(W, H, SPP, DEPTH, seed=1, variant=args.variant, shard_index=rank, shard_count=world, band_rows=band,
                               serial_passes=True)
-    kms, pms = [], []
+    kms, pms, sms_ = [], [], []
     for _ in range(min(3, args.steps)):
         flush_buf.zero_()
         be.render_device(cam, p_serial, sync=True)
         kms.append(be.timing()["kernel_ms"])
         pms.append(be.timing()["primary_ms"])
-    kt = torch.tensor([statistics.mean(kms), statistics.mean(pms)], dtype=torch.float64, device=dev)
+        sms_.append(be.timing()["second_ms"])
+    kt = torch.tensor([statistics.mean(kms), statistics.mean(pms), statistics.mean(sms_)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-    kern_ms, prim_ms = float(kt[0].item()), float(kt[1].item())
+    kern_ms, prim_ms, second_ms = float(kt[0].item()), float(kt[1].item()), float(kt[2].item())
     be.render_device(cam, p, sync=True)
     launches_per_step = be.timing()["launches"]
     passes_per_step = be.timing()["passes"]
@@ -370,13 +372,26 @@ def main():
         peak_tf, sms = be.fp32_peak(400)
         per_gpu_paths = total_paths / world
         two_stage = passes_per_step > 0
+        stages = None
         if two_stage:
-            # dominant kernel = the persistent secondary megakernel: its algorithmic flop (brute-force search of every
-            # segment after the camera segment; its shading flop is left out, an undercount of < 1 %) over the sum of
-            # its launch durations in one step
-            dom_name = "rz_path_kernel<QUEUE> (secondary megakernel of the two-stage K1)"
-            dom_ms = kern_ms - prim_ms
-            dom_flop = per_gpu_paths * fl["f_secondary"]
+            # Staged K1.  The roofline kernel is the persistent megakernel (the FP32-bound brute-force search the north star
+            # describes): algorithmic flop = its segments x F_isect (shading left out: an undercount of < 1 %), time = sum of
+            # its launch durations in one step with serial passes (tails included).  The other stages are listed beside it.
+            scale = per_gpu_paths / max(1, stats["paths"])            # stats pass ran fewer spp
+            n_sph = max(1, tinfo["n_static"] + tinfo["n_moving"])
+            f_test = fl["f_isect"] / n_sph                            # mean flop per sphere test of this scene
+            meg_ms = kern_ms - prim_ms - second_ms
+            def stage(name, st, ms):
+                flop = st["sphere_tests"] * scale * f_test
+                return {"kernel": name, "ms_per_step": ms, "segments": st["segments"] * scale, "sphere_tests": st["sphere_tests"] * scale,
+                        "achieved_tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else None,
+                        "frac": flop / (ms * 1e-3) / 1e12 / peak_tf if ms > 0 and peak_tf else None}
+            stages = [stage("rz_primary_kernel (camera segments, tile-frustum cull)", stage_stats[0], prim_ms),
+                      stage("sort + rz_second_kernel x3 (sorted segments, per-unit cull)", stage_stats[1], second_ms),
+                      stage("rz_path_kernel<QUEUE> (persistent brute-force megakernel)", stage_stats[2], meg_ms)]
+            dom_name = "rz_path_kernel<QUEUE> (persistent brute-force megakernel of the staged K1)"
+            dom_ms = meg_ms
+            dom_flop = stage_stats[2]["segments"] * scale * fl["f_isect"]
         else:
             dom_name = "rz_path_kernel (" + variant_ran + ")" if variant_ran != "bvh" else "rz_bvh_kernel"
             dom_ms = kern_ms
@@ -389,16 +404,16 @@ def main():
                     "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
                     "kernel_ms_per_launch": dom_ms / max(1, passes_per_step), "launches_per_step": max(1, passes_per_step),
                     "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / kern_ms,
-                    "primary_kernel_ms_per_step": prim_ms if two_stage else None,
+                    "stages": stages,
                     "all_kernels_ms_per_step_serial": kern_ms,
                     "whole_step_achieved": step_flops, "whole_step_frac": step_flops / peak_tf if peak_tf else None,
-                    "flop_per_path": fl["f_path"], "flop_per_path_dominant_kernel": fl["f_secondary"] if two_stage else fl["f_path"],
+                    "flop_per_path": fl["f_path"], "flop_per_path_dominant_kernel": dom_flop / per_gpu_paths,
                     "segments_per_path": fl["segments_per_path"], "sphere_tests_per_path": fl["tests_per_path"],
                     "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran, per_gpu_paths / max(1, passes_per_step)),
-                    "hbm_bytes_algorithmic": (35 * W * H + (128 * total_paths if two_stage else 0)) // world,
+                    "hbm_bytes_algorithmic": int(35 * W * H / world + (136 * (stage_stats[1]["segments"] + stage_stats[2]["paths"] + stats["paths"]) * per_gpu_paths / max(1, stats["paths"]) if two_stage else 0)),
                     "note": "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test); "
                             "tensor cores unused by design; HBM traffic = 35 B/pixel of framebuffer once per render, plus, in the "
-                            "two-stage form, <= 128 B per path through the primary->secondary queue (upper bound: every path survives)"}
+                            "staged form, 64 B written + 64 B read (+ 8 B of sort key/index) per path and queue hop (upper bound)"}
         out = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

@@ -218,6 +218,10 @@ int rayz_cuda_primary_ids(RzContext *ctx, const RzCamera *cam, uint32_t width, u
                           int use_bvh, int32_t *out_ids);
 
 int rayz_cuda_stats(RzContext *ctx, RzStats *out);
+
+/* The same counters per stage of the staged K1 (RZ_VARIANT_MEGA): 0 = primary kernel (camera segments),
+ * 1 = sorted stages, 2 = persistent megakernel.  Other variants count everything under stage 0. */
+int rayz_cuda_stage_stats(RzContext *ctx, uint32_t stage, RzStats *out);
 int rayz_cuda_timing(RzContext *ctx, RzTiming *out);
 
 /* K6: dependent-free FFMA chains on every SM of device 0; returns achieved FP32 TFLOP/s

@@ -78,6 +78,7 @@ SYMBOLS = {
     "rayz_cuda_context_rows": (C.c_uint32, [C.c_void_p] + [C.c_uint32] * 4),
     "rayz_cuda_primary_ids": (C.c_int, [C.c_void_p, C.POINTER(RzCamera), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
     "rayz_cuda_stats": (C.c_int, [C.c_void_p, C.POINTER(RzStats)]),
+    "rayz_cuda_stage_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(RzStats)]),
     "rayz_cuda_timing": (C.c_int, [C.c_void_p, C.POINTER(RzTiming)]),
     "rayz_cuda_fp32_peak": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "rayz_cuda_last_error": (C.c_char_p, []),

@@ -152,6 +152,7 @@ struct RzContext {
     bool have_scene = false;
     uint32_t n_spheres = 0;
     RzStats stats{};
+    RzStats stage_stats[3]{};   // staged K1: primary kernel / sorted stages / persistent megakernel (single-kernel variants: all in [0])
     bool stats_valid = false;
     RzTiming timing{};
     int rays_per_thread = 2;
@@ -711,17 +712,24 @@ static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
     ctx->timing.second_ms = smax;
     ctx->timing.passes = passes;
     if (collect_stats) {
-        RzStats tot;
+        RzStats tot, stage[3];
         memset(&tot, 0, sizeof tot);
+        memset(stage, 0, sizeof stage);
         for (Dev &D : ctx->devs) {
-            RzStatsDev h;
+            RzStatsDev h[3];
             RZ_CUDA(cudaSetDevice(D.id));
-            RZ_CUDA(cudaMemcpy(&h, D.stats.p, sizeof h, cudaMemcpyDeviceToHost));
-            tot.paths += h.v[0]; tot.segments += h.v[1]; tot.sphere_tests += h.v[2]; tot.node_tests += h.v[3];
-            tot.hits_diffuse += h.v[4]; tot.hits_metallic += h.v[5]; tot.hits_dielectric += h.v[6];
-            tot.ended_sky += h.v[7]; tot.ended_absorbed += h.v[8]; tot.ended_depth += h.v[9];
+            RZ_CUDA(cudaMemcpy(h, D.stats.p, sizeof h, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < 3; k++) {
+                RzStats *dst[2] = {&tot, &stage[k]};
+                for (RzStats *t : dst) {
+                    t->paths += h[k].v[0]; t->segments += h[k].v[1]; t->sphere_tests += h[k].v[2]; t->node_tests += h[k].v[3];
+                    t->hits_diffuse += h[k].v[4]; t->hits_metallic += h[k].v[5]; t->hits_dielectric += h[k].v[6];
+                    t->ended_sky += h[k].v[7]; t->ended_absorbed += h[k].v[8]; t->ended_depth += h[k].v[9];
+                }
+            }
         }
         ctx->stats = tot;
+        for (int k = 0; k < 3; k++) ctx->stage_stats[k] = stage[k];
         ctx->stats_valid = true;
     }
     return RZ_OK;
@@ -766,11 +774,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         int rc;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u))) return rc;
         if ((rc = D.counter.alloc(16))) return rc;
-        if ((rc = D.stats.alloc(1))) return rc;
+        if ((rc = D.stats.alloc(3))) return rc;   // [0] whole render / primary kernel, [1] sorted stages, [2] persistent megakernel
         RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
         RZ_CUDA(cudaMemsetAsync(D.accum.p, 0, (size_t)n_tiles * 32u * 4u * sizeof(unsigned long long), D.stream));
         RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 16 * sizeof(unsigned int), D.stream));
-        if (p->collect_stats) RZ_CUDA(cudaMemsetAsync(D.stats.p, 0, sizeof(RzStatsDev), D.stream));
+        if (p->collect_stats) RZ_CUDA(cudaMemsetAsync(D.stats.p, 0, 3 * sizeof(RzStatsDev), D.stream));
 
         RzPathArgs a;
         memset(&a, 0, sizeof a);
@@ -811,7 +819,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     // (4.3 GB per buffer; two buffers per side, two sides: 17 GB + 3 GB of keys/indices of the 180 GB of HBM).
                     const uint64_t unit_paths = 32ull * a.chunk;
                     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
-                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 26;
+                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
                     // sorted stages after the camera segment: measured at config 2 (Mpaths/s): 0 -> 2141, 1 -> 2824, 2 -> 3127, 3 -> 3248,
                     // 4 -> 3222, 6 -> 3077 (each stage re-sorts the pass; later segments are few)
                     const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
@@ -895,6 +903,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                             RzPathArgs a2 = a;
                             a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p;
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
+                            a2.stats = D.stats.p + 1;
                             RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
                             launches += 4;   // sort = histogram + 2 passes (cub), + the sorted-segment kernel
                             std::swap(qa, qb); std::swap(ca, cb);
@@ -902,6 +911,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         a3.q_in = qa; a3.q_in_count = ca;
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 1], st));
                         a3.unit_counter = ctr + 2;
+                        a3.stats = D.stats.p + 2;
                         RZ_CUDA(rz_launch_path(&a3, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 2], st));
                         launches += 1;
@@ -1020,6 +1030,13 @@ extern "C" int rayz_cuda_stats(RzContext *ctx, RzStats *out) {
     if (!ctx || !out) return rz_fail(RZ_ERR_INVALID_ARG, "stats: NULL argument");
     if (!ctx->stats_valid) return rz_fail(RZ_ERR_INVALID_ARG, "stats: last render did not run with collect_stats (or was not synchronised)");
     *out = ctx->stats;
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_stage_stats(RzContext *ctx, uint32_t stage, RzStats *out) {
+    if (!ctx || !out || stage > 2) return rz_fail(RZ_ERR_INVALID_ARG, "stage_stats: bad argument");
+    if (!ctx->stats_valid) return rz_fail(RZ_ERR_INVALID_ARG, "stage_stats: last render did not run with collect_stats (or was not synchronised)");
+    *out = ctx->stage_stats[stage];
     return RZ_OK;
 }
 

@@ -290,6 +290,12 @@ class Backend:
         abi.check(self.lib.rayz_cuda_primary_ids(self._h, C.byref(cam), width, height, 1 if use_bvh else 0, out.ctypes.data))
         return out
 
+    def stage_stats(self, stage: int) -> dict:
+        """Counters of one stage of the staged K1: 0 primary kernel, 1 sorted stages, 2 persistent megakernel."""
+        s = abi.RzStats()
+        abi.check(self.lib.rayz_cuda_stage_stats(self._h, stage, C.byref(s)))
+        return s.as_dict()
+
     def stats(self) -> dict:
         s = abi.RzStats()
         abi.check(self.lib.rayz_cuda_stats(self._h, C.byref(s)))
