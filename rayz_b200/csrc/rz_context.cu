@@ -853,12 +853,23 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const double lv = std::sqrt(cam->defocus_v[0] * cam->defocus_v[0] + cam->defocus_v[1] * cam->defocus_v[1] + cam->defocus_v[2] * cam->defocus_v[2]);
                     a.lens_radius = cam->defocus ? (float)(std::max(lu, lv) * 1.001) : 0.f;
                     a.queue_cap = (uint32_t)cap;
-                    float ext = 0.f;
+                    float ext = 0.f, e3[3];
+                    uint32_t bits[3] = {0, 0, 0};
                     for (int ax = 0; ax < 3; ax++) {
                         a.sb_lo[ax] = ctx->sb_lo[ax]; a.sb_hi[ax] = ctx->sb_hi[ax];
-                        const float e = ctx->sb_hi[ax] - ctx->sb_lo[ax];
-                        a.sb_inv_cell[ax] = (e > 0.f && e < 1.0e30f) ? 8.0f / e : 0.f;
-                        if (e < 1.0e30f) ext = std::max(ext, e);
+                        e3[ax] = ctx->sb_hi[ax] - ctx->sb_lo[ax];
+                        if (!(e3[ax] > 0.f) || !(e3[ax] < 1.0e30f)) e3[ax] = 0.f;
+                        ext = std::max(ext, e3[ax]);
+                    }
+                    for (int b = 0; b < 9; b++) {   // each key bit halves the cells of the axis whose cells are currently largest
+                        int best = 0;
+                        for (int ax = 1; ax < 3; ax++)
+                            if (e3[ax] / (float)(1u << bits[ax]) > e3[best] / (float)(1u << bits[best])) best = ax;
+                        bits[best]++;
+                    }
+                    for (int ax = 0; ax < 3; ax++) {
+                        a.sb_cell_bits[ax] = bits[ax];
+                        a.sb_inv_cell[ax] = e3[ax] > 0.f ? (float)(1u << bits[ax]) / e3[ax] : 0.f;
                     }
                     a.huge_radius = ctx->huge_radius;
                     a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;

@@ -107,7 +107,8 @@ struct RzPathArgs {
     uint32_t unit_base;               // first work unit of this pass (primary kernel)
     float focus_dist, lens_radius;    // thin-lens numbers for the tile-frustum cull (derived from the camera)
     float sb_lo[3], sb_hi[3];         // box around every sphere that is not "huge" (radius <= huge_radius), motion included
-    float sb_inv_cell[3];             // 8 / extent per axis (sort-key cells)
+    float sb_inv_cell[3];             // cells per unit length along each axis (sort-key cells)
+    uint32_t sb_cell_bits[3];         // 9 key bits shared out so that cells come out as cubic as possible
     float huge_radius;                // spheres above this radius are never culled (the r = 1000 ground)
     float reach_unit;                 // max extent of the box / 32: classes of the sort key's reach field
     uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)

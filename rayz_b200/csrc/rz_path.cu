@@ -186,17 +186,20 @@ __device__ __forceinline__ float rz_box_exit(const RzPathArgs &a, const RzRay &r
     return t;
 }
 
-// Sort key of a scattered ray: [origin cell 3x3 bits][direction octant 3 bits][reach class 2 bits].  Rays with
-// equal keys start in the same eighth-per-axis cell of the scene, head into the same octant and stay inside the
+// Sort key of a scattered ray: [origin cell 9 bits][direction octant 3 bits][reach class 4 bits] = 16 bits.  Rays with
+// equal keys start in the same cell of the sphere box (the 9 bits are shared out over the axes by extent), head into the same octant and stay inside the
 // sphere box for a similar distance — which is what the second-segment kernel's per-unit cull feeds on.
 __device__ __forceinline__ uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
-    const int cx = min(7, max(0, (int)((ray.o.x - a.sb_lo[0]) * a.sb_inv_cell[0])));
-    const int cy = min(7, max(0, (int)((ray.o.y - a.sb_lo[1]) * a.sb_inv_cell[1])));
-    const int cz = min(7, max(0, (int)((ray.o.z - a.sb_lo[2]) * a.sb_inv_cell[2])));
+    const int nx = (1 << a.sb_cell_bits[0]) - 1, ny = (1 << a.sb_cell_bits[1]) - 1, nz = (1 << a.sb_cell_bits[2]) - 1;
+    const int cx = min(nx, max(0, (int)((ray.o.x - a.sb_lo[0]) * a.sb_inv_cell[0])));
+    const int cy = min(ny, max(0, (int)((ray.o.y - a.sb_lo[1]) * a.sb_inv_cell[1])));
+    const int cz = min(nz, max(0, (int)((ray.o.z - a.sb_lo[2]) * a.sb_inv_cell[2])));
+    const uint32_t cell = (uint32_t)(((cx << a.sb_cell_bits[1]) | cy) << a.sb_cell_bits[2]) | (uint32_t)cz;   // 9 bits
     const uint32_t oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
     const float te = rz_box_exit(a, ray);
-    const uint32_t reach = te < a.reach_unit ? 0u : te < 3.2f * a.reach_unit ? 1u : te < 10.f * a.reach_unit ? 2u : 3u;
-    return ((uint32_t)((cx << 6) | (cy << 3) | cz) << 5) | (oct << 2) | reach;
+    // 16 reach classes, two per octave of te / reach_unit from 1/4 up
+    const int reach = min(15, max(0, (int)(2.0f * __log2f(fmaxf(te / a.reach_unit, 0.25f)) + 4.0f)));
+    return (cell << 7) | (oct << 4) | (uint32_t)reach;
 }
 
 // Ballot-compacted append of the warp's surviving paths (one atomic per warp).
