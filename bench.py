@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "mega", "bvh", "wavefront"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "mega", "mega_single", "bvh", "wavefront"])
     ap.add_argument("--width", type=int, default=0, help="override workload width (quick checks only)")
     ap.add_argument("--spp", type=int, default=0, help="override workload spp (quick checks only)")
     ap.add_argument("--ref-spp", type=int, default=0, help="--impl reference: spp of the bounded sample")
@@ -326,7 +326,7 @@ def main():
     be.render_device(cam, p, sync=True)
     launches_per_step = be.timing()["launches"]
     passes_per_step = be.timing()["passes"]
-    variant_ran = {1: "mega", 2: "wavefront", 3: "bvh"}.get(be.timing()["variant"], "?")
+    variant_ran = {1: "mega", 2: "wavefront", 3: "bvh", 4: "mega_single"}.get(be.timing()["variant"], "?")
 
     # ---- e2e: reference-facing call with host buffers (rank 0 drives all N GPUs through the
     # library's own multi-device context: this is what the single-process Zig host would call)
@@ -359,13 +359,15 @@ def main():
     # ---- the other kernel variants on the same workload (one timed render each; informational)
     variants = {}
     if world == 1 and not args.no_variants:
-        for v in ("mega", "bvh", "wavefront"):
+        for v in ("mega", "mega_single", "bvh", "wavefront"):
             pv = Backend.params(W, H, SPP, DEPTH, seed=1, variant=v)
             be.render_device(cam, pv, sync=True)
             flush_buf.zero_()
             be.render_device(cam, pv, sync=True)
             t = be.timing()
             variants[v] = {"mpaths_s": total_paths / (t["kernel_ms"] * 1e-3) / 1e6, "kernel_ms": t["kernel_ms"], "launches": t["launches"]}
+            if v == "mega_single":   # the pure FP32-bound form: every segment searched by brute force in one kernel
+                variants[v]["algorithmic_tflops"] = total_paths * (stats["segments"] / max(1, stats["paths"])) * (tinfo["n_static"] * 16 + tinfo["n_moving"] * 22) / (t["kernel_ms"] * 1e-3) / 1e12
 
     if rank == 0:
         fl = algorithmic_flops_per_path(stats, tinfo["n_static"], tinfo["n_moving"])
@@ -427,6 +429,8 @@ def main():
         if e2e:
             out["e2e"] = e2e
         if variants:
+            if "mega_single" in variants and peak_tf:
+                variants["mega_single"]["frac_of_fp32_peak"] = variants["mega_single"]["algorithmic_tflops"] / peak_tf
             out["variants"] = variants
         if not args.no_cpu_baseline and world == 1:
             import oracle

@@ -41,7 +41,7 @@ int main(int argc, char **argv) {
         else if (a == "--grid") grid = std::atoi(val());
         else if (a == "--variant") {
             const std::string v = val();
-            variant = v == "mega" ? RZ_VARIANT_MEGA : v == "wavefront" ? RZ_VARIANT_WAVEFRONT : v == "bvh" ? RZ_VARIANT_BVH : RZ_VARIANT_AUTO;
+            variant = v == "mega" ? RZ_VARIANT_MEGA : v == "mega_single" ? RZ_VARIANT_MEGA_SINGLE : v == "wavefront" ? RZ_VARIANT_WAVEFRONT : v == "bvh" ? RZ_VARIANT_BVH : RZ_VARIANT_AUTO;
         } else if (!out_fname && a.rfind("--", 0) != 0) out_fname = argv[i];
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }

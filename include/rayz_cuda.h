@@ -51,10 +51,13 @@ enum { RZ_DIFFUSE_UNIT_SPHERE = 0, RZ_DIFFUSE_UNIT_SPHERE_SURFACE = 1, RZ_DIFFUS
 
 /* Kernel variants (RzRenderParams.variant). */
 enum {
-    RZ_VARIANT_AUTO = 0,      /* brute-force smem megakernel when the scene fits, else BVH   */
-    RZ_VARIANT_MEGA = 1,      /* K1: persistent megakernel, scene staged in shared memory     */
+    RZ_VARIANT_AUTO = 0,      /* staged brute-force K1 when the scene fits shared memory, else BVH */
+    RZ_VARIANT_MEGA = 1,      /* K1: scene staged in shared memory; primary kernel -> sorted stages ->
+                               * persistent brute-force megakernel          */
     RZ_VARIANT_WAVEFRONT = 2, /* K2: staged wavefront with warp-ballot compaction             */
-    RZ_VARIANT_BVH = 3        /* K3: persistent megakernel traversing the device BVH          */
+    RZ_VARIANT_BVH = 3,       /* K3: persistent megakernel traversing the device BVH          */
+    RZ_VARIANT_MEGA_SINGLE = 4 /* K1 as ONE persistent kernel (every segment brute force, paths
+                               * regenerated in place): the pure FP32-bound form, 59 % of FP32 peak */
 };
 
 /*

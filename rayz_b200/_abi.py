@@ -18,7 +18,7 @@ MAT_DIFFUSE, MAT_METALLIC, MAT_DIELECTRIC = 0, 1, 2
 TEX_CHECKER, TEX_SOLID = 0, 1
 DIFFUSE_UNIT_SPHERE, DIFFUSE_UNIT_SPHERE_SURFACE, DIFFUSE_HEMISPHERE = 0, 1, 2
 VARIANT_AUTO, VARIANT_MEGA, VARIANT_WAVEFRONT, VARIANT_BVH = 0, 1, 2, 3
-VARIANTS = {"auto": 0, "mega": 1, "wavefront": 2, "bvh": 3}
+VARIANTS = {"auto": 0, "mega": 1, "wavefront": 2, "bvh": 3, "mega_single": 4}
 
 _dp, _up = C.POINTER(C.c_double), C.POINTER(C.c_uint32)
 
