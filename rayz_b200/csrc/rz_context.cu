@@ -748,6 +748,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
     uint32_t variant = p->variant;
     const uint32_t brute_smem = (ctx->devs[0].brute.n_pad * 2 - ctx->devs[0].brute.n_static_pad) * 16u;
     if (variant == RZ_VARIANT_AUTO) variant = brute_smem <= RZ_SMEM_BUDGET ? RZ_VARIANT_MEGA : RZ_VARIANT_BVH;
+    const bool mega_single = variant == RZ_VARIANT_MEGA_SINGLE;
+    if (mega_single) variant = RZ_VARIANT_MEGA;
     if (variant != RZ_VARIANT_MEGA && variant != RZ_VARIANT_BVH && variant != RZ_VARIANT_WAVEFRONT)
         return rz_fail(RZ_ERR_INVALID_ARG, "render: unknown variant %u", p->variant);
     if (variant == RZ_VARIANT_MEGA && brute_smem > RZ_SMEM_BUDGET)
@@ -809,8 +811,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                 if (variant == RZ_VARIANT_BVH) {
                     RZ_CUDA(rz_launch_bvh(&a, (int)p->collect_stats, D.sms, D.stream));
                     launches += 1;
-                } else if (getenv("RZ_MEGA_SINGLE") || rz_primary_smem_bytes(&a) > 227u * 1024u) {
-                    // single-stage form (development A/B, or a set whose pair lists do not fit beside it)
+                } else if (mega_single || rz_primary_smem_bytes(&a) > 227u * 1024u) {
+                    // one persistent kernel (RZ_VARIANT_MEGA_SINGLE, or a set whose pair lists do not fit beside it)
                     RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
                     launches += 1;
                 } else {
@@ -950,7 +952,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
     RZ_CUDA(cudaEventRecord(D0.ev[4], D0.stream));
 
     ctx->timing.launches = launches;
-    ctx->timing.variant = variant;
+    ctx->timing.variant = mega_single ? (uint32_t)RZ_VARIANT_MEGA_SINGLE : variant;
     ctx->stats_valid = false;
     if (sync) {
         for (uint32_t d = 0; d < ND; d++) {
