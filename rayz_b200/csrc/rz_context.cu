@@ -822,10 +822,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const uint64_t unit_paths = 32ull * a.chunk;
                     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
                     const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
-                    // sorted stages after the camera segment: measured at config 2 (Mpaths/s): 0 -> 2141, 1 -> 2824, 2 -> 3127, 3 -> 3248,
-                    // 4 -> 3222, 6 -> 3077 (each stage re-sorts the pass; later segments are few)
+                    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene): 0 -> 2141 / 1945,
+                    // 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899 (each stage re-sorts the pass; later
+                    // segments are few unless paths are long)
                     const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
-                    const int n_second = ctx->n_spheres >= 64u ? (senv ? std::min(8, std::max(0, atoi(senv))) : 3) : 0;
+                    const int n_second = ctx->n_spheres >= 64u ? (senv ? std::min(8, std::max(0, atoi(senv))) : 4) : 0;
                     const bool second_stage = n_second > 0;
                     const uint64_t cap = std::max<uint64_t>(unit_paths, std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << qlog));
                     const uint32_t units_per_pass = (uint32_t)std::max<uint64_t>(1, cap / unit_paths);
