@@ -244,6 +244,16 @@ struct Tracer {
         cfg.n_devices = (int32_t)devices.size();
         for (size_t i = 0; i < devices.size() && i < 8; i++) cfg.device_ids[i] = devices[i];
         check(rayz_cuda_create(&cfg, &ctx));
+        const RzRenderParams p = renderParams();
+        check(rayz_cuda_reserve(ctx, &p));   // like Image.initEmpty in Tracer.init: before the timer
+    }
+
+    RzRenderParams renderParams() const {
+        RzRenderParams p;
+        std::memset(&p, 0, sizeof p);
+        p.width = (uint32_t)img.w; p.height = (uint32_t)img.h; p.spp = (uint32_t)samples_per_px; p.max_depth = (uint32_t)max_bounces;
+        p.seed = render_seed; p.variant = variant;
+        return p;
     }
 
     size_t render() {
@@ -275,10 +285,7 @@ struct Tracer {
         s.tex_kind = tk.data(); s.tex_color = tcol.data(); s.tex_scale = ts.data(); s.tex_even = te.data(); s.tex_odd = to.data();
         check(rayz_cuda_upload_scene(ctx, &s));
 
-        RzRenderParams p;
-        std::memset(&p, 0, sizeof p);
-        p.width = (uint32_t)img.w; p.height = (uint32_t)img.h; p.spp = (uint32_t)samples_per_px; p.max_depth = (uint32_t)max_bounces;
-        p.seed = render_seed; p.variant = variant;
+        const RzRenderParams p = renderParams();
         const RzCamera cam = camera.flat();
         std::vector<float> lin(img.w * img.h * 4);
         img.rgb8.resize(img.w * img.h * 3);

@@ -199,6 +199,11 @@ int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *scene);
 int rayz_cuda_render(RzContext *ctx, const RzCamera *cam, const RzRenderParams *params,
                      float *out_linear_rgba, uint8_t *out_rgb8, uint64_t *out_paths);
 
+/* Optional: allocate everything a render with these parameters needs (accumulators, result buffers, the
+ * staged K1's queues: up to ~40 GB) ahead of time, like Image.initEmpty in Tracer.init (renderer.zig:29-64),
+ * so that the first rayz_cuda_render does not pay for it. */
+int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *params);
+
 /* Same, but results stay in HBM on device_ids[0]; pointers (valid until the next render or
  * destroy) are returned instead of copied.  With `sync` == 0 the call only enqueues. */
 int rayz_cuda_render_device(RzContext *ctx, const RzCamera *cam, const RzRenderParams *params,

@@ -70,6 +70,7 @@ SYMBOLS = {
     "rayz_cuda_destroy": (None, [C.c_void_p]),
     "rayz_cuda_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rayz_cuda_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(RzScene)]),
+    "rayz_cuda_reserve": (C.c_int, [C.c_void_p, C.POINTER(RzRenderParams)]),
     "rayz_cuda_render": (C.c_int, [C.c_void_p, C.POINTER(RzCamera), C.POINTER(RzRenderParams), C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_uint64)]),
     "rayz_cuda_render_device": (C.c_int, [C.c_void_p, C.POINTER(RzCamera), C.POINTER(RzRenderParams), C.POINTER(C.c_void_p),

@@ -685,6 +685,50 @@ static RzCamF32 cam_to_f32(const RzCamera *c) {
 }
 
 
+// Pass/queue sizing of the staged K1 (see render_impl).
+struct QueuePlan {
+    uint64_t unit_paths = 0, cap = 0;
+    uint32_t units_per_pass = 1, n_pass = 1;
+    int n_sides = 1, n_second = 0;
+    bool second_stage = false;
+};
+
+static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres) {
+    QueuePlan q;
+    q.unit_paths = 32ull * chunk;
+    const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
+    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
+    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene): 0 -> 2141 / 1945,
+    // 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899 (each stage re-sorts the pass; later
+    // segments are few unless paths are long)
+    const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
+    q.n_second = enough_spheres ? (senv ? std::min(8, std::max(0, atoi(senv))) : 4) : 0;
+    q.second_stage = q.n_second > 0;
+    q.cap = std::max<uint64_t>(q.unit_paths, std::min<uint64_t>((uint64_t)n_units * q.unit_paths, 1ull << qlog));
+    q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
+    q.n_pass = (n_units + q.units_per_pass - 1) / q.units_per_pass;
+    q.n_sides = (q.n_pass > 1 && !serial) ? 2 : 1;
+    return q;
+}
+
+static int alloc_queues(Dev &D, const QueuePlan &q) {
+    int rc;
+    for (int sd = 0; sd < q.n_sides; sd++) {
+        if ((rc = D.q1[sd].alloc((size_t)q.cap * 4u))) return rc;
+        if (q.second_stage) {
+            if ((rc = D.q2[sd].alloc((size_t)q.cap * 4u)) || (rc = D.keys[sd].alloc((size_t)q.cap)) || (rc = D.keys_sorted[sd].alloc((size_t)q.cap)) ||
+                (rc = D.idx_sorted[sd].alloc((size_t)q.cap)) || (rc = D.sort_temp[sd].alloc(rz_sort_temp_bytes((uint32_t)q.cap) + 256)))
+                return rc;
+        }
+    }
+    if (q.second_stage && D.iota_n < q.cap) {
+        if ((rc = D.iota.alloc((size_t)q.cap))) return rc;
+        RZ_CUDA(rz_iota(D.iota.p, (uint32_t)q.cap, D.stream));
+        D.iota_n = (uint32_t)q.cap;
+    }
+    return RZ_OK;
+}
+
 // Device timings (CUDA events) and, if asked for, the counters of the render that just finished on every stream.
 static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
     float kmax = 0, rmax = 0, pmax = 0, smax = 0;
@@ -819,34 +863,16 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     // staged K1: primary kernel (tile-culled camera segments) -> queue -> sort -> second-segment kernel (culled per
                     // sorted unit) -> queue -> persistent megakernel.  Passes are sized by the queues: <= 2^26 entries of 64 B
                     // (4.3 GB per buffer; two buffers per side, two sides: 17 GB + 3 GB of keys/indices of the 180 GB of HBM).
-                    const uint64_t unit_paths = 32ull * a.chunk;
-                    const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
-                    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
-                    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene): 0 -> 2141 / 1945,
-                    // 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899 (each stage re-sorts the pass; later
-                    // segments are few unless paths are long)
-                    const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
-                    const int n_second = ctx->n_spheres >= 64u ? (senv ? std::min(8, std::max(0, atoi(senv))) : 4) : 0;
-                    const bool second_stage = n_second > 0;
-                    const uint64_t cap = std::max<uint64_t>(unit_paths, std::min<uint64_t>((uint64_t)a.n_units * unit_paths, 1ull << qlog));
-                    const uint32_t units_per_pass = (uint32_t)std::max<uint64_t>(1, cap / unit_paths);
-                    const uint32_t total_units = a.n_units;
-                    const uint32_t n_pass = (total_units + units_per_pass - 1) / units_per_pass;
                     const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
-                    const int n_sides = (n_pass > 1 && !serial) ? 2 : 1;
-                    for (int sd = 0; sd < n_sides; sd++) {
-                        if ((rc = D.q1[sd].alloc((size_t)cap * 4u))) return rc;
-                        if (second_stage) {
-                            if ((rc = D.q2[sd].alloc((size_t)cap * 4u)) || (rc = D.keys[sd].alloc((size_t)cap)) || (rc = D.keys_sorted[sd].alloc((size_t)cap)) ||
-                                (rc = D.idx_sorted[sd].alloc((size_t)cap)) || (rc = D.sort_temp[sd].alloc(rz_sort_temp_bytes((uint32_t)cap) + 256)))
-                                return rc;
-                        }
-                    }
-                    if (second_stage && D.iota_n < cap) {
-                        if ((rc = D.iota.alloc((size_t)cap))) return rc;
-                        RZ_CUDA(rz_iota(D.iota.p, (uint32_t)cap, D.stream));
-                        D.iota_n = (uint32_t)cap;
-                        RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));   // the second stream must see it too
+                    const QueuePlan qp = plan_queues(a.n_units, a.chunk, serial, ctx->n_spheres >= 64u);
+                    const uint64_t unit_paths = qp.unit_paths, cap = qp.cap;
+                    const uint32_t units_per_pass = qp.units_per_pass, total_units = a.n_units, n_pass = qp.n_pass;
+                    const int n_sides = qp.n_sides, n_second = qp.n_second;
+                    const bool second_stage = qp.second_stage;
+                    {
+                        const uint32_t iota_before = D.iota_n;
+                        if ((rc = alloc_queues(D, qp))) return rc;
+                        if (D.iota_n != iota_before) RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));   // the second stream must see the iota too
                     }
                     const double pcx = cam->px_origin[0] + 0.5 * (p->width - 1) * cam->px_du[0] + 0.5 * (p->height - 1) * cam->px_dv[0] - cam->look_from[0];
                     const double pcy = cam->px_origin[1] + 0.5 * (p->width - 1) * cam->px_du[1] + 0.5 * (p->height - 1) * cam->px_dv[1] - cam->look_from[1];
@@ -962,6 +988,38 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         }
         { const int rc = collect_timing_and_stats(ctx, p->collect_stats != 0); if (rc) return rc; }
         ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+    }
+    return RZ_OK;
+}
+
+// Pre-allocates what a render with these parameters will need (accumulators, result buffers, the staged K1's queues), so
+// that the first render does not pay cudaMalloc for ~40 GB: the counterpart of Image.initEmpty in Tracer.init
+// (renderer.zig:29-64, image.zig:10-17), which the reference also does before main starts its timer.
+extern "C" int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *p) {
+    if (!ctx || !p) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: NULL argument");
+    if (p->width == 0 || p->height == 0 || p->spp == 0) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: width, height and spp must be > 0");
+    const uint32_t S = p->shard_count <= 1 ? 1 : p->shard_count, s = p->shard_count <= 1 ? 0 : p->shard_index;
+    if (s >= S) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: shard_index %u >= shard_count %u", s, S);
+    const uint32_t band = p->band_rows ? p->band_rows : 4, ND = (uint32_t)ctx->devs.size();
+    DeviceGuard guard;
+    int rc;
+    Dev &D0 = ctx->devs[0];
+    RZ_CUDA(cudaSetDevice(D0.id));
+    const uint32_t rows_ctx = rayz_cuda_context_rows(ctx, p->height, p->shard_index, p->shard_count, p->band_rows);
+    if ((rc = D0.out_linear.alloc((size_t)rows_ctx * p->width)) || (rc = D0.out_rgb8.alloc((size_t)rows_ctx * p->width * 3))) return rc;
+    for (uint32_t d = 0; d < ND; d++) {
+        Dev &D = ctx->devs[d];
+        RZ_CUDA(cudaSetDevice(D.id));
+        const uint32_t rows = rayz_cuda_shard_rows(p->height, s * ND + d, S * ND, band);
+        const uint32_t n_tiles = (rows * p->width + 31u) / 32u;
+        if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u)) || (rc = D.counter.alloc(16)) || (rc = D.stats.alloc(3))) return rc;
+        if (p->variant == RZ_VARIANT_AUTO || p->variant == RZ_VARIANT_MEGA) {
+            const uint32_t chunk = std::min(ctx->chunk, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
+            if ((uint64_t)n_tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
+            const QueuePlan qp = plan_queues(n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0, !ctx->have_scene || ctx->n_spheres >= 64u);
+            if ((rc = alloc_queues(D, qp))) return rc;
+        }
+        RZ_CUDA(cudaStreamSynchronize(D.stream));
     }
     return RZ_OK;
 }

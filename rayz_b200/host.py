@@ -261,6 +261,10 @@ class Backend:
         p.flags = 1 if serial_passes else 0   # RZ_RENDER_SERIAL_PASSES
         return p
 
+    def reserve(self, p: abi.RzRenderParams):
+        """rayz_cuda_reserve: allocate the per-render device buffers ahead of the first render."""
+        abi.check(self.lib.rayz_cuda_reserve(self._h, C.byref(p)))
+
     def shard_rows(self, p: abi.RzRenderParams) -> int:
         return int(self.lib.rayz_cuda_context_rows(self._h, p.height, p.shard_index, p.shard_count, p.band_rows))
 
