@@ -162,13 +162,13 @@ def algorithmic_flops_per_path(stats: dict, n_static: int, n_moving: int) -> dic
             "f_secondary": max(0.0, S - 1.0) * f_isect}
 
 
-def ncu_traffic(variant: str, paths_per_launch: float):
-    """dram__bytes_read + dram__bytes_write of the dominant kernel per launch, scaled from the committed ncu --set full
-    capture (profiles/traffic.json: bytes per path of a 40-spp config-2 render; the traffic is the primary->secondary
-    queue, 64 B per surviving path, plus the first touch of the accumulators)."""
+def ncu_traffic(variant: str, kernel: str, paths_per_launch: float):
+    """dram__bytes_read + dram__bytes_write of the roofline kernel per launch, scaled from the committed ncu --set full
+    captures (profiles/traffic.json: bytes per path of the pass, measured on a 40-spp config-2 render; the traffic is the
+    64-byte queue entries between the stages plus the first touch of the accumulators)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            per_path = json.load(f).get(variant, {}).get("dram_bytes_per_path_secondary_kernel")
+            per_path = json.load(f).get(variant, {}).get(kernel.split(" ")[0].split("<")[0])
         return None if per_path is None else per_path * paths_per_launch
     except Exception:
         return None
@@ -312,17 +312,18 @@ def main():
     # persistent secondary kernel (the dominant one).
     p_serial = Backend.params(W, H, SPP, DEPTH, seed=1, variant=args.variant, shard_index=rank, shard_count=world, band_rows=band,
                               serial_passes=True)
-    kms, pms, sms_ = [], [], []
+    kms, pms, sms_, oms = [], [], [], []
     for _ in range(min(3, args.steps)):
         flush_buf.zero_()
         be.render_device(cam, p_serial, sync=True)
         kms.append(be.timing()["kernel_ms"])
         pms.append(be.timing()["primary_ms"])
         sms_.append(be.timing()["second_ms"])
-    kt = torch.tensor([statistics.mean(kms), statistics.mean(pms), statistics.mean(sms_)], dtype=torch.float64, device=dev)
+        oms.append(be.timing()["sort_ms"])
+    kt = torch.tensor([statistics.mean(kms), statistics.mean(pms), statistics.mean(sms_), statistics.mean(oms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-    kern_ms, prim_ms, second_ms = float(kt[0].item()), float(kt[1].item()), float(kt[2].item())
+    kern_ms, prim_ms, second_ms, sort_ms = (float(x) for x in kt.tolist())
     be.render_device(cam, p, sync=True)
     launches_per_step = be.timing()["launches"]
     passes_per_step = be.timing()["passes"]
@@ -376,42 +377,45 @@ def main():
         two_stage = passes_per_step > 0
         stages = None
         if two_stage:
-            # Staged K1.  The roofline kernel is the persistent megakernel (the FP32-bound brute-force search the north star
-            # describes): algorithmic flop = its segments x F_isect (shading left out: an undercount of < 1 %), time = sum of
-            # its launch durations in one step with serial passes (tails included).  The other stages are listed beside it.
-            scale = per_gpu_paths / max(1, stats["paths"])            # stats pass ran fewer spp
+            # Staged K1: per-kernel durations from a render with serial passes (CUDA events around every launch, tails
+            # included), algorithmic flop from each kernel's own sphere-test counter (16 per stationary, 22 per moving test;
+            # shading flop left out: an undercount of < 1 %).  The roofline kernel is the one with the largest share of the step.
+            scale = per_gpu_paths / max(1, stats["paths"])            # the stats pass ran fewer spp
             n_sph = max(1, tinfo["n_static"] + tinfo["n_moving"])
             f_test = fl["f_isect"] / n_sph                            # mean flop per sphere test of this scene
-            meg_ms = kern_ms - prim_ms - second_ms
-            def stage(name, st, ms):
+            meg_ms = kern_ms - prim_ms - second_ms - sort_ms
+            n_stage = max(1, (launches_per_step - 2 * passes_per_step - 1) // (4 * passes_per_step))   # sorted stages per pass
+            def stage(name, st, ms, launches):
                 flop = st["sphere_tests"] * scale * f_test
-                return {"kernel": name, "ms_per_step": ms, "segments": st["segments"] * scale, "sphere_tests": st["sphere_tests"] * scale,
+                return {"kernel": name, "ms_per_step": ms, "launches_per_step": launches, "share_of_step": ms / kern_ms,
+                        "segments": st["segments"] * scale, "sphere_tests": st["sphere_tests"] * scale, "flop": flop,
                         "achieved_tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else None,
                         "frac": flop / (ms * 1e-3) / 1e12 / peak_tf if ms > 0 and peak_tf else None}
-            stages = [stage("rz_primary_kernel (camera segments, tile-frustum cull)", stage_stats[0], prim_ms),
-                      stage("sort + rz_second_kernel x3 (sorted segments, per-unit cull)", stage_stats[1], second_ms),
-                      stage("rz_path_kernel<QUEUE> (persistent brute-force megakernel)", stage_stats[2], meg_ms)]
-            dom_name = "rz_path_kernel<QUEUE> (persistent brute-force megakernel of the staged K1)"
-            dom_ms = meg_ms
-            dom_flop = stage_stats[2]["segments"] * scale * fl["f_isect"]
+            stages = [stage("rz_primary_kernel (camera segments, tile-frustum cull)", stage_stats[0], prim_ms, passes_per_step),
+                      stage("rz_second_kernel (sorted segments 2.." + str(n_stage + 1) + ", per-unit cull)", stage_stats[1], second_ms, passes_per_step * n_stage),
+                      stage("rz_path_kernel<QUEUE> (persistent brute-force megakernel, later segments)", stage_stats[2], meg_ms, passes_per_step),
+                      {"kernel": "cub::DeviceRadixSort (queue keys between the stages; library)", "ms_per_step": sort_ms, "share_of_step": sort_ms / kern_ms}]
+            dom = max(stages[:3], key=lambda x: x["ms_per_step"])
+            dom_name, dom_ms, dom_flop, dom_launches = dom["kernel"], dom["ms_per_step"], dom["flop"], dom["launches_per_step"]
         else:
             dom_name = "rz_path_kernel (" + variant_ran + ")" if variant_ran != "bvh" else "rz_bvh_kernel"
             dom_ms = kern_ms
             dom_flop = per_gpu_paths * fl["f_path"]
+            dom_launches = 1
         achieved = dom_flop / (dom_ms * 1e-3) / 1e12
         step_flops = per_gpu_paths * fl["f_path"] / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "fp32", "kernel": dom_name, "achieved": achieved, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                     "peak_source": "measured live: K6 FFMA/FFMA2 microbenchmark (MEASURED_PEAKS.json has no FP32 figure)",
                     "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
-                    "kernel_ms_per_launch": dom_ms / max(1, passes_per_step), "launches_per_step": max(1, passes_per_step),
+                    "kernel_ms_per_launch": dom_ms / max(1, dom_launches), "launches_per_step": dom_launches,
                     "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / kern_ms,
                     "stages": stages,
                     "all_kernels_ms_per_step_serial": kern_ms,
                     "whole_step_achieved": step_flops, "whole_step_frac": step_flops / peak_tf if peak_tf else None,
                     "flop_per_path": fl["f_path"], "flop_per_path_dominant_kernel": dom_flop / per_gpu_paths,
                     "segments_per_path": fl["segments_per_path"], "sphere_tests_per_path": fl["tests_per_path"],
-                    "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran, per_gpu_paths / max(1, passes_per_step)),
+                    "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran, dom_name, per_gpu_paths / max(1, dom_launches)),
                     "hbm_bytes_algorithmic": int(35 * W * H / world + (136 * (stage_stats[1]["segments"] + stage_stats[2]["paths"] + stats["paths"]) * per_gpu_paths / max(1, stats["paths"]) if two_stage else 0)),
                     "note": "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test); "
                             "tensor cores unused by design; HBM traffic = 35 B/pixel of framebuffer once per render, plus, in the "

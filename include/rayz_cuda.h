@@ -169,8 +169,8 @@ typedef struct RzTiming {
     float primary_ms;      /* staged K1: sum of the primary (camera-segment) kernels' durations; a clean
                             * share of kernel_ms only with RZ_RENDER_SERIAL_PASSES (passes overlap otherwise) */
     uint32_t passes;       /* staged K1: passes (primary / sort + second / megakernel) of the render, else 0 */
-    float second_ms;       /* staged K1: sum of the sort + second-segment kernel durations (clean with serial passes) */
-    uint32_t reserved0;
+    float second_ms;       /* staged K1: sum of the sorted-segment kernels' durations (clean with serial passes) */
+    float sort_ms;         /* staged K1: sum of the key sorts' durations (clean with serial passes)             */
 } RzTiming;
 
 typedef struct RzContext RzContext;

@@ -142,7 +142,9 @@ struct Dev {
     DBuf<float> sink;
     void *wf_scratch = nullptr;
     size_t wf_scratch_bytes = 0;
-    std::vector<cudaEvent_t> pass_ev;   // two-stage K1: [2i] after the primary kernel of pass i, [2i+1] after the secondary
+    std::vector<cudaEvent_t> pass_ev;   // staged K1: [3i] after the primary kernel of pass i, [3i+1] after the sorted stages, [3i+2] after the megakernel
+    std::vector<cudaEvent_t> stage_ev;  // staged K1: per pass and sorted stage, [2k] after the sort, [2k+1] after the kernel
+    uint32_t n_second = 0;              // sorted stages per pass of the last render
     uint32_t passes = 0;                // passes of the last render (0 = not the two-stage form)
     bool serial_passes = false;
 };
@@ -480,6 +482,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
         for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
         for (auto &ev : D.pass_ev) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : D.stage_ev) if (ev) cudaEventDestroy(ev);
         if (D.ev_s2) cudaEventDestroy(D.ev_s2);
         if (D.stream2) { cudaStreamSynchronize(D.stream2); cudaStreamDestroy(D.stream2); }
         if (D.own_stream) cudaStreamDestroy(D.own_stream);
@@ -731,10 +734,10 @@ static int alloc_queues(Dev &D, const QueuePlan &q) {
 
 // Device timings (CUDA events) and, if asked for, the counters of the render that just finished on every stream.
 static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
-    float kmax = 0, rmax = 0, pmax = 0, smax = 0;
+    float kmax = 0, rmax = 0, pmax = 0, smax = 0, somax = 0;
     uint32_t passes = 0;
     for (Dev &D : ctx->devs) {
-        float k = 0, r = 0, pr = 0, se = 0;
+        float k = 0, r = 0, pr = 0, se = 0, so = 0;
         RZ_CUDA(cudaSetDevice(D.id));
         RZ_CUDA(cudaEventElapsedTime(&k, D.ev[1], D.ev[2]));
         RZ_CUDA(cudaEventElapsedTime(&r, D.ev[2], D.ev[3]));
@@ -744,16 +747,22 @@ static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
             float ms = 0;
             RZ_CUDA(cudaEventElapsedTime(&ms, i < back ? D.ev[1] : D.pass_ev[3 * (i - back) + 2], D.pass_ev[3 * i]));
             pr += ms;
-            RZ_CUDA(cudaEventElapsedTime(&ms, D.pass_ev[3 * i], D.pass_ev[3 * i + 1]));
-            se += ms;
+            for (uint32_t g = 0; g < D.n_second; g++) {   // sort, then the sorted-segment kernel
+                const size_t b = 2 * ((size_t)i * D.n_second + g);
+                RZ_CUDA(cudaEventElapsedTime(&ms, g == 0 ? D.pass_ev[3 * i] : D.stage_ev[b - 1], D.stage_ev[b]));
+                so += ms;
+                RZ_CUDA(cudaEventElapsedTime(&ms, D.stage_ev[b], D.stage_ev[b + 1]));
+                se += ms;
+            }
         }
-        kmax = std::max(kmax, k); rmax = std::max(rmax, r); pmax = std::max(pmax, pr); smax = std::max(smax, se);
+        kmax = std::max(kmax, k); rmax = std::max(rmax, r); pmax = std::max(pmax, pr); smax = std::max(smax, se); somax = std::max(somax, so);
         passes = std::max(passes, D.passes);
     }
     ctx->timing.kernel_ms = kmax;
     ctx->timing.resolve_ms = rmax;
     ctx->timing.primary_ms = pmax;
     ctx->timing.second_ms = smax;
+    ctx->timing.sort_ms = somax;
     ctx->timing.passes = passes;
     if (collect_stats) {
         RzStats tot, stage[3];
@@ -846,6 +855,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
 
         RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
         D.passes = 0;
+        D.n_second = 0;
         if (n_local > 0) {
             if (variant == RZ_VARIANT_WAVEFRONT) {
                 uint32_t l = 0;
@@ -907,7 +917,13 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         RZ_CUDA(cudaEventCreate(&e));
                         D.pass_ev.push_back(e);
                     }
+                    while (D.stage_ev.size() < 2 * (size_t)n_pass * (size_t)n_second) {
+                        cudaEvent_t e = nullptr;
+                        RZ_CUDA(cudaEventCreate(&e));
+                        D.stage_ev.push_back(e);
+                    }
                     D.passes = n_pass;
+                    D.n_second = (uint32_t)n_second;
                     D.serial_passes = serial;
                     // Passes alternate between two streams and two sets of buffers: the persistent kernel ends with a tail of a
                     // few long paths (measured ~2 ms per pass), which the next pass's kernels fill.
@@ -937,6 +953,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                             // cub sorts every slot of the pass (the live count is only known on the device); unused slots carry key 0xffffffff
                             RZ_CUDA(rz_sort_keys(D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, pass_paths, D.sort_temp[side].p,
                                                  D.sort_temp[side].n, st));
+                            RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg)], st));
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(cb, 0, sizeof(unsigned int), st));           // recycled output counter
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned int), st));      // the stage's unit counter
                             if (more) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(uint32_t), st));   // keys of the next stage
@@ -945,6 +962,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
                             a2.stats = D.stats.p + 1;
                             RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
+                            RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg) + 1], st));
                             launches += 4;   // sort = histogram + 2 passes (cub), + the sorted-segment kernel
                             std::swap(qa, qb); std::swap(ca, cb);
                         }
