@@ -32,7 +32,7 @@ extern "C" cudaError_t rz_path_warm(void);
 extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a);
 extern "C" cudaError_t rz_launch_second(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" size_t rz_sort_temp_bytes(uint32_t n);
-extern "C" cudaError_t rz_sort_keys(const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *iota, uint32_t *idx_out, uint32_t n,
+extern "C" cudaError_t rz_sort_keys(const unsigned short *keys_in, unsigned short *keys_out, const uint32_t *iota, uint32_t *idx_out, uint32_t n,
                                     void *temp, size_t temp_bytes, cudaStream_t stream);
 extern "C" cudaError_t rz_iota(uint32_t *p, uint32_t n, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
@@ -131,7 +131,8 @@ struct Dev {
     DBuf<unsigned long long> accum;
     // staged K1, one set per side (passes alternate between two streams): q1 = after the camera segment, q2 = after the second
     DBuf<float4> q1[2], q2[2];
-    DBuf<uint32_t> keys[2], keys_sorted[2], idx_sorted[2], iota;
+    DBuf<unsigned short> keys[2], keys_sorted[2];
+    DBuf<uint32_t> idx_sorted[2], iota;
     DBuf<unsigned char> sort_temp[2];
     uint32_t iota_n = 0;
     DBuf<unsigned int> counter;
@@ -939,7 +940,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         RzPathArgs a1 = a;
                         a1.q_out = D.q1[side].p; a1.q_out_count = ctr + 3; a1.q_out_keys = second_stage ? D.keys[side].p : nullptr;
                         a1.unit_base = u0; a1.n_units = pass_units; a1.unit_counter = ctr;
-                        if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(uint32_t), st));
+                        if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(unsigned short), st));
                         RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, st));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass], st));
                         launches += 1;
@@ -956,7 +957,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg)], st));
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(cb, 0, sizeof(unsigned int), st));           // recycled output counter
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned int), st));      // the stage's unit counter
-                            if (more) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(uint32_t), st));   // keys of the next stage
+                            if (more) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(unsigned short), st));   // keys of the next stage
                             RzPathArgs a2 = a;
                             a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p;
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;

@@ -102,7 +102,7 @@ struct RzPathArgs {
     const uint32_t *q_in_idx;         // K1c: entry indices in key order
     float4 *q_out;
     unsigned int *q_out_count;
-    uint32_t *q_out_keys;             // K1a only
+    unsigned short *q_out_keys;       // 16-bit sort key per appended entry (when a sorted stage follows)
     uint32_t queue_cap;               // entries each queue buffer holds
     uint32_t unit_base;               // first work unit of this pass (primary kernel)
     float focus_dist, lens_radius;    // thin-lens numbers for the tile-frustum cull (derived from the camera)

@@ -217,7 +217,7 @@ __device__ __forceinline__ void rz_queue_push(const RzPathArgs &a, bool cont, un
         __stcs(q + 1, make_float4(ray.d.x, ray.d.y, ray.d.z, __int_as_float(ray.self_k)));
         __stcs(q + 2, make_float4(thr.x, thr.y, thr.z, __uint_as_float(seg)));
         __stcs(q + 3, make_float4(__uint_as_float(lp), __uint_as_float(gpix), __uint_as_float(sample), 0.f));
-        if (a.q_out_keys) a.q_out_keys[e] = rz_sort_key(a, ray);
+        if (a.q_out_keys) a.q_out_keys[e] = (unsigned short)rz_sort_key(a, ray);
     }
 }
 
