@@ -75,6 +75,7 @@ pub const RzContext = opaque {};
 
 pub extern fn rayz_cuda_create(cfg: ?*const RzConfig, out: *?*RzContext) c_int;
 pub extern fn rayz_cuda_destroy(ctx: ?*RzContext) void;
+pub extern fn rayz_cuda_reserve(ctx: *RzContext, params: *const RzRenderParams) c_int;
 pub extern fn rayz_cuda_upload_scene(ctx: *RzContext, scene: *const RzScene) c_int;
 pub extern fn rayz_cuda_render(ctx: *RzContext, cam: *const RzCamera, params: *const RzRenderParams, out_linear_rgba: ?[*]f32, out_rgb8: ?[*]u8, out_paths: ?*u64) c_int;
 pub extern fn rayz_cuda_primary_ids(ctx: *RzContext, cam: *const RzCamera, width: u32, height: u32, use_bvh: c_int, out_ids: [*]i32) c_int;
