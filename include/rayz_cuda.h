@@ -51,7 +51,8 @@ enum { RZ_DIFFUSE_UNIT_SPHERE = 0, RZ_DIFFUSE_UNIT_SPHERE_SURFACE = 1, RZ_DIFFUS
 
 /* Kernel variants (RzRenderParams.variant). */
 enum {
-    RZ_VARIANT_AUTO = 0,      /* staged brute-force K1 when the scene fits shared memory, else BVH */
+    RZ_VARIANT_AUTO = 0,      /* staged brute-force K1 when the scene fits shared memory and the job has
+                               * >= 2^26 paths per device, else the BVH kernel (same image either way) */
     RZ_VARIANT_MEGA = 1,      /* K1: scene staged in shared memory; primary kernel -> sorted stages ->
                                * persistent brute-force megakernel          */
     RZ_VARIANT_WAVEFRONT = 2, /* K2: staged wavefront with warp-ballot compaction             */
