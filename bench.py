@@ -417,7 +417,11 @@ def main():
                     "segments_per_path": fl["segments_per_path"], "sphere_tests_per_path": fl["tests_per_path"],
                     "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran, dom_name, per_gpu_paths / max(1, dom_launches)),
                     "hbm_bytes_algorithmic": int(35 * W * H / world + (136 * (stage_stats[1]["segments"] + stage_stats[2]["paths"] + stats["paths"]) * per_gpu_paths / max(1, stats["paths"]) if two_stage else 0)),
-                    "note": "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test); "
+                    "note": "The default (staged K1) wins by NOT doing arithmetic: tile-frustum and sorted-unit culls cut the sphere tests per "
+                            "path from segments*n_spheres (1329) to ~273, so its FP32 fraction is below that of K1 run as one brute-force "
+                            "kernel, which variants.mega_single reports (frac_of_fp32_peak, the north star's 40 % target). "
+                            "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test) of the tests each "
+                            "kernel actually counted; "
                             "tensor cores unused by design; HBM traffic = 35 B/pixel of framebuffer once per render, plus, in the "
                             "staged form, 64 B written + 64 B read (+ 8 B of sort key/index) per path and queue hop (upper bound)"}
         out = {
