@@ -266,8 +266,14 @@ def main():
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # ---- which kernel family the workload resolves to (RZ_VARIANT_AUTO picks by job size): one untimed render, then every
+    # other pass names that variant explicitly, so the smaller stats pass counts the same kernels
+    be.render_device(cam, p, sync=True)
+    resolved = {1: "mega", 2: "wavefront", 3: "bvh", 4: "mega_single"}.get(be.timing()["variant"], args.variant)
+    p = Backend.params(W, H, SPP, DEPTH, seed=1, variant=resolved, shard_index=rank, shard_count=world, band_rows=band)
+
     # ---- stats pass (not timed): segments/path for the algorithmic flop count
-    ps = Backend.params(W, H, min(SPP, 8), DEPTH, seed=1, variant=args.variant, shard_index=rank, shard_count=world,
+    ps = Backend.params(W, H, min(SPP, 8), DEPTH, seed=1, variant=resolved, shard_index=rank, shard_count=world,
                         band_rows=band, collect_stats=True)
     be.render_device(cam, ps, sync=True)
     stats = be.stats()
@@ -310,7 +316,7 @@ def main():
     # The two-stage megakernel overlaps its passes on two streams; for clean per-kernel durations this pass asks for
     # serial passes (RZ_RENDER_SERIAL_PASSES): primary_ms = camera-segment kernels, kernel_ms - primary_ms = the
     # persistent secondary kernel (the dominant one).
-    p_serial = Backend.params(W, H, SPP, DEPTH, seed=1, variant=args.variant, shard_index=rank, shard_count=world, band_rows=band,
+    p_serial = Backend.params(W, H, SPP, DEPTH, seed=1, variant=resolved, shard_index=rank, shard_count=world, band_rows=band,
                               serial_passes=True)
     kms, pms, sms_, oms = [], [], [], []
     for _ in range(min(3, args.steps)):
@@ -338,7 +344,7 @@ def main():
             be2 = Backend(tuple(range(world))) if world > 1 else be
             if args.rays_per_thread or args.chunk:
                 be2.set_tuning(args.rays_per_thread, args.chunk)
-            pe = Backend.params(W, H, SPP, DEPTH, seed=1, variant=args.variant)
+            pe = Backend.params(W, H, SPP, DEPTH, seed=1, variant=args.variant)   # the call a user makes: AUTO unless overridden
             lin_h = torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy()
             rgb_h = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory().numpy()
             def step_e2e():

@@ -7,7 +7,7 @@ timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/e_bench_n1.json 2>
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/e_bench_ref.json 2> gpurun_out/e_bench_ref.err
 ( time host/_build/rayz_host 1200 gpurun_out/e_out_1200.ppm --spp 500 --seed 42 ) > gpurun_out/e_host_1gpu.log 2>&1
 md5sum gpurun_out/e_out_1200.ppm >> gpurun_out/e_host_1gpu.log; rm -f gpurun_out/e_out_1200.ppm
-CMD="python bench.py --steps 2 --warmup 3 --spp 40 --no-cpu-baseline --no-e2e --no-variants"
+CMD="python bench.py --steps 2 --warmup 3 --spp 40 --variant mega --no-cpu-baseline --no-e2e --no-variants"
 $CMD > gpurun_out/e_ncu_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/e_launches.csv $CMD > gpurun_out/e_ncu_launches.log 2>&1
 $CMD > gpurun_out/e_ncu_plain2.log 2>&1 && \
