@@ -583,3 +583,22 @@ def test_staged_cull_is_conservative_on_hostile_scenes(seed):
     n_diff = int((ref != out).any(axis=-1).sum())
     assert n_diff <= 3, f"{n_diff} pixels differ between bvh and brute force"
     assert float(np.abs(ref - out).mean()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_reserve_then_render_and_auto_policy(scene42):
+    """rayz_cuda_reserve pre-allocates the per-render buffers (before or after the scene upload) without changing results;
+    RZ_VARIANT_AUTO resolves to the BVH kernel for small jobs and to the staged K1 for large ones (same image)."""
+    w, spp = 256, 8
+    cam, h = cam_for(w)
+    fresh = Backend((0,))
+    p = Backend.params(w, h, spp, 50, seed=3, variant="mega")
+    fresh.reserve(p)                                   # no scene yet
+    fresh.upload_scene(scene42)
+    fresh.reserve(p)                                   # idempotent
+    a, _, _ = fresh.render(cam, p)
+    b, _, _ = fresh.render(cam, Backend.params(w, h, spp, 50, seed=3, variant="auto"))
+    assert fresh.timing()["variant"] == 3              # 256x144x8 paths: far below 2^26 -> BVH kernel
+    assert np.array_equal(a, b)
+    with pytest.raises(abi.BackendError):
+        fresh.reserve(Backend.params(0, h, spp))
