@@ -36,7 +36,75 @@ constexpr int RZ_STACK = 96;   // LBVH depth bound: 63 Morton bits + 32 index ti
 // leaf reference: ~((count - 1) << 28 | first); first < 2^28, count <= 8
 __device__ __forceinline__ int rz_leaf_ref(int child, uint32_t cnt) { return ~((int)((cnt - 1u) << 28) | ~child); }
 
+// One while-while round for this lane's ray: descend through internal nodes to the next leaf (or until the warp's round
+// is cut short), then test that leaf.  Shared by the persistent kernel and the staged (sorted) kernels.
 template <bool STATS>
+__device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *__restrict__ nodes, const RzRay &ray, float ix, float iy,
+                                             float iz, int &cur, int &sp, int (&stack)[RZ_STACK], float &bt, int &bk, int descend_min,
+                                             unsigned long long &c_nodes, unsigned long long &c_sph) {
+    // (1) descend through internal nodes until this lane holds a leaf or runs dry; the round ends early
+    //     once fewer than `descend_min` lanes are still descending, so that lanes holding a leaf do not idle
+    //     behind a few long descents (those lanes simply resume in the next round)
+    while ((unsigned)cur < (unsigned)RZ_SENTINEL) {
+        // slab test of AABB.hit (hit.zig:70-98) with multiply-by-inverse; boxes are padded outward at build time
+        float tn0, tf0, tn1, tf1;
+        int4 q3;
+        if (STATS) c_nodes += 2;
+        const float ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
+        {
+            const float4 q0 = __ldg(nodes + cur * 4 + 0);  // lox0 lox1 hix0 hix1
+            const float4 q1 = __ldg(nodes + cur * 4 + 1);  // loy0 loy1 hiy0 hiy1
+            const float4 q2 = __ldg(nodes + cur * 4 + 2);  // loz0 loz1 hiz0 hiz1
+            q3 = __ldg(reinterpret_cast<const int4 *>(nodes + cur * 4 + 3));
+            const float ax0 = (q0.x - ox) * ix, bx0 = (q0.z - ox) * ix, ax1 = (q0.y - ox) * ix, bx1 = (q0.w - ox) * ix;
+            const float ay0 = (q1.x - oy) * iy, by0 = (q1.z - oy) * iy, ay1 = (q1.y - oy) * iy, by1 = (q1.w - oy) * iy;
+            const float az0 = (q2.x - oz) * iz, bz0 = (q2.z - oz) * iz, az1 = (q2.y - oz) * iz, bz1 = (q2.w - oz) * iz;
+            tn0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), a.t_min));
+            tf0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), bt));
+            tn1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), a.t_min));
+            tf1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), bt));
+        }
+        const bool h0 = (tn0 <= tf0 * 1.0000004f) && (q3.x >= 0 || q3.z != 0);   // an unused slot is a leaf of 0 spheres
+        const bool h1 = (tn1 <= tf1 * 1.0000004f) && (q3.y >= 0 || q3.w != 0);
+        // child references: internal index >= 0, or a leaf (encoded negative, carries its count)
+        const int c0 = q3.x >= 0 ? q3.x : rz_leaf_ref(q3.x, (uint32_t)q3.z);
+        const int c1 = q3.y >= 0 ? q3.y : rz_leaf_ref(q3.y, (uint32_t)q3.w);
+        if (h0 && h1) {
+            const bool swap = tn1 < tn0;
+            if (sp < RZ_STACK) stack[sp++] = swap ? c0 : c1;
+            cur = swap ? c1 : c0;
+        } else if (h0) {
+            cur = c0;
+        } else if (h1) {
+            cur = c1;
+        } else {
+            cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
+        }
+        if (__popc(__activemask()) < descend_min) break;
+    }
+    // (2) leaf phase
+    if (cur < 0) {
+        const int code = ~cur;
+        const int first = code & 0x0fffffff;
+        const int cnt = (code >> 28) + 1;
+        for (int e = 0; e < cnt; e++) {
+            const int k = first + e;
+            const float4 s = __ldg(a.set.cr + k);
+            const float4 v = __ldg(a.set.vel + k);
+            if (STATS) c_sph++;
+            const float ocx = fmaf(v.x, ray.time, s.x - ray.o.x);   // same order as the packed searches
+            const float ocy = fmaf(v.y, ray.time, s.y - ray.o.y);
+            const float ocz = fmaf(v.z, ray.time, s.z - ray.o.z);
+            const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
+            const float cc = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, s.w)));
+            const float disc = fmaf(b, b, -cc);
+            if (disc > 0.0f) rz_consider(k, b, disc, ray.self_k, a.t_min, bt, bk);
+        }
+        cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
+    }
+}
+
+template <bool STATS, bool QUEUE>
 __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -45,6 +113,8 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
     // warp-uniform work-unit state (as in rz_path_kernel)
     bool have_unit = true;
     uint32_t unit_lp0 = 0, unit_s0 = 0, unit_paths = 0, k_next = 0;
+    const uint32_t n_entries = QUEUE ? min(*a.q_in_count, a.queue_cap) : 0u;   // QUEUE: paths start from queue entries (512 per unit)
+    const uint32_t n_units = QUEUE ? (n_entries + 511u) / 512u : a.n_units;
 
     // per-lane path state
     RzRay ray;
@@ -90,31 +160,48 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
                     unsigned u = 0;
                     if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
                     u = __shfl_sync(0xffffffffu, u, 0);
-                    if (u >= a.n_units) { have_unit = false; break; }
-                    const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
-                    unit_lp0 = tile * 32u;
-                    unit_s0 = chunk * a.chunk;
-                    unit_paths = 32u * min(a.chunk, a.spp - unit_s0);
+                    if (u >= n_units) { have_unit = false; break; }
+                    if (QUEUE) {
+                        unit_lp0 = u * 512u;                       // first queue entry of the unit
+                        unit_paths = min(512u, n_entries - unit_lp0);
+                    } else {
+                        const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
+                        unit_lp0 = tile * 32u;
+                        unit_s0 = chunk * a.chunk;
+                        unit_paths = 32u * min(a.chunk, a.spp - unit_s0);
+                    }
                     k_next = 0;
                     continue;
                 }
                 const uint32_t rank = __popc(mask & lt_mask);
                 if (need && rank < avail) {
                     const uint32_t k = k_next + rank;
-                    const uint32_t nlp = unit_lp0 + (k & 31u);
-                    if (nlp < a.n_local_px) {
-                        uint32_t pi, pj;
-                        rz_local_to_global(nlp, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
-                        lp = nlp;
-                        gpix = pj * a.width + pi;
-                        sample = a.sample_offset + unit_s0 + (k >> 5);
-                        ray = rz_camera_ray(a.cam, pi, pj, gpix, sample, a.seed_lo, a.seed_hi);
-                        thr = f3(1.f, 1.f, 1.f);
-                        seg = 0;
-                        alive = a.max_depth > 0u;
-                        if (STATS) { c_paths++; if (!alive) c_depth++; }
-                        if (alive) start_traversal();
-                        need = !alive;
+                    if (QUEUE) {
+                        const float4 *e = a.q_in + (size_t)(unit_lp0 + k) * 4u;
+                        const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
+                        ray.o = f3(qa.x, qa.y, qa.z); ray.time = qa.w;
+                        ray.d = f3(qb.x, qb.y, qb.z); ray.self_k = __float_as_int(qb.w);
+                        thr = f3(qc.x, qc.y, qc.z); seg = __float_as_uint(qc.w);
+                        lp = __float_as_uint(qd.x); gpix = __float_as_uint(qd.y); sample = __float_as_uint(qd.z);
+                        alive = true;
+                        start_traversal();
+                        need = false;
+                    } else {
+                        const uint32_t nlp = unit_lp0 + (k & 31u);
+                        if (nlp < a.n_local_px) {
+                            uint32_t pi, pj;
+                            rz_local_to_global(nlp, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
+                            lp = nlp;
+                            gpix = pj * a.width + pi;
+                            sample = a.sample_offset + unit_s0 + (k >> 5);
+                            ray = rz_camera_ray(a.cam, pi, pj, gpix, sample, a.seed_lo, a.seed_hi);
+                            thr = f3(1.f, 1.f, 1.f);
+                            seg = 0;
+                            alive = a.max_depth > 0u;
+                            if (STATS) { c_paths++; if (!alive) c_depth++; }
+                            if (alive) start_traversal();
+                            need = !alive;
+                        }
                     }
                 }
                 k_next += min((uint32_t)__popc(mask), avail);
@@ -126,66 +213,7 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
         // keep stepping while enough lanes are busy; once work has run out, drain completely
         const int active_min = have_unit ? (int)a.bvh_active_min : 1;
         while (__popc(__ballot_sync(0xffffffffu, cur != RZ_SENTINEL)) >= active_min) {
-            // (1) descend through internal nodes until this lane holds a leaf or runs dry; the round ends early
-            //     once fewer than `descend_min` lanes are still descending, so that lanes holding a leaf do not idle
-            //     behind a few long descents (those lanes simply resume in the next round)
-            while ((unsigned)cur < (unsigned)RZ_SENTINEL) {
-                // slab test of AABB.hit (hit.zig:70-98) with multiply-by-inverse; boxes are padded outward at build time
-                float tn0, tf0, tn1, tf1;
-                int4 q3;
-                if (STATS) c_nodes += 2;
-                const float ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
-                {
-                    const float4 q0 = __ldg(nodes + cur * 4 + 0);  // lox0 lox1 hix0 hix1
-                    const float4 q1 = __ldg(nodes + cur * 4 + 1);  // loy0 loy1 hiy0 hiy1
-                    const float4 q2 = __ldg(nodes + cur * 4 + 2);  // loz0 loz1 hiz0 hiz1
-                    q3 = __ldg(reinterpret_cast<const int4 *>(nodes + cur * 4 + 3));
-                    const float ax0 = (q0.x - ox) * ix, bx0 = (q0.z - ox) * ix, ax1 = (q0.y - ox) * ix, bx1 = (q0.w - ox) * ix;
-                    const float ay0 = (q1.x - oy) * iy, by0 = (q1.z - oy) * iy, ay1 = (q1.y - oy) * iy, by1 = (q1.w - oy) * iy;
-                    const float az0 = (q2.x - oz) * iz, bz0 = (q2.z - oz) * iz, az1 = (q2.y - oz) * iz, bz1 = (q2.w - oz) * iz;
-                    tn0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), a.t_min));
-                    tf0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), bt));
-                    tn1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), a.t_min));
-                    tf1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), bt));
-                }
-                const bool h0 = (tn0 <= tf0 * 1.0000004f) && (q3.x >= 0 || q3.z != 0);   // an unused slot is a leaf of 0 spheres
-                const bool h1 = (tn1 <= tf1 * 1.0000004f) && (q3.y >= 0 || q3.w != 0);
-                // child references: internal index >= 0, or a leaf (encoded negative, carries its count)
-                const int c0 = q3.x >= 0 ? q3.x : rz_leaf_ref(q3.x, (uint32_t)q3.z);
-                const int c1 = q3.y >= 0 ? q3.y : rz_leaf_ref(q3.y, (uint32_t)q3.w);
-                if (h0 && h1) {
-                    const bool swap = tn1 < tn0;
-                    if (sp < RZ_STACK) stack[sp++] = swap ? c0 : c1;
-                    cur = swap ? c1 : c0;
-                } else if (h0) {
-                    cur = c0;
-                } else if (h1) {
-                    cur = c1;
-                } else {
-                    cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
-                }
-                if (__popc(__activemask()) < descend_min) break;
-            }
-            // (2) leaf phase
-            if (cur < 0) {
-                const int code = ~cur;
-                const int first = code & 0x0fffffff;
-                const int cnt = (code >> 28) + 1;
-                for (int e = 0; e < cnt; e++) {
-                    const int k = first + e;
-                    const float4 s = __ldg(a.set.cr + k);
-                    const float4 v = __ldg(a.set.vel + k);
-                    if (STATS) c_sph++;
-                    const float ocx = fmaf(v.x, ray.time, s.x - ray.o.x);   // same order as the packed searches
-                    const float ocy = fmaf(v.y, ray.time, s.y - ray.o.y);
-                    const float ocz = fmaf(v.z, ray.time, s.z - ray.o.z);
-                    const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
-                    const float cc = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, s.w)));
-                    const float disc = fmaf(b, b, -cc);
-                    if (disc > 0.0f) rz_consider(k, b, disc, ray.self_k, a.t_min, bt, bk);
-                }
-                cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
-            }
+            rz_bvh_round<STATS>(a, nodes, ray, ix, iy, iz, cur, sp, stack, bt, bk, descend_min, c_nodes, c_sph);
         }
     }
 
@@ -200,9 +228,99 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
     }
 }
 
-template <bool STATS>
-cudaError_t launch(const RzPathArgs &a, int sm_count, cudaStream_t stream) {
-    auto kern = rz_bvh_kernel<STATS>;
+// Staged form for large jobs on large scenes: the first segments of every path are traced one segment per launch, camera
+// rays tile by tile and scattered rays in SORTED order (key of rz_sort_key: origin cell, octant, reach), 32 rays per warp at
+// a time.  Rays that start together and head the same way walk the same nodes, so the warp stays converged and the nodes stay
+// in L1; survivors go to the next queue, and the tail of the paths to the persistent kernel above (QUEUE).
+template <bool STATS, bool CAMERA>
+__global__ void __launch_bounds__(128, 6) rz_bvh_stage_kernel(const RzPathArgs a) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float4 *__restrict__ nodes = reinterpret_cast<const float4 *>(a.bvh);
+    const uint32_t n_in = CAMERA ? 0u : min(*a.q_in_count, a.queue_cap);
+    const uint32_t n_units = CAMERA ? a.n_units : (n_in + 511u) / 512u;
+    const int descend_min = (int)a.bvh_descend_min;
+    int stack[RZ_STACK];
+    unsigned long long c_paths = 0, c_segs = 0, c_nodes = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
+
+    while (true) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        uint32_t n_batches, pi = 0, pj = 0, lp0 = 0, gpix0 = 0, s0 = 0, e0 = 0, ne = 0;
+        bool valid = true;
+        if (CAMERA) {
+            u += a.unit_base;
+            const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
+            lp0 = tile * 32u + lane;
+            valid = lp0 < a.n_local_px;
+            if (valid) rz_local_to_global(lp0, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
+            gpix0 = pj * a.width + pi;
+            s0 = chunk * a.chunk;
+            n_batches = min(a.chunk, a.spp - s0);
+        } else {
+            e0 = u * 512u; ne = min(512u, n_in - e0);
+            n_batches = (ne + 31u) / 32u;
+        }
+        for (uint32_t b = 0; b < n_batches; b++) {
+            RzRay ray;
+            float3 thr = f3(1.f, 1.f, 1.f);
+            uint32_t seg = 0, lp = lp0, gpix = gpix0, smp = 0;
+            bool live;
+            if (CAMERA) {
+                smp = a.sample_offset + s0 + b;
+                live = valid && a.max_depth > 0u;
+                if (STATS && valid) { c_paths++; if (!live) c_depth++; }
+                if (live) ray = rz_camera_ray(a.cam, pi, pj, gpix, smp, a.seed_lo, a.seed_hi);
+            } else {
+                const uint32_t i = b * 32u + lane;
+                live = i < ne;
+                if (live) {
+                    const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + i] * 4u;
+                    const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
+                    ray.o = f3(qa.x, qa.y, qa.z); ray.time = qa.w;
+                    ray.d = f3(qb.x, qb.y, qb.z); ray.self_k = __float_as_int(qb.w);
+                    thr = f3(qc.x, qc.y, qc.z); seg = __float_as_uint(qc.w);
+                    lp = __float_as_uint(qd.x); gpix = __float_as_uint(qd.y); smp = __float_as_uint(qd.z);
+                }
+            }
+            if (!live) { ray.o = f3(0.f, 0.f, 0.f); ray.d = f3(0.f, 1.f, 0.f); ray.time = 0.f; ray.self_k = -1; }
+            const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
+            float bt = 3.0e38f;
+            int bk = -1, sp = 0, cur = live ? 0 : RZ_SENTINEL;
+            while (__any_sync(0xffffffffu, cur != RZ_SENTINEL))
+                rz_bvh_round<STATS>(a, nodes, ray, ix, iy, iz, cur, sp, stack, bt, bk, descend_min, c_nodes, c_sph);
+            bool cont = false;
+            if (live) {
+                if (STATS) c_segs++;
+                uint32_t kind;
+                const int res = rz_shade_segment(a, ray, thr, seg, lp, gpix, smp, bk, kind);
+                if (STATS) {
+                    if (kind < 3u) c_hit[kind]++;
+                    if (res == RZ_END_SKY) c_sky++;
+                    if (res == RZ_END_ABSORBED) c_abs++;
+                    if (res == RZ_END_DEPTH) c_depth++;
+                }
+                cont = res == RZ_CONT;
+            }
+            rz_queue_push(a, cont, lane, lt_mask, ray, thr, seg, lp, gpix, smp);
+        }
+    }
+
+    if (STATS) {
+        unsigned long long v[10] = {c_paths, c_segs, c_sph, c_nodes, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            unsigned long long sum = v[i];
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0 && sum) atomicAdd(&a.stats->v[i], sum);
+        }
+    }
+}
+
+template <class K>
+cudaError_t launch_kernel(K kern, const RzPathArgs &a, int sm_count, cudaStream_t stream) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
     if (e != cudaSuccess) return e;
@@ -215,16 +333,32 @@ cudaError_t launch(const RzPathArgs &a, int sm_count, cudaStream_t stream) {
 
 extern "C" cudaError_t rz_bvh_warm(void) {
     cudaFuncAttributes fa;
-    return cudaFuncGetAttributes(&fa, rz_bvh_kernel<false>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, rz_bvh_kernel<false, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_bvh_stage_kernel<false, true>);
+    return e;
 }
 
-extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
-    RzPathArgs b = *a;
+static void rz_bvh_tuning(RzPathArgs &b) {
     const char *env = getenv("RZ_BVH_ACTIVE_MIN");   // tuning experiments (defaults are the measured optimum)
     b.bvh_active_min = env ? (uint32_t)atoi(env) : 8u;
     const char *env2 = getenv("RZ_BVH_DESCEND_MIN");
     b.bvh_descend_min = env2 ? (uint32_t)atoi(env2) : 24u;
     if (b.bvh_active_min < 1u) b.bvh_active_min = 1u;
     if (b.bvh_active_min > 32u) b.bvh_active_min = 32u;
-    return collect_stats ? launch<true>(b, sm_count, stream) : launch<false>(b, sm_count, stream);
+}
+
+// The persistent kernel: whole paths from the camera (q_in == nullptr) or the tails of paths from a queue.
+extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
+    RzPathArgs b = *a;
+    rz_bvh_tuning(b);
+    if (b.q_in) return collect_stats ? launch_kernel(rz_bvh_kernel<true, true>, b, sm_count, stream) : launch_kernel(rz_bvh_kernel<false, true>, b, sm_count, stream);
+    return collect_stats ? launch_kernel(rz_bvh_kernel<true, false>, b, sm_count, stream) : launch_kernel(rz_bvh_kernel<false, false>, b, sm_count, stream);
+}
+
+// One segment per launch: camera segments (q_in == nullptr) or the sorted entries of q_in; survivors -> q_out.
+extern "C" cudaError_t rz_launch_bvh_stage(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
+    RzPathArgs b = *a;
+    rz_bvh_tuning(b);
+    if (!b.q_in) return collect_stats ? launch_kernel(rz_bvh_stage_kernel<true, true>, b, sm_count, stream) : launch_kernel(rz_bvh_stage_kernel<false, true>, b, sm_count, stream);
+    return collect_stats ? launch_kernel(rz_bvh_stage_kernel<true, false>, b, sm_count, stream) : launch_kernel(rz_bvh_stage_kernel<false, false>, b, sm_count, stream);
 }

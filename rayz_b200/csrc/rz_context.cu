@@ -38,6 +38,7 @@ extern "C" cudaError_t rz_iota(uint32_t *p, uint32_t n, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_bvh_warm(void);
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t rz_launch_bvh_stage(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n);
 extern "C" cudaError_t rz_lbvh_build(uint32_t n, const double4 *c64, const double4 *v64, const uint32_t *mat, void *scratch,
                                      size_t scratch_bytes, RzBvhNode *nodes, float4 *o_cr, float4 *o_vel, double4 *o_c64,
@@ -697,7 +698,7 @@ struct QueuePlan {
     bool second_stage = false;
 };
 
-static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres) {
+static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family = false) {
     QueuePlan q;
     q.unit_paths = 32ull * chunk;
     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
@@ -706,7 +707,11 @@ static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool
     // 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899 (each stage re-sorts the pass; later
     // segments are few unless paths are long)
     const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
-    q.n_second = enough_spheres ? (senv ? std::min(8, std::max(0, atoi(senv))) : 4) : 0;
+    const char *benv = getenv("RZ_BVH_STAGES");      // tuning experiment
+    // BVH family: sorted stages measured as a loss (config-2 scene 3521 -> 3277 -> 3065 Mpaths/s for 0, 1, 2 stages; 100k spheres 1582 -> 1427
+    // -> 1327): batches without in-loop ray replacement cost more than coherence gains; only the coherent camera stage is kept
+    if (bvh_family) q.n_second = enough_spheres ? (benv ? std::min(8, std::max(0, atoi(benv))) : 0) : 0;
+    else q.n_second = enough_spheres ? (senv ? std::min(8, std::max(0, atoi(senv))) : 4) : 0;
     q.second_stage = q.n_second > 0;
     q.cap = std::max<uint64_t>(q.unit_paths, std::min<uint64_t>((uint64_t)n_units * q.unit_paths, 1ull << qlog));
     q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
@@ -870,10 +875,14 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                 RZ_CUDA(rz_wavefront_render(&a, D.sms, (int)p->collect_stats, D.stream, &D.wf_scratch, &D.wf_scratch_bytes, &l));
                 launches += l;
             } else {
-                if (variant == RZ_VARIANT_BVH) {
+                // K3 on a big job: the same staged pipeline with BVH traversal instead of culled lists (sorted rays stay converged)
+                const bool bvh_family = variant == RZ_VARIANT_BVH;
+                const bool bvh_staged = bvh_family && !getenv("RZ_BVH_NO_STAGES") &&
+                                        (uint64_t)n_local * p->spp >= (1ull << 26);
+                if (bvh_family && !bvh_staged) {
                     RZ_CUDA(rz_launch_bvh(&a, (int)p->collect_stats, D.sms, D.stream));
                     launches += 1;
-                } else if (mega_single || rz_primary_smem_bytes(&a) > 227u * 1024u) {
+                } else if (!bvh_family && (mega_single || rz_primary_smem_bytes(&a) > 227u * 1024u)) {
                     // one persistent kernel (RZ_VARIANT_MEGA_SINGLE, or a set whose pair lists do not fit beside it)
                     RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
                     launches += 1;
@@ -882,7 +891,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     // sorted unit) -> queue -> persistent megakernel.  Passes are sized by the queues: <= 2^26 entries of 64 B
                     // (4.3 GB per buffer; two buffers per side, two sides: 17 GB + 3 GB of keys/indices of the 180 GB of HBM).
                     const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
-                    const QueuePlan qp = plan_queues(a.n_units, a.chunk, serial, ctx->n_spheres >= 64u);
+                    const QueuePlan qp = plan_queues(a.n_units, a.chunk, serial, ctx->n_spheres >= 64u, bvh_family);
                     const uint64_t unit_paths = qp.unit_paths, cap = qp.cap;
                     const uint32_t units_per_pass = qp.units_per_pass, total_units = a.n_units, n_pass = qp.n_pass;
                     const int n_sides = qp.n_sides, n_second = qp.n_second;
@@ -948,7 +957,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         a1.q_out = D.q1[side].p; a1.q_out_count = ctr + 3; a1.q_out_keys = second_stage ? D.keys[side].p : nullptr;
                         a1.unit_base = u0; a1.n_units = pass_units; a1.unit_counter = ctr;
                         if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(unsigned short), st));
-                        RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, st));
+                        if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a1, (int)p->collect_stats, D.sms, st));
+                        else RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, st));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass], st));
                         launches += 1;
                         RzPathArgs a3 = a;
@@ -969,7 +979,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                             a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p;
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
                             a2.stats = D.stats.p + 1;
-                            RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
+                            if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a2, (int)p->collect_stats, D.sms, st));
+                            else RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg) + 1], st));
                             launches += 4;   // sort = histogram + 2 passes (cub), + the sorted-segment kernel
                             std::swap(qa, qb); std::swap(ca, cb);
@@ -978,7 +989,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 1], st));
                         a3.unit_counter = ctr + 2;
                         a3.stats = D.stats.p + 2;
-                        RZ_CUDA(rz_launch_path(&a3, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
+                        if (bvh_family) RZ_CUDA(rz_launch_bvh(&a3, (int)p->collect_stats, D.sms, st));
+                        else RZ_CUDA(rz_launch_path(&a3, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 2], st));
                         launches += 1;
                     }
@@ -1039,7 +1051,7 @@ extern "C" int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *p) {
         const uint32_t rows = rayz_cuda_shard_rows(p->height, s * ND + d, S * ND, band);
         const uint32_t n_tiles = (rows * p->width + 31u) / 32u;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u)) || (rc = D.counter.alloc(16)) || (rc = D.stats.alloc(3))) return rc;
-        if (p->variant == RZ_VARIANT_AUTO || p->variant == RZ_VARIANT_MEGA) {
+        if (p->variant == RZ_VARIANT_AUTO || p->variant == RZ_VARIANT_MEGA || (p->variant == RZ_VARIANT_BVH && (uint64_t)rows * p->width * p->spp >= (1ull << 26))) {
             const uint32_t chunk = std::min(ctx->chunk, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
             if ((uint64_t)n_tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
             const QueuePlan qp = plan_queues(n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0, !ctx->have_scene || ctx->n_spheres >= 64u);

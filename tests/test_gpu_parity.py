@@ -602,3 +602,27 @@ def test_reserve_then_render_and_auto_policy(scene42):
     assert np.array_equal(a, b)
     with pytest.raises(abi.BackendError):
         fresh.reserve(Backend.params(0, h, spp))
+
+
+@pytest.mark.gpu
+def test_big_job_staged_bvh_equals_staged_bruteforce(be, scene42, monkeypatch):
+    """Above 2^26 paths per device the BVH variant also runs staged (coherent camera stage -> queue -> persistent kernel);
+    81 M paths: it must equal the staged brute-force K1 and its own unstaged form bit for bit."""
+    w, spp = 1200, 100
+    cam, h = cam_for(w)
+    be.upload_scene(scene42)
+    a, a8, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=21, variant="mega"))
+    assert be.timing()["passes"] >= 1
+    b, b8, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=21, variant="bvh", collect_stats=True))
+    assert be.timing()["variant"] == 3 and be.timing()["passes"] >= 1
+    st = be.stats()
+    assert st["paths"] == w * h * spp and be.stage_stats(0)["segments"] == st["paths"]
+    assert np.array_equal(a, b) and np.array_equal(a8, b8)
+    monkeypatch.setenv("RZ_BVH_NO_STAGES", "1")
+    c, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=21, variant="bvh"))
+    assert be.timing()["passes"] == 0
+    assert np.array_equal(a, c)
+    monkeypatch.delenv("RZ_BVH_NO_STAGES")
+    monkeypatch.setenv("RZ_BVH_STAGES", "2")
+    d, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=21, variant="bvh"))
+    assert np.array_equal(a, d)
