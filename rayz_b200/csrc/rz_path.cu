@@ -1,25 +1,33 @@
-// rz_path.cu — K1: the persistent FP32 brute-force path-tracing megakernel for sm_100a.
+// rz_path.cu — K1: the brute-force FP32 path tracer for sm_100a, three kernels.
 //
 // Replaces the body of Tracer.render's pixel loop and everything under it
 // (reference src/renderer.zig:85-96, bounceRay :103-126, BVH.findHit hit.zig:181-216,
 // Sphere.hitInner geom.zig:38-66, Material.scatter material.zig:167-176).
 //
-// Execution model
+//   rz_primary_kernel  (K1a)  camera segments; sphere set culled against each 32-pixel tile's frustum
+//   rz_second_kernel   (K1c)  the next few segments, one per launch, over queue entries sorted by
+//                             (origin cell, octant, reach); sphere set culled from each unit's actual rays
+//   rz_path_kernel     (K1b)  every later segment (QUEUE), or — as RZ_VARIANT_MEGA_SINGLE — the whole path
+//                             loop in one persistent kernel
+// The host (rz_context.cu) runs them in passes sized by the HBM queues between them.  All three use the same packed
+// arithmetic per sphere (rz_search.cuh), the same shading and RNG keys: the image does not depend on the staging.
+//
+// Execution model of rz_path_kernel
 //   * persistent CTAs, grid = SMs x resident CTAs; each WARP pulls work units
-//     (32-pixel tile x `chunk` samples) from one global atomic counter;
+//     (32-pixel tile x `chunk` samples, or 512 queue entries) from one global atomic counter;
 //   * every lane carries R independent paths ("streams").  When a path ends its stream is
-//     REGENERATED at once with the next (pixel, sample) of the warp's unit (ballot + popc
-//     rank), so the warp-uniform closest-hit loop always runs with full lanes: there is no
-//     tail of long paths holding 31 idle lanes;
+//     REGENERATED at once with the next path of the warp's unit (ballot + popc rank), so the
+//     warp-uniform closest-hit loop always runs with full lanes: there is no tail of long
+//     paths holding 31 idle lanes;
 //   * radiance is accumulated with 64-bit fixed-point (2^-32) integer atomics, so the sum is
-//     exact and independent of execution order => bit-identical images for any scheduling and
-//     any multi-GPU row sharding;
-//   * K1: the whole sphere set is staged once per CTA into shared memory with a 1-D bulk
+//     exact and independent of execution order => bit-identical images for any scheduling,
+//     staging and multi-GPU row sharding;
+//   * the whole sphere set is staged once per CTA into shared memory with a 1-D bulk
 //     async copy (cp.async.bulk + mbarrier, SASS UBLKCP) and searched by brute force with
 //     warp-uniform (broadcast) LDS.128 operands and Blackwell packed FP32x2 arithmetic
 //     (FFMA2/FADD2/FMUL2, two spheres per instruction): 11 issue slots per stationary
 //     sphere PAIR and ray, 14 per moving pair (rz_search_brute2);
-//   * large scenes use the BVH kernel of rz_bvh_trace.cu (K3) instead.
+//   * large scenes use the BVH kernels of rz_bvh_trace.cu (K3) instead.
 #include <algorithm>
 #include <cstdlib>
 
