@@ -100,6 +100,7 @@ struct RzPathArgs {
     const float4 *q_in;
     const unsigned int *q_in_count;   // entries in q_in (device counter written by the producing kernel)
     const uint32_t *q_in_idx;         // K1c: entry indices in key order
+    const unsigned short *q_in_keys;  // K1c: the keys in the same order (the sort's key output)
     float4 *q_out;
     unsigned int *q_out_count;
     unsigned short *q_out_keys;       // 16-bit sort key per appended entry (when a sorted stage follows)

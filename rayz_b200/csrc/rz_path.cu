@@ -368,17 +368,29 @@ __global__ void __launch_bounds__(128) rz_second_kernel(const RzPathArgs a) {
         // ---- what the unit's rays have in common
         float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, T = 0.f;
         unsigned all_pos = 7u, all_neg = 7u;
+        // Bounds from the sorted KEYS, not from the entries: decoding 512 16-bit keys (1 KB, coalesced) replaces a gather of
+        // 512 x 32 B through the index that was 18 % of this kernel's warp-state samples.  The key gives conservative bounds:
+        // the origin lies in its cell (open-ended for the outermost cells, where out-of-box origins are clamped), the octant
+        // is exact, and the reach is below the upper edge of its class (the top class is unbounded).
+        const int nbx = (int)a.sb_cell_bits[0], nby = (int)a.sb_cell_bits[1], nbz = (int)a.sb_cell_bits[2];
         for (uint32_t i = lane; i < ne; i += 32u) {
-            const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + i] * 4u;
-            const float4 qa = __ldg(e), qb = __ldg(e + 1);
-            RzRay r;
-            r.o = f3(qa.x, qa.y, qa.z); r.d = f3(qb.x, qb.y, qb.z); r.time = qa.w; r.self_k = -1;
-            blo[0] = fminf(blo[0], qa.x); blo[1] = fminf(blo[1], qa.y); blo[2] = fminf(blo[2], qa.z);
-            bhi[0] = fmaxf(bhi[0], qa.x); bhi[1] = fmaxf(bhi[1], qa.y); bhi[2] = fmaxf(bhi[2], qa.z);
-            if (qb.x < 0.f) all_pos &= ~1u; if (qb.x > 0.f) all_neg &= ~1u;
-            if (qb.y < 0.f) all_pos &= ~2u; if (qb.y > 0.f) all_neg &= ~2u;
-            if (qb.z < 0.f) all_pos &= ~4u; if (qb.z > 0.f) all_neg &= ~4u;
-            T = fmaxf(T, rz_box_exit(a, r));
+            const uint32_t key = a.q_in_keys[e0 + i];
+            const int reach = (int)(key & 15u);
+            const uint32_t oct = (key >> 4) & 7u;
+            const uint32_t cell = key >> 7;
+            const int c3[3] = {(int)(cell >> (nby + nbz)), (int)((cell >> nbz) & ((1u << nby) - 1u)), (int)(cell & ((1u << nbz) - 1u))};
+            const int n3[3] = {(1 << nbx) - 1, (1 << nby) - 1, (1 << nbz) - 1};
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++) {
+                const float w = a.sb_inv_cell[ax] > 0.f ? 1.0f / a.sb_inv_cell[ax] : 3.0e38f;   // cell width
+                const float lo = c3[ax] <= 0 ? -3.0e38f : fmaf((float)c3[ax], w, a.sb_lo[ax]) - 1e-4f * w;
+                const float hi = c3[ax] >= n3[ax] ? 3.0e38f : fmaf((float)(c3[ax] + 1), w, a.sb_lo[ax]) + 1e-4f * w;
+                blo[ax] = fminf(blo[ax], lo);
+                bhi[ax] = fmaxf(bhi[ax], hi);
+                if ((oct >> ax) & 1u) all_pos &= ~(1u << ax); else all_neg &= ~(1u << ax);   // key bit set <=> d < 0
+            }
+            // class c holds te / reach_unit in [2^((c-4)/2), 2^((c-3)/2)); class 15 is open-ended
+            T = fmaxf(T, reach >= 15 ? 3.0e38f : a.reach_unit * exp2f(0.5f * (float)(reach - 3)) * 1.0001f);
         }
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
