@@ -298,24 +298,26 @@ __global__ void __launch_bounds__(128) rz_primary_kernel(const RzPathArgs a) {
             }
             rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
             if (STATS) c_sph += (unsigned long long)(2 * (n_ls + n_lm)) * (live[0] ? 1u : 0u) + (unsigned long long)(2 * (n_ls + n_lm)) * (live[1] ? 1u : 0u);
+            bool cont[2] = {false, false};
+            float3 thr[2] = {f3(1.f, 1.f, 1.f), f3(1.f, 1.f, 1.f)};
+            uint32_t seg[2] = {0u, 0u};
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                float3 thr = f3(1.f, 1.f, 1.f);
-                uint32_t seg = 0, kind = 3u;
-                bool cont = false;
+                uint32_t kind = 3u;
                 if (live[r]) {
                     if (STATS) c_segs++;
-                    const int res = rz_shade_segment(a, rays[r], thr, seg, lp, gpix, smp[r], bk[r], kind);
+                    const int res = rz_shade_segment(a, rays[r], thr[r], seg[r], lp, gpix, smp[r], bk[r], kind);
                     if (STATS) {
                         if (kind < 3u) c_hit[kind]++;
                         if (res == RZ_END_SKY) c_sky++;
                         if (res == RZ_END_ABSORBED) c_abs++;
                         if (res == RZ_END_DEPTH) c_depth++;
                     }
-                    cont = res == RZ_CONT;
+                    cont[r] = res == RZ_CONT;
                 }
-                rz_queue_push(a, cont, lane, lt_mask, rays[r], thr, seg, lp, gpix, smp[r]);
             }
+            const uint32_t lp2[2] = {lp, lp}, gpix2[2] = {gpix, gpix};
+            rz_queue_push2(a, cont, lane, lt_mask, rays, thr, seg, lp2, gpix2, smp);
         }
         __syncwarp();   // the lists are rewritten for the next unit
     }
@@ -473,9 +475,9 @@ __global__ void __launch_bounds__(128) rz_second_kernel(const RzPathArgs a) {
             }
             rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
             if (STATS) c_sph += (unsigned long long)(2 * (n_ls + n_lm)) * ((live[0] ? 1u : 0u) + (live[1] ? 1u : 0u));
+            bool cont[2] = {false, false};
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                bool cont = false;
                 if (live[r]) {
                     if (STATS) c_segs++;
                     uint32_t kind;
@@ -486,10 +488,10 @@ __global__ void __launch_bounds__(128) rz_second_kernel(const RzPathArgs a) {
                         if (res == RZ_END_ABSORBED) c_abs++;
                         if (res == RZ_END_DEPTH) c_depth++;
                     }
-                    cont = res == RZ_CONT;
+                    cont[r] = res == RZ_CONT;
                 }
-                rz_queue_push(a, cont, lane, lt_mask, rays[r], thr[r], seg[r], lp[r], gpix[r], smp[r]);
             }
+            rz_queue_push2(a, cont, lane, lt_mask, rays, thr, seg, lp, gpix, smp);
         }
         __syncwarp();
     }

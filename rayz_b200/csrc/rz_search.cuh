@@ -317,3 +317,27 @@ __device__ __forceinline__ void rz_queue_push(const RzPathArgs &a, bool cont, un
     }
 }
 
+// Two rays per lane in one go: one atomic for both ballots (the atomic's round trip, exposed through the shuffle that
+// follows it, was ~5 % of the sorted-stage kernel's samples when issued once per ray).
+__device__ __forceinline__ void rz_queue_push2(const RzPathArgs &a, const bool (&cont)[2], unsigned lane, unsigned lt_mask, const RzRay (&ray)[2],
+                                               const float3 (&thr)[2], const uint32_t (&seg)[2], const uint32_t (&lp)[2], const uint32_t (&gpix)[2],
+                                               const uint32_t (&sample)[2]) {
+    const unsigned m0 = __ballot_sync(0xffffffffu, cont[0]), m1 = __ballot_sync(0xffffffffu, cont[1]);
+    const unsigned n0 = (unsigned)__popc(m0), n1 = (unsigned)__popc(m1);
+    if (n0 + n1 == 0u) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.q_out_count, n0 + n1);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned e2[2] = {base + (unsigned)__popc(m0 & lt_mask), base + n0 + (unsigned)__popc(m1 & lt_mask)};
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        if (cont[r] && e2[r] < a.queue_cap) {
+            float4 *q = a.q_out + (size_t)e2[r] * 4u;
+            __stcs(q + 0, make_float4(ray[r].o.x, ray[r].o.y, ray[r].o.z, ray[r].time));
+            __stcs(q + 1, make_float4(ray[r].d.x, ray[r].d.y, ray[r].d.z, __int_as_float(ray[r].self_k)));
+            __stcs(q + 2, make_float4(thr[r].x, thr[r].y, thr[r].z, __uint_as_float(seg[r])));
+            __stcs(q + 3, make_float4(__uint_as_float(lp[r]), __uint_as_float(gpix[r]), __uint_as_float(sample[r]), 0.f));
+            if (a.q_out_keys) a.q_out_keys[e2[r]] = (unsigned short)rz_sort_key(a, ray[r]);
+        }
+    }
+}
