@@ -156,7 +156,7 @@ def algorithmic_flops_per_path(stats: dict, n_static: int, n_moving: int) -> dic
     n = max(1, n_static + n_moving)
     f_isect = n_static * 16 + n_moving * 22
     tests_per_path = stats["sphere_tests"] / paths if stats.get("sphere_tests") else S * n
-    f_search = f_isect * tests_per_path / n
+    f_search = f_isect * tests_per_path / n + 18 * stats.get("node_tests", 0) / paths   # + box tests of the kernels that walk the BVH
     f_path = f_search + (S - p_sky) * 70 + 45 + p_sky * 19
     return {"segments_per_path": S, "p_sky": p_sky, "f_isect": f_isect, "f_path": f_path, "tests_per_path": tests_per_path,
             "f_secondary": max(0.0, S - 1.0) * f_isect}
@@ -392,14 +392,17 @@ def main():
             meg_ms = kern_ms - prim_ms - second_ms - sort_ms
             n_stage = max(1, (launches_per_step - 2 * passes_per_step - 1) // (4 * passes_per_step))   # sorted stages per pass
             def stage(name, st, ms, launches):
-                flop = st["sphere_tests"] * scale * f_test
+                # a kernel that walked the BVH counted box tests too: 18 flop per box, 22 per (general) sphere test
+                flop = (st["sphere_tests"] * 22 + st["node_tests"] * 18) * scale if st["node_tests"] else st["sphere_tests"] * scale * f_test
                 return {"kernel": name, "ms_per_step": ms, "launches_per_step": launches, "share_of_step": ms / kern_ms,
-                        "segments": st["segments"] * scale, "sphere_tests": st["sphere_tests"] * scale, "flop": flop,
+                        "segments": st["segments"] * scale, "sphere_tests": st["sphere_tests"] * scale,
+                        "node_tests": st["node_tests"] * scale, "flop": flop,
                         "achieved_tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else None,
                         "frac": flop / (ms * 1e-3) / 1e12 / peak_tf if ms > 0 and peak_tf else None}
             stages = [stage("rz_primary_kernel (camera segments, tile-frustum cull)", stage_stats[0], prim_ms, passes_per_step),
                       stage("rz_second_kernel (sorted segments 2.." + str(n_stage + 1) + ", per-unit cull)", stage_stats[1], second_ms, passes_per_step * n_stage),
-                      stage("rz_path_kernel<QUEUE> (persistent brute-force megakernel, later segments)", stage_stats[2], meg_ms, passes_per_step),
+                      stage("rz_bvh_kernel<QUEUE> (persistent BVH kernel, later segments)" if stage_stats[2]["node_tests"] else
+                            "rz_path_kernel<QUEUE> (persistent brute-force megakernel, later segments)", stage_stats[2], meg_ms, passes_per_step),
                       {"kernel": "cub::DeviceRadixSort (queue keys between the stages; library)", "ms_per_step": sort_ms, "share_of_step": sort_ms / kern_ms}]
             dom = max(stages[:3], key=lambda x: x["ms_per_step"])
             dom_name, dom_ms, dom_flop, dom_launches = dom["kernel"], dom["ms_per_step"], dom["flop"], dom["launches_per_step"]

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
                         const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
                         ray.o = f3(qa.x, qa.y, qa.z); ray.time = qa.w;
                         ray.d = f3(qb.x, qb.y, qb.z); ray.self_k = __float_as_int(qb.w);
+                        if (a.self_map && ray.self_k >= 0) ray.self_k = a.self_map[ray.self_k];   // entry written by a brute-force stage
                         thr = f3(qc.x, qc.y, qc.z); seg = __float_as_uint(qc.w);
                         lp = __float_as_uint(qd.x); gpix = __float_as_uint(qd.y); sample = __float_as_uint(qd.z);
                         alive = true;

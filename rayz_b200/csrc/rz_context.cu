@@ -119,6 +119,7 @@ struct Dev {
     SetBufs brute, bvhset;
     DBuf<RzBvhNode> bvh;
     uint32_t bvh_nodes = 0;
+    DBuf<int32_t> brute_to_bvh;       // staged K1 with a BVH tail: position in `brute` -> position in `bvhset` (empty: no such tail)
     DBuf<RzRefNode> refnodes;
     DBuf<uint32_t> reforder;
     DBuf<double4> c64_orig, v64_orig;
@@ -474,7 +475,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
     for (Dev &D : ctx->devs) {
         if (cudaSetDevice(D.id) != cudaSuccess) continue;
         if (D.own_stream) cudaStreamSynchronize(D.own_stream);
-        D.brute.release(); D.bvhset.release(); D.bvh.release(); D.refnodes.release(); D.reforder.release();
+        D.brute.release(); D.bvhset.release(); D.bvh.release(); D.brute_to_bvh.release(); D.refnodes.release(); D.reforder.release();
         D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
         D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
@@ -612,6 +613,15 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     }
     const uint32_t brute_smem = (bs.n_pad * 2 - bs.n_static_pad) * 16u;
     const bool upload_brute = brute_smem <= RZ_SMEM_BUDGET;   // larger scenes can only run the BVH variant
+    // staged K1 hands the tail of its paths to the BVH kernel: queue entries name the sphere a ray starts on by its position
+    // in the brute-force set, the BVH kernel wants the position in its own (leaf-ordered) set
+    std::vector<int32_t> b2v;
+    if (!device_build && upload_brute) {
+        std::vector<int32_t> pos(n, -1);
+        for (uint32_t k = 0; k < (uint32_t)sb.order.size(); k++) pos[sb.order[k]] = (int32_t)k;
+        b2v.assign(bs.orig.size(), -1);
+        for (size_t j = 0; j < bs.orig.size(); j++) if (bs.orig[j] >= 0) b2v[j] = pos[(size_t)bs.orig[j]];
+    }
 
     // ---- materials / textures
     std::vector<uint32_t> mk(nm), mt(nm), mm(nm), tk(nt), te(nt), to(nt);
@@ -638,10 +648,12 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
         if ((rc = D.c64_orig.upload(c64o, D.stream))) return rc;
         if ((rc = D.v64_orig.upload(v64o, D.stream))) return rc;
         if ((rc = D.mat_orig.upload(mato, D.stream))) return rc;
+        if (b2v.empty()) D.brute_to_bvh.release();
         if (!device_build) {
             if ((rc = upload_set(D.bvhset, vs, D.stream))) return rc;
             if ((rc = D.bvh.upload(sb.nodes, D.stream))) return rc;
             D.bvh_nodes = (uint32_t)sb.nodes.size();
+            if (!b2v.empty() && (rc = D.brute_to_bvh.upload(b2v, D.stream))) return rc;
         } else {
             const size_t scratch = rz_lbvh_scratch_bytes(n);
             if ((rc = D.lbvh_scratch.alloc(scratch))) return rc;
@@ -698,20 +710,21 @@ struct QueuePlan {
     bool second_stage = false;
 };
 
-static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family = false) {
+static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family = false, bool bvh_tail = true) {
     QueuePlan q;
     q.unit_paths = 32ull * chunk;
     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
     const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
-    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene): 0 -> 2141 / 1945,
-    // 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899 (each stage re-sorts the pass; later
-    // segments are few unless paths are long)
+    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene).  BVH tail: 0 -> 4185 / 3390,
+    // 1 -> 4739 / 3500, 2 -> 4942 / 3657, 3 -> 4935 / 3789, 4 -> 4829 / 3781, 5 -> 4662.  Brute-force tail (earlier
+    // build): 0 -> 2141 / 1945, 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899.  Each stage
+    // re-sorts the pass; later segments are few unless paths are long.
     const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
     const char *benv = getenv("RZ_BVH_STAGES");      // tuning experiment
     // BVH family: sorted stages measured as a loss (config-2 scene 3521 -> 3277 -> 3065 Mpaths/s for 0, 1, 2 stages; 100k spheres 1582 -> 1427
     // -> 1327): batches without in-loop ray replacement cost more than coherence gains; only the coherent camera stage is kept
     if (bvh_family) q.n_second = enough_spheres ? (benv ? std::min(8, std::max(0, atoi(benv))) : 0) : 0;
-    else q.n_second = enough_spheres ? (senv ? std::min(8, std::max(0, atoi(senv))) : 4) : 0;
+    else q.n_second = enough_spheres ? (senv ? std::min(8, std::max(0, atoi(senv))) : (bvh_tail ? 3 : 4)) : 0;
     q.second_stage = q.n_second > 0;
     q.cap = std::max<uint64_t>(q.unit_paths, std::min<uint64_t>((uint64_t)n_units * q.unit_paths, 1ull << qlog));
     q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
@@ -891,7 +904,12 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     // sorted unit) -> queue -> persistent megakernel.  Passes are sized by the queues: <= 2^26 entries of 64 B
                     // (4.3 GB per buffer; two buffers per side, two sides: 17 GB + 3 GB of keys/indices of the 180 GB of HBM).
                     const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
-                    const QueuePlan qp = plan_queues(a.n_units, a.chunk, serial, ctx->n_spheres >= 64u, bvh_family);
+                    // The tail of the paths (whatever survives the sorted stages: incoherent, few) goes to the BVH kernel when the
+                    // host-built tree is there — ~28 node + sphere tests per segment instead of every sphere of the set
+                    // (config 2: 29.2 -> 11.1 ms behind four sorted stages).
+                    const char *tail_env = getenv("RZ_TAIL");   // tuning experiment: "brute" keeps the brute-force megakernel
+                    const bool bvh_tail = !bvh_family && D.brute_to_bvh.p != nullptr && !(tail_env && !strcmp(tail_env, "brute"));
+                    const QueuePlan qp = plan_queues(a.n_units, a.chunk, serial, ctx->n_spheres >= 64u, bvh_family, bvh_tail);
                     const uint64_t unit_paths = qp.unit_paths, cap = qp.cap;
                     const uint32_t units_per_pass = qp.units_per_pass, total_units = a.n_units, n_pass = qp.n_pass;
                     const int n_sides = qp.n_sides, n_second = qp.n_second;
@@ -989,7 +1007,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 1], st));
                         a3.unit_counter = ctr + 2;
                         a3.stats = D.stats.p + 2;
-                        if (bvh_family) RZ_CUDA(rz_launch_bvh(&a3, (int)p->collect_stats, D.sms, st));
+                        if (bvh_tail) { a3.set = D.bvhset.view(); a3.self_map = D.brute_to_bvh.p; }
+                        if (bvh_family || bvh_tail) RZ_CUDA(rz_launch_bvh(&a3, (int)p->collect_stats, D.sms, st));
                         else RZ_CUDA(rz_launch_path(&a3, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 2], st));
                         launches += 1;

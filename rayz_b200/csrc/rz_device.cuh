@@ -112,6 +112,7 @@ struct RzPathArgs {
     uint32_t sb_cell_bits[3];         // 9 key bits shared out so that cells come out as cubic as possible
     float huge_radius;                // spheres above this radius are never culled (the r = 1000 ground)
     float reach_unit;                 // max extent of the box / 32: classes of the sort key's reach field
+    const int32_t *self_map;     // K3 fed by a K1 queue: position in the brute-force set -> position in the BVH-ordered set (null: same set)
     uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)
     uint32_t bvh_descend_min;    // K3: a descend round ends once fewer lanes than this are still descending
 };

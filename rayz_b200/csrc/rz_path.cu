@@ -33,6 +33,17 @@
 
 #include "rz_search.cuh"
 
+// Resident CTAs per SM the staged kernels are compiled for (register cap = 65536 / (128 * N)); undefined = ptxas decides.
+#ifndef RZ_SECOND_MINB
+#define RZ_SECOND_MINB 7   // 72 registers: the sorted-stage kernel waits on its gathers, a seventh CTA hides more of them (45.6 -> 44.3 ms)
+#endif
+#define RZ_SECOND_BOUNDS __launch_bounds__(128, RZ_SECOND_MINB)
+#ifdef RZ_PRIMARY_MINB
+#define RZ_PRIMARY_BOUNDS __launch_bounds__(128, RZ_PRIMARY_MINB)
+#else
+#define RZ_PRIMARY_BOUNDS __launch_bounds__(128)
+#endif
+
 // ------------------------------------------------------------------------------ the kernel
 struct RzStream {
     RzRay ray;
@@ -189,7 +200,7 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
 // Paths that scatter are appended, ballot-compacted, to the HBM queue the secondary kernel starts from; paths
 // that leave the scene or are absorbed accumulate here.  36 % of all segments are camera segments.
 template <bool STATS>
-__global__ void __launch_bounds__(128) rz_primary_kernel(const RzPathArgs a) {
+__global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
     float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
@@ -343,7 +354,7 @@ __global__ void __launch_bounds__(128) rz_primary_kernel(const RzPathArgs a) {
 // behind the origin box on such an axis and lies within T + r of the box.  The packed search runs over that
 // list (15 % of the spheres on the RTOW scene) with the same arithmetic per sphere, so (t, k) is unchanged.
 template <bool STATS>
-__global__ void __launch_bounds__(128) rz_second_kernel(const RzPathArgs a) {
+__global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
     float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);

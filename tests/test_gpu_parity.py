@@ -503,7 +503,10 @@ def test_device_lbvh_100k_spheres_config4():
 # spheres a ray cannot hit, so every form must equal the single persistent kernel bit for bit.
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-def test_staged_megakernel_equals_single_kernel_bitwise_and_stage_stats(be, scene42):
+@pytest.mark.parametrize("tail", ["bvh", "brute"])
+def test_staged_megakernel_equals_single_kernel_bitwise_and_stage_stats(be, scene42, monkeypatch, tail):
+    """tail = which kernel takes the paths after the sorted stages: the BVH kernel (default) or the brute-force megakernel."""
+    monkeypatch.setenv("RZ_TAIL", tail)
     w, spp = 320, 24
     cam, h = cam_for(w)
     be.upload_scene(scene42)
@@ -521,7 +524,11 @@ def test_staged_megakernel_equals_single_kernel_bitwise_and_stage_stats(be, scen
         assert sum(s[k] for s in st) == s2[k], k
     assert s1["sphere_tests"] == s1["segments"] * n                    # brute force tests everything
     assert st[0]["segments"] == s2["paths"] and st[0]["paths"] == s2["paths"]   # one camera segment per path
-    assert st[2]["sphere_tests"] == st[2]["segments"] * n              # the persistent stage is brute force too
+    if tail == "brute":
+        assert st[2]["sphere_tests"] == st[2]["segments"] * n and st[2]["node_tests"] == 0   # the persistent stage is brute force too
+    else:
+        assert 0 < st[2]["sphere_tests"] < 0.05 * st[2]["segments"] * n and st[2]["node_tests"] > st[2]["segments"]   # it walked the tree
+    assert st[0]["node_tests"] == 0 and st[1]["node_tests"] == 0
     assert st[0]["sphere_tests"] < 0.15 * st[0]["segments"] * n        # tile-frustum cull
     assert st[1]["sphere_tests"] < 0.50 * st[1]["segments"] * n        # sorted-unit cull
     assert s2["sphere_tests"] < 0.4 * s1["sphere_tests"]
@@ -544,17 +551,18 @@ def test_staged_megakernel_many_small_passes(be, scene42, monkeypatch):
     assert np.array_equal(ref, out)
     out2, _, _ = fresh.render(cam, Backend.params(w, h, spp, 50, seed=11, variant="mega", serial_passes=True))
     assert np.array_equal(ref, out2)
-    for stages in ("0", "1", "5"):
+    for stages, tail in (("0", "bvh"), ("1", "brute"), ("5", "bvh"), ("4", "brute")):
         monkeypatch.setenv("RZ_SECOND_STAGES", stages)
+        monkeypatch.setenv("RZ_TAIL", tail)
         out3, _, _ = fresh.render(cam, Backend.params(w, h, spp, 50, seed=11, variant="mega"))
-        assert np.array_equal(ref, out3), stages
+        assert np.array_equal(ref, out3), (stages, tail)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_staged_cull_is_conservative_on_hostile_scenes(seed):
+def test_staged_cull_is_conservative_on_hostile_scenes(seed, monkeypatch):
     """Fast movers, a wide lens, the camera inside a sphere, spheres behind the camera, glass: the culled searches must
-    find exactly the hits of the BVH kernel and of the single brute-force kernel."""
+    find exactly the hits of the single brute-force kernel (and of the BVH kernel, up to its documented FP32 edge)."""
     rng = np.random.default_rng(seed)
     pool = rayz_b200.MemPool()
     ground = pool.add_diffuse(pool.add_checker(0.5, pool.add_solid((0.2, 0.3, 0.1)), pool.add_solid((0.9, 0.9, 0.9))))
@@ -572,8 +580,12 @@ def test_staged_cull_is_conservative_on_hostile_scenes(seed):
     be = Backend((0,))
     be.upload_scene(scene)
     ref, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega_single"))
+    monkeypatch.setenv("RZ_TAIL", "brute")             # culled lists + brute-force tail: the same FP32 test on fewer spheres
     out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega"))
     assert np.array_equal(ref, out)
+    monkeypatch.delenv("RZ_TAIL")                      # default: the tail of the paths walks the BVH (see below)
+    out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega"))
+    assert int((ref != out).any(axis=-1).sum()) <= 3 and float(np.abs(ref - out).mean()) < 1e-4
     # K3 prunes with (outward-rounded, exact) boxes while the brute-force kernels test every sphere with an FP32 test whose
     # apparent surface is fuzzy by ~3 |oc|^2 eps / (2 r): a grazing ray from far away can "hit" a sphere a hair outside its
     # box.  K3 then rejects what is in truth a miss, so it may differ from brute force in a pixel or two (measured: 0, 1, 0
