@@ -390,7 +390,9 @@ def main():
             n_sph = max(1, tinfo["n_static"] + tinfo["n_moving"])
             f_test = fl["f_isect"] / n_sph                            # mean flop per sphere test of this scene
             meg_ms = kern_ms - prim_ms - second_ms - sort_ms
-            n_stage = max(1, (launches_per_step - 2 * passes_per_step - 1) // (4 * passes_per_step))   # sorted stages per pass
+            # launches = passes * (primary + n_stage * k + tail) + resolve; k = 5 (selector, 3 cub kernels, stage kernel) or 4 (plain sort)
+            body = launches_per_step - 2 * passes_per_step - 1
+            n_stage = max(1, next((body // (k * passes_per_step) for k in (5, 4) if body % (k * passes_per_step) == 0), body // (5 * passes_per_step)))
             def stage(name, st, ms, launches):
                 # a kernel that walked the BVH counted box tests too: 18 flop per box, 22 per (general) sphere test
                 flop = (st["sphere_tests"] * 22 + st["node_tests"] * 18) * scale if st["node_tests"] else st["sphere_tests"] * scale * f_test

@@ -35,6 +35,11 @@ extern "C" size_t rz_sort_temp_bytes(uint32_t n);
 extern "C" cudaError_t rz_sort_keys(const unsigned short *keys_in, unsigned short *keys_out, const uint32_t *iota, uint32_t *idx_out, uint32_t n,
                                     void *temp, size_t temp_bytes, cudaStream_t stream);
 extern "C" cudaError_t rz_iota(uint32_t *p, uint32_t n, cudaStream_t stream);
+struct RzSortGraph;   // rz_sort.cu: the same sort as a CUDA graph that sizes itself from a device counter
+extern "C" cudaError_t rz_sort_graph_create(RzSortGraph **out, const unsigned short *keys_in, unsigned short *keys_out, const uint32_t *iota,
+                                            uint32_t *idx_out, uint32_t cap, void *temp, size_t temp_bytes, const unsigned int *count);
+extern "C" cudaError_t rz_sort_graph_launch(RzSortGraph *g, cudaStream_t stream);
+extern "C" void rz_sort_graph_destroy(RzSortGraph *g);
 extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_bvh_warm(void);
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
@@ -136,6 +141,13 @@ struct Dev {
     DBuf<unsigned short> keys[2], keys_sorted[2];
     DBuf<uint32_t> idx_sorted[2], iota;
     DBuf<unsigned char> sort_temp[2];
+    // device-sized sort (rz_sort.cu), one graph per side, rebuilt when the buffers it captured move or change size
+    struct SortGraphSlot {
+        RzSortGraph *g = nullptr;
+        const void *key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        uint32_t cap = 0;
+        bool failed = false;
+    } sort_graph[2];
     uint32_t iota_n = 0;
     DBuf<unsigned int> counter;
     DBuf<RzStatsDev> stats;
@@ -480,6 +492,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
         D.accum.release(); D.counter.release(); D.iota.release();
+        for (int sd = 0; sd < 2; sd++) { rz_sort_graph_destroy(D.sort_graph[sd].g); D.sort_graph[sd].g = nullptr; }
         for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.sort_temp[sd].release(); } D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
         D.ids.release(); D.sink.release();
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
@@ -751,6 +764,27 @@ static int alloc_queues(Dev &D, const QueuePlan &q) {
     return RZ_OK;
 }
 
+// The device-sized sort of one side, (re)built on first use for these buffers; nullptr = use the plain full-size sort
+// (small passes, where the sort costs nothing anyway; RZ_SORT_GRAPH=0; or a driver without SWITCH conditional nodes).
+static RzSortGraph *sort_graph_for(Dev &D, int side, uint32_t cap) {
+    Dev::SortGraphSlot &S = D.sort_graph[side];
+    const char *env = getenv("RZ_SORT_GRAPH");   // tuning experiment
+    if ((env && atoi(env) == 0) || cap < (1u << 22)) return nullptr;
+    const unsigned int *count = D.counter.p + 8 * side + 5;
+    const void *key[6] = {D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, D.sort_temp[side].p, count};
+    if (S.g && S.cap == cap && !memcmp(S.key, key, sizeof key)) return S.g;
+    if (S.failed && S.cap == cap && !memcmp(S.key, key, sizeof key)) return nullptr;
+    rz_sort_graph_destroy(S.g);
+    S.g = nullptr;
+    memcpy(S.key, key, sizeof key);
+    S.cap = cap;
+    const cudaError_t e = rz_sort_graph_create(&S.g, D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, cap, D.sort_temp[side].p,
+                                               D.sort_temp[side].n, count);
+    S.failed = e != cudaSuccess;
+    if (S.failed) { S.g = nullptr; if (getenv("RZ_SORT_GRAPH_VERBOSE")) fprintf(stderr, "[rayz_cuda] sort graph: %s\n", cudaGetErrorString(e)); }
+    return S.g;
+}
+
 // Device timings (CUDA events) and, if asked for, the counters of the render that just finished on every stream.
 static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
     float kmax = 0, rmax = 0, pmax = 0, smax = 0, somax = 0;
@@ -974,7 +1008,10 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         RzPathArgs a1 = a;
                         a1.q_out = D.q1[side].p; a1.q_out_count = ctr + 3; a1.q_out_keys = second_stage ? D.keys[side].p : nullptr;
                         a1.unit_base = u0; a1.n_units = pass_units; a1.unit_counter = ctr;
-                        if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(unsigned short), st));
+                        // the device-sized sort may cover up to a sixteenth of the buffer more than the live entries: clear all of it
+                        RzSortGraph *sg = second_stage ? sort_graph_for(D, side, (uint32_t)cap) : nullptr;
+                        const size_t key_slots = sg ? (size_t)cap : (size_t)pass_paths;
+                        if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, key_slots * sizeof(unsigned short), st));
                         if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a1, (int)p->collect_stats, D.sms, st));
                         else RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, st));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass], st));
@@ -986,13 +1023,19 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         unsigned int *ca = ctr + 3, *cb = ctr + 4;
                         for (int stg = 0; stg < n_second; stg++) {
                             const bool more = stg + 1 < n_second;
-                            // cub sorts every slot of the pass (the live count is only known on the device); unused slots carry key 0xffffffff
-                            RZ_CUDA(rz_sort_keys(D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, pass_paths, D.sort_temp[side].p,
-                                                 D.sort_temp[side].n, st));
+                            // unused slots carry key 0xffff.  Big passes: the sort sizes itself from the live count on the device
+                            // (rz_sort.cu); small ones sort every slot of the pass.
+                            if (sg) {
+                                RZ_CUDA(cudaMemcpyAsync(ctr + 5, ca, sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+                                RZ_CUDA(rz_sort_graph_launch(sg, st));
+                            } else {
+                                RZ_CUDA(rz_sort_keys(D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, pass_paths, D.sort_temp[side].p,
+                                                     D.sort_temp[side].n, st));
+                            }
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg)], st));
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(cb, 0, sizeof(unsigned int), st));           // recycled output counter
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned int), st));      // the stage's unit counter
-                            if (more) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, (size_t)pass_paths * sizeof(unsigned short), st));   // keys of the next stage
+                            if (more) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, key_slots * sizeof(unsigned short), st));   // keys of the next stage
                             RzPathArgs a2 = a;
                             a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p; a2.q_in_keys = D.keys_sorted[side].p;
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
@@ -1000,7 +1043,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                             if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a2, (int)p->collect_stats, D.sms, st));
                             else RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg) + 1], st));
-                            launches += 4;   // sort = histogram + 2 passes (cub), + the sorted-segment kernel
+                            launches += sg ? 5 : 4;   // sort = (selector +) histogram + 2 passes (cub), + the sorted-segment kernel
                             std::swap(qa, qb); std::swap(ca, cb);
                         }
                         a3.q_in = qa; a3.q_in_count = ca;
@@ -1075,6 +1118,8 @@ extern "C" int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *p) {
             if ((uint64_t)n_tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
             const QueuePlan qp = plan_queues(n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0, !ctx->have_scene || ctx->n_spheres >= 64u);
             if ((rc = alloc_queues(D, qp))) return rc;
+            if (qp.second_stage && p->variant != RZ_VARIANT_BVH)
+                for (int sd = 0; sd < qp.n_sides; sd++) (void)sort_graph_for(D, sd, (uint32_t)qp.cap);   // built here rather than inside the first render
         }
         RZ_CUDA(cudaStreamSynchronize(D.stream));
     }

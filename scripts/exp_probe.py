@@ -11,7 +11,7 @@ tag = [a for a in sys.argv[1:] if not a.startswith("--")]
 tag = tag[0] if tag else "default"
 
 def setenv(**kw):
-    for k in ("RZ_TAIL", "RZ_SECOND_STAGES", "RZ_BVH_ACTIVE_MIN", "RZ_BVH_DESCEND_MIN"):
+    for k in ("RZ_TAIL", "RZ_SECOND_STAGES", "RZ_BVH_ACTIVE_MIN", "RZ_BVH_DESCEND_MIN", "RZ_SORT_GRAPH"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -32,7 +32,10 @@ def timing(be, t, spp=500, **env):
 t = rayz_b200.random_bouncing(1200, seed=42)
 be = Backend((0,)); be.upload_scene(t.pool.arrays())
 if quick:
-    for ns in (2, 3, 4):
+    os.environ["RZ_SORT_GRAPH_VERBOSE"] = "1"
+    timing(be, t, RZ_SORT_GRAPH=0)
+    timing(be, t, RZ_SORT_GRAPH=1)
+    for ns in (2, 4):
         timing(be, t, RZ_SECOND_STAGES=ns)
     sys.exit(0)
 

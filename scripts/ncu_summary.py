@@ -68,6 +68,23 @@ def main():
         lines.append("")
     except StopIteration:
         pass
+    # the same samples grouped by CUDA source line (needs -lineinfo + --import-source on)
+    try:
+        cs = list(csv.reader(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]).splitlines()))
+        cur, agg = "?", []
+        for r in cs:
+            if len(r) == 2 and r[0] == "File Path":
+                cur = r[1].split("/")[-1]
+            elif len(r) > 10 and r[0].isdigit() and r[6].isdigit() and r[7].isdigit():
+                agg.append((cur, int(r[0]), r[1].strip()[:100].replace("|", "/"), int(r[6]), int(r[7])))
+        ts = sum(a[3] for a in agg) or 1
+        tn = sum(a[4] for a in agg) or 1
+        lines += ["## hottest CUDA source lines (all launches of the report)", "", "| file:line | samples % | warp instr % | source |", "|---|---|---|---|"]
+        for a in sorted(agg, key=lambda a: -a[3])[:30]:
+            lines.append(f"| {a[0]}:{a[1]} | {100 * a[3] / ts:.1f} | {100 * a[4] / tn:.1f} | `{a[2]}` |")
+        lines.append("")
+    except Exception as e:   # older captures without source import
+        lines += [f"(no CUDA source correlation: {e})", ""]
     open(out, "w").write("\n".join(lines) + "\n")
     print("wrote", out)
 
