@@ -51,10 +51,12 @@ enum { RZ_DIFFUSE_UNIT_SPHERE = 0, RZ_DIFFUSE_UNIT_SPHERE_SURFACE = 1, RZ_DIFFUS
 
 /* Kernel variants (RzRenderParams.variant). */
 enum {
-    RZ_VARIANT_AUTO = 0,      /* staged brute-force K1 when the scene fits shared memory and the job has
+    RZ_VARIANT_AUTO = 0,      /* staged K1 when the scene fits shared memory and the job has
                                * >= 2^26 paths per device, else the BVH kernel (same image either way) */
-    RZ_VARIANT_MEGA = 1,      /* K1: scene staged in shared memory; primary kernel -> sorted stages ->
-                               * persistent brute-force megakernel          */
+    RZ_VARIANT_MEGA = 1,      /* K1: scene staged in shared memory; primary kernel -> sorted stages (culled
+                               * brute force) -> persistent kernel for the tail of the paths: the BVH
+                               * kernel, or the brute-force megakernel without a host-built tree
+                               *                                              */
     RZ_VARIANT_WAVEFRONT = 2, /* K2: staged wavefront with warp-ballot compaction             */
     RZ_VARIANT_BVH = 3,       /* K3: persistent megakernel traversing the device BVH          */
     RZ_VARIANT_MEGA_SINGLE = 4 /* K1 as ONE persistent kernel (every segment brute force, paths
@@ -169,7 +171,7 @@ typedef struct RzTiming {
                             * host SAH wall time, or device LBVH by CUDA events (max over devices) */
     float primary_ms;      /* staged K1: sum of the primary (camera-segment) kernels' durations; a clean
                             * share of kernel_ms only with RZ_RENDER_SERIAL_PASSES (passes overlap otherwise) */
-    uint32_t passes;       /* staged K1: passes (primary / sort + second / megakernel) of the render, else 0 */
+    uint32_t passes;       /* staged K1: passes (primary / sort + sorted stages / tail kernel) of the render, else 0 */
     float second_ms;       /* staged K1: sum of the sorted-segment kernels' durations (clean with serial passes) */
     float sort_ms;         /* staged K1: sum of the key sorts' durations (clean with serial passes)             */
 } RzTiming;

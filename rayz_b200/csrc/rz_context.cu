@@ -715,6 +715,8 @@ static RzCamF32 cam_to_f32(const RzCamera *c) {
 }
 
 
+static const uint32_t RZ_SORT_GRAPH_MIN_CAP = 1u << 22;   // passes below this sort every slot (microseconds), no graph is built
+
 // Pass/queue sizing of the staged K1 (see render_impl).
 struct QueuePlan {
     uint64_t unit_paths = 0, cap = 0;
@@ -728,18 +730,20 @@ static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool
     q.unit_paths = 32ull * chunk;
     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
     const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
-    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene).  BVH tail: 0 -> 4185 / 3390,
-    // 1 -> 4739 / 3500, 2 -> 4942 / 3657, 3 -> 4935 / 3789, 4 -> 4829 / 3781, 5 -> 4662.  Brute-force tail (earlier
-    // build): 0 -> 2141 / 1945, 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899.  Each stage
-    // re-sorts the pass; later segments are few unless paths are long.
+    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene).  BVH tail, every sort
+    // over the whole pass: 0 -> 4185 / 3390, 1 -> 4739 / 3500, 2 -> 4942 / 3657, 3 -> 4935 / 3789, 4 -> 4829 / 3781,
+    // 5 -> 4662; with the device-sized sort (big passes) a stage costs less: 2 -> 5167, 3 -> 5337, 4 -> 5393.  Brute-force
+    // tail (earlier build): 0 -> 2141 / 1945, 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899.
     const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
     const char *benv = getenv("RZ_BVH_STAGES");      // tuning experiment
     // BVH family: sorted stages measured as a loss (config-2 scene 3521 -> 3277 -> 3065 Mpaths/s for 0, 1, 2 stages; 100k spheres 1582 -> 1427
     // -> 1327): batches without in-loop ray replacement cost more than coherence gains; only the coherent camera stage is kept
     if (bvh_family) q.n_second = enough_spheres ? (benv ? std::min(8, std::max(0, atoi(benv))) : 0) : 0;
-    else q.n_second = enough_spheres ? (senv ? std::min(8, std::max(0, atoi(senv))) : (bvh_tail ? 3 : 4)) : 0;
-    q.second_stage = q.n_second > 0;
+    else q.n_second = -1;   // decided below, once the pass size is known
     q.cap = std::max<uint64_t>(q.unit_paths, std::min<uint64_t>((uint64_t)n_units * q.unit_paths, 1ull << qlog));
+    if (q.n_second < 0)
+        q.n_second = !enough_spheres ? 0 : senv ? std::min(8, std::max(0, atoi(senv))) : (bvh_tail && q.cap < RZ_SORT_GRAPH_MIN_CAP) ? 3 : 4;
+    q.second_stage = q.n_second > 0;
     q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
     q.n_pass = (n_units + q.units_per_pass - 1) / q.units_per_pass;
     q.n_sides = (q.n_pass > 1 && !serial) ? 2 : 1;
@@ -769,7 +773,7 @@ static int alloc_queues(Dev &D, const QueuePlan &q) {
 static RzSortGraph *sort_graph_for(Dev &D, int side, uint32_t cap) {
     Dev::SortGraphSlot &S = D.sort_graph[side];
     const char *env = getenv("RZ_SORT_GRAPH");   // tuning experiment
-    if ((env && atoi(env) == 0) || cap < (1u << 22)) return nullptr;
+    if ((env && atoi(env) == 0) || cap < RZ_SORT_GRAPH_MIN_CAP) return nullptr;
     const unsigned int *count = D.counter.p + 8 * side + 5;
     const void *key[6] = {D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, D.sort_temp[side].p, count};
     if (S.g && S.cap == cap && !memcmp(S.key, key, sizeof key)) return S.g;
@@ -934,9 +938,10 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
                     launches += 1;
                 } else {
-                    // staged K1: primary kernel (tile-culled camera segments) -> queue -> sort -> second-segment kernel (culled per
-                    // sorted unit) -> queue -> persistent megakernel.  Passes are sized by the queues: <= 2^26 entries of 64 B
-                    // (4.3 GB per buffer; two buffers per side, two sides: 17 GB + 3 GB of keys/indices of the 180 GB of HBM).
+                    // staged K1: primary kernel (tile-culled camera segments) -> queue -> [sort -> sorted-segment kernel (culled per
+                    // unit) -> queue] x n_second -> persistent tail kernel (BVH, or brute force).  Passes are sized by the queues:
+                    // <= 2^27 entries of 64 B (8.6 GB per buffer; two buffers per side, two sides: ~40 GB with keys and indices
+                    // of the 180 GB of HBM).
                     const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
                     // The tail of the paths (whatever survives the sorted stages: incoherent, few) goes to the BVH kernel when the
                     // host-built tree is there — ~28 node + sphere tests per segment instead of every sphere of the set
@@ -969,7 +974,9 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         if (!(e3[ax] > 0.f) || !(e3[ax] < 1.0e30f)) e3[ax] = 0.f;
                         ext = std::max(ext, e3[ax]);
                     }
-                    for (int b = 0; b < 9; b++) {   // each key bit halves the cells of the axis whose cells are currently largest
+                    const char *cb_env = getenv("RZ_CELL_BITS");   // tuning experiment (the key has room for 9)
+                    const int cell_bits = cb_env ? std::min(9, std::max(0, atoi(cb_env))) : 9;
+                    for (int b = 0; b < cell_bits; b++) {   // each key bit halves the cells of the axis whose cells are currently largest
                         int best = 0;
                         for (int ax = 1; ax < 3; ax++)
                             if (e3[ax] / (float)(1u << bits[ax]) > e3[best] / (float)(1u << bits[best])) best = ax;

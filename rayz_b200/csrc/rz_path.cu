@@ -7,9 +7,10 @@
 //   rz_primary_kernel  (K1a)  camera segments; sphere set culled against each 32-pixel tile's frustum
 //   rz_second_kernel   (K1c)  the next few segments, one per launch, over queue entries sorted by
 //                             (origin cell, octant, reach); sphere set culled from each unit's actual rays
-//   rz_path_kernel     (K1b)  every later segment (QUEUE), or — as RZ_VARIANT_MEGA_SINGLE — the whole path
-//                             loop in one persistent kernel
-// The host (rz_context.cu) runs them in passes sized by the HBM queues between them.  All three use the same packed
+//   rz_path_kernel     (K1b)  the whole path loop in one persistent kernel (RZ_VARIANT_MEGA_SINGLE), or (QUEUE) every
+//                             segment after the sorted stages when no host-built BVH is there for the tail
+// The host (rz_context.cu) runs them in passes sized by the HBM queues between them; by default the tail of the paths —
+// what survives the sorted stages — goes to the BVH kernel of rz_bvh_trace.cu instead of K1b.  All use the same packed
 // arithmetic per sphere (rz_search.cuh), the same shading and RNG keys: the image does not depend on the staging.
 //
 // Execution model of rz_path_kernel

@@ -1,5 +1,5 @@
-// rz_sort.cu — key/index radix sort between the primary and the second-segment kernel of the staged K1
-// (cub::DeviceRadixSort: library plumbing, 16-bit keys => two 8-bit passes over 6 bytes per entry).
+// rz_sort.cu — key/index radix sort between the stages of the staged K1 (cub::DeviceRadixSort: library plumbing,
+// 16-bit keys => two 8-bit passes over 6 bytes per entry), plain or wrapped in a CUDA graph that sizes it on the device.
 #include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <algorithm>

@@ -11,7 +11,7 @@ tag = [a for a in sys.argv[1:] if not a.startswith("--")]
 tag = tag[0] if tag else "default"
 
 def setenv(**kw):
-    for k in ("RZ_TAIL", "RZ_SECOND_STAGES", "RZ_BVH_ACTIVE_MIN", "RZ_BVH_DESCEND_MIN", "RZ_SORT_GRAPH"):
+    for k in ("RZ_TAIL", "RZ_SECOND_STAGES", "RZ_BVH_ACTIVE_MIN", "RZ_BVH_DESCEND_MIN", "RZ_SORT_GRAPH", "RZ_CELL_BITS"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -31,6 +31,28 @@ def timing(be, t, spp=500, **env):
 
 t = rayz_b200.random_bouncing(1200, seed=42)
 be = Backend((0,)); be.upload_scene(t.pool.arrays())
+def tests_per_segment(be, t, spp=500, **env):
+    setenv(**env)
+    p = Backend.params(t.img.w, t.img.h, spp, 50, seed=1, variant="mega", collect_stats=True)
+    be.render_device(t.camera.rz, p)
+    st = [be.stage_stats(k) for k in range(3)]
+    print(f"[{tag}] {env} tests/segment: primary {st[0]['sphere_tests']/max(1,st[0]['segments']):.1f} sorted {st[1]['sphere_tests']/max(1,st[1]['segments']):.1f} "
+          f"(segments {st[1]['segments']/1e6:.0f} M) tail {st[2]['sphere_tests']/max(1,st[2]['segments']):.1f} + {st[2]['node_tests']/max(1,st[2]['segments']):.1f} boxes", flush=True)
+
+if "--cells" in sys.argv:
+    for cb in (9, 8, 7, 6, 5, 3):
+        tests_per_segment(be, t, RZ_CELL_BITS=cb)
+        timing(be, t, RZ_CELL_BITS=cb)
+    for ns in (1, 2, 3, 4):
+        tests_per_segment(be, t, RZ_SECOND_STAGES=ns)
+    sys.exit(0)
+if "--stages" in sys.argv:
+    tg = rayz_b200.random_bouncing(1200, seed=42, glass_heavy=True)
+    bg = Backend((0,)); bg.upload_scene(tg.pool.arrays())
+    for ns in (3, 4, 5, 6):
+        timing(be, t, RZ_SECOND_STAGES=ns)
+        timing(bg, tg, RZ_SECOND_STAGES=ns)
+    sys.exit(0)
 if quick:
     os.environ["RZ_SORT_GRAPH_VERBOSE"] = "1"
     timing(be, t, RZ_SORT_GRAPH=0)
