@@ -725,14 +725,18 @@ struct QueuePlan {
     bool second_stage = false;
 };
 
-static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family = false, bool bvh_tail = true) {
+static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family = false, bool bvh_tail = true, int qlog_cap = 28) {
     QueuePlan q;
     q.unit_paths = 32ull * chunk;
+    // Queue size = pass size.  Measured at config 2 (405 M paths): 2^26 -> 5140, 2^27 -> 5405, 2^28 -> 5529 Mpaths/s (fewer,
+    // longer launches; fewer tails).  2^28 entries are 17 GB per queue and 77 GB for both sides with keys, indices and sort
+    // space — 43 % of the 180 GB of HBM; plan_and_alloc_queues steps down if the device cannot give that much.
     const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
-    const int qlog = qenv ? std::min(28, std::max(16, atoi(qenv))) : 27;
+    const int qlog = std::min(qlog_cap, qenv ? std::min(28, std::max(16, atoi(qenv))) : 28);
     // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene).  BVH tail, every sort
     // over the whole pass: 0 -> 4185 / 3390, 1 -> 4739 / 3500, 2 -> 4942 / 3657, 3 -> 4935 / 3789, 4 -> 4829 / 3781,
-    // 5 -> 4662; with the device-sized sort (big passes) a stage costs less: 2 -> 5167, 3 -> 5337, 4 -> 5393.  Brute-force
+    // 5 -> 4662; with the device-sized sort (big passes) a stage costs less: 2 -> 5167, 3 -> 5337, 4 -> 5393, and with
+    // 2^28-entry queues 3 -> 5426 / 4025, 4 -> 5510 / 4130, 5 -> 5549 / 4214, 6 -> 5547 / 4264.  Brute-force
     // tail (earlier build): 0 -> 2141 / 1945, 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899.
     const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
     const char *benv = getenv("RZ_BVH_STAGES");      // tuning experiment
@@ -742,7 +746,7 @@ static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool
     else q.n_second = -1;   // decided below, once the pass size is known
     q.cap = std::max<uint64_t>(q.unit_paths, std::min<uint64_t>((uint64_t)n_units * q.unit_paths, 1ull << qlog));
     if (q.n_second < 0)
-        q.n_second = !enough_spheres ? 0 : senv ? std::min(8, std::max(0, atoi(senv))) : (bvh_tail && q.cap < RZ_SORT_GRAPH_MIN_CAP) ? 3 : 4;
+        q.n_second = !enough_spheres ? 0 : senv ? std::min(8, std::max(0, atoi(senv))) : !bvh_tail ? 4 : q.cap < RZ_SORT_GRAPH_MIN_CAP ? 3 : 5;
     q.second_stage = q.n_second > 0;
     q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
     q.n_pass = (n_units + q.units_per_pass - 1) / q.units_per_pass;
@@ -766,6 +770,22 @@ static int alloc_queues(Dev &D, const QueuePlan &q) {
         D.iota_n = (uint32_t)q.cap;
     }
     return RZ_OK;
+}
+
+// Plans the passes and allocates their queues; when the device cannot give the memory (others share it, or a smaller part),
+// the plan is redone with queues half the size, down to 2^22 entries.
+static int plan_and_alloc_queues(Dev &D, QueuePlan &qp, uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family,
+                                 bool bvh_tail) {
+    for (int qlog = 28;; qlog--) {
+        qp = plan_queues(n_units, chunk, serial, enough_spheres, bvh_family, bvh_tail, qlog);
+        const int rc = alloc_queues(D, qp);
+        if (rc != RZ_ERR_OOM || qlog <= 22 || qp.cap < (1ull << qlog)) return rc;   // done, a real error, or nothing left to shrink
+        cudaGetLastError();
+        for (int sd = 0; sd < 2; sd++) {
+            rz_sort_graph_destroy(D.sort_graph[sd].g); D.sort_graph[sd] = Dev::SortGraphSlot();
+            D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.sort_temp[sd].release();
+        }
+    }
 }
 
 // The device-sized sort of one side, (re)built on first use for these buffers; nullptr = use the plain full-size sort
@@ -948,16 +968,16 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     // (config 2: 29.2 -> 11.1 ms behind four sorted stages).
                     const char *tail_env = getenv("RZ_TAIL");   // tuning experiment: "brute" keeps the brute-force megakernel
                     const bool bvh_tail = !bvh_family && D.brute_to_bvh.p != nullptr && !(tail_env && !strcmp(tail_env, "brute"));
-                    const QueuePlan qp = plan_queues(a.n_units, a.chunk, serial, ctx->n_spheres >= 64u, bvh_family, bvh_tail);
+                    QueuePlan qp;
+                    {
+                        const uint32_t iota_before = D.iota_n;
+                        if ((rc = plan_and_alloc_queues(D, qp, a.n_units, a.chunk, serial, ctx->n_spheres >= 64u, bvh_family, bvh_tail))) return rc;
+                        if (D.iota_n != iota_before) RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));   // the second stream must see the iota too
+                    }
                     const uint64_t unit_paths = qp.unit_paths, cap = qp.cap;
                     const uint32_t units_per_pass = qp.units_per_pass, total_units = a.n_units, n_pass = qp.n_pass;
                     const int n_sides = qp.n_sides, n_second = qp.n_second;
                     const bool second_stage = qp.second_stage;
-                    {
-                        const uint32_t iota_before = D.iota_n;
-                        if ((rc = alloc_queues(D, qp))) return rc;
-                        if (D.iota_n != iota_before) RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));   // the second stream must see the iota too
-                    }
                     const double pcx = cam->px_origin[0] + 0.5 * (p->width - 1) * cam->px_du[0] + 0.5 * (p->height - 1) * cam->px_dv[0] - cam->look_from[0];
                     const double pcy = cam->px_origin[1] + 0.5 * (p->width - 1) * cam->px_du[1] + 0.5 * (p->height - 1) * cam->px_dv[1] - cam->look_from[1];
                     const double pcz = cam->px_origin[2] + 0.5 * (p->width - 1) * cam->px_du[2] + 0.5 * (p->height - 1) * cam->px_dv[2] - cam->look_from[2];
@@ -1123,8 +1143,10 @@ extern "C" int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *p) {
         if (p->variant == RZ_VARIANT_AUTO || p->variant == RZ_VARIANT_MEGA || (p->variant == RZ_VARIANT_BVH && (uint64_t)rows * p->width * p->spp >= (1ull << 26))) {
             const uint32_t chunk = std::min(ctx->chunk, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
             if ((uint64_t)n_tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
-            const QueuePlan qp = plan_queues(n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0, !ctx->have_scene || ctx->n_spheres >= 64u);
-            if ((rc = alloc_queues(D, qp))) return rc;
+            QueuePlan qp;
+            if ((rc = plan_and_alloc_queues(D, qp, n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0,
+                                            !ctx->have_scene || ctx->n_spheres >= 64u, false, true)))
+                return rc;
             if (qp.second_stage && p->variant != RZ_VARIANT_BVH)
                 for (int sd = 0; sd < qp.n_sides; sd++) (void)sort_graph_for(D, sd, (uint32_t)qp.cap);   // built here rather than inside the first render
         }

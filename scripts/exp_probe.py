@@ -11,7 +11,7 @@ tag = [a for a in sys.argv[1:] if not a.startswith("--")]
 tag = tag[0] if tag else "default"
 
 def setenv(**kw):
-    for k in ("RZ_TAIL", "RZ_SECOND_STAGES", "RZ_BVH_ACTIVE_MIN", "RZ_BVH_DESCEND_MIN", "RZ_SORT_GRAPH", "RZ_CELL_BITS"):
+    for k in ("RZ_TAIL", "RZ_SECOND_STAGES", "RZ_BVH_ACTIVE_MIN", "RZ_BVH_DESCEND_MIN", "RZ_SORT_GRAPH", "RZ_CELL_BITS", "RZ_QUEUE_LOG2"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -45,6 +45,12 @@ if "--cells" in sys.argv:
         timing(be, t, RZ_CELL_BITS=cb)
     for ns in (1, 2, 3, 4):
         tests_per_segment(be, t, RZ_SECOND_STAGES=ns)
+    sys.exit(0)
+if "--queue" in sys.argv:
+    for q in (27, 28, 26):
+        b = Backend((0,)); b.upload_scene(t.pool.arrays())     # buffers are sized at the first render of a context
+        timing(b, t, RZ_QUEUE_LOG2=q)
+        b.close()
     sys.exit(0)
 if "--stages" in sys.argv:
     tg = rayz_b200.random_bouncing(1200, seed=42, glass_heavy=True)

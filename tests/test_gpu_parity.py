@@ -559,6 +559,31 @@ def test_staged_megakernel_many_small_passes(be, scene42, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_device_sized_sort_equals_full_sort(scene42, monkeypatch):
+    """Passes of >= 2^22 slots sort through the CUDA graph whose SWITCH node picks the cub sort covering the live entries
+    (rz_sort.cu); the order of the live entries — and so the image — must be the one the full-size sort gives."""
+    w, spp = 1200, 8
+    cam, h = cam_for(w)                                  # 6.5 M paths: one pass above the graph threshold
+    imgs, launches = {}, {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RZ_SORT_GRAPH", mode)
+        fresh = Backend((0,))
+        fresh.upload_scene(scene42)
+        imgs[mode], _, _ = fresh.render(cam, Backend.params(w, h, spp, 50, seed=9, variant="mega"))
+        launches[mode] = fresh.timing()["launches"]
+        again, _, _ = fresh.render(cam, Backend.params(w, h, spp, 50, seed=9, variant="mega"))   # the graph is reused
+        assert np.array_equal(imgs[mode], again)
+        fresh.close()
+    assert np.array_equal(imgs["0"], imgs["1"])
+    assert launches["1"] == launches["0"] + 4            # one selector kernel per sorted stage: the graph path really ran
+    monkeypatch.delenv("RZ_SORT_GRAPH")
+    ref = Backend((0,))
+    ref.upload_scene(scene42)
+    single, _, _ = ref.render(cam, Backend.params(w, h, spp, 50, seed=9, variant="mega_single"))
+    assert np.array_equal(imgs["1"], single)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_staged_cull_is_conservative_on_hostile_scenes(seed, monkeypatch):
     """Fast movers, a wide lens, the camera inside a sphere, spheres behind the camera, glass: the culled searches must
