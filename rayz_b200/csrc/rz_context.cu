@@ -133,6 +133,7 @@ struct Dev {
     uint32_t n_refnodes = 0;
     DBuf<uint32_t> m_kind, m_tex, m_method, t_kind, t_even, t_odd;
     DBuf<float> m_fuzz, m_ior;
+    DBuf<float4> m_rec;
     DBuf<float4> t_color;
     DBuf<double> t_inv_scale;
     DBuf<unsigned long long> accum;
@@ -173,7 +174,8 @@ struct RzContext {
     bool stats_valid = false;
     RzTiming timing{};
     int rays_per_thread = 2;
-    uint32_t chunk = 16;
+    uint32_t chunk = 16;          // samples per work unit of the persistent kernels (32 pixels x chunk paths)
+    uint32_t chunk_primary = 64;  // ... of the staged K1's primary kernel, which builds a culled list per unit: 16 -> 15.9 ms, 32 -> 14.6, 64 -> 14.5, 125 -> 15.3
     uint32_t flags = 0;
     float sb_lo[3] = {0, 0, 0}, sb_hi[3] = {0, 0, 0}, huge_radius = 3.0e38f;   // box of the non-huge spheres (staged K1 sort key / cull)
     // host copy of the sphere boxes: the reference-shaped BVH of K0 is built on first use
@@ -489,7 +491,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         if (D.own_stream) cudaStreamSynchronize(D.own_stream);
         D.brute.release(); D.bvhset.release(); D.bvh.release(); D.brute_to_bvh.release(); D.refnodes.release(); D.reforder.release();
         D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
-        D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
+        D.m_rec.release(); D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
         D.accum.release(); D.counter.release(); D.iota.release();
         for (int sd = 0; sd < 2; sd++) { rz_sort_graph_destroy(D.sort_graph[sd].g); D.sort_graph[sd].g = nullptr; }
@@ -518,7 +520,7 @@ extern "C" int rayz_cuda_set_stream(RzContext *ctx, void *cuda_stream) {
 extern "C" int rayz_cuda_set_tuning(RzContext *ctx, int rays_per_thread, uint32_t chunk) {
     if (!ctx) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_set_tuning: ctx is NULL");
     if (rays_per_thread == 1 || rays_per_thread == 2) ctx->rays_per_thread = rays_per_thread;
-    if (chunk >= 1 && chunk <= 4096) ctx->chunk = chunk;
+    if (chunk >= 1 && chunk <= 4096) { ctx->chunk = chunk; ctx->chunk_primary = chunk; }
     return RZ_OK;
 }
 
@@ -651,6 +653,16 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
         tc[i] = make_float4((float)sc->tex_color[3 * i], (float)sc->tex_color[3 * i + 1], (float)sc->tex_color[3 * i + 2], 0.f);
         ts[i] = sc->tex_kind[i] == RZ_TEX_CHECKER ? 1.0 / sc->tex_scale[i] : 0.0;
     }
+    // the same facts per material in one 32-byte record (RzMaterials::rec)
+    std::vector<float4> mrec(2 * (size_t)nm);
+    for (uint32_t i = 0; i < nm; i++) {
+        const bool solid = mk[i] != RZ_MAT_DIELECTRIC && nt > 0 && tk[mt[i]] != RZ_TEX_CHECKER;
+        const uint32_t bits = (mk[i] & 3u) | ((mm[i] & 3u) << 2) | (solid ? 16u : 0u);
+        float fb, ft;
+        memcpy(&fb, &bits, 4); memcpy(&ft, &mt[i], 4);
+        mrec[2 * (size_t)i] = make_float4(fb, mf[i], mi[i], ft);
+        mrec[2 * (size_t)i + 1] = solid ? tc[mt[i]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     DeviceGuard guard;
     for (Dev &D : ctx->devs) {
@@ -682,7 +694,7 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
                                   V.c64.p, V.v64.p, V.mat.p, V.orig.p, D.stream));
             RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
         }
-        if ((rc = D.m_kind.upload(mk, D.stream)) || (rc = D.m_tex.upload(mt, D.stream)) || (rc = D.m_method.upload(mm, D.stream)) ||
+        if ((rc = D.m_rec.upload(mrec, D.stream)) || (rc = D.m_kind.upload(mk, D.stream)) || (rc = D.m_tex.upload(mt, D.stream)) || (rc = D.m_method.upload(mm, D.stream)) ||
             (rc = D.m_fuzz.upload(mf, D.stream)) || (rc = D.m_ior.upload(mi, D.stream)) || (rc = D.t_kind.upload(tk, D.stream)) ||
             (rc = D.t_even.upload(te, D.stream)) || (rc = D.t_odd.upload(to, D.stream)) || (rc = D.t_color.upload(tc, D.stream)) ||
             (rc = D.t_inv_scale.upload(ts, D.stream)))
@@ -922,7 +934,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         RzPathArgs a;
         memset(&a, 0, sizeof a);
         a.set = (variant == RZ_VARIANT_BVH) ? D.bvhset.view() : D.brute.view();
-        a.mats.kind = D.m_kind.p; a.mats.fuzz = D.m_fuzz.p; a.mats.ior = D.m_ior.p; a.mats.tex = D.m_tex.p; a.mats.method = D.m_method.p;
+        a.mats.kind = D.m_kind.p; a.mats.fuzz = D.m_fuzz.p; a.mats.ior = D.m_ior.p; a.mats.tex = D.m_tex.p; a.mats.method = D.m_method.p; a.mats.rec = D.m_rec.p;
         a.texs.kind = D.t_kind.p; a.texs.color = D.t_color.p; a.texs.inv_scale = D.t_inv_scale.p; a.texs.even = D.t_even.p; a.texs.odd = D.t_odd.p;
         a.bvh = D.bvh.p; a.bvh_nodes = D.bvh_nodes;
         a.cam = cam_to_f32(cam);
@@ -960,9 +972,14 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                 } else {
                     // staged K1: primary kernel (tile-culled camera segments) -> queue -> [sort -> sorted-segment kernel (culled per
                     // unit) -> queue] x n_second -> persistent tail kernel (BVH, or brute force).  Passes are sized by the queues:
-                    // <= 2^27 entries of 64 B (8.6 GB per buffer; two buffers per side, two sides: ~40 GB with keys and indices
+                    // <= 2^28 entries of 64 B (17 GB per buffer; two buffers per side, two sides: 77 GB with keys and indices
                     // of the 180 GB of HBM).
                     const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
+                    if (!bvh_family) {   // the primary kernel's own work-unit size
+                        a.chunk = std::min(ctx->chunk_primary, p->spp);
+                        a.n_chunks = (p->spp + a.chunk - 1) / a.chunk;
+                        a.n_units = n_tiles * a.n_chunks;
+                    }
                     // The tail of the paths (whatever survives the sorted stages: incoherent, few) goes to the BVH kernel when the
                     // host-built tree is there — ~28 node + sphere tests per segment instead of every sphere of the set
                     // (config 2: 29.2 -> 11.1 ms behind four sorted stages).
@@ -1141,7 +1158,7 @@ extern "C" int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *p) {
         const uint32_t n_tiles = (rows * p->width + 31u) / 32u;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u)) || (rc = D.counter.alloc(16)) || (rc = D.stats.alloc(3))) return rc;
         if (p->variant == RZ_VARIANT_AUTO || p->variant == RZ_VARIANT_MEGA || (p->variant == RZ_VARIANT_BVH && (uint64_t)rows * p->width * p->spp >= (1ull << 26))) {
-            const uint32_t chunk = std::min(ctx->chunk, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
+            const uint32_t chunk = std::min(p->variant == RZ_VARIANT_BVH ? ctx->chunk : ctx->chunk_primary, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
             if ((uint64_t)n_tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
             QueuePlan qp;
             if ((rc = plan_and_alloc_queues(D, qp, n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0,

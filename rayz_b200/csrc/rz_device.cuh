@@ -47,6 +47,17 @@ struct RzMaterials {
     const float *ior;
     const uint32_t *tex;
     const uint32_t *method; // RZ_DIFFUSE_* (material.zig:67-71)
+    const float4 *rec;      // [2 * n_materials] the same facts flattened for the shading step, one 32-byte record per material:
+                            //   (bits: kind | method << 2 | root-texture-is-solid << 4, fuzz, ior, bits: texture) (r, g, b, 0 of a solid root)
+                            // one load after set.mat[k] instead of a chain of four dependent ones (kind -> tex -> tex kind -> colour)
+};
+
+// What the shading step needs to know about a material (decoded RzMaterials::rec).
+struct RzMatRec {
+    uint32_t kind, method, tex;
+    bool solid;      // the root texture is a solid colour: `color` is the attenuation, no texture walk
+    float fuzz, ior;
+    float3 color;
 };
 
 struct RzTextures {
@@ -304,14 +315,14 @@ RZ_HD float rz_reflectance(float cosv, float ri) {
 // Material.scatter (material.zig:167-176).  Returns false when the path is absorbed
 // (MetallicMaterial.scatter -> null, :116-117).  `ray` is replaced by the scattered ray,
 // `att` receives the attenuation.  u = four uniforms of this bounce's Philox block.
-RZ_HD bool rz_scatter(const RzMaterials &M, const RzTextures &T, uint32_t mat, uint32_t kind, const RzHit &h, int k,
-                      float4 u, RzRay &ray, float3 &att) {
+RZ_HD bool rz_scatter(const RzMatRec &M, const RzTextures &T, const RzHit &h, int k, float4 u, RzRay &ray, float3 &att) {
+    const uint32_t kind = M.kind;
     float3 nd;
     if (kind == 0u) {
         // DiffuseMaterial.scatter (:77-101).  HEMISPHERE (default, :74): direction of a uniform
         // ball sample flipped into the normal's hemisphere == uniform over the hemisphere,
         // no cosine weighting, attenuation = albedo.
-        const uint32_t method = M.method[mat];
+        const uint32_t method = M.method;
         const float3 s = rz_uniform_sphere(u.x, u.y);
         if (method == 2u) {
             nd = dot3(s, h.n) > 0.0f ? s : s * -1.0f;
@@ -322,20 +333,20 @@ RZ_HD bool rz_scatter(const RzMaterials &M, const RzTextures &T, uint32_t mat, u
             if (dot3(t, t) < 1e-12f) t = h.n;
             nd = normalize3(t);
         }
-        att = rz_texture(T, M.tex[mat], h.px, h.py, h.pz);
+        att = M.solid ? M.color : rz_texture(T, M.tex, h.px, h.py, h.pz);
     } else if (kind == 1u) {
         // MetallicMaterial.scatter (:108-131): unit mirror direction + min(fuzz,1) * unit vector
         const float dn = dot3(ray.d, h.n);
         float3 r = ray.d - h.n * (2.0f * dn);
-        const float fuzz = M.fuzz[mat];
+        const float fuzz = M.fuzz;
         if (fuzz > 0.0f) r = r + rz_uniform_sphere(u.x, u.y) * fminf(fuzz, 1.0f);
         if (!(dot3(r, h.n) > 0.0f)) return false;
         nd = normalize3(r);
-        att = rz_texture(T, M.tex[mat], h.px, h.py, h.pz);
+        att = M.solid ? M.color : rz_texture(T, M.tex, h.px, h.py, h.pz);
     } else {
         // DielectricMaterial.scatter (:137-159).  The reference leaves cos/sin/sqrt unclamped
         // (NaN on rounding, mapped to 0 at output by V3.sqrt); FP32 clamps to stay NaN-free.
-        const float ior = M.ior[mat];
+        const float ior = M.ior;
         const float eta = h.front ? 1.0f / ior : ior;
         const float cos_t = fminf(-dot3(ray.d, h.n), 1.0f);
         const float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));

@@ -256,13 +256,19 @@ __device__ __forceinline__ int rz_shade_segment(const RzPathArgs &a, RzRay &ray,
     const int k = bk & ~RZ_FAR_BIT;
     const RzHit h = rz_refine_hit(a.set, ray, k, (bk & RZ_FAR_BIT) != 0);
     const uint32_t mat = a.set.mat[k];
-    const uint32_t kind = a.mats.kind[mat];
+    const float4 m0 = __ldg(a.mats.rec + 2u * mat), m1 = __ldg(a.mats.rec + 2u * mat + 1u);
+    const uint32_t mbits = __float_as_uint(m0.x);
+    RzMatRec M;
+    M.kind = mbits & 3u; M.method = (mbits >> 2) & 3u; M.solid = ((mbits >> 4) & 1u) != 0u;
+    M.fuzz = m0.y; M.ior = m0.z; M.tex = __float_as_uint(m0.w);
+    M.color = f3(m1.x, m1.y, m1.z);
+    const uint32_t kind = M.kind;
     kind_out = kind < 3u ? kind : 0u;
     seg++;
     const uint4 rb = rz_philox(gpix, sample, seg, 0u, a.seed_lo, a.seed_hi);
     const float4 u = make_float4(rz_u01(rb.x >> 8), rz_u01(rb.y >> 8), rz_u01(rb.z >> 8), rz_u01(rb.w >> 8));
     float3 att;
-    if (!rz_scatter(a.mats, a.texs, mat, kind, h, k, u, ray, att)) return RZ_END_ABSORBED;  // black (renderer.zig:109,120)
+    if (!rz_scatter(M, a.texs, h, k, u, ray, att)) return RZ_END_ABSORBED;  // black (renderer.zig:109,120)
     thr = thr * att;
     if (seg >= a.max_depth) return RZ_END_DEPTH;  // depth == 0 => black (renderer.zig:104-105)
     return RZ_CONT;

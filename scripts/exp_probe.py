@@ -46,6 +46,13 @@ if "--cells" in sys.argv:
     for ns in (1, 2, 3, 4):
         tests_per_segment(be, t, RZ_SECOND_STAGES=ns)
     sys.exit(0)
+if "--chunk" in sys.argv:
+    for ch in (16, 32, 64, 125, 250):
+        b = Backend((0,)); b.upload_scene(t.pool.arrays()); b.set_tuning(0, ch)
+        print("chunk", ch, end=" ")
+        timing(b, t)
+        b.close()
+    sys.exit(0)
 if "--queue" in sys.argv:
     for q in (27, 28, 26):
         b = Backend((0,)); b.upload_scene(t.pool.arrays())     # buffers are sized at the first render of a context

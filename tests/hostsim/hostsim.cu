@@ -104,7 +104,12 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
                         const uint4 rb = rz_philox(gpix, s, seg, 0u, k0, k1);
                         const float4 u = make_float4(rz_u01(rb.x >> 8), rz_u01(rb.y >> 8), rz_u01(rb.z >> 8), rz_u01(rb.w >> 8));
                         float3 att;
-                        if (!rz_scatter(M, T, mat, kind, hit, k, u, ray, att)) { ct[8]++; break; }
+                        // decoded from the SoA arrays, and always through the texture walk: an independent check of the
+                        // flattened per-material records (and their solid-colour shortcut) the device kernels read
+                        RzMatRec R;
+                        R.kind = kind; R.method = M.method[mat]; R.tex = M.tex[mat]; R.solid = false;
+                        R.fuzz = M.fuzz[mat]; R.ior = M.ior[mat]; R.color = f3(0.f, 0.f, 0.f);
+                        if (!rz_scatter(R, T, hit, k, u, ray, att)) { ct[8]++; break; }
                         thr = thr * att;
                         if (seg >= max_depth) { ct[9]++; break; }
                     }
