@@ -1052,7 +1052,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         RzPathArgs a1 = a;
                         a1.q_out = D.q1[side].p; a1.q_out_count = ctr + 3; a1.q_out_keys = second_stage ? D.keys[side].p : nullptr;
                         a1.unit_base = u0; a1.n_units = pass_units; a1.unit_counter = ctr;
-                        // the device-sized sort may cover up to a sixteenth of the buffer more than the live entries: clear all of it
+                        // the device-sized sort may cover a bucket (1/32 of the buffer) more than the live entries: clear all of it
                         RzSortGraph *sg = second_stage ? sort_graph_for(D, side, (uint32_t)cap) : nullptr;
                         const size_t key_slots = sg ? (size_t)cap : (size_t)pass_paths;
                         if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, key_slots * sizeof(unsigned short), st));

@@ -387,8 +387,11 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         // the origin lies in its cell (open-ended for the outermost cells, where out-of-box origins are clamped), the octant
         // is exact, and the reach is below the upper edge of its class (the top class is unbounded).
         const int nbx = (int)a.sb_cell_bits[0], nby = (int)a.sb_cell_bits[1], nbz = (int)a.sb_cell_bits[2];
+        uint32_t prev_key = 0xffffffffu;   // the keys are sorted: a lane mostly meets the key it has just decoded
         for (uint32_t i = lane; i < ne; i += 32u) {
             const uint32_t key = a.q_in_keys[e0 + i];
+            if (key == prev_key) continue;
+            prev_key = key;
             const int reach = (int)(key & 15u);
             const uint32_t oct = (key >> 4) & 7u;
             const uint32_t cell = key >> 7;

@@ -33,10 +33,10 @@ extern "C" cudaError_t rz_iota(uint32_t *p, uint32_t n, cudaStream_t stream) {
 // The number of live entries of a queue is only known on the device, and cub takes its item count from the host.  Sorting
 // every slot of a pass costs 1.0 ms per sort at 2^27-slot passes although 66 % / 40 % / 25 % of the slots are live after the
 // first three segments.  So the sort is a CUDA graph with a SWITCH conditional node: a one-thread kernel reads the live count
-// and selects the body whose (captured) cub sort covers the next sixteenth of the buffer above it.  No host round trip, and the
+// and selects the body whose (captured) cub sort covers the next 1/RZ_SORT_BUCKETS of the buffer above it.  No host round trip, and the
 // pass loop stays one uninterrupted stream of launches.  Slots between the count and the sorted size carry the unused key
 // 0xffff (the caller clears the whole buffer), so the order of the live entries is the one a full sort gives.
-#define RZ_SORT_BUCKETS 16
+#define RZ_SORT_BUCKETS 32
 
 struct RzSortGraph {
     cudaGraph_t graph = nullptr;
