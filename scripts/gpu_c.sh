@@ -13,5 +13,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-fil
 $CMD > gpurun_out/e_ncu_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:rz_bvh_kernel -s 2 -c 1 -o gpurun_out/e_prof_tail $CMD > gpurun_out/e_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rz_primary_kernel -s 2 -c 1 -o gpurun_out/e_prof_primary $CMD > gpurun_out/e_ncu_full2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rz_second_kernel -s 6 -c 1 -o gpurun_out/e_prof_second $CMD > gpurun_out/e_ncu_full3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rz_second_kernel -s 10 -c 1 -o gpurun_out/e_prof_second $CMD > gpurun_out/e_ncu_full3.log 2>&1
 tail -n 3 gpurun_out/e_pytest.log gpurun_out/e_host_1gpu.log; cut -c1-300 gpurun_out/e_bench_n1.json
