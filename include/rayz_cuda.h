@@ -203,7 +203,7 @@ int rayz_cuda_render(RzContext *ctx, const RzCamera *cam, const RzRenderParams *
                      float *out_linear_rgba, uint8_t *out_rgb8, uint64_t *out_paths);
 
 /* Optional: allocate everything a render with these parameters needs (accumulators, result buffers, the
- * staged K1's queues: up to ~40 GB) ahead of time, like Image.initEmpty in Tracer.init (renderer.zig:29-64),
+ * staged K1's queues: up to 77 GB) ahead of time, like Image.initEmpty in Tracer.init (renderer.zig:29-64),
  * so that the first rayz_cuda_render does not pay for it. */
 int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *params);
 
