@@ -113,3 +113,23 @@ def test_upload_scene_validation_without_gpu():
     assert b"NULL" in lib.rayz_cuda_last_error()
     assert lib.rayz_cuda_render(None, None, None, None, None, None) == -1
     assert lib.rayz_cuda_primary_ids(None, None, 1, 1, 1, None) == -1
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract is ONE JSON line on stdout; libraries that write to fd 1 (NCCL's version banner) must not leak
+    into it.  The reference arm runs on the CPU, so the contract can be checked here on a tiny sample."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, runpy, sys; os.write(1, b''); sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', "
+            "'--ref-spp', '1']; import bench; bench._claim_stdout(); os.write(1, b'library noise on fd 1\\n'); bench.main()")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mpaths/s" and d["unit"] == "Mpaths/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "library noise" in r.stderr
