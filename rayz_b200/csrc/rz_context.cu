@@ -1003,28 +1003,9 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const double lv = std::sqrt(cam->defocus_v[0] * cam->defocus_v[0] + cam->defocus_v[1] * cam->defocus_v[1] + cam->defocus_v[2] * cam->defocus_v[2]);
                     a.lens_radius = cam->defocus ? (float)(std::max(lu, lv) * 1.001) : 0.f;
                     a.queue_cap = (uint32_t)cap;
-                    float ext = 0.f, e3[3];
-                    uint32_t bits[3] = {0, 0, 0};
-                    for (int ax = 0; ax < 3; ax++) {
-                        a.sb_lo[ax] = ctx->sb_lo[ax]; a.sb_hi[ax] = ctx->sb_hi[ax];
-                        e3[ax] = ctx->sb_hi[ax] - ctx->sb_lo[ax];
-                        if (!(e3[ax] > 0.f) || !(e3[ax] < 1.0e30f)) e3[ax] = 0.f;
-                        ext = std::max(ext, e3[ax]);
-                    }
                     const char *cb_env = getenv("RZ_CELL_BITS");   // tuning experiment (the key has room for 9)
-                    const int cell_bits = cb_env ? std::min(9, std::max(0, atoi(cb_env))) : 9;
-                    for (int b = 0; b < cell_bits; b++) {   // each key bit halves the cells of the axis whose cells are currently largest
-                        int best = 0;
-                        for (int ax = 1; ax < 3; ax++)
-                            if (e3[ax] / (float)(1u << bits[ax]) > e3[best] / (float)(1u << bits[best])) best = ax;
-                        bits[best]++;
-                    }
-                    for (int ax = 0; ax < 3; ax++) {
-                        a.sb_cell_bits[ax] = bits[ax];
-                        a.sb_inv_cell[ax] = e3[ax] > 0.f ? (float)(1u << bits[ax]) / e3[ax] : 0.f;
-                    }
+                    rz_key_grid(a, ctx->sb_lo, ctx->sb_hi, cb_env ? std::min(9, std::max(0, atoi(cb_env))) : 9);
                     a.huge_radius = ctx->huge_radius;
-                    a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;
                     while (D.pass_ev.size() < 3 * (size_t)n_pass) {
                         cudaEvent_t e = nullptr;
                         RZ_CUDA(cudaEventCreate(&e));

@@ -376,3 +376,88 @@ RZ_HD void rz_local_to_global(uint32_t lp, uint32_t width, uint32_t shard_index,
     const uint32_t within = lr - lb * band_rows;
     j = (lb * shard_count + shard_index) * band_rows + within;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Sort key of the staged K1's queues, and its decoder.  Host + device: tests/hostsim checks on the CPU
+// that the bounds rz_key_bounds derives from a key contain every ray rz_sort_key maps to that key.
+// ---------------------------------------------------------------------------------------------
+// When does a ray leave the box around all non-huge spheres for good?  (<= 0: it never enters it.)
+RZ_HD float rz_box_exit(const RzPathArgs &a, const RzRay &ray) {
+    float t = 3.0e38f;
+    const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        if (d[ax] > 0.f) t = fminf(t, (a.sb_hi[ax] - o[ax]) / d[ax]);
+        else if (d[ax] < 0.f) t = fminf(t, (a.sb_lo[ax] - o[ax]) / d[ax]);
+        else if (o[ax] < a.sb_lo[ax] || o[ax] > a.sb_hi[ax]) t = 0.f;
+    }
+    return t;
+}
+
+RZ_HD int rz_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Host side: the key's grid over the box [lo, hi] around the non-huge spheres.  `cell_bits` key bits (<= 9) are shared out
+// over the axes — each bit halves the cells of the axis whose cells are currently largest, so cells come out as cubic as
+// the extents allow; reach classes are measured in units of 1/32 of the longest extent.
+inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3], int cell_bits) {
+    float ext = 0.f, e3[3];
+    uint32_t bits[3] = {0, 0, 0};
+    for (int ax = 0; ax < 3; ax++) {
+        a.sb_lo[ax] = lo[ax]; a.sb_hi[ax] = hi[ax];
+        e3[ax] = hi[ax] - lo[ax];
+        if (!(e3[ax] > 0.f) || !(e3[ax] < 1.0e30f)) e3[ax] = 0.f;
+        ext = e3[ax] > ext ? e3[ax] : ext;
+    }
+    for (int b = 0; b < cell_bits; b++) {
+        int best = 0;
+        for (int ax = 1; ax < 3; ax++)
+            if (e3[ax] / (float)(1u << bits[ax]) > e3[best] / (float)(1u << bits[best])) best = ax;
+        bits[best]++;
+    }
+    for (int ax = 0; ax < 3; ax++) {
+        a.sb_cell_bits[ax] = bits[ax];
+        a.sb_inv_cell[ax] = e3[ax] > 0.f ? (float)(1u << bits[ax]) / e3[ax] : 0.f;
+    }
+    a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;
+}
+
+// Sort key of a scattered ray: [origin cell 9 bits][direction octant 3 bits][reach class 4 bits] = 16 bits.  Rays with
+// equal keys start in the same cell of the sphere box (the 9 bits are shared out over the axes by extent), head into the same
+// octant and stay inside the sphere box for a similar distance — which is what the sorted-segment kernel's per-unit cull feeds on.
+RZ_HD uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
+    const int nx = (1 << a.sb_cell_bits[0]) - 1, ny = (1 << a.sb_cell_bits[1]) - 1, nz = (1 << a.sb_cell_bits[2]) - 1;
+    const int cx = rz_clampi((int)((ray.o.x - a.sb_lo[0]) * a.sb_inv_cell[0]), 0, nx);
+    const int cy = rz_clampi((int)((ray.o.y - a.sb_lo[1]) * a.sb_inv_cell[1]), 0, ny);
+    const int cz = rz_clampi((int)((ray.o.z - a.sb_lo[2]) * a.sb_inv_cell[2]), 0, nz);
+    const uint32_t cell = (uint32_t)(((cx << a.sb_cell_bits[1]) | cy) << a.sb_cell_bits[2]) | (uint32_t)cz;   // 9 bits
+    const uint32_t oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
+    const float te = rz_box_exit(a, ray);
+    // 16 reach classes, two per octave of te / reach_unit from 1/4 up
+#ifdef __CUDA_ARCH__
+    const float l2 = __log2f(fmaxf(te / a.reach_unit, 0.25f));
+#else
+    const float l2 = log2f(fmaxf(te / a.reach_unit, 0.25f));
+#endif
+    const int reach = rz_clampi((int)(2.0f * l2 + 4.0f), 0, 15);
+    return (cell << 7) | (oct << 4) | (uint32_t)reach;
+}
+
+// What a key says about its rays, conservatively: the origin lies in [lo, hi] (the key's cell, open-ended for the outermost
+// cells, where out-of-box origins are clamped), the direction's signs are `oct` (bit set <=> component < 0), and the ray
+// leaves the sphere box before T (the upper edge of the reach class; the top class is unbounded).
+RZ_HD void rz_key_bounds(const RzPathArgs &a, uint32_t key, float (&lo)[3], float (&hi)[3], uint32_t &oct, float &T) {
+    const int nbx = (int)a.sb_cell_bits[0], nby = (int)a.sb_cell_bits[1], nbz = (int)a.sb_cell_bits[2];
+    const int reach = (int)(key & 15u);
+    oct = (key >> 4) & 7u;
+    const uint32_t cell = key >> 7;
+    const int c3[3] = {(int)(cell >> (nby + nbz)), (int)((cell >> nbz) & ((1u << nby) - 1u)), (int)(cell & ((1u << nbz) - 1u))};
+    const int n3[3] = {(1 << nbx) - 1, (1 << nby) - 1, (1 << nbz) - 1};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        const float w = a.sb_inv_cell[ax] > 0.f ? 1.0f / a.sb_inv_cell[ax] : 3.0e38f;   // cell width
+        lo[ax] = c3[ax] <= 0 ? -3.0e38f : fmaf((float)c3[ax], w, a.sb_lo[ax]) - 1e-4f * w;
+        hi[ax] = c3[ax] >= n3[ax] ? 3.0e38f : fmaf((float)(c3[ax] + 1), w, a.sb_lo[ax]) + 1e-4f * w;
+    }
+    // class c holds te / reach_unit in [2^((c-4)/2), 2^((c-3)/2)); class 15 is open-ended
+    T = reach >= 15 ? 3.0e38f : a.reach_unit * exp2f(0.5f * (float)(reach - 3)) * 1.0001f;
+}

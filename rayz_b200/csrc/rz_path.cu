@@ -386,28 +386,21 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         // 512 x 32 B through the index that was 18 % of this kernel's warp-state samples.  The key gives conservative bounds:
         // the origin lies in its cell (open-ended for the outermost cells, where out-of-box origins are clamped), the octant
         // is exact, and the reach is below the upper edge of its class (the top class is unbounded).
-        const int nbx = (int)a.sb_cell_bits[0], nby = (int)a.sb_cell_bits[1], nbz = (int)a.sb_cell_bits[2];
         uint32_t prev_key = 0xffffffffu;   // the keys are sorted: a lane mostly meets the key it has just decoded
         for (uint32_t i = lane; i < ne; i += 32u) {
             const uint32_t key = a.q_in_keys[e0 + i];
             if (key == prev_key) continue;
             prev_key = key;
-            const int reach = (int)(key & 15u);
-            const uint32_t oct = (key >> 4) & 7u;
-            const uint32_t cell = key >> 7;
-            const int c3[3] = {(int)(cell >> (nby + nbz)), (int)((cell >> nbz) & ((1u << nby) - 1u)), (int)(cell & ((1u << nbz) - 1u))};
-            const int n3[3] = {(1 << nbx) - 1, (1 << nby) - 1, (1 << nbz) - 1};
+            float lo[3], hi[3], Tk;
+            uint32_t oct;
+            rz_key_bounds(a, key, lo, hi, oct, Tk);
 #pragma unroll
             for (int ax = 0; ax < 3; ax++) {
-                const float w = a.sb_inv_cell[ax] > 0.f ? 1.0f / a.sb_inv_cell[ax] : 3.0e38f;   // cell width
-                const float lo = c3[ax] <= 0 ? -3.0e38f : fmaf((float)c3[ax], w, a.sb_lo[ax]) - 1e-4f * w;
-                const float hi = c3[ax] >= n3[ax] ? 3.0e38f : fmaf((float)(c3[ax] + 1), w, a.sb_lo[ax]) + 1e-4f * w;
-                blo[ax] = fminf(blo[ax], lo);
-                bhi[ax] = fmaxf(bhi[ax], hi);
+                blo[ax] = fminf(blo[ax], lo[ax]);
+                bhi[ax] = fmaxf(bhi[ax], hi[ax]);
                 if ((oct >> ax) & 1u) all_pos &= ~(1u << ax); else all_neg &= ~(1u << ax);   // key bit set <=> d < 0
             }
-            // class c holds te / reach_unit in [2^((c-4)/2), 2^((c-3)/2)); class 15 is open-ended
-            T = fmaxf(T, reach >= 15 ? 3.0e38f : a.reach_unit * exp2f(0.5f * (float)(reach - 3)) * 1.0001f);
+            T = fmaxf(T, Tk);
         }
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll

@@ -275,35 +275,7 @@ __device__ __forceinline__ int rz_shade_segment(const RzPathArgs &a, RzRay &ray,
 }
 
 // ------------------------------------------------------------------------------ queue helpers
-// When does a ray leave the box around all non-huge spheres for good?  (<= 0: it never enters it.)
-__device__ __forceinline__ float rz_box_exit(const RzPathArgs &a, const RzRay &ray) {
-    float t = 3.0e38f;
-    const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
-#pragma unroll
-    for (int ax = 0; ax < 3; ax++) {
-        if (d[ax] > 0.f) t = fminf(t, (a.sb_hi[ax] - o[ax]) / d[ax]);
-        else if (d[ax] < 0.f) t = fminf(t, (a.sb_lo[ax] - o[ax]) / d[ax]);
-        else if (o[ax] < a.sb_lo[ax] || o[ax] > a.sb_hi[ax]) t = 0.f;
-    }
-    return t;
-}
-
-// Sort key of a scattered ray: [origin cell 9 bits][direction octant 3 bits][reach class 4 bits] = 16 bits.  Rays with
-// equal keys start in the same cell of the sphere box (the 9 bits are shared out over the axes by extent), head into the same octant and stay inside the
-// sphere box for a similar distance — which is what the second-segment kernel's per-unit cull feeds on.
-__device__ __forceinline__ uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
-    const int nx = (1 << a.sb_cell_bits[0]) - 1, ny = (1 << a.sb_cell_bits[1]) - 1, nz = (1 << a.sb_cell_bits[2]) - 1;
-    const int cx = min(nx, max(0, (int)((ray.o.x - a.sb_lo[0]) * a.sb_inv_cell[0])));
-    const int cy = min(ny, max(0, (int)((ray.o.y - a.sb_lo[1]) * a.sb_inv_cell[1])));
-    const int cz = min(nz, max(0, (int)((ray.o.z - a.sb_lo[2]) * a.sb_inv_cell[2])));
-    const uint32_t cell = (uint32_t)(((cx << a.sb_cell_bits[1]) | cy) << a.sb_cell_bits[2]) | (uint32_t)cz;   // 9 bits
-    const uint32_t oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
-    const float te = rz_box_exit(a, ray);
-    // 16 reach classes, two per octave of te / reach_unit from 1/4 up
-    const int reach = min(15, max(0, (int)(2.0f * __log2f(fmaxf(te / a.reach_unit, 0.25f)) + 4.0f)));
-    return (cell << 7) | (oct << 4) | (uint32_t)reach;
-}
-
+// (the sort key and its decoder, rz_sort_key / rz_key_bounds, live in rz_device.cuh: host + device, property-tested on the CPU)
 // Ballot-compacted append of the warp's surviving paths (one atomic per warp).
 __device__ __forceinline__ void rz_queue_push(const RzPathArgs &a, bool cont, unsigned lane, unsigned lt_mask, const RzRay &ray, float3 thr,
                                               uint32_t seg, uint32_t lp, uint32_t gpix, uint32_t sample) {

@@ -125,3 +125,51 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
     if (counters) { for (int i = 0; i < 10; i++) { counters[i] = 0; for (auto &c : cnt) counters[i] += c[i]; } counters[2] = counters[1] * n; }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Property check of the staged K1's sort key (rz_device.cuh: rz_key_grid / rz_sort_key / rz_key_bounds): for random rays
+// in and around the sphere box, the bounds decoded from a ray's key must contain the ray — origin inside the key's cell
+// box, direction signs equal to the key's octant, exit time from the sphere box below the key's reach bound.  The
+// sorted-stage kernel culls spheres from exactly these bounds, so a violation here would be a missed hit there.
+// Returns the number of violations; counts[0..15] = rays per reach class, counts[16] = distinct keys seen.
+// ---------------------------------------------------------------------------------------------
+extern "C" uint64_t hostsim_key_check(const float *lo, const float *hi, int cell_bits, uint64_t n_rays, uint64_t seed, uint64_t *counts) {
+    RzPathArgs a;
+    memset(&a, 0, sizeof a);
+    const float l3[3] = {lo[0], lo[1], lo[2]}, h3[3] = {hi[0], hi[1], hi[2]};
+    rz_key_grid(a, l3, h3, cell_bits);
+    std::vector<unsigned char> seen(65536, 0);
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
+    auto u01 = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (float)((s >> 40) * (1.0 / 16777216.0)); };
+    for (int i = 0; i < 17; i++) counts[i] = 0;
+    for (uint64_t r = 0; r < n_rays; r++) {
+        RzRay ray;
+        float o[3], d[3];
+        for (int ax = 0; ax < 3; ax++) {
+            const float e = h3[ax] - l3[ax];
+            o[ax] = l3[ax] + e * (1.6f * u01() - 0.3f);            // 30 % of the extent beyond the box on either side
+            if (u01() < 0.02f) o[ax] = u01() < 0.5f ? l3[ax] : h3[ax];   // exactly on a face
+            d[ax] = 2.0f * u01() - 1.0f;
+            if (u01() < 0.03f) d[ax] = u01() < 0.5f ? 0.0f : -0.0f;     // axis-parallel rays
+            if (u01() < 0.03f) d[ax] *= 1e-6f;                          // grazing
+        }
+        const float len = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (!(len > 1e-12f)) { d[0] = 0.f; d[1] = 1.f; d[2] = 0.f; } else { d[0] /= len; d[1] /= len; d[2] /= len; }
+        ray.o = f3(o[0], o[1], o[2]); ray.d = f3(d[0], d[1], d[2]); ray.time = 0.f; ray.self_k = -1;
+        const uint32_t key = rz_sort_key(a, ray);
+        if (key > 0xffffu) { bad++; continue; }
+        float blo[3], bhi[3], T;
+        uint32_t oct;
+        rz_key_bounds(a, key, blo, bhi, oct, T);
+        bool ok = true;
+        for (int ax = 0; ax < 3; ax++) {
+            ok = ok && o[ax] >= blo[ax] && o[ax] <= bhi[ax];
+            ok = ok && (((oct >> ax) & 1u) != 0u) == (d[ax] < 0.f);
+        }
+        ok = ok && rz_box_exit(a, ray) <= T;
+        if (!ok) bad++;
+        counts[key & 15u]++;
+        if (!seen[key]) { seen[key] = 1; counts[16]++; }
+    }
+    return bad;
+}

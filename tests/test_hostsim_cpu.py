@@ -57,3 +57,27 @@ def test_fp32_depth_semantics(hostsim):
     assert (out == 0).all() and cnt[1] == 0 and cnt[9] == 32 * 18 * 2       # renderer.zig:104-105
     out, cnt = run(hostsim, arrays, t.camera.rz, 32, 18, 2, depth=1)
     assert cnt[1] == 32 * 18 * 2                                            # one closest-hit query per path
+
+
+@pytest.mark.parametrize("lo,hi,bits", [
+    ((-11.6, -0.1, -11.6), (11.6, 2.1, 11.6), 9),      # the RTOW scene's box around the non-huge spheres: a thin slab
+    ((-3.0, -3.0, -3.0), (3.0, 3.0, 3.0), 9),          # a cube: 3 bits per axis
+    ((0.0, 0.0, 0.0), (100.0, 0.5, 1.0), 6),           # one long axis takes every bit
+    ((-1.0, 2.0, -1.0), (1.0, 2.0, 1.0), 9),           # a degenerate (flat) box
+    ((-5.0, -5.0, -5.0), (5.0, 5.0, 5.0), 0),          # no cell bits at all
+])
+def test_sort_key_bounds_contain_their_rays(hostsim, lo, hi, bits):
+    """Staged K1: the sorted-stage kernel culls the sphere set from bounds decoded from the queue's 16-bit sort keys.
+    For 2 M random rays in and around the box (faces, axis-parallel and grazing directions included) the decoded bounds
+    must contain the ray that produced the key: origin cell, direction octant, reach.  (rz_device.cuh, compiled as host code.)"""
+    hostsim.hostsim_key_check.restype = C.c_uint64
+    hostsim.hostsim_key_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+    l = np.array(lo, dtype=np.float32)
+    h = np.array(hi, dtype=np.float32)
+    counts = np.zeros(17, dtype=np.uint64)
+    n = 2_000_000
+    bad = hostsim.hostsim_key_check(l.ctypes.data, h.ctypes.data, bits, n, 7, counts.ctypes.data)
+    assert bad == 0, f"{bad} of {n} rays fall outside the bounds of their own key"
+    assert int(counts[:16].sum()) == n
+    assert int((counts[:16] > 0).sum()) >= 6            # the reach classes are really exercised
+    assert int(counts[16]) > (1 << bits) * 4            # and so are cells x octants
