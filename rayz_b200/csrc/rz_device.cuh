@@ -461,3 +461,111 @@ RZ_HD void rz_key_bounds(const RzPathArgs &a, uint32_t key, float (&lo)[3], floa
     // class c holds te / reach_unit in [2^((c-4)/2), 2^((c-3)/2)); class 15 is open-ended
     T = reach >= 15 ? 3.0e38f : a.reach_unit * exp2f(0.5f * (float)(reach - 3)) * 1.0001f;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The two culls of the staged K1, as host + device functions (tests/hostsim checks on the CPU that neither ever drops a
+// sphere one of its rays hits).  A sphere enters as its packed operands: centre at shutter time 0, velocity, w = -r^2.
+// ---------------------------------------------------------------------------------------------
+// Primary kernel: cone around the camera rays of a 32-pixel tile.
+struct RzTileCone {
+    float3 apex, ax;     // lens centre; unit axis = normalised sum of the tile's unit pixel directions
+    float tan_t;         // tangent of the half-angle (to the farthest pixel corner), with margin
+    float inv_f;         // 1 / (0.9 focus distance): growth of the thin-lens blur beyond the focus plane
+    float lens_radius;
+    bool cull;           // false: very wide tiles (tiny images) test everything
+};
+
+// direction from the lens centre to the centre of pixel (pi, pj) on the focus plane (not normalised)
+RZ_HD float3 rz_tile_pixel_dir(const RzCamF32 &cam, uint32_t pi, uint32_t pj) {
+    return cam.px_origin + cam.px_du * (float)pi + cam.px_dv * (float)pj - cam.look_from;
+}
+
+// smallest cosine between the axis and the four corners of the pixel whose centre direction is pc
+RZ_HD float rz_tile_corner_cos(const RzCamF32 &cam, float3 pc, float3 ax) {
+    float cmin = 1.0f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float3 q = pc + cam.px_du * ((c & 1) ? 0.5f : -0.5f) + cam.px_dv * ((c & 2) ? 0.5f : -0.5f);
+        cmin = fminf(cmin, dot3(ax, normalize3(q)));
+    }
+    return cmin;
+}
+
+// ax_sum: sum of the valid pixels' unit directions; normalises it and returns false if the tile has no direction
+RZ_HD bool rz_tile_axis(float3 &ax_sum) {
+    const float al = dot3(ax_sum, ax_sum);
+    ax_sum = al > 1e-12f ? ax_sum * rz_rsqrt(al) : f3(0.f, 0.f, 1.f);
+    return al > 1e-12f;
+}
+
+RZ_HD RzTileCone rz_tile_cone(const RzCamF32 &cam, float3 ax, bool has_axis, float cmin, float focus_dist, float lens_radius) {
+    RzTileCone C;
+    C.apex = cam.look_from;
+    C.ax = ax;
+    C.cull = cmin > 0.2f && has_axis;
+    C.tan_t = C.cull ? sqrtf(fmaxf(0.f, 1.f - cmin * cmin)) / cmin * 1.05f + 1e-4f : 0.f;
+    C.inv_f = 1.0f / fmaxf(0.9f * focus_dist, 1e-6f);
+    C.lens_radius = lens_radius;
+    return C;
+}
+
+RZ_HD bool rz_tile_keep(const RzTileCone &C, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
+    if (!(w < 0.f)) return false;                         // padding entry (-r^2 = +1)
+    if (!C.cull) return true;
+    const float vl = sqrtf(vx * vx + vy * vy + vz * vz);
+    const float re = sqrtf(-w) + 0.5f * vl;               // sphere swept over time in [0,1): midpoint + half the travel
+    const float3 vv = f3(fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)) - C.apex;
+    const float h = dot3(vv, C.ax), d2 = dot3(vv, vv);
+    const float smax = fmaxf(h + re, 0.f);                // farthest along-axis extent of the sphere
+    // cone radius there + thin-lens blur (grows beyond the focus plane) + margins for FP32 and the 1.05 above
+    const float rad = re * 1.02f + 0.02f + C.lens_radius * (1.f + smax * C.inv_f) + smax * C.tan_t;
+    if (d2 <= rad * rad) return true;                     // apex inside / next to the sphere
+    if (h + re < 0.f) return false;                       // entirely behind the camera
+    return fmaxf(d2 - h * h, 0.f) <= rad * rad;
+}
+
+// Sorted-stage kernel: what the rays of one unit have in common, merged from the bounds of their keys (rz_key_bounds).
+struct RzUnitBounds {
+    float lo[3], hi[3];          // box of the origins
+    float T;                     // longest stay inside the sphere box
+    unsigned all_pos, all_neg;   // bit ax set: every ray has d[ax] >= 0 / d[ax] < 0
+};
+
+RZ_HD void rz_unit_bounds_init(RzUnitBounds &U) {
+    for (int ax = 0; ax < 3; ax++) { U.lo[ax] = 3.0e38f; U.hi[ax] = -3.0e38f; }
+    U.T = 0.f; U.all_pos = 7u; U.all_neg = 7u;
+}
+
+RZ_HD void rz_unit_bounds_add_key(RzUnitBounds &U, const RzPathArgs &a, uint32_t key) {
+    float lo[3], hi[3], Tk;
+    uint32_t oct;
+    rz_key_bounds(a, key, lo, hi, oct, Tk);
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        U.lo[ax] = fminf(U.lo[ax], lo[ax]);
+        U.hi[ax] = fmaxf(U.hi[ax], hi[ax]);
+        if ((oct >> ax) & 1u) U.all_pos &= ~(1u << ax); else U.all_neg &= ~(1u << ax);   // key bit set <=> d < 0
+    }
+    U.T = fmaxf(U.T, Tk);
+}
+
+// after the merge over the unit: +inf-safe, with margin for the FP32 evaluation of the exits
+RZ_HD void rz_unit_bounds_finish(RzUnitBounds &U) { U.T = fminf(U.T, 1.0e30f) * 1.001f; }
+
+RZ_HD bool rz_unit_keep(const RzUnitBounds &U, float huge_radius, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
+    if (!(w < 0.f)) return false;                                  // padding entry
+    const float r = sqrtf(-w);
+    if (r > huge_radius) return true;                              // outside the sphere box: never culled
+    const float re = (r + 0.5f * sqrtf(vx * vx + vy * vy + vz * vz)) * 1.02f + 0.02f;   // swept over the shutter + margin
+    const float c[3] = {fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)};
+    float d2 = 0.f;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        if (((U.all_pos >> ax) & 1u) && c[ax] + re < U.lo[ax]) return false;   // every ray moves up this axis: sphere is behind
+        if (((U.all_neg >> ax) & 1u) && c[ax] - re > U.hi[ax]) return false;
+        const float dd = fmaxf(0.f, fmaxf(U.lo[ax] - c[ax], c[ax] - U.hi[ax]));
+        d2 = fmaf(dd, dd, d2);
+    }
+    const float rad = U.T + re;
+    return d2 <= rad * rad;                                        // within reach of some ray of the unit
+}

@@ -214,7 +214,6 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const float3 apex = a.cam.look_from;
     unsigned long long c_paths = 0, c_segs = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
 
     while (true) {
@@ -231,38 +230,17 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
         const uint32_t gpix = pj * a.width + pi;
 
         // ---- cone around the tile's camera rays: axis = mean pixel direction, half-angle from the pixel corners
-        const float3 pc = a.cam.px_origin + a.cam.px_du * (float)pi + a.cam.px_dv * (float)pj - apex;
+        const float3 pc = rz_tile_pixel_dir(a.cam, pi, pj);
         float3 ax = valid ? normalize3(pc) : f3(0.f, 0.f, 0.f);
         for (int o = 16; o > 0; o >>= 1) {
             ax.x += __shfl_xor_sync(0xffffffffu, ax.x, o); ax.y += __shfl_xor_sync(0xffffffffu, ax.y, o); ax.z += __shfl_xor_sync(0xffffffffu, ax.z, o);
         }
-        const float al = dot3(ax, ax);
-        ax = al > 1e-12f ? ax * rz_rsqrt(al) : f3(0.f, 0.f, 1.f);
-        float cmin = 1.0f;
-        if (valid) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const float3 q = pc + a.cam.px_du * ((c & 1) ? 0.5f : -0.5f) + a.cam.px_dv * ((c & 2) ? 0.5f : -0.5f);
-                cmin = fminf(cmin, dot3(ax, normalize3(q)));
-            }
-        }
+        const bool has_axis = rz_tile_axis(ax);
+        float cmin = valid ? rz_tile_corner_cos(a.cam, pc, ax) : 1.0f;
         for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
-        const bool cull = cmin > 0.2f && al > 1e-12f;   // very wide tiles (tiny images): test everything
-        const float tan_t = cull ? sqrtf(fmaxf(0.f, 1.f - cmin * cmin)) / cmin * 1.05f + 1e-4f : 0.f;
-        const float inv_f = 1.0f / fmaxf(0.9f * a.focus_dist, 1e-6f);
+        const RzTileCone cone = rz_tile_cone(a.cam, ax, has_axis, cmin, a.focus_dist, a.lens_radius);
         auto keep = [&](float cx, float cy, float cz, float vx, float vy, float vz, float w) -> bool {
-            if (!(w < 0.f)) return false;                         // padding entry (-r^2 = +1)
-            if (!cull) return true;
-            const float vl = sqrtf(vx * vx + vy * vy + vz * vz);
-            const float re = sqrtf(-w) + 0.5f * vl;               // sphere swept over time in [0,1): midpoint + half the travel
-            const float3 vv = f3(fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)) - apex;
-            const float h = dot3(vv, ax), d2 = dot3(vv, vv);
-            const float smax = fmaxf(h + re, 0.f);                // farthest along-axis extent of the sphere
-            // cone radius there + thin-lens blur (grows beyond the focus plane) + margins for FP32 and the 1.05 above
-            const float rad = re * 1.02f + 0.02f + a.lens_radius * (1.f + smax * inv_f) + smax * tan_t;
-            if (d2 <= rad * rad) return true;                     // apex inside / next to the sphere
-            if (h + re < 0.f) return false;                       // entirely behind the camera
-            return fmaxf(d2 - h * h, 0.f) <= rad * rad;
+            return rz_tile_keep(cone, cx, cy, cz, vx, vy, vz, w);
         };
         int n_ls = 0, n_lm = 0;
         for (uint32_t p0 = 0; p0 < n_sp; p0 += 32u) {
@@ -380,8 +358,8 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         const uint32_t e0 = u * 512u, ne = min(512u, n_in - e0);
 
         // ---- what the unit's rays have in common
-        float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, T = 0.f;
-        unsigned all_pos = 7u, all_neg = 7u;
+        RzUnitBounds U;
+        rz_unit_bounds_init(U);
         // Bounds from the sorted KEYS, not from the entries: decoding 512 16-bit keys (1 KB, coalesced) replaces a gather of
         // 512 x 32 B through the index that was 18 % of this kernel's warp-state samples.  The key gives conservative bounds:
         // the origin lies in its cell (open-ended for the outermost cells, where out-of-box origins are clamped), the octant
@@ -391,44 +369,21 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
             const uint32_t key = a.q_in_keys[e0 + i];
             if (key == prev_key) continue;
             prev_key = key;
-            float lo[3], hi[3], Tk;
-            uint32_t oct;
-            rz_key_bounds(a, key, lo, hi, oct, Tk);
-#pragma unroll
-            for (int ax = 0; ax < 3; ax++) {
-                blo[ax] = fminf(blo[ax], lo[ax]);
-                bhi[ax] = fmaxf(bhi[ax], hi[ax]);
-                if ((oct >> ax) & 1u) all_pos &= ~(1u << ax); else all_neg &= ~(1u << ax);   // key bit set <=> d < 0
-            }
-            T = fmaxf(T, Tk);
+            rz_unit_bounds_add_key(U, a, key);
         }
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
             for (int ax = 0; ax < 3; ax++) {
-                blo[ax] = fminf(blo[ax], __shfl_xor_sync(0xffffffffu, blo[ax], o));
-                bhi[ax] = fmaxf(bhi[ax], __shfl_xor_sync(0xffffffffu, bhi[ax], o));
+                U.lo[ax] = fminf(U.lo[ax], __shfl_xor_sync(0xffffffffu, U.lo[ax], o));
+                U.hi[ax] = fmaxf(U.hi[ax], __shfl_xor_sync(0xffffffffu, U.hi[ax], o));
             }
-            T = fmaxf(T, __shfl_xor_sync(0xffffffffu, T, o));
-            all_pos &= __shfl_xor_sync(0xffffffffu, all_pos, o);
-            all_neg &= __shfl_xor_sync(0xffffffffu, all_neg, o);
+            U.T = fmaxf(U.T, __shfl_xor_sync(0xffffffffu, U.T, o));
+            U.all_pos &= __shfl_xor_sync(0xffffffffu, U.all_pos, o);
+            U.all_neg &= __shfl_xor_sync(0xffffffffu, U.all_neg, o);
         }
-        T = fminf(T, 1.0e30f) * 1.001f;   // +inf-safe; margin for the FP32 evaluation of the exits
+        rz_unit_bounds_finish(U);
         auto keep = [&](float cx, float cy, float cz, float vx, float vy, float vz, float w) -> bool {
-            if (!(w < 0.f)) return false;                                  // padding entry
-            const float r = sqrtf(-w);
-            if (r > a.huge_radius) return true;                            // outside the sphere box: never culled
-            const float re = (r + 0.5f * sqrtf(vx * vx + vy * vy + vz * vz)) * 1.02f + 0.02f;   // swept over the shutter + margin
-            const float c[3] = {fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)};
-            float d2 = 0.f;
-#pragma unroll
-            for (int ax = 0; ax < 3; ax++) {
-                if (((all_pos >> ax) & 1u) && c[ax] + re < blo[ax]) return false;   // every ray moves up this axis: sphere is behind
-                if (((all_neg >> ax) & 1u) && c[ax] - re > bhi[ax]) return false;
-                const float dd = fmaxf(0.f, fmaxf(blo[ax] - c[ax], c[ax] - bhi[ax]));
-                d2 = fmaf(dd, dd, d2);
-            }
-            const float rad = T + re;
-            return d2 <= rad * rad;                                        // within reach of some ray of the unit
+            return rz_unit_keep(U, a.huge_radius, cx, cy, cz, vx, vy, vz, w);
         };
         int n_ls = 0, n_lm = 0;
         for (uint32_t p0 = 0; p0 < n_sp; p0 += 32u) {

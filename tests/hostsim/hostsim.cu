@@ -173,3 +173,151 @@ extern "C" uint64_t hostsim_key_check(const float *lo, const float *hi, int cell
     }
     return bad;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Property checks of the two culls of the staged K1 (rz_device.cuh: rz_tile_keep, rz_unit_keep): a sphere that one of the
+// rays HITS (the kernels' own FP32 test, sphere evaluated at the ray's time) must never be culled.  Spheres are generated
+// around points on the rays, so about half of them are hit.  out[0] = violations, out[1] = hits checked, out[2] = hit
+// spheres the cull kept (== out[1] when there is no violation), out[3] = misses the cull dropped (it does cull).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Rng {
+    uint64_t s;
+    explicit Rng(uint64_t seed) : s(seed * 0x9E3779B97F4A7C15ull + 0x1234567ull) {}
+    float u01() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (float)((s >> 40) * (1.0 / 16777216.0)); }
+    float sym() { return 2.0f * u01() - 1.0f; }
+};
+
+// the kernels' sphere test: does the line hit, and is a root ahead of t_min?
+bool ray_hits(const RzRay &ray, const float c0[3], const float v[3], float r, float t_min) {
+    const float ocx = fmaf(v[0], ray.time, c0[0] - ray.o.x), ocy = fmaf(v[1], ray.time, c0[1] - ray.o.y), ocz = fmaf(v[2], ray.time, c0[2] - ray.o.z);
+    const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
+    const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, -(r * r))));
+    const float disc = fmaf(b, b, -c);
+    return disc > 0.0f && b + sqrtf(disc) > t_min;
+}
+
+// a sphere near the point the ray reaches at parameter t: centre at the ray's time within 1.5 r of it
+void sphere_near(Rng &g, const RzRay &ray, float t, float r, float vmax, float c0[3], float v[3]) {
+    const float p[3] = {ray.o.x + t * ray.d.x, ray.o.y + t * ray.d.y, ray.o.z + t * ray.d.z};
+    const bool moving = g.u01() < 0.6f;
+    for (int ax = 0; ax < 3; ax++) {
+        v[ax] = moving ? vmax * g.sym() : 0.0f;
+        c0[ax] = p[ax] + 1.5f * r * g.sym() * 0.8f - v[ax] * ray.time;
+    }
+}
+}  // namespace
+
+extern "C" int hostsim_tile_cull_check(const RzCamera *cam, uint32_t w, uint32_t h, uint64_t n_tiles, uint64_t seed, uint64_t *out) {
+    RzCamF32 C;
+    C.look_from = make_float3((float)cam->look_from[0], (float)cam->look_from[1], (float)cam->look_from[2]);
+    C.px_du = make_float3((float)cam->px_du[0], (float)cam->px_du[1], (float)cam->px_du[2]);
+    C.px_dv = make_float3((float)cam->px_dv[0], (float)cam->px_dv[1], (float)cam->px_dv[2]);
+    C.px_origin = make_float3((float)cam->px_origin[0], (float)cam->px_origin[1], (float)cam->px_origin[2]);
+    C.defocus_u = make_float3((float)cam->defocus_u[0], (float)cam->defocus_u[1], (float)cam->defocus_u[2]);
+    C.defocus_v = make_float3((float)cam->defocus_v[0], (float)cam->defocus_v[1], (float)cam->defocus_v[2]);
+    C.defocus = cam->defocus;
+    // the two thin-lens numbers the library derives from the camera (rz_context.cu, render_impl)
+    double pcd[3], lu = 0, lv = 0, f2 = 0;
+    for (int ax = 0; ax < 3; ax++) {
+        pcd[ax] = cam->px_origin[ax] + 0.5 * (w - 1) * cam->px_du[ax] + 0.5 * (h - 1) * cam->px_dv[ax] - cam->look_from[ax];
+        f2 += pcd[ax] * pcd[ax]; lu += cam->defocus_u[ax] * cam->defocus_u[ax]; lv += cam->defocus_v[ax] * cam->defocus_v[ax];
+    }
+    const float focus_dist = (float)std::sqrt(f2);
+    const float lens_radius = cam->defocus ? (float)(std::sqrt(std::max(lu, lv)) * 1.001) : 0.f;
+    Rng g(seed);
+    for (int i = 0; i < 4; i++) out[i] = 0;
+    const uint32_t n_px = w * h;
+    for (uint64_t t = 0; t < n_tiles; t++) {
+        const uint32_t tile = (uint32_t)(g.u01() * (float)((n_px + 31u) / 32u)) % ((n_px + 31u) / 32u);
+        // ---- the cone, lane by lane as the kernel builds it
+        float3 ax = f3(0.f, 0.f, 0.f), pcs[32];
+        uint32_t pis[32], pjs[32];
+        bool valid[32];
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            const uint32_t lp = tile * 32u + lane;
+            valid[lane] = lp < n_px;
+            pis[lane] = pjs[lane] = 0;
+            if (valid[lane]) rz_local_to_global(lp, w, 0, 1, 4, pis[lane], pjs[lane]);
+            pcs[lane] = rz_tile_pixel_dir(C, pis[lane], pjs[lane]);
+            if (valid[lane]) ax = ax + normalize3(pcs[lane]);
+        }
+        const bool has_axis = rz_tile_axis(ax);
+        float cmin = 1.0f;
+        for (uint32_t lane = 0; lane < 32; lane++)
+            if (valid[lane]) cmin = fminf(cmin, rz_tile_corner_cos(C, pcs[lane], ax));
+        const RzTileCone cone = rz_tile_cone(C, ax, has_axis, cmin, focus_dist, lens_radius);
+        // ---- camera rays of the tile against spheres placed around them
+        for (int k = 0; k < 64; k++) {
+            const uint32_t lane = (uint32_t)(g.u01() * 32.f) & 31u;
+            if (!valid[lane]) continue;
+            const uint32_t gpix = pjs[lane] * w + pis[lane], sample = (uint32_t)(g.u01() * 4096.f);
+            const RzRay ray = rz_camera_ray(C, pis[lane], pjs[lane], gpix, sample, (uint32_t)seed, 77u);
+            for (int j = 0; j < 6; j++) {
+                const float tt = 0.05f + 40.0f * g.u01() * g.u01();
+                const float r = 0.03f + 2.0f * g.u01() * g.u01();
+                float c0[3], v[3];
+                sphere_near(g, ray, tt, r, j < 2 ? 6.0f : 0.8f, c0, v);
+                const bool hit = ray_hits(ray, c0, v, r, 1e-4f);
+                const bool kept = rz_tile_keep(cone, c0[0], c0[1], c0[2], v[0], v[1], v[2], -(r * r));
+                if (hit) { out[1]++; if (kept) out[2]++; else out[0]++; }
+                else if (!kept) out[3]++;
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cell_bits, float huge_radius, uint64_t n_units, uint64_t seed,
+                                       uint64_t *out) {
+    RzPathArgs a;
+    memset(&a, 0, sizeof a);
+    const float l3[3] = {lo[0], lo[1], lo[2]}, h3[3] = {hi[0], hi[1], hi[2]};
+    rz_key_grid(a, l3, h3, cell_bits);
+    a.huge_radius = huge_radius;
+    Rng g(seed);
+    for (int i = 0; i < 4; i++) out[i] = 0;
+    const float ext = std::max(h3[0] - l3[0], std::max(h3[1] - l3[1], h3[2] - l3[2]));
+    for (uint64_t u = 0; u < n_units; u++) {
+        // ---- a unit: rays that start close together and head roughly the same way (what the sort puts side by side)
+        RzRay rays[16];
+        float bo[3], bd[3];
+        for (int ax = 0; ax < 3; ax++) { bo[ax] = l3[ax] + (h3[ax] - l3[ax]) * (1.3f * g.u01() - 0.15f); bd[ax] = g.sym(); }
+        const float spread = g.u01() < 0.5f ? 0.05f : 0.6f, jitter = ext / 64.0f * g.u01();
+        RzUnitBounds U;
+        rz_unit_bounds_init(U);
+        for (int k = 0; k < 16; k++) {
+            float d[3];
+            for (int ax = 0; ax < 3; ax++) d[ax] = bd[ax] + spread * g.sym();
+            const float len = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            if (!(len > 1e-6f)) { d[0] = 0.f; d[1] = 1.f; d[2] = 0.f; } else { d[0] /= len; d[1] /= len; d[2] /= len; }
+            rays[k].o = f3(bo[0] + jitter * g.sym(), bo[1] + jitter * g.sym(), bo[2] + jitter * g.sym());
+            rays[k].d = f3(d[0], d[1], d[2]); rays[k].time = g.u01(); rays[k].self_k = -1;
+            rz_unit_bounds_add_key(U, a, rz_sort_key(a, rays[k]));
+        }
+        rz_unit_bounds_finish(U);
+        // ---- spheres around the rays: ordinary ones lie inside the sphere box over the whole shutter interval (that is
+        // what the box is), huge ones anywhere
+        for (int k = 0; k < 16; k++) {
+            for (int j = 0; j < 8; j++) {
+                const bool huge = j == 7;
+                const float r = huge ? huge_radius * (1.5f + 50.f * g.u01()) : fminf(huge_radius, 0.02f * ext * (0.1f + g.u01()));
+                // j == 6: a sphere BEHIND the ray's origin (never hit; a coherent unit's sign test should drop it)
+                const float tt = j == 6 ? -(0.05f * ext + 0.5f * ext * g.u01()) : 0.02f * ext + 1.2f * ext * g.u01() * g.u01();
+                float c0[3], v[3];
+                sphere_near(g, rays[k], tt, r, j < 3 ? 0.1f * ext : 0.01f * ext, c0, v);
+                bool inside = true;
+                for (int ax = 0; ax < 3 && !huge; ax++) {
+                    const float p0 = c0[ax], p1 = c0[ax] + v[ax];
+                    inside = inside && fminf(p0, p1) - r >= l3[ax] && fmaxf(p0, p1) + r <= h3[ax];
+                }
+                if (!inside) continue;
+                const bool hit = ray_hits(rays[k], c0, v, r, 1e-4f);
+                const bool kept = rz_unit_keep(U, a.huge_radius, c0[0], c0[1], c0[2], v[0], v[1], v[2], -(r * r));
+                if (hit) { out[1]++; if (kept) out[2]++; else out[0]++; }
+                else if (!kept) out[3]++;
+            }
+        }
+    }
+    return 0;
+}

@@ -81,3 +81,47 @@ def test_sort_key_bounds_contain_their_rays(hostsim, lo, hi, bits):
     assert int(counts[:16].sum()) == n
     assert int((counts[:16] > 0).sum()) >= 6            # the reach classes are really exercised
     assert int(counts[16]) > (1 << bits) * 4            # and so are cells x octants
+
+
+def _cam(width, defocus_angle, look_from=(13, 2, 3), look_at=(0, 0, 0), vfov=20.0, focus=10.0):
+    h = int(width / rayz_b200.host.ASPECT_RATIO)
+    return rayz_b200.Camera.init(vfov, focus, defocus_angle, look_from, look_at, (0, 1, 0), h, width).rz, h
+
+
+@pytest.mark.parametrize("width,defocus,look_from,vfov", [
+    (1200, 0.6, (13, 2, 3), 20.0),        # the benchmark camera (rayz.zig:152-160)
+    (400, 0.0, (13, 2, 3), 20.0),         # pinhole
+    (160, 8.0, (0, 1.0, 8.0), 50.0),      # wide lens, wide field of view, coarse pixels
+    (33, 2.0, (3, 3, 2), 90.0),           # tiles that wrap around image rows
+])
+def test_primary_tile_cull_never_drops_a_hit_sphere(hostsim, width, defocus, look_from, vfov):
+    """Staged K1, primary kernel: the cone cull of a 32-pixel tile (rz_tile_keep, the function the kernel calls) must keep
+    every sphere — moving ones included — that a camera ray of the tile hits."""
+    hostsim.hostsim_tile_cull_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+    cam, h = _cam(width, defocus, look_from=look_from, vfov=vfov)
+    out = np.zeros(4, dtype=np.uint64)
+    assert hostsim.hostsim_tile_cull_check(C.addressof(cam), width, h, 4000, 3, out.ctypes.data) == 0
+    bad, hits, kept, culled_misses = (int(x) for x in out)
+    assert hits > 200_000 and kept == hits and bad == 0, (bad, hits)
+    if width >= 400:
+        assert culled_misses > 1_000      # and it does cull, even though every test sphere sits next to a ray of the tile
+
+
+@pytest.mark.parametrize("lo,hi,bits,huge", [
+    ((-11.6, -0.1, -11.6), (11.6, 2.1, 11.6), 9, 1.6),
+    ((-6.0, -0.5, -6.0), (6.0, 7.0, 9.5), 9, 4.8),
+    ((-3.0, -3.0, -3.0), (3.0, 3.0, 3.0), 5, 1.0),
+    ((0.0, 0.0, 0.0), (100.0, 0.5, 1.0), 9, 0.2),
+])
+def test_sorted_unit_cull_never_drops_a_hit_sphere(hostsim, lo, hi, bits, huge):
+    """Staged K1, sorted-stage kernel: bounds merged from the keys of a unit's rays (rz_unit_bounds_add_key) and the cull
+    built on them (rz_unit_keep) must keep every sphere inside the sphere box that one of the rays hits, and every huge one."""
+    hostsim.hostsim_unit_cull_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]
+    l = np.array(lo, dtype=np.float32)
+    h = np.array(hi, dtype=np.float32)
+    out = np.zeros(4, dtype=np.uint64)
+    assert hostsim.hostsim_unit_cull_check(l.ctypes.data, h.ctypes.data, bits, huge, 20000, 5, out.ctypes.data) == 0
+    bad, hits, kept, culled_misses = (int(x) for x in out)
+    assert hits > 100_000 and kept == hits and bad == 0, (bad, hits)
+    if hi[1] - lo[1] > 1.0:               # (in the 0.5-high box hardly any test sphere fits inside)
+        assert culled_misses > 5_000      # and it does cull (the spheres placed behind coherent units)
