@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 #include <atomic>
+#include <algorithm>
 
 #include "../../include/rayz_cuda.h"
 #include "../../rayz_b200/csrc/rz_device.cuh"
@@ -317,6 +318,165 @@ extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cel
                 if (hit) { out[1]++; if (kept) out[2]++; else out[0]++; }
                 else if (!kept) out[3]++;
             }
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The staged K1 on a real scene, stage by stage, on the CPU: camera rays searched over their tile's culled list, scattered
+// rays binned by sort key into units of 512 and searched over their unit's culled list — each against the brute-force
+// search over every sphere.  The closest hit (t and sphere) must be identical, which is the claim the staged form rests on
+// ("the culls only ever drop spheres a ray cannot reach").  Uses the functions the kernels call (rz_device.cuh).
+// out[0] = mismatches (primary), out[1] = primary rays, out[2] = sum of primary list sizes,
+// out[3] = mismatches (sorted units), out[4] = rays in units, out[5] = sum of unit list sizes (per ray), out[6] = units.
+// ---------------------------------------------------------------------------------------------
+extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t tile_stride,
+                                    uint64_t seed, uint64_t *out) {
+    const uint32_t n = sc->n_spheres;
+    std::vector<float4> cr(n), vel(n);
+    std::vector<double4> c64(n), v64(n);
+    std::vector<uint32_t> smat(n);
+    std::vector<int32_t> orig(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const double *c = sc->sphere_center + 3 * i, *v = sc->sphere_velocity + 3 * i; const double r = sc->sphere_radius[i];
+        cr[i] = make_float4((float)c[0], (float)c[1], (float)c[2], -(float)(r * r));
+        vel[i] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)r);
+        c64[i] = make_double4(c[0], c[1], c[2], r); v64[i] = make_double4(v[0], v[1], v[2], 0);
+        smat[i] = sc->sphere_material[i]; orig[i] = (int32_t)i;
+    }
+    const uint32_t nm = sc->n_materials, nt = sc->n_textures;
+    std::vector<uint32_t> mk(nm), mt(nm), mm(nm), tk(nt), te(nt), to(nt);
+    std::vector<float> mf(nm), mi(nm); std::vector<float4> tc(nt); std::vector<double> ts(nt);
+    for (uint32_t i = 0; i < nm; i++) { mk[i] = sc->mat_kind[i]; mt[i] = sc->mat_kind[i] == 2 ? 0 : sc->mat_texture[i]; mm[i] = sc->mat_method ? sc->mat_method[i] : 2; mf[i] = (float)sc->mat_fuzz[i]; mi[i] = (float)sc->mat_ior[i]; }
+    for (uint32_t i = 0; i < nt; i++) { tk[i] = sc->tex_kind[i]; te[i] = sc->tex_even[i]; to[i] = sc->tex_odd[i];
+        tc[i] = make_float4((float)sc->tex_color[3*i], (float)sc->tex_color[3*i+1], (float)sc->tex_color[3*i+2], 0); ts[i] = sc->tex_kind[i] == 0 ? 1.0 / sc->tex_scale[i] : 0; }
+    RzSphereSet S; S.cr = cr.data(); S.vel = vel.data(); S.c64 = c64.data(); S.v64 = v64.data(); S.mat = smat.data(); S.orig = orig.data(); S.n = n; S.n_static = 0; S.n_static_pad = 0; S.n_pad = n;
+    RzTextures T; T.kind = tk.data(); T.color = tc.data(); T.inv_scale = ts.data(); T.even = te.data(); T.odd = to.data();
+    RzCamF32 C;
+    C.look_from = make_float3((float)cam->look_from[0], (float)cam->look_from[1], (float)cam->look_from[2]);
+    C.px_du = make_float3((float)cam->px_du[0], (float)cam->px_du[1], (float)cam->px_du[2]);
+    C.px_dv = make_float3((float)cam->px_dv[0], (float)cam->px_dv[1], (float)cam->px_dv[2]);
+    C.px_origin = make_float3((float)cam->px_origin[0], (float)cam->px_origin[1], (float)cam->px_origin[2]);
+    C.defocus_u = make_float3((float)cam->defocus_u[0], (float)cam->defocus_u[1], (float)cam->defocus_u[2]);
+    C.defocus_v = make_float3((float)cam->defocus_v[0], (float)cam->defocus_v[1], (float)cam->defocus_v[2]);
+    C.defocus = cam->defocus;
+    double f2 = 0, lu = 0, lv = 0;
+    for (int ax = 0; ax < 3; ax++) {
+        const double pc = cam->px_origin[ax] + 0.5 * (w - 1) * cam->px_du[ax] + 0.5 * (h - 1) * cam->px_dv[ax] - cam->look_from[ax];
+        f2 += pc * pc; lu += cam->defocus_u[ax] * cam->defocus_u[ax]; lv += cam->defocus_v[ax] * cam->defocus_v[ax];
+    }
+    const float focus_dist = (float)std::sqrt(f2), lens_radius = cam->defocus ? (float)(std::sqrt(std::max(lu, lv)) * 1.001) : 0.f;
+    // the sphere box as the library sets it up at upload (rz_context.cu: box of the spheres up to 8 x the median radius,
+    // motion over the shutter included, padded by 0.1 % + 1e-3)
+    RzPathArgs a;
+    memset(&a, 0, sizeof a);
+    {
+        std::vector<double> rad(sc->sphere_radius, sc->sphere_radius + n);
+        std::nth_element(rad.begin(), rad.begin() + n / 2, rad.end());
+        const double huge = 8.0 * rad[n / 2];
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        bool any = false;
+        for (uint32_t i = 0; i < n; i++) {
+            if (sc->sphere_radius[i] > huge) continue;
+            any = true;
+            for (int ax = 0; ax < 3; ax++) {
+                const double c0 = sc->sphere_center[3 * i + ax], c1 = c0 + sc->sphere_velocity[3 * i + ax], r = sc->sphere_radius[i];
+                lo[ax] = std::min(lo[ax], std::min(c0, c1) - r); hi[ax] = std::max(hi[ax], std::max(c0, c1) + r);
+            }
+        }
+        float l3[3], h3[3];
+        for (int ax = 0; ax < 3; ax++) {
+            const double pad = any ? 1e-3 * (hi[ax] - lo[ax]) + 1e-3 : 0.0;
+            l3[ax] = any ? (float)(lo[ax] - pad) : -3.0e38f; h3[ax] = any ? (float)(hi[ax] + pad) : 3.0e38f;
+        }
+        rz_key_grid(a, l3, h3, 9);
+        a.huge_radius = (float)huge;
+    }
+    const float t_min = 1e-4f;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 7; i++) out[i] = 0;
+    auto search = [&](const RzRay &ray, const std::vector<uint32_t> *list, float &bt, int &bk) {
+        bt = 3.0e38f; bk = -1;
+        const uint32_t cnt = list ? (uint32_t)list->size() : n;
+        for (uint32_t q = 0; q < cnt; q++) {
+            const uint32_t k = list ? (*list)[q] : q;
+            const float4 sp = cr[k], v = vel[k];
+            const float ocx = fmaf(v.x, ray.time, sp.x - ray.o.x), ocy = fmaf(v.y, ray.time, sp.y - ray.o.y), ocz = fmaf(v.z, ray.time, sp.z - ray.o.z);
+            const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
+            const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, sp.w)));
+            const float disc = fmaf(b, b, -c);
+            if (disc > 0.0f) consider((int)k, b, disc, ray.self_k, t_min, bt, bk);
+        }
+    };
+    struct Entry { uint32_t key; RzRay ray; };
+    std::vector<Entry> queue;
+    const uint32_t n_px = w * h, n_tiles = (n_px + 31u) / 32u;
+    std::vector<uint32_t> list;
+    for (uint32_t tile = 0; tile < n_tiles; tile += std::max(1u, tile_stride)) {
+        // ---- primary kernel: the tile's cone and list
+        float3 ax = f3(0.f, 0.f, 0.f), pcs[32];
+        uint32_t pis[32], pjs[32];
+        bool valid[32];
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            const uint32_t lp = tile * 32u + lane;
+            valid[lane] = lp < n_px;
+            pis[lane] = pjs[lane] = 0;
+            if (valid[lane]) rz_local_to_global(lp, w, 0, 1, 4, pis[lane], pjs[lane]);
+            pcs[lane] = rz_tile_pixel_dir(C, pis[lane], pjs[lane]);
+            if (valid[lane]) ax = ax + normalize3(pcs[lane]);
+        }
+        const bool has_axis = rz_tile_axis(ax);
+        float cmin = 1.0f;
+        for (uint32_t lane = 0; lane < 32; lane++)
+            if (valid[lane]) cmin = fminf(cmin, rz_tile_corner_cos(C, pcs[lane], ax));
+        const RzTileCone cone = rz_tile_cone(C, ax, has_axis, cmin, focus_dist, lens_radius);
+        list.clear();
+        for (uint32_t k = 0; k < n; k++)
+            if (rz_tile_keep(cone, cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w)) list.push_back(k);
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            if (!valid[lane]) continue;
+            const uint32_t gpix = pjs[lane] * w + pis[lane];
+            for (uint32_t s = 0; s < spp; s++) {
+                RzRay ray = rz_camera_ray(C, pis[lane], pjs[lane], gpix, s, k0, k1);
+                float bt, bt2; int bk, bk2;
+                search(ray, nullptr, bt, bk);
+                search(ray, &list, bt2, bk2);
+                out[1]++; out[2] += list.size();
+                if (bk != bk2 || bt != bt2) out[0]++;
+                if (bk < 0) continue;
+                // scatter, as rz_shade_segment does, and queue the new ray under its key
+                const int k = bk & ~RZ_FAR_BIT;
+                const RzHit hit = rz_refine_hit(S, ray, k, (bk & RZ_FAR_BIT) != 0);
+                const uint32_t mat = smat[k];
+                RzMatRec R;
+                R.kind = mk[mat]; R.method = mm[mat]; R.tex = mt[mat]; R.solid = false; R.fuzz = mf[mat]; R.ior = mi[mat]; R.color = f3(0.f, 0.f, 0.f);
+                const uint4 rb = rz_philox(gpix, s, 1u, 0u, k0, k1);
+                const float4 u = make_float4(rz_u01(rb.x >> 8), rz_u01(rb.y >> 8), rz_u01(rb.z >> 8), rz_u01(rb.w >> 8));
+                float3 att;
+                if (!rz_scatter(R, T, hit, k, u, ray, att)) continue;
+                queue.push_back(Entry{rz_sort_key(a, ray), ray});
+            }
+        }
+    }
+    // ---- sorted-stage kernel: stable sort by key, units of 512, bounds from the keys, cull, search
+    std::stable_sort(queue.begin(), queue.end(), [](const Entry &x, const Entry &y) { return x.key < y.key; });
+    for (size_t e0 = 0; e0 < queue.size(); e0 += 512) {
+        const size_t ne = std::min<size_t>(512, queue.size() - e0);
+        RzUnitBounds U;
+        rz_unit_bounds_init(U);
+        for (size_t i = 0; i < ne; i++) rz_unit_bounds_add_key(U, a, queue[e0 + i].key);
+        rz_unit_bounds_finish(U);
+        list.clear();
+        for (uint32_t k = 0; k < n; k++)
+            if (rz_unit_keep(U, a.huge_radius, cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w)) list.push_back(k);
+        out[6]++;
+        for (size_t i = 0; i < ne; i++) {
+            float bt, bt2; int bk, bk2;
+            search(queue[e0 + i].ray, nullptr, bt, bk);
+            search(queue[e0 + i].ray, &list, bt2, bk2);
+            out[4]++; out[5] += list.size();
+            if (bk != bk2 || bt != bt2) out[3]++;
         }
     }
     return 0;

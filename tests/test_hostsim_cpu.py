@@ -125,3 +125,22 @@ def test_sorted_unit_cull_never_drops_a_hit_sphere(hostsim, lo, hi, bits, huge):
     assert hits > 100_000 and kept == hits and bad == 0, (bad, hits)
     if hi[1] - lo[1] > 1.0:               # (in the 0.5-high box hardly any test sphere fits inside)
         assert culled_misses > 5_000      # and it does cull (the spheres placed behind coherent units)
+
+
+@pytest.mark.parametrize("glass", [False, True])
+def test_staged_searches_equal_brute_force_on_the_benchmark_scene(hostsim, glass):
+    """The staged K1's claim, stage by stage, on the RTOW scene (moving spheres, the r = 1000 ground, thin lens): a camera
+    ray searched over its tile's culled list, and a scattered ray searched over the culled list of its sorted unit, find
+    exactly the closest hit (t and sphere) of the search over every sphere."""
+    hostsim.hostsim_staged_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
+    t = rayz_b200.random_bouncing(400, seed=42, glass_heavy=glass)
+    sc, keep = scene_struct(t.pool.arrays())
+    out = np.zeros(7, dtype=np.uint64)
+    assert hostsim.hostsim_staged_check(C.addressof(sc), C.addressof(t.camera.rz), 400, 225, 4, 3, 17, out.ctypes.data) == 0
+    bad1, rays1, list1, bad2, rays2, list2, units = (int(x) for x in out)
+    n = len(t.pool.arrays()["sphere_radius"])
+    assert rays1 > 100_000 and rays2 > 50_000 and units > 100
+    assert bad1 == 0, f"{bad1} of {rays1} camera rays find a different hit over the tile list"
+    assert bad2 == 0, f"{bad2} of {rays2} scattered rays find a different hit over the unit list"
+    assert list1 / rays1 < 0.15 * n          # the tile cull keeps a small part of the set ...
+    assert list2 / rays2 < 0.90 * n          # ... the unit cull hardly bites at 1.5 rays per key (12 % of the set at 500 spp on the GPU)
