@@ -193,13 +193,14 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
 }
 
 // ------------------------------------------------------------------------------ primary kernel
-// Stage 1 of the two-stage K1: the camera segment of every path (Camera.getRay camera.zig:59-77 + the first
+// Stage 1 of the staged K1: the camera segment of every path (Camera.getRay camera.zig:59-77 + the first
 // bounceRay level renderer.zig:103-126).  Camera rays of a 32-pixel tile are coherent, so the warp first
 // culls the sphere set against the tile's frustum — a cone around the tile's mean direction, widened by the
 // pixel footprint, the thin-lens blur and each sphere's motion — and the packed search then runs over the
 // surviving handful of sphere pairs instead of all of them (rz_search_list2: same arithmetic, same (t, k)).
-// Paths that scatter are appended, ballot-compacted, to the HBM queue the secondary kernel starts from; paths
-// that leave the scene or are absorbed accumulate here.  36 % of all segments are camera segments.
+// Paths that scatter are appended, ballot-compacted, to the HBM queue the sorted stages start from; paths
+// that leave the scene or are absorbed accumulate here.  36 % of all segments are camera segments.  The cull
+// (rz_tile_cone / rz_tile_keep, rz_device.cuh) is host + device and property-tested on the CPU.
 template <bool STATS>
 __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
@@ -323,15 +324,15 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------ second-segment kernel
-// Stage 2 of the staged K1: the segment after the camera segment (48 % of what would otherwise be the persistent
-// kernel's searches).  Scattered rays are incoherent, but their queue entries have been SORTED by
-// (origin cell, direction octant, reach class) (rz_sort_key + cub radix sort), so 512 consecutive entries start
-// close together, head the same way and leave the sphere layer after a similar distance.  Per unit the warp
-// derives from the ACTUAL rays: the box of their origins, the axes on which all of them move the same way, and
-// the longest stay T inside the box around the non-huge spheres; a sphere can then only be hit if it is not
-// behind the origin box on such an axis and lies within T + r of the box.  The packed search runs over that
-// list (15 % of the spheres on the RTOW scene) with the same arithmetic per sphere, so (t, k) is unchanged.
+// ------------------------------------------------------------------------------ sorted-segment kernel
+// The stages after the camera segment, one launch per segment (segments 2..6 by default).  Scattered rays are incoherent,
+// but their queue entries have been SORTED by (origin cell, direction octant, reach class) (rz_sort_key + cub radix sort),
+// so 512 consecutive entries start close together, head the same way and leave the sphere layer after a similar distance.
+// Per unit the warp merges the bounds its sorted KEYS stand for (rz_key_bounds: the cells of the origins, the axes on which
+// every ray moves the same way, the longest stay T inside the box around the non-huge spheres); a sphere can then only be
+// hit if it is not behind the cell box on such an axis and lies within T + r of it (rz_unit_keep).  The packed search runs
+// over that list (12 % of the spheres on the RTOW scene at 500 spp) with the same arithmetic per sphere, so (t, k) is
+// unchanged.  Both functions are host + device and property-tested on the CPU (tests/test_hostsim_cpu.py).
 template <bool STATS>
 __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
