@@ -146,7 +146,7 @@ def run_reference(args, rank: int, world: int):
 def algorithmic_flops_per_path(stats: dict, n_static: int, n_moving: int) -> dict:
     """F_path = sum over segments of the search flop + (S - p_sky)*F_shade + F_cam + p_sky*F_sky.
 
-    A brute-force search costs F_isect = 16*n_static + 22*n_moving.  The two-stage megakernel runs the camera
+    A brute-force search costs F_isect = 16*n_static + 22*n_moving.  The staged K1 runs the camera
     segment of each path over a tile-culled list instead, so the search flop is scaled by the sphere tests the
     kernels actually counted (`sphere_tests`), not assumed to be segments * n_spheres.
     f_secondary = search flop of the segments after the first (what the dominant, persistent kernel does)."""
@@ -329,7 +329,7 @@ def main():
     value = total_paths / (ms_per_step * 1e-3) / 1e6
 
     # ---- path-kernel duration per launch (library CUDA events on the same stream), own pass
-    # The two-stage megakernel overlaps its passes on two streams; for clean per-kernel durations this pass asks for
+    # The staged K1 overlaps its passes on two streams; for clean per-kernel durations this pass asks for
     # serial passes (RZ_RENDER_SERIAL_PASSES): primary_ms = camera-segment kernels, kernel_ms - primary_ms = the
     # persistent secondary kernel (the dominant one).
     p_serial = Backend.params(W, H, SPP, DEPTH, seed=1, variant=resolved, shard_index=rank, shard_count=world, band_rows=band,

@@ -128,7 +128,7 @@ typedef struct RzRenderParams {
 } RzRenderParams;
 
 /* RzRenderParams.flags */
-#define RZ_RENDER_SERIAL_PASSES 1u /* two-stage K1: run the passes back to back on one stream instead of
+#define RZ_RENDER_SERIAL_PASSES 1u /* staged K1: run the passes back to back on one stream instead of
                                     * overlapping them on two, so that RzTiming.primary_ms and
                                     * kernel_ms - primary_ms are clean per-kernel durations (profiling) */
 
@@ -231,7 +231,7 @@ int rayz_cuda_primary_ids(RzContext *ctx, const RzCamera *cam, uint32_t width, u
 int rayz_cuda_stats(RzContext *ctx, RzStats *out);
 
 /* The same counters per stage of the staged K1 (RZ_VARIANT_MEGA): 0 = primary kernel (camera segments),
- * 1 = sorted stages, 2 = persistent megakernel.  Other variants count everything under stage 0. */
+ * 1 = sorted stages, 2 = persistent tail kernel.  Other variants count everything under stage 0. */
 int rayz_cuda_stage_stats(RzContext *ctx, uint32_t stage, RzStats *out);
 int rayz_cuda_timing(RzContext *ctx, RzTiming *out);
 

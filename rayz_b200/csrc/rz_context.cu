@@ -118,7 +118,7 @@ struct SetBufs {
 struct Dev {
     int id = 0, sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t stream2 = nullptr;   // two-stage K1: odd passes run here so that a pass fills the tail of the previous one
+    cudaStream_t stream2 = nullptr;   // staged K1: odd passes run here so that a pass fills the tail of the previous one
     cudaEvent_t ev_s2 = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, path0, path1, resolve1, done
     SetBufs brute, bvhset;
@@ -158,10 +158,10 @@ struct Dev {
     DBuf<float> sink;
     void *wf_scratch = nullptr;
     size_t wf_scratch_bytes = 0;
-    std::vector<cudaEvent_t> pass_ev;   // staged K1: [3i] after the primary kernel of pass i, [3i+1] after the sorted stages, [3i+2] after the megakernel
+    std::vector<cudaEvent_t> pass_ev;   // staged K1: [3i] after the primary kernel of pass i, [3i+1] after the sorted stages, [3i+2] after the tail kernel
     std::vector<cudaEvent_t> stage_ev;  // staged K1: per pass and sorted stage, [2k] after the sort, [2k+1] after the kernel
     uint32_t n_second = 0;              // sorted stages per pass of the last render
-    uint32_t passes = 0;                // passes of the last render (0 = not the two-stage form)
+    uint32_t passes = 0;                // passes of the last render (0 = not the staged form)
     bool serial_passes = false;
 };
 
@@ -170,7 +170,7 @@ struct RzContext {
     bool have_scene = false;
     uint32_t n_spheres = 0;
     RzStats stats{};
-    RzStats stage_stats[3]{};   // staged K1: primary kernel / sorted stages / persistent megakernel (single-kernel variants: all in [0])
+    RzStats stage_stats[3]{};   // staged K1: primary kernel / sorted stages / persistent tail kernel (single-kernel variants: all in [0])
     bool stats_valid = false;
     RzTiming timing{};
     int rays_per_thread = 2;
@@ -925,7 +925,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         int rc;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u))) return rc;
         if ((rc = D.counter.alloc(16))) return rc;
-        if ((rc = D.stats.alloc(3))) return rc;   // [0] whole render / primary kernel, [1] sorted stages, [2] persistent megakernel
+        if ((rc = D.stats.alloc(3))) return rc;   // [0] whole render / primary kernel, [1] sorted stages, [2] persistent tail kernel
         RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
         RZ_CUDA(cudaMemsetAsync(D.accum.p, 0, (size_t)n_tiles * 32u * 4u * sizeof(unsigned long long), D.stream));
         RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 16 * sizeof(unsigned int), D.stream));

@@ -295,7 +295,7 @@ class Backend:
         return out
 
     def stage_stats(self, stage: int) -> dict:
-        """Counters of one stage of the staged K1: 0 primary kernel, 1 sorted stages, 2 persistent megakernel."""
+        """Counters of one stage of the staged K1: 0 primary kernel, 1 sorted stages, 2 persistent tail kernel (BVH, or the brute-force megakernel)."""
         s = abi.RzStats()
         abi.check(self.lib.rayz_cuda_stage_stats(self._h, stage, C.byref(s)))
         return s.as_dict()
