@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RAYZ_CUDA_ABI_VERSION 2
+#define RAYZ_CUDA_ABI_VERSION 3
 
 enum {
     RZ_OK = 0,
@@ -39,7 +39,9 @@ enum {
     RZ_ERR_NCCL = -3, /* reserved: peer exchange failure (P2P copy) */
     RZ_ERR_OOM = -4,
     RZ_ERR_UNSUPPORTED = -5,
-    RZ_ERR_NO_SCENE = -6
+    RZ_ERR_NO_SCENE = -6,
+    RZ_ERR_INTERNAL = -7 /* a device-side capacity was exceeded during the render (queue slot, traversal stack): work
+                          * would have been dropped, so the result is withheld instead of returned darker */
 };
 
 /* Material kinds — order of `Material = union(enum)` in material.zig:162-165. */
@@ -203,7 +205,7 @@ int rayz_cuda_render(RzContext *ctx, const RzCamera *cam, const RzRenderParams *
                      float *out_linear_rgba, uint8_t *out_rgb8, uint64_t *out_paths);
 
 /* Optional: allocate everything a render with these parameters needs (accumulators, result buffers, the
- * staged K1's queues: up to 77 GB) ahead of time, like Image.initEmpty in Tracer.init (renderer.zig:29-64),
+ * staged K1's queues: up to ~31 GB at the default pass size) ahead of time, like Image.initEmpty in Tracer.init (renderer.zig:29-64),
  * so that the first rayz_cuda_render does not pay for it. */
 int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *params);
 
@@ -238,6 +240,34 @@ int rayz_cuda_timing(RzContext *ctx, RzTiming *out);
 /* K6: dependent-free FFMA chains on every SM of device 0; returns achieved FP32 TFLOP/s
  * (2 flop per FFMA) over ~`millis` ms and the SM count. Roofline denominator. */
 int rayz_cuda_fp32_peak(RzContext *ctx, uint32_t millis, double *out_tflops, int32_t *out_sms);
+
+/*
+ * Tuning (experiments and tests; every field has a measured default, DESIGN.md sections 3 and 5).  Not part of the
+ * reference-facing contract: the reference has no such knobs.  Read the current values, change what you want, set.
+ * The library reads NO environment variables.
+ */
+typedef struct RzTuning {
+    uint32_t struct_size;     /* sizeof(RzTuning) of the caller (checked)                                              */
+    int32_t rays_per_thread;  /* K1b / wavefront: independent paths per lane, 1 or 2 (default 2)                        */
+    uint32_t chunk;           /* samples per work unit (32 pixels x chunk) of the persistent kernels (default 16)       */
+    uint32_t chunk_primary;   /* ... of the staged K1's primary kernel, which builds one culled list per unit (64)      */
+    int32_t queue_log2;       /* staged K1: queue entries per pass = 2^queue_log2, 16..28 (default 27: 6.4 GB per queue
+                               * buffer; 28 is ~2 % faster on 405 M-path renders and doubles the reservation)           */
+    int32_t second_stages;    /* staged K1: sorted stages after the camera segment, 0..8; -1 = automatic (default)      */
+    int32_t bvh_stages;       /* staged BVH kernel: sorted stages, 0..8 (default 0: measured as a loss)                 */
+    int32_t tail_brute;       /* staged K1: 1 = the tail of the paths stays brute force (default 0: BVH kernel)         */
+    int32_t bvh_staged;       /* BVH variant: 1 = jobs of >= 2^26 paths run a camera stage + queue first (default 1)    */
+    int32_t cell_bits;        /* sort key: bits of the origin cell, 0..9 (default 9)                                    */
+    int32_t bvh_active_min;   /* K3: lanes that must still traverse for a burst to go on, 1..32 (default 8)             */
+    int32_t bvh_descend_min;  /* K3: a descend round ends below this many descending lanes (default 24)                 */
+    int32_t sah_leaf;         /* host SAH builder: max spheres per leaf, 1..8 (default 4); applies at the next upload   */
+    double sah_node_cost;     /* host SAH builder: cost of a node visit relative to a sphere test (default 0.5)         */
+    uint32_t unit_entries;    /* sorted-stage kernel: queue entries per work unit, 64..4096, multiple of 64 (default 512) */
+    uint32_t debug_queue_cap; /* tests: pretend the queues hold only this many entries (0 = off) -> RZ_ERR_INTERNAL     */
+    uint32_t debug_stack_cap; /* tests: pretend the K3 traversal stack holds only this many entries (0 = off)           */
+} RzTuning;
+int rayz_cuda_get_tuning(RzContext *ctx, RzTuning *out);
+int rayz_cuda_set_tuning(RzContext *ctx, const RzTuning *tuning);
 
 const char *rayz_cuda_last_error(void);
 

@@ -6,8 +6,8 @@ Importing the package does not load CUDA; the first backend call does, and fails
 library or a GPU is missing (there is no CPU fallback).
 """
 from . import _abi as abi  # noqa: F401
-from .host import (ASPECT_RATIO, Backend, Camera, Image, MemPool, Tracer, Xoshiro256, random_bouncing,  # noqa: F401
-                   scene_struct)
+from .host import (ASPECT_RATIO, Backend, Camera, Image, MemPool, Tracer, Xoshiro256, penultimate_scene,  # noqa: F401
+                   random_bouncing, scene_struct)
 
-__all__ = ["abi", "ASPECT_RATIO", "Backend", "Camera", "Image", "MemPool", "Tracer", "Xoshiro256", "random_bouncing",
+__all__ = ["abi", "ASPECT_RATIO", "Backend", "Camera", "Image", "MemPool", "Tracer", "Xoshiro256", "penultimate_scene", "random_bouncing",
            "scene_struct"]

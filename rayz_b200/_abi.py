@@ -13,7 +13,7 @@ SO_PATH = os.path.join(HERE, "lib", "librayz_cuda.so")
 
 RZ_OK = 0
 ERRORS = {-1: "RZ_ERR_INVALID_ARG", -2: "RZ_ERR_CUDA", -3: "RZ_ERR_NCCL", -4: "RZ_ERR_OOM", -5: "RZ_ERR_UNSUPPORTED",
-          -6: "RZ_ERR_NO_SCENE"}
+          -6: "RZ_ERR_NO_SCENE", -7: "RZ_ERR_INTERNAL"}
 MAT_DIFFUSE, MAT_METALLIC, MAT_DIELECTRIC = 0, 1, 2
 TEX_CHECKER, TEX_SOLID = 0, 1
 DIFFUSE_UNIT_SPHERE, DIFFUSE_UNIT_SPHERE_SURFACE, DIFFUSE_HEMISPHERE = 0, 1, 2
@@ -63,6 +63,17 @@ class RzTiming(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved0"}
 
 
+class RzTuning(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("rays_per_thread", C.c_int32), ("chunk", C.c_uint32), ("chunk_primary", C.c_uint32),
+                ("queue_log2", C.c_int32), ("second_stages", C.c_int32), ("bvh_stages", C.c_int32), ("tail_brute", C.c_int32),
+                ("bvh_staged", C.c_int32), ("cell_bits", C.c_int32), ("bvh_active_min", C.c_int32), ("bvh_descend_min", C.c_int32),
+                ("sah_leaf", C.c_int32), ("sah_node_cost", C.c_double), ("unit_entries", C.c_uint32), ("debug_queue_cap", C.c_uint32),
+                ("debug_stack_cap", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 # every symbol include/rayz_cuda.h declares: (restype, argtypes)
 SYMBOLS = {
     "rayz_cuda_abi_version": (C.c_uint32, []),
@@ -82,11 +93,13 @@ SYMBOLS = {
     "rayz_cuda_stage_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(RzStats)]),
     "rayz_cuda_timing": (C.c_int, [C.c_void_p, C.POINTER(RzTiming)]),
     "rayz_cuda_fp32_peak": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "rayz_cuda_get_tuning": (C.c_int, [C.c_void_p, C.POINTER(RzTuning)]),
+    "rayz_cuda_set_tuning": (C.c_int, [C.c_void_p, C.POINTER(RzTuning)]),
     "rayz_cuda_last_error": (C.c_char_p, []),
 }
-# experiment knobs outside the reference-facing header
+# test hooks outside the reference-facing header
 EXTRA_SYMBOLS = {
-    "rayz_cuda_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
+    "rayz_cuda_debug_sort_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -112,7 +125,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-    if lib.rayz_cuda_abi_version() != 2:
+    if lib.rayz_cuda_abi_version() != 3:
         raise ImportError("librayz_cuda.so ABI version mismatch")
     _lib = lib
     return lib

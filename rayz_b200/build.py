@@ -31,7 +31,7 @@ UNITS = {
     "rz_bvh_trace.cu": ["--use_fast_math"],
     "rz_context.cu": [],
 }
-HEADERS = ["rz_device.cuh", "rz_search.cuh", "rz_search_variants.cuh", os.path.join("..", "..", "include", "rayz_cuda.h")]
+HEADERS = ["rz_device.cuh", "rz_search.cuh", os.path.join("..", "..", "include", "rayz_cuda.h")]
 
 
 def _nvcc() -> str:

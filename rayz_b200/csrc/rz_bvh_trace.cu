@@ -24,8 +24,6 @@
 // 9 % SLOWER and is not used.
 // Sphere tests, hit refinement, shading, RNG keys and accumulation are the shared device functions of
 // rz_search.cuh / rz_device.cuh: images equal the brute-force kernel's bit for bit.
-#include <cstdlib>
-
 #include "rz_search.cuh"
 
 namespace {
@@ -71,7 +69,8 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
         const int c1 = q3.y >= 0 ? q3.y : rz_leaf_ref(q3.y, (uint32_t)q3.w);
         if (h0 && h1) {
             const bool swap = tn1 < tn0;
-            if (sp < RZ_STACK) stack[sp++] = swap ? c0 : c1;
+            if (sp < (int)a.stack_cap) stack[sp++] = swap ? c0 : c1;
+            else atomicOr(a.err, (unsigned)RZ_DEV_ERR_STACK_OVERFLOW);   // a dropped subtree would darken the image silently
             cur = swap ? c1 : c0;
         } else if (h0) {
             cur = c0;
@@ -92,13 +91,9 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
             const float4 s = __ldg(a.set.cr + k);
             const float4 v = __ldg(a.set.vel + k);
             if (STATS) c_sph++;
-            const float ocx = fmaf(v.x, ray.time, s.x - ray.o.x);   // same order as the packed searches
-            const float ocy = fmaf(v.y, ray.time, s.y - ray.o.y);
-            const float ocz = fmaf(v.z, ray.time, s.z - ray.o.z);
-            const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
-            const float cc = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, s.w)));
-            const float disc = fmaf(b, b, -cc);
-            if (disc > 0.0f) rz_consider(k, b, disc, ray.self_k, a.t_min, bt, bk);
+            float nb, nd;   // the one sphere test of the backend (rz_device.cuh): bit-identical to the packed searches
+            rz_sphere_test(s.x, s.y, s.z, v.x, v.y, v.z, s.w, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.time, nb, nd);
+            if (nd < 0.0f) rz_consider(k, nb, nd, ray.self_k, a.t_min, bt, bk);
         }
         cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
     }
@@ -239,7 +234,8 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_stage_kernel(const RzPathArgs a
     const unsigned lt_mask = (1u << lane) - 1u;
     const float4 *__restrict__ nodes = reinterpret_cast<const float4 *>(a.bvh);
     const uint32_t n_in = CAMERA ? 0u : min(*a.q_in_count, a.queue_cap);
-    const uint32_t n_units = CAMERA ? a.n_units : (n_in + 511u) / 512u;
+    const uint32_t ue = a.unit_entries;
+    const uint32_t n_units = CAMERA ? a.n_units : (n_in + ue - 1u) / ue;
     const int descend_min = (int)a.bvh_descend_min;
     int stack[RZ_STACK];
     unsigned long long c_paths = 0, c_segs = 0, c_nodes = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
@@ -261,7 +257,7 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_stage_kernel(const RzPathArgs a
             s0 = chunk * a.chunk;
             n_batches = min(a.chunk, a.spp - s0);
         } else {
-            e0 = u * 512u; ne = min(512u, n_in - e0);
+            e0 = u * ue; ne = min(ue, n_in - e0);
             n_batches = (ne + 31u) / 32u;
         }
         for (uint32_t b = 0; b < n_batches; b++) {
@@ -339,13 +335,11 @@ extern "C" cudaError_t rz_bvh_warm(void) {
     return e;
 }
 
-static void rz_bvh_tuning(RzPathArgs &b) {
-    const char *env = getenv("RZ_BVH_ACTIVE_MIN");   // tuning experiments (defaults are the measured optimum)
-    b.bvh_active_min = env ? (uint32_t)atoi(env) : 8u;
-    const char *env2 = getenv("RZ_BVH_DESCEND_MIN");
-    b.bvh_descend_min = env2 ? (uint32_t)atoi(env2) : 24u;
-    if (b.bvh_active_min < 1u) b.bvh_active_min = 1u;
+static void rz_bvh_tuning(RzPathArgs &b) {   // defaults are the measured optimum (file header); RzTuning overrides them
+    if (b.bvh_active_min < 1u) b.bvh_active_min = 8u;
     if (b.bvh_active_min > 32u) b.bvh_active_min = 32u;
+    if (b.bvh_descend_min < 1u) b.bvh_descend_min = 24u;
+    if (b.stack_cap < 1u || b.stack_cap > (uint32_t)RZ_STACK) b.stack_cap = (uint32_t)RZ_STACK;
 }
 
 // The persistent kernel: whole paths from the camera (q_in == nullptr) or the tails of paths from a queue.

@@ -20,7 +20,7 @@ struct RzRefNode { double low[3], high[3]; int32_t left, right, start, end; };
 struct RzIdsArgs {
     const RzRefNode *nodes; const uint32_t *order; const double4 *c64; const double4 *v64;
     uint32_t n_spheres, n_nodes; double look_from[3], px_du[3], px_dv[3], px_origin[3];
-    uint32_t width, height; int use_bvh; int32_t *out;
+    uint32_t width, height; int use_bvh; int32_t *out; unsigned int *err;
 };
 struct RzResolveArgs {
     const unsigned long long *accum; float4 *out_linear; uint8_t *out_rgb8;
@@ -31,15 +31,10 @@ extern "C" cudaError_t rz_launch_path(const RzPathArgs *a, int rays_per_thread, 
 extern "C" cudaError_t rz_path_warm(void);
 extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a);
 extern "C" cudaError_t rz_launch_second(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
-extern "C" size_t rz_sort_temp_bytes(uint32_t n);
-extern "C" cudaError_t rz_sort_keys(const unsigned short *keys_in, unsigned short *keys_out, const uint32_t *iota, uint32_t *idx_out, uint32_t n,
-                                    void *temp, size_t temp_bytes, cudaStream_t stream);
-extern "C" cudaError_t rz_iota(uint32_t *p, uint32_t n, cudaStream_t stream);
-struct RzSortGraph;   // rz_sort.cu: the same sort as a CUDA graph that sizes itself from a device counter
-extern "C" cudaError_t rz_sort_graph_create(RzSortGraph **out, const unsigned short *keys_in, unsigned short *keys_out, const uint32_t *iota,
-                                            uint32_t *idx_out, uint32_t cap, void *temp, size_t temp_bytes, const unsigned int *count);
-extern "C" cudaError_t rz_sort_graph_launch(RzSortGraph *g, cudaStream_t stream);
-extern "C" void rz_sort_graph_destroy(RzSortGraph *g);
+extern "C" size_t rz_bin_scratch_bytes(void);
+extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned int *count, uint32_t cap, unsigned int *bins,
+                                   unsigned short *keys_out, uint32_t *idx_out, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t rz_sort_warm(void);
 extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_bvh_warm(void);
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
@@ -140,17 +135,10 @@ struct Dev {
     // staged K1, one set per side (passes alternate between two streams): q1 = after the camera segment, q2 = after the second
     DBuf<float4> q1[2], q2[2];
     DBuf<unsigned short> keys[2], keys_sorted[2];
-    DBuf<uint32_t> idx_sorted[2], iota;
-    DBuf<unsigned char> sort_temp[2];
-    // device-sized sort (rz_sort.cu), one graph per side, rebuilt when the buffers it captured move or change size
-    struct SortGraphSlot {
-        RzSortGraph *g = nullptr;
-        const void *key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-        uint32_t cap = 0;
-        bool failed = false;
-    } sort_graph[2];
-    uint32_t iota_n = 0;
+    DBuf<uint32_t> idx_sorted[2];
+    DBuf<unsigned int> bins[2];       // rz_sort.cu: per-key counts / cursors of the side's sort
     DBuf<unsigned int> counter;
+    DBuf<unsigned int> errword;       // device error word (RZ_DEV_ERR_*), cleared at the start of every render / ids call
     DBuf<RzStatsDev> stats;
     DBuf<float4> out_linear;
     DBuf<uint8_t> out_rgb8;
@@ -173,9 +161,7 @@ struct RzContext {
     RzStats stage_stats[3]{};   // staged K1: primary kernel / sorted stages / persistent tail kernel (single-kernel variants: all in [0])
     bool stats_valid = false;
     RzTiming timing{};
-    int rays_per_thread = 2;
-    uint32_t chunk = 16;          // samples per work unit of the persistent kernels (32 pixels x chunk paths)
-    uint32_t chunk_primary = 64;  // ... of the staged K1's primary kernel, which builds a culled list per unit: 16 -> 15.9 ms, 32 -> 14.6, 64 -> 14.5, 125 -> 15.3
+    RzTuning tun;                 // rayz_cuda_get/set_tuning; defaults in default_tuning()
     uint32_t flags = 0;
     float sb_lo[3] = {0, 0, 0}, sb_hi[3] = {0, 0, 0}, huge_radius = 3.0e38f;   // box of the non-huge spheres (staged K1 sort key / cull)
     // host copy of the sphere boxes: the reference-shaped BVH of K0 is built on first use
@@ -408,8 +394,8 @@ struct HostSet {
         return pk;
     }
     void pad_to(size_t count) {
-        while (cr.size() < count) {  // -r^2 = +1 => discriminant b^2 - |oc|^2 - 1 < 0: never hit
-            cr.push_back(make_float4(0.f, 0.f, 0.f, 1.0f));
+        while (cr.size() < count) {  // w = -r^2 = +1e30 => nd = |l|^2 + 1e30 > 0 by 20 orders of magnitude more than any rounding: never hit
+            cr.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
             vel.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
         }
     }
@@ -431,6 +417,7 @@ int upload_set(SetBufs &d, const HostSet &h, cudaStream_t s) {
 }  // namespace
 
 // ------------------------------------------------------------------------------ API
+static RzTuning default_tuning();
 extern "C" uint32_t rayz_cuda_abi_version(void) { return RAYZ_CUDA_ABI_VERSION; }
 extern "C" const char *rayz_cuda_last_error(void) { return g_err; }
 
@@ -448,6 +435,7 @@ extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
     DeviceGuard guard;
     RzContext *ctx = new RzContext();
     ctx->flags = cfg ? cfg->flags : 0u;
+    ctx->tun = default_tuning();
     ctx->devs.resize(nd);
     for (int d = 0; d < nd; d++) {
         Dev &D = ctx->devs[d];
@@ -468,7 +456,7 @@ extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
         if ((e = cudaStreamCreateWithFlags(&D.stream2, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreateWithFlags(&D.ev_s2, cudaEventDisableTiming)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         for (auto &ev : D.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
-        if ((e = rz_path_warm()) != cudaSuccess || (e = rz_bvh_warm()) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "loading the path kernels: %s", cudaGetErrorString(e)); }
+        if ((e = rz_path_warm()) != cudaSuccess || (e = rz_bvh_warm()) != cudaSuccess || (e = rz_sort_warm()) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "loading the path kernels: %s", cudaGetErrorString(e)); }
         if (d > 0) {
             // the resolve kernel of device d stores straight into device 0's buffers (NVLink P2P)
             int can = 0;
@@ -493,9 +481,9 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
         D.m_rec.release(); D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
-        D.accum.release(); D.counter.release(); D.iota.release();
-        for (int sd = 0; sd < 2; sd++) { rz_sort_graph_destroy(D.sort_graph[sd].g); D.sort_graph[sd].g = nullptr; }
-        for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.sort_temp[sd].release(); } D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
+        D.accum.release(); D.counter.release(); D.errword.release();
+        for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.bins[sd].release(); }
+        D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
         D.ids.release(); D.sink.release();
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
         for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
@@ -515,12 +503,46 @@ extern "C" int rayz_cuda_set_stream(RzContext *ctx, void *cuda_stream) {
     return RZ_OK;
 }
 
-// Tunables for experiments (not part of the reference-facing ABI): rays per thread {1,2} and
-// samples per work unit.
-extern "C" int rayz_cuda_set_tuning(RzContext *ctx, int rays_per_thread, uint32_t chunk) {
-    if (!ctx) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_set_tuning: ctx is NULL");
-    if (rays_per_thread == 1 || rays_per_thread == 2) ctx->rays_per_thread = rays_per_thread;
-    if (chunk >= 1 && chunk <= 4096) { ctx->chunk = chunk; ctx->chunk_primary = chunk; }
+// Tuning (include/rayz_cuda.h: RzTuning).  The library reads no environment variables.
+static RzTuning default_tuning() {
+    RzTuning t;
+    memset(&t, 0, sizeof t);
+    t.struct_size = (uint32_t)sizeof(RzTuning);
+    t.rays_per_thread = 2;
+    t.chunk = 16;
+    t.chunk_primary = 64;   // the primary kernel builds a culled list per unit: 16 -> 15.9 ms, 32 -> 14.6, 64 -> 14.5, 125 -> 15.3
+    t.queue_log2 = 27;
+    t.second_stages = -1;
+    t.bvh_stages = 0;
+    t.tail_brute = 0;
+    t.bvh_staged = 1;
+    t.cell_bits = 9;
+    t.bvh_active_min = 8;
+    t.bvh_descend_min = 24;
+    t.sah_leaf = 4;
+    t.sah_node_cost = 0.5;
+    t.unit_entries = 512;
+    return t;
+}
+
+extern "C" int rayz_cuda_get_tuning(RzContext *ctx, RzTuning *out) {
+    if (!ctx || !out) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_get_tuning: NULL argument");
+    *out = ctx->tun;
+    return RZ_OK;
+}
+
+extern "C" int rayz_cuda_set_tuning(RzContext *ctx, const RzTuning *t) {
+    if (!ctx || !t) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_set_tuning: NULL argument");
+    if (t->struct_size != sizeof(RzTuning)) return rz_fail(RZ_ERR_INVALID_ARG, "rayz_cuda_set_tuning: struct_size %u, expected %zu", t->struct_size, sizeof(RzTuning));
+    if (t->rays_per_thread != 1 && t->rays_per_thread != 2) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: rays_per_thread must be 1 or 2");
+    if (t->chunk < 1 || t->chunk > 4096 || t->chunk_primary < 1 || t->chunk_primary > 4096) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: chunk out of [1, 4096]");
+    if (t->queue_log2 < 16 || t->queue_log2 > 28) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: queue_log2 out of [16, 28]");
+    if (t->second_stages < -1 || t->second_stages > 8 || t->bvh_stages < 0 || t->bvh_stages > 8) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: stages out of range");
+    if (t->cell_bits < 0 || t->cell_bits > 9) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: cell_bits out of [0, 9]");
+    if (t->bvh_active_min < 1 || t->bvh_active_min > 32 || t->bvh_descend_min < 1 || t->bvh_descend_min > 32) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: BVH lane thresholds out of [1, 32]");
+    if (t->sah_leaf < 1 || t->sah_leaf > 8 || !(t->sah_node_cost >= 0)) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: SAH parameters out of range");
+    if (t->unit_entries < 64 || t->unit_entries > 4096 || (t->unit_entries & 63u)) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: unit_entries must be a multiple of 64 in [64, 4096]");
+    ctx->tun = *t;
     return RZ_OK;
 }
 
@@ -613,8 +635,8 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     double host_build_us = 0;
     if (!device_build) {
         const auto t0 = std::chrono::steady_clock::now();
-        if (const char *e = getenv("RZ_SAH_LEAF")) sb.LEAF = std::min(8, std::max(1, atoi(e)));     // tuning experiments
-        if (const char *e = getenv("RZ_SAH_NODE_COST")) sb.node_cost = atof(e);
+        sb.LEAF = ctx->tun.sah_leaf;
+        sb.node_cost = ctx->tun.sah_node_cost;
         sb.p.resize(n);
         for (uint32_t i = 0; i < n; i++) {
             sb.p[i].b = sphere_box(*sc, i);
@@ -727,8 +749,6 @@ static RzCamF32 cam_to_f32(const RzCamera *c) {
 }
 
 
-static const uint32_t RZ_SORT_GRAPH_MIN_CAP = 1u << 22;   // passes below this sort every slot (microseconds), no graph is built
-
 // Pass/queue sizing of the staged K1 (see render_impl).
 struct QueuePlan {
     uint64_t unit_paths = 0, cap = 0;
@@ -737,28 +757,24 @@ struct QueuePlan {
     bool second_stage = false;
 };
 
-static QueuePlan plan_queues(uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family = false, bool bvh_tail = true, int qlog_cap = 28) {
+static QueuePlan plan_queues(const RzTuning &tun, uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family, bool bvh_tail,
+                             int qlog_cap) {
     QueuePlan q;
     q.unit_paths = 32ull * chunk;
-    // Queue size = pass size.  Measured at config 2 (405 M paths): 2^26 -> 5140, 2^27 -> 5405, 2^28 -> 5529 Mpaths/s (fewer,
-    // longer launches; fewer tails).  2^28 entries are 17 GB per queue and 77 GB for both sides with keys, indices and sort
-    // space — 43 % of the 180 GB of HBM; plan_and_alloc_queues steps down if the device cannot give that much.
-    const char *qenv = getenv("RZ_QUEUE_LOG2");   // tuning experiments
-    const int qlog = std::min(qlog_cap, qenv ? std::min(28, std::max(16, atoi(qenv))) : 28);
-    // sorted stages after the camera segment, measured (Mpaths/s, config 2 / glass-heavy scene).  BVH tail, every sort
-    // over the whole pass: 0 -> 4185 / 3390, 1 -> 4739 / 3500, 2 -> 4942 / 3657, 3 -> 4935 / 3789, 4 -> 4829 / 3781,
-    // 5 -> 4662; with the device-sized sort (big passes) a stage costs less: 2 -> 5167, 3 -> 5337, 4 -> 5393, and with
-    // 2^28-entry queues 3 -> 5426 / 4025, 4 -> 5510 / 4130, 5 -> 5549 / 4214, 6 -> 5547 / 4264.  Brute-force
-    // tail (earlier build): 0 -> 2141 / 1945, 2 -> 3421 / 2322, 3 -> 3634 / 2635, 4 -> 3648 / 2797, 5 -> 3576 / 2899.
-    const char *senv = getenv("RZ_SECOND_STAGES");   // tuning experiment
-    const char *benv = getenv("RZ_BVH_STAGES");      // tuning experiment
-    // BVH family: sorted stages measured as a loss (config-2 scene 3521 -> 3277 -> 3065 Mpaths/s for 0, 1, 2 stages; 100k spheres 1582 -> 1427
-    // -> 1327): batches without in-loop ray replacement cost more than coherence gains; only the coherent camera stage is kept
-    if (bvh_family) q.n_second = enough_spheres ? (benv ? std::min(8, std::max(0, atoi(benv))) : 0) : 0;
-    else q.n_second = -1;   // decided below, once the pass size is known
+    // Queue size = pass size.  Measured at config 2 (405 M paths, round 1): 2^26 -> 5140, 2^27 -> 5405, 2^28 -> 5529 Mpaths/s
+    // (fewer, longer launches; fewer tails).  The default is 2^27 entries (RzTuning::queue_log2): 6.4 GB per queue buffer,
+    // ~31 GB for both sides with keys and indices; plan_and_alloc_queues steps down if the device cannot give that much.
+    const int qlog = std::min(qlog_cap, tun.queue_log2);
+    // Sorted stages after the camera segment, measured in round 1 (Mpaths/s, config 2 / glass-heavy scene), BVH tail:
+    // 3 -> 5426 / 4025, 4 -> 5510 / 4130, 5 -> 5549 / 4214, 6 -> 5547 / 4264; brute-force tail: 3 -> 3634 / 2635, 4 -> 3648 /
+    // 2797, 5 -> 3576 / 2899.  BVH family: sorted stages measured as a loss (config-2 scene 3521 -> 3277 -> 3065 Mpaths/s for
+    // 0, 1, 2 stages; 100k spheres 1582 -> 1427 -> 1327): batches without in-loop ray replacement cost more than coherence
+    // gains; only the coherent camera stage is kept.
+    // NOTE: none of this depends on the job's size, shard count or on how much memory the device had left, so that a sharded
+    // render runs exactly the kernels — and therefore computes exactly the pixels — of the full-frame one.
+    if (bvh_family) q.n_second = enough_spheres ? tun.bvh_stages : 0;
+    else q.n_second = !enough_spheres ? 0 : tun.second_stages >= 0 ? tun.second_stages : !bvh_tail ? 4 : 5;
     q.cap = std::max<uint64_t>(q.unit_paths, std::min<uint64_t>((uint64_t)n_units * q.unit_paths, 1ull << qlog));
-    if (q.n_second < 0)
-        q.n_second = !enough_spheres ? 0 : senv ? std::min(8, std::max(0, atoi(senv))) : !bvh_tail ? 4 : q.cap < RZ_SORT_GRAPH_MIN_CAP ? 3 : 5;
     q.second_stage = q.n_second > 0;
     q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
     q.n_pass = (n_units + q.units_per_pass - 1) / q.units_per_pass;
@@ -772,53 +788,26 @@ static int alloc_queues(Dev &D, const QueuePlan &q) {
         if ((rc = D.q1[sd].alloc((size_t)q.cap * 4u))) return rc;
         if (q.second_stage) {
             if ((rc = D.q2[sd].alloc((size_t)q.cap * 4u)) || (rc = D.keys[sd].alloc((size_t)q.cap)) || (rc = D.keys_sorted[sd].alloc((size_t)q.cap)) ||
-                (rc = D.idx_sorted[sd].alloc((size_t)q.cap)) || (rc = D.sort_temp[sd].alloc(rz_sort_temp_bytes((uint32_t)q.cap) + 256)))
+                (rc = D.idx_sorted[sd].alloc((size_t)q.cap)) || (rc = D.bins[sd].alloc(rz_bin_scratch_bytes() / sizeof(unsigned int))))
                 return rc;
         }
-    }
-    if (q.second_stage && D.iota_n < q.cap) {
-        if ((rc = D.iota.alloc((size_t)q.cap))) return rc;
-        RZ_CUDA(rz_iota(D.iota.p, (uint32_t)q.cap, D.stream));
-        D.iota_n = (uint32_t)q.cap;
     }
     return RZ_OK;
 }
 
 // Plans the passes and allocates their queues; when the device cannot give the memory (others share it, or a smaller part),
-// the plan is redone with queues half the size, down to 2^22 entries.
-static int plan_and_alloc_queues(Dev &D, QueuePlan &qp, uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres, bool bvh_family,
-                                 bool bvh_tail) {
+// the plan is redone with queues half the size, down to 2^22 entries.  Only the pass size changes, never which kernels run.
+static int plan_and_alloc_queues(const RzTuning &tun, Dev &D, QueuePlan &qp, uint32_t n_units, uint32_t chunk, bool serial, bool enough_spheres,
+                                 bool bvh_family, bool bvh_tail) {
     for (int qlog = 28;; qlog--) {
-        qp = plan_queues(n_units, chunk, serial, enough_spheres, bvh_family, bvh_tail, qlog);
+        qp = plan_queues(tun, n_units, chunk, serial, enough_spheres, bvh_family, bvh_tail, qlog);
         const int rc = alloc_queues(D, qp);
         if (rc != RZ_ERR_OOM || qlog <= 22 || qp.cap < (1ull << qlog)) return rc;   // done, a real error, or nothing left to shrink
         cudaGetLastError();
         for (int sd = 0; sd < 2; sd++) {
-            rz_sort_graph_destroy(D.sort_graph[sd].g); D.sort_graph[sd] = Dev::SortGraphSlot();
-            D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.sort_temp[sd].release();
+            D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release();
         }
     }
-}
-
-// The device-sized sort of one side, (re)built on first use for these buffers; nullptr = use the plain full-size sort
-// (small passes, where the sort costs nothing anyway; RZ_SORT_GRAPH=0; or a driver without SWITCH conditional nodes).
-static RzSortGraph *sort_graph_for(Dev &D, int side, uint32_t cap) {
-    Dev::SortGraphSlot &S = D.sort_graph[side];
-    const char *env = getenv("RZ_SORT_GRAPH");   // tuning experiment
-    if ((env && atoi(env) == 0) || cap < RZ_SORT_GRAPH_MIN_CAP) return nullptr;
-    const unsigned int *count = D.counter.p + 8 * side + 5;
-    const void *key[6] = {D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, D.sort_temp[side].p, count};
-    if (S.g && S.cap == cap && !memcmp(S.key, key, sizeof key)) return S.g;
-    if (S.failed && S.cap == cap && !memcmp(S.key, key, sizeof key)) return nullptr;
-    rz_sort_graph_destroy(S.g);
-    S.g = nullptr;
-    memcpy(S.key, key, sizeof key);
-    S.cap = cap;
-    const cudaError_t e = rz_sort_graph_create(&S.g, D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, cap, D.sort_temp[side].p,
-                                               D.sort_temp[side].n, count);
-    S.failed = e != cudaSuccess;
-    if (S.failed) { S.g = nullptr; if (getenv("RZ_SORT_GRAPH_VERBOSE")) fprintf(stderr, "[rayz_cuda] sort graph: %s\n", cudaGetErrorString(e)); }
-    return S.g;
 }
 
 // Device timings (CUDA events) and, if asked for, the counters of the render that just finished on every stream.
@@ -846,6 +835,13 @@ static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
         }
         kmax = std::max(kmax, k); rmax = std::max(rmax, r); pmax = std::max(pmax, pr); smax = std::max(smax, se); somax = std::max(somax, so);
         passes = std::max(passes, D.passes);
+    }
+    for (Dev &D : ctx->devs) {   // a device-side capacity was exceeded: work was dropped, the result is not to be used
+        unsigned int ew = 0;
+        RZ_CUDA(cudaSetDevice(D.id));
+        RZ_CUDA(cudaMemcpy(&ew, D.errword.p, sizeof ew, cudaMemcpyDeviceToHost));
+        if (ew) return rz_fail(RZ_ERR_INTERNAL, "render: device %d reported%s%s (error word 0x%x): paths were dropped, result withheld", D.id,
+                               (ew & RZ_DEV_ERR_QUEUE_OVERFLOW) ? " a queue overflow" : "", (ew & RZ_DEV_ERR_STACK_OVERFLOW) ? " a traversal-stack overflow" : "", ew);
     }
     ctx->timing.kernel_ms = kmax;
     ctx->timing.resolve_ms = rmax;
@@ -890,12 +886,14 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
     uint32_t variant = p->variant;
     const uint32_t brute_smem = (ctx->devs[0].brute.n_pad * 2 - ctx->devs[0].brute.n_static_pad) * 16u;
     if (variant == RZ_VARIANT_AUTO) {
-        // Every variant returns the same image, so AUTO is free to pick by cost: the staged brute-force K1 when the sphere set
-        // fits shared memory AND the job is big enough to amortise its ~19 launches per pass (measured one-shot, 485 spheres:
-        // 0.9 M paths 3.9 ms vs 0.8 ms for the BVH kernel, 8 M 6.3 vs 2.8, 81 M 23.8 vs 25.3, 405 M 104 vs 125); else the BVH kernel.
-        const uint64_t job_paths = (uint64_t)rayz_cuda_context_rows(ctx, p->height, p->shard_index, p->shard_count, p->band_rows) * p->width * p->spp /
-                                   std::max<uint64_t>(1, ctx->devs.size());
-        variant = (brute_smem <= RZ_SMEM_BUDGET && job_paths >= (1ull << 26)) ? RZ_VARIANT_MEGA : RZ_VARIANT_BVH;
+        // AUTO picks by cost: the staged brute-force K1 when the sphere set fits shared memory AND the frame is big enough to
+        // amortise its ~25 launches per pass (measured one-shot, 485 spheres: 0.9 M paths 3.9 ms vs 0.8 ms for the BVH kernel,
+        // 8 M 6.3 vs 2.8, 81 M 23.8 vs 25.3, 405 M 104 vs 125); else the BVH kernel.  The choice looks at the WHOLE FRAME
+        // (width x height x spp), never at this shard's or device's share of it: every shard of a frame runs the same
+        // kernels, so a sharded render equals the full-frame one bit for bit (the two kernel families themselves can
+        // differ in a pixel or two: FP32 sphere test against exact boxes, tests/test_gpu_parity.py).
+        const uint64_t frame_paths = (uint64_t)p->width * p->height * p->spp;
+        variant = (brute_smem <= RZ_SMEM_BUDGET && frame_paths >= (1ull << 26)) ? RZ_VARIANT_MEGA : RZ_VARIANT_BVH;
     }
     const bool mega_single = variant == RZ_VARIANT_MEGA_SINGLE;
     if (mega_single) variant = RZ_VARIANT_MEGA;
@@ -924,11 +922,12 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         const uint32_t n_tiles = (n_local + 31u) / 32u;
         int rc;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u))) return rc;
-        if ((rc = D.counter.alloc(16))) return rc;
+        if ((rc = D.counter.alloc(16)) || (rc = D.errword.alloc(4))) return rc;
         if ((rc = D.stats.alloc(3))) return rc;   // [0] whole render / primary kernel, [1] sorted stages, [2] persistent tail kernel
         RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
         RZ_CUDA(cudaMemsetAsync(D.accum.p, 0, (size_t)n_tiles * 32u * 4u * sizeof(unsigned long long), D.stream));
         RZ_CUDA(cudaMemsetAsync(D.counter.p, 0, 16 * sizeof(unsigned int), D.stream));
+        RZ_CUDA(cudaMemsetAsync(D.errword.p, 0, 4 * sizeof(unsigned int), D.stream));
         if (p->collect_stats) RZ_CUDA(cudaMemsetAsync(D.stats.p, 0, 3 * sizeof(RzStatsDev), D.stream));
 
         RzPathArgs a;
@@ -941,13 +940,17 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         a.accum = D.accum.p; a.unit_counter = D.counter.p; a.stats = D.stats.p;
         a.width = p->width; a.height = p->height; a.n_local_px = n_local;
         a.spp = p->spp; a.sample_offset = p->sample_offset; a.max_depth = p->max_depth;
-        a.chunk = std::min(ctx->chunk, p->spp);
+        a.chunk = std::min(ctx->tun.chunk, p->spp);
         a.n_chunks = (p->spp + a.chunk - 1) / a.chunk;
         if ((uint64_t)n_tiles * a.n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "render: too many work units");
         a.n_units = n_tiles * a.n_chunks;
         a.shard_index = sh_index; a.shard_count = sh_count; a.band_rows = band;
         a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
         a.t_min = p->t_min > 0 ? p->t_min : 1e-4f;
+        a.err = D.errword.p;
+        a.unit_entries = ctx->tun.unit_entries;
+        a.bvh_active_min = (uint32_t)ctx->tun.bvh_active_min; a.bvh_descend_min = (uint32_t)ctx->tun.bvh_descend_min;
+        a.stack_cap = ctx->tun.debug_stack_cap;   // 0 = the kernel's own RZ_STACK
 
         RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
         D.passes = 0;
@@ -960,37 +963,30 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
             } else {
                 // K3 on a big job: the same staged pipeline with BVH traversal instead of culled lists (sorted rays stay converged)
                 const bool bvh_family = variant == RZ_VARIANT_BVH;
-                const bool bvh_staged = bvh_family && !getenv("RZ_BVH_NO_STAGES") &&
-                                        (uint64_t)n_local * p->spp >= (1ull << 26);
+                const bool bvh_staged = bvh_family && ctx->tun.bvh_staged && (uint64_t)n_local * p->spp >= (1ull << 26);
                 if (bvh_family && !bvh_staged) {
                     RZ_CUDA(rz_launch_bvh(&a, (int)p->collect_stats, D.sms, D.stream));
                     launches += 1;
                 } else if (!bvh_family && (mega_single || rz_primary_smem_bytes(&a) > 227u * 1024u)) {
                     // one persistent kernel (RZ_VARIANT_MEGA_SINGLE, or a set whose pair lists do not fit beside it)
-                    RZ_CUDA(rz_launch_path(&a, ctx->rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
+                    RZ_CUDA(rz_launch_path(&a, ctx->tun.rays_per_thread, (int)p->collect_stats, D.sms, D.stream, nullptr));
                     launches += 1;
                 } else {
                     // staged K1: primary kernel (tile-culled camera segments) -> queue -> [sort -> sorted-segment kernel (culled per
-                    // unit) -> queue] x n_second -> persistent tail kernel (BVH, or brute force).  Passes are sized by the queues:
-                    // <= 2^28 entries of 64 B (17 GB per buffer; two buffers per side, two sides: 77 GB with keys and indices
-                    // of the 180 GB of HBM).
+                    // unit) -> queue] x n_second -> persistent tail kernel (BVH, or brute force).  Passes are sized by the queues
+                    // (RzTuning::queue_log2, default 2^27 entries per buffer; two buffers per side, two sides).
                     const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
                     if (!bvh_family) {   // the primary kernel's own work-unit size
-                        a.chunk = std::min(ctx->chunk_primary, p->spp);
+                        a.chunk = std::min(ctx->tun.chunk_primary, p->spp);
                         a.n_chunks = (p->spp + a.chunk - 1) / a.chunk;
                         a.n_units = n_tiles * a.n_chunks;
                     }
                     // The tail of the paths (whatever survives the sorted stages: incoherent, few) goes to the BVH kernel when the
                     // host-built tree is there — ~28 node + sphere tests per segment instead of every sphere of the set
                     // (config 2: 29.2 -> 11.1 ms behind four sorted stages).
-                    const char *tail_env = getenv("RZ_TAIL");   // tuning experiment: "brute" keeps the brute-force megakernel
-                    const bool bvh_tail = !bvh_family && D.brute_to_bvh.p != nullptr && !(tail_env && !strcmp(tail_env, "brute"));
+                    const bool bvh_tail = !bvh_family && D.brute_to_bvh.p != nullptr && !ctx->tun.tail_brute;
                     QueuePlan qp;
-                    {
-                        const uint32_t iota_before = D.iota_n;
-                        if ((rc = plan_and_alloc_queues(D, qp, a.n_units, a.chunk, serial, ctx->n_spheres >= 64u, bvh_family, bvh_tail))) return rc;
-                        if (D.iota_n != iota_before) RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));   // the second stream must see the iota too
-                    }
+                    if ((rc = plan_and_alloc_queues(ctx->tun, D, qp, a.n_units, a.chunk, serial, ctx->n_spheres >= 64u, bvh_family, bvh_tail))) return rc;
                     const uint64_t unit_paths = qp.unit_paths, cap = qp.cap;
                     const uint32_t units_per_pass = qp.units_per_pass, total_units = a.n_units, n_pass = qp.n_pass;
                     const int n_sides = qp.n_sides, n_second = qp.n_second;
@@ -1002,9 +998,8 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const double lu = std::sqrt(cam->defocus_u[0] * cam->defocus_u[0] + cam->defocus_u[1] * cam->defocus_u[1] + cam->defocus_u[2] * cam->defocus_u[2]);
                     const double lv = std::sqrt(cam->defocus_v[0] * cam->defocus_v[0] + cam->defocus_v[1] * cam->defocus_v[1] + cam->defocus_v[2] * cam->defocus_v[2]);
                     a.lens_radius = cam->defocus ? (float)(std::max(lu, lv) * 1.001) : 0.f;
-                    a.queue_cap = (uint32_t)cap;
-                    const char *cb_env = getenv("RZ_CELL_BITS");   // tuning experiment (the key has room for 9)
-                    rz_key_grid(a, ctx->sb_lo, ctx->sb_hi, cb_env ? std::min(9, std::max(0, atoi(cb_env))) : 9);
+                    a.queue_cap = ctx->tun.debug_queue_cap ? std::min((uint32_t)cap, ctx->tun.debug_queue_cap) : (uint32_t)cap;
+                    rz_key_grid(a, ctx->sb_lo, ctx->sb_hi, ctx->tun.cell_bits);
                     a.huge_radius = ctx->huge_radius;
                     while (D.pass_ev.size() < 3 * (size_t)n_pass) {
                         cudaEvent_t e = nullptr;
@@ -1029,14 +1024,9 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         unsigned int *ctr = D.counter.p + 8 * side;   // [0..2] unit counters of K1a/K1c/K1b, [3] entries in q1, [4] entries in q2
                         if (pass >= (uint32_t)n_sides) RZ_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned int), st));
                         const uint32_t pass_units = std::min(units_per_pass, total_units - u0);
-                        const uint32_t pass_paths = (uint32_t)std::min<uint64_t>(cap, (uint64_t)pass_units * unit_paths);
                         RzPathArgs a1 = a;
                         a1.q_out = D.q1[side].p; a1.q_out_count = ctr + 3; a1.q_out_keys = second_stage ? D.keys[side].p : nullptr;
                         a1.unit_base = u0; a1.n_units = pass_units; a1.unit_counter = ctr;
-                        // the device-sized sort may cover a bucket (1/32 of the buffer) more than the live entries: clear all of it
-                        RzSortGraph *sg = second_stage ? sort_graph_for(D, side, (uint32_t)cap) : nullptr;
-                        const size_t key_slots = sg ? (size_t)cap : (size_t)pass_paths;
-                        if (second_stage) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, key_slots * sizeof(unsigned short), st));
                         if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a1, (int)p->collect_stats, D.sms, st));
                         else RZ_CUDA(rz_launch_primary(&a1, (int)p->collect_stats, D.sms, st));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass], st));
@@ -1048,19 +1038,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         unsigned int *ca = ctr + 3, *cb = ctr + 4;
                         for (int stg = 0; stg < n_second; stg++) {
                             const bool more = stg + 1 < n_second;
-                            // unused slots carry key 0xffff.  Big passes: the sort sizes itself from the live count on the device
-                            // (rz_sort.cu); small ones sort every slot of the pass.
-                            if (sg) {
-                                RZ_CUDA(cudaMemcpyAsync(ctr + 5, ca, sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
-                                RZ_CUDA(rz_sort_graph_launch(sg, st));
-                            } else {
-                                RZ_CUDA(rz_sort_keys(D.keys[side].p, D.keys_sorted[side].p, D.iota.p, D.idx_sorted[side].p, pass_paths, D.sort_temp[side].p,
-                                                     D.sort_temp[side].n, st));
-                            }
+                            // group the entries by key (rz_sort.cu: count / scan / scatter, sized on the device from the live count)
+                            RZ_CUDA(rz_bin_sort(D.keys[side].p, ca, a.queue_cap, D.bins[side].p, D.keys_sorted[side].p, D.idx_sorted[side].p, D.sms, st));
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg)], st));
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(cb, 0, sizeof(unsigned int), st));           // recycled output counter
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned int), st));      // the stage's unit counter
-                            if (more) RZ_CUDA(cudaMemsetAsync(D.keys[side].p, 0xff, key_slots * sizeof(unsigned short), st));   // keys of the next stage
                             RzPathArgs a2 = a;
                             a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p; a2.q_in_keys = D.keys_sorted[side].p;
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
@@ -1068,7 +1050,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                             if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a2, (int)p->collect_stats, D.sms, st));
                             else RZ_CUDA(rz_launch_second(&a2, (int)p->collect_stats, D.sms, st));
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg) + 1], st));
-                            launches += sg ? 5 : 4;   // sort = (selector +) histogram + 2 passes (cub), + the sorted-segment kernel
+                            launches += 4;   // count + scan + scatter (rz_sort.cu) + the sorted-segment kernel
                             std::swap(qa, qb); std::swap(ca, cb);
                         }
                         a3.q_in = qa; a3.q_in_count = ca;
@@ -1077,7 +1059,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         a3.stats = D.stats.p + 2;
                         if (bvh_tail) { a3.set = D.bvhset.view(); a3.self_map = D.brute_to_bvh.p; }
                         if (bvh_family || bvh_tail) RZ_CUDA(rz_launch_bvh(&a3, (int)p->collect_stats, D.sms, st));
-                        else RZ_CUDA(rz_launch_path(&a3, ctx->rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
+                        else RZ_CUDA(rz_launch_path(&a3, ctx->tun.rays_per_thread, (int)p->collect_stats, D.sms, st, nullptr));
                         RZ_CUDA(cudaEventRecord(D.pass_ev[3 * pass + 2], st));
                         launches += 1;
                     }
@@ -1137,16 +1119,14 @@ extern "C" int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *p) {
         RZ_CUDA(cudaSetDevice(D.id));
         const uint32_t rows = rayz_cuda_shard_rows(p->height, s * ND + d, S * ND, band);
         const uint32_t n_tiles = (rows * p->width + 31u) / 32u;
-        if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u)) || (rc = D.counter.alloc(16)) || (rc = D.stats.alloc(3))) return rc;
+        if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u)) || (rc = D.counter.alloc(16)) || (rc = D.errword.alloc(4)) || (rc = D.stats.alloc(3))) return rc;
         if (p->variant == RZ_VARIANT_AUTO || p->variant == RZ_VARIANT_MEGA || (p->variant == RZ_VARIANT_BVH && (uint64_t)rows * p->width * p->spp >= (1ull << 26))) {
-            const uint32_t chunk = std::min(p->variant == RZ_VARIANT_BVH ? ctx->chunk : ctx->chunk_primary, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
+            const uint32_t chunk = std::min(p->variant == RZ_VARIANT_BVH ? ctx->tun.chunk : ctx->tun.chunk_primary, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
             if ((uint64_t)n_tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
             QueuePlan qp;
-            if ((rc = plan_and_alloc_queues(D, qp, n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0,
+            if ((rc = plan_and_alloc_queues(ctx->tun, D, qp, n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0,
                                             !ctx->have_scene || ctx->n_spheres >= 64u, false, true)))
                 return rc;
-            if (qp.second_stage && p->variant != RZ_VARIANT_BVH)
-                for (int sd = 0; sd < qp.n_sides; sd++) (void)sort_graph_for(D, sd, (uint32_t)qp.cap);   // built here rather than inside the first render
         }
         RZ_CUDA(cudaStreamSynchronize(D.stream));
     }
@@ -1221,9 +1201,41 @@ extern "C" int rayz_cuda_primary_ids(RzContext *ctx, const RzCamera *cam, uint32
     a.n_spheres = ctx->n_spheres; a.n_nodes = D.n_refnodes;
     for (int i = 0; i < 3; i++) { a.look_from[i] = cam->look_from[i]; a.px_du[i] = cam->px_du[i]; a.px_dv[i] = cam->px_dv[i]; a.px_origin[i] = cam->px_origin[i]; }
     a.width = width; a.height = height; a.use_bvh = use_bvh; a.out = D.ids.p;
+    if ((rc = D.errword.alloc(4))) return rc;
+    a.err = D.errword.p;
+    RZ_CUDA(cudaMemsetAsync(D.errword.p, 0, 4 * sizeof(unsigned int), D.stream));
     RZ_CUDA(rz_launch_ids(&a, D.stream));
     RZ_CUDA(cudaMemcpyAsync(out_ids, D.ids.p, (size_t)width * height * sizeof(int32_t), cudaMemcpyDeviceToHost, D.stream));
+    unsigned int ew = 0;
+    RZ_CUDA(cudaMemcpyAsync(&ew, D.errword.p, sizeof ew, cudaMemcpyDeviceToHost, D.stream));
     RZ_CUDA(cudaStreamSynchronize(D.stream));
+    if (ew) return rz_fail(RZ_ERR_INTERNAL, "primary_ids: traversal stack overflow (error word 0x%x)", ew);
+    return RZ_OK;
+}
+
+// Test hook (not in the header): runs the staged K1's key sort (rz_sort.cu) on caller-supplied keys, so that a test can
+// check the grouping directly: keys_out ascending, idx_out a permutation of [0, n), keys_in[idx_out[j]] == keys_out[j].
+extern "C" int rayz_cuda_debug_sort_keys(RzContext *ctx, const unsigned short *keys, uint32_t n, unsigned short *keys_out, uint32_t *idx_out) {
+    if (!ctx || !keys || !keys_out || !idx_out || n == 0 || n > (1u << 28)) return rz_fail(RZ_ERR_INVALID_ARG, "debug_sort_keys: bad argument");
+    DeviceGuard guard;
+    Dev &D = ctx->devs[0];
+    RZ_CUDA(cudaSetDevice(D.id));
+    DBuf<unsigned short> ki, ko;
+    DBuf<uint32_t> io;
+    DBuf<unsigned int> bins, cnt;
+    int rc;
+    if ((rc = ki.alloc(n)) || (rc = ko.alloc(n)) || (rc = io.alloc(n)) || (rc = bins.alloc(rz_bin_scratch_bytes() / sizeof(unsigned int))) || (rc = cnt.alloc(1))) {
+        ki.release(); ko.release(); io.release(); bins.release(); cnt.release();
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(ki.p, keys, (size_t)n * sizeof(unsigned short), cudaMemcpyHostToDevice, D.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.p, &n, sizeof n, cudaMemcpyHostToDevice, D.stream);
+    if (e == cudaSuccess) e = rz_bin_sort(ki.p, cnt.p, n, bins.p, ko.p, io.p, D.sms, D.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(keys_out, ko.p, (size_t)n * sizeof(unsigned short), cudaMemcpyDeviceToHost, D.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx_out, io.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+    ki.release(); ko.release(); io.release(); bins.release(); cnt.release();
+    if (e != cudaSuccess) return rz_fail(RZ_ERR_CUDA, "debug_sort_keys: %s", cudaGetErrorString(e));
     return RZ_OK;
 }
 

@@ -81,6 +81,9 @@ struct RzCamF32 {
     int defocus;
 };
 
+// bits of the device error word (RzPathArgs::err): a render that sets one returns RZ_ERR_INTERNAL
+enum { RZ_DEV_ERR_QUEUE_OVERFLOW = 1u, RZ_DEV_ERR_STACK_OVERFLOW = 2u };
+
 struct RzStatsDev {
     unsigned long long v[10];  // order of RzStats (include/rayz_cuda.h)
 };
@@ -123,6 +126,9 @@ struct RzPathArgs {
     uint32_t sb_cell_bits[3];         // 9 key bits shared out so that cells come out as cubic as possible
     float huge_radius;                // spheres above this radius are never culled (the r = 1000 ground)
     float reach_unit;                 // max extent of the box / 32: classes of the sort key's reach field
+    unsigned int *err;           // device error word (RZ_DEV_ERR_* bits): set instead of silently dropping work
+    uint32_t unit_entries;       // sorted-stage kernels: queue entries per work unit (multiple of 64)
+    uint32_t stack_cap;          // K3: usable entries of the per-lane traversal stack (<= RZ_STACK; smaller only in tests)
     const int32_t *self_map;     // K3 fed by a K1 queue: position in the brute-force set -> position in the BVH-ordered set (null: same set)
     uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)
     uint32_t bvh_descend_min;    // K3: a descend round ends once fewer lanes than this are still descending
@@ -212,6 +218,52 @@ struct RzRay {
                    // re-intersection is resolved analytically instead of by an epsilon:
                    // leaving outward -> cannot re-hit a convex sphere; inward -> far root.
 };
+
+// ---------------------------------------------------------------------------------------------
+// The ray-sphere test every search of the backend uses (packed FP32x2 or scalar, brute force, culled list or BVH leaf):
+// Sphere.hitInner (geom.zig:38-58) for a unit-length direction, in the cancellation-free form of Hearn & Baker /
+// Ray Tracing Gems ch. 7:
+//     oc = (C - o) + v * time            centre(t) = center.origin + center.dir * ray.time   (geom.zig:40)
+//     nb = -(oc . d)                     = -half_b
+//     l  = oc + nb * d                   the perpendicular from the centre to the ray's line
+//     nd = l . l - r^2                   = -discriminant; the line meets the sphere iff nd < 0
+// The textbook discriminant b^2 - (|oc|^2 - r^2) subtracts two numbers of size |oc|^2: 200 units from a sphere of radius 0.2
+// its absolute error (~2e-3) is 5 % of r^2.  Here |l| ~ r near the silhouette, so the error stays ~|oc| eps r (1e-4 of r^2 at
+// the same distance).  Same instruction count in the packed form (12 FP32x2 per sphere pair against 9 + 2 scalar).
+// Every implementation follows THIS operation order per sphere (IEEE rn), so all searches return bit-identical (t, k).
+// ---------------------------------------------------------------------------------------------
+#define RZ_FAR_BIT 0x40000000
+
+RZ_HD void rz_sphere_test(float cx, float cy, float cz, float vx, float vy, float vz, float w, float ox, float oy, float oz,
+                          float dx, float dy, float dz, float time, float &nb, float &nd) {
+    const float ocx = fmaf(vx, time, cx - ox), ocy = fmaf(vy, time, cy - oy), ocz = fmaf(vz, time, cz - oz);
+    nb = fmaf(ocz, -dz, fmaf(ocy, -dy, ocx * -dx));
+    const float lx = fmaf(nb, dx, ocx), ly = fmaf(nb, dy, ocy), lz = fmaf(nb, dz, ocz);
+    nd = fmaf(lz, lz, fmaf(ly, ly, fmaf(lx, lx, w)));
+}
+
+// A sphere whose line test came out negative (nd < 0).  Root rule of Sphere.hitInner (geom.zig:52-58): the near root if it
+// lies in (t_min, best), else the far root.  For the sphere the ray starts on, the t ~ 0 root is excluded analytically
+// (RzRay::self_k) instead of by an epsilon.  t_min (default 1e-4) is the FP32 stand-in for renderer.zig:107's 1e-10: a ray
+// that starts within t_min of ANOTHER sphere's surface takes that sphere's far root, where the reference would still
+// take the near one down to 1e-10 — contact rings ~1e-4 wide around touching spheres (documented deviation).
+RZ_HD void rz_consider(int k, float nb, float nd, int self_k, float t_min, float &bt, int &bk) {
+    const float sq = sqrtf(-nd);
+    const float b = -nb;
+    float t = b - sq;
+    int tag = k;
+    if (k == self_k) {
+        t = (b > 0.0f) ? b + sq : -1.0f;
+        tag = k | RZ_FAR_BIT;
+    } else if (t < t_min) {
+        t = b + sq;
+        tag = k | RZ_FAR_BIT;
+    }
+    if (t > t_min && t < bt) {
+        bt = t;
+        bk = tag;
+    }
+}
 
 // Camera.getRay with rng (camera.zig:59-77): jittered pixel position, thin-lens origin on the
 // defocus disk, time in [0,1).  Disk sample is polar instead of rejection (same distribution).

@@ -30,6 +30,7 @@ struct RzIdsArgs {
     uint32_t width, height;
     int use_bvh;
     int32_t *out;
+    unsigned int *err;          // device error word: bit 2 = traversal stack overflow (never silently dropped)
 };
 
 struct D3 { double x, y, z; };
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(128) rz_ids_kernel(const RzIdsArgs a) {
             if (!aabb_hit(n, ro, rd, tmin, best)) continue;
             if (n.left >= 0) {
                 if (sp < 63) { stack[sp++] = n.right; stack[sp++] = n.left; }
+                else atomicOr(a.err, 2u);   // the reference-shaped tree is balanced (depth <= log2 n + 1): cannot happen below 2^60 spheres
                 continue;
             }
             for (int32_t i = n.start; i < n.end; i++) {

@@ -30,7 +30,6 @@
 //     sphere PAIR and ray, 14 per moving pair (rz_search_brute2);
 //   * large scenes use the BVH kernels of rz_bvh_trace.cu (K3) instead.
 #include <algorithm>
-#include <cstdlib>
 
 #include "rz_search.cuh"
 
@@ -348,7 +347,8 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t n_in = min(*a.q_in_count, a.queue_cap);
-    const uint32_t n_units = (n_in + 511u) / 512u;
+    const uint32_t ue = a.unit_entries;
+    const uint32_t n_units = (n_in + ue - 1u) / ue;
     unsigned long long c_segs = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
 
     while (true) {
@@ -356,7 +356,7 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
-        const uint32_t e0 = u * 512u, ne = min(512u, n_in - e0);
+        const uint32_t e0 = u * ue, ne = min(ue, n_in - e0);
 
         // ---- what the unit's rays have in common
         RzUnitBounds U;

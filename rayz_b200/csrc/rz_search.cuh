@@ -5,7 +5,6 @@
 #pragma once
 #include "rz_device.cuh"
 
-#define RZ_FAR_BIT 0x40000000
 
 // ------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t rz_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -37,43 +36,54 @@ __device__ __forceinline__ void rz_mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
-// ------------------------------------------------------------------------------ candidates
-// Rare path of the search: a sphere whose discriminant is positive.  Root rule of
-// Sphere.hitInner (geom.zig:52-58): near root if inside (t_min, best), else far root.  For the
-// sphere the ray starts on, the t~0 root is excluded analytically (see RzRay::self_k).
-__device__ __forceinline__ void rz_consider(int k, float b, float disc, int self_k, float t_min, float &bt, int &bk) {
-    const float sq = sqrtf(disc);
-    float t = b - sq;
-    int tag = k;
-    if (k == self_k) {
-        t = (b > 0.0f) ? b + sq : -1.0f;
-        tag = k | RZ_FAR_BIT;
-    } else if (t < t_min) {
-        t = b + sq;
-        tag = k | RZ_FAR_BIT;
-    }
-    if (t > t_min && t < bt) {
-        bt = t;
-        bk = tag;
-    }
-}
-
 // ------------------------------------------------------------------------------ K1 search, packed
-// The same arithmetic issued as Blackwell packed-FP32 instructions (PTX add/mul/fma.rn.f32x2 ->
-// SASS FADD2 / FMUL2 / FFMA2): one instruction works on TWO SPHERES (the .x/.y halves of a 64-bit
-// register pair) against one ray, whose operands enter as 32-bit broadcast registers
-// (`R.F32` in SASS), so rays cost no extra registers.  Per ray and sphere PAIR:
-//   stationary: 3 FADD2 + FMUL2 + 2 FFMA2 (b) + 3 FFMA2 (c) + 2 FFMA (disc, needs a negation the
-//               packed forms do not have)                       = 11 issue slots for 2 tests
-//   moving    : + 3 FFMA2 for centre(t) = c0 + v * time (geom.zig:40)  = 14 issue slots
-// versus 20 / 26 scalar instructions.  Every half follows the operation order of
-// the scalar search (rz_search_variants.cuh, and the K3 leaf test) exactly (IEEE rn, FTZ): bit-identical (t, k).
+// rz_sphere_test (rz_device.cuh) issued as Blackwell packed-FP32 instructions (PTX add/mul/fma.rn.f32x2 -> SASS FADD2 /
+// FMUL2 / FFMA2): one instruction works on TWO SPHERES (the .x/.y halves of a 64-bit register pair) against one ray, whose
+// operands enter as 32-bit broadcast registers (`R.F32` in SASS), so rays cost no extra registers.  Per ray and sphere PAIR:
+//   stationary: 3 FADD2 (oc) + FMUL2 + 2 FFMA2 (nb) + 3 FFMA2 (l) + 3 FFMA2 (nd) = 12 issue slots for 2 tests
+//   moving    : + 3 FFMA2 for centre(t) = c0 + v * time (geom.zig:40)              = 15 issue slots
+// Every half follows the operation order of rz_sphere_test exactly (IEEE rn, FTZ): bit-identical (t, k) in every search.
 // s_pk: pair-interleaved sphere set in shared memory (layout: RzSphereSet::pk).
-// G2 = sphere pairs per loop iteration (2 => 4 spheres share one max/branch, as before).
 __device__ __forceinline__ float2 rz_f2(float x, float y) { return make_float2(x, y); }
 
+// the ray's operands as the packed test wants them: -o (so that C - o is an add) and -d (so that nb needs no negation)
+struct RzRayOps {
+    float nox, noy, noz, ndx, ndy, ndz, dx, dy, dz, time;
+};
+__device__ __forceinline__ RzRayOps rz_ray_ops(const RzRay &r) {
+    RzRayOps q;
+    q.nox = -r.o.x; q.noy = -r.o.y; q.noz = -r.o.z;
+    q.ndx = -r.d.x; q.ndy = -r.d.y; q.ndz = -r.d.z;
+    q.dx = r.d.x; q.dy = r.d.y; q.dz = r.d.z;
+    q.time = r.time;
+    return q;
+}
+
+// two stationary spheres (A = cx0 cx1 cy0 cy1, B = cz0 cz1 w0 w1) against one ray
+__device__ __forceinline__ void rz_test2_static(const float4 A, const float4 B, const RzRayOps &q, float2 &nb, float2 &nd) {
+    const float2 ocx = __fadd2_rn(rz_f2(A.x, A.y), rz_f2(q.nox, q.nox));
+    const float2 ocy = __fadd2_rn(rz_f2(A.z, A.w), rz_f2(q.noy, q.noy));
+    const float2 ocz = __fadd2_rn(rz_f2(B.x, B.y), rz_f2(q.noz, q.noz));
+    nb = __ffma2_rn(ocz, rz_f2(q.ndz, q.ndz), __ffma2_rn(ocy, rz_f2(q.ndy, q.ndy), __fmul2_rn(ocx, rz_f2(q.ndx, q.ndx))));
+    const float2 lx = __ffma2_rn(nb, rz_f2(q.dx, q.dx), ocx), ly = __ffma2_rn(nb, rz_f2(q.dy, q.dy), ocy), lz = __ffma2_rn(nb, rz_f2(q.dz, q.dz), ocz);
+    nd = __ffma2_rn(lz, lz, __ffma2_rn(ly, ly, __ffma2_rn(lx, lx, rz_f2(B.z, B.w))));
+}
+
+// two moving spheres (+ VA = vx0 vx1 vy0 vy1, VB = vz0 vz1 . .).  oc = (c0 - o) + v * time: each instruction reads ONE register
+// pair that came from shared memory (two "cold" 64-bit sources cost an FFMA2 ~3.3 cycles instead of 2)
+__device__ __forceinline__ void rz_test2_moving(const float4 A, const float4 B, const float4 VA, const float4 VB, const RzRayOps &q, float2 &nb,
+                                                float2 &nd) {
+    const float2 tm = rz_f2(q.time, q.time);
+    const float2 ocx = __ffma2_rn(rz_f2(VA.x, VA.y), tm, __fadd2_rn(rz_f2(A.x, A.y), rz_f2(q.nox, q.nox)));
+    const float2 ocy = __ffma2_rn(rz_f2(VA.z, VA.w), tm, __fadd2_rn(rz_f2(A.z, A.w), rz_f2(q.noy, q.noy)));
+    const float2 ocz = __ffma2_rn(rz_f2(VB.x, VB.y), tm, __fadd2_rn(rz_f2(B.x, B.y), rz_f2(q.noz, q.noz)));
+    nb = __ffma2_rn(ocz, rz_f2(q.ndz, q.ndz), __ffma2_rn(ocy, rz_f2(q.ndy, q.ndy), __fmul2_rn(ocx, rz_f2(q.ndx, q.ndx))));
+    const float2 lx = __ffma2_rn(nb, rz_f2(q.dx, q.dx), ocx), ly = __ffma2_rn(nb, rz_f2(q.dy, q.dy), ocy), lz = __ffma2_rn(nb, rz_f2(q.dz, q.dz), ocz);
+    nd = __ffma2_rn(lz, lz, __ffma2_rn(ly, ly, __ffma2_rn(lx, lx, rz_f2(B.z, B.w))));
+}
+
 // Where the packed search reads the sphere operands from: shared memory (production).  A constant-bank source that feeds
-// them through the uniform datapath is kept, with the other measured-and-rejected forms, in rz_search_variants.cuh.
+// them through the uniform datapath was measured and rejected (scripts/rz_search_variants.cuh).
 struct RzSrcShared {
     const float4 *p;
     __device__ __forceinline__ float4 operator[](int i) const { return p[i]; }
@@ -87,78 +97,65 @@ struct RzSrcShared {
 #ifndef RZ_TRIGGER
 #define RZ_TRIGGER(c) (c)
 #endif
+// Brute force over the whole set (RZ_VARIANT_MEGA_SINGLE, the wavefront's intersect stage, the brute-force tail).
+// G2 = sphere pairs per loop iteration (2 => 8 tests of 2 rays share one min tree + branch).  Sphere operands are warp-uniform
+// LDS.128 broadcasts; only when some lane has nd < 0 does the warp enter the rare path (rz_consider: square root, root rule).
 template <int R, int G2, class SRC>
 __device__ __forceinline__ void rz_search_brute2(const SRC src, int n_static_pad, int n_pad,
                                                  const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
-    float nox[R], noy[R], noz[R];
+    RzRayOps q[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) { nox[r] = -ray[r].o.x; noy[r] = -ray[r].o.y; noz[r] = -ray[r].o.z; }
-    int q = 0;   // float4 index into the pair-interleaved set
+    for (int r = 0; r < R; r++) q[r] = rz_ray_ops(ray[r]);
+    int f = 0;   // float4 index into the pair-interleaved set
     int k = 0;
 #pragma unroll 1
-    for (; k < n_static_pad; k += 2 * G2, q += 2 * G2) {
+    for (; k < n_static_pad; k += 2 * G2, f += 2 * G2) {
         float4 A[G2], B[G2];
 #pragma unroll
-        for (int j = 0; j < G2; j++) { A[j] = src[q + 2 * j]; B[j] = src[q + 2 * j + 1]; }
-        float2 b[R][G2], disc[R][G2];
-        float m = -1.0f;
+        for (int j = 0; j < G2; j++) { A[j] = src[f + 2 * j]; B[j] = src[f + 2 * j + 1]; }
+        float2 nb[R][G2], nd[R][G2];
+        float m = 1.0f;
 #pragma unroll
         for (int r = 0; r < R; r++) {
 #pragma unroll
             for (int j = 0; j < G2; j++) {
-                const float2 ocx = __fadd2_rn(rz_f2(A[j].x, A[j].y), rz_f2(nox[r], nox[r]));
-                const float2 ocy = __fadd2_rn(rz_f2(A[j].z, A[j].w), rz_f2(noy[r], noy[r]));
-                const float2 ocz = __fadd2_rn(rz_f2(B[j].x, B[j].y), rz_f2(noz[r], noz[r]));
-                b[r][j] = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
-                                     __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
-                const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B[j].z, B[j].w))));
-                disc[r][j] = rz_f2(fmaf(b[r][j].x, b[r][j].x, -c.x), fmaf(b[r][j].y, b[r][j].y, -c.y));
-                m = fmaxf(m, fmaxf(disc[r][j].x, disc[r][j].y));
+                rz_test2_static(A[j], B[j], q[r], nb[r][j], nd[r][j]);
+                m = fminf(m, fminf(nd[r][j].x, nd[r][j].y));
             }
         }
-        if (RZ_TRIGGER(m > 0.0f)) {
+        if (RZ_TRIGGER(m < 0.0f)) {
 #pragma unroll
             for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int j = 0; j < G2; j++) {
-                    if (disc[r][j].x > 0.0f) rz_consider(k + 2 * j, b[r][j].x, disc[r][j].x, ray[r].self_k, t_min, bt[r], bk[r]);
-                    if (disc[r][j].y > 0.0f) rz_consider(k + 2 * j + 1, b[r][j].y, disc[r][j].y, ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (nd[r][j].x < 0.0f) rz_consider(k + 2 * j, nb[r][j].x, nd[r][j].x, ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (nd[r][j].y < 0.0f) rz_consider(k + 2 * j + 1, nb[r][j].y, nd[r][j].y, ray[r].self_k, t_min, bt[r], bk[r]);
                 }
         }
     }
     constexpr int kMovingUnroll = RZ_MOVING_UNROLL;
 #pragma unroll kMovingUnroll
-    for (; k < n_pad; k += 2 * G2, q += 4 * G2) {
+    for (; k < n_pad; k += 2 * G2, f += 4 * G2) {
         float4 A[G2], B[G2], VA[G2], VB[G2];
 #pragma unroll
-        for (int j = 0; j < G2; j++) { A[j] = src[q + 4 * j]; B[j] = src[q + 4 * j + 1]; VA[j] = src[q + 4 * j + 2]; VB[j] = src[q + 4 * j + 3]; }
-        float2 b[R][G2], disc[R][G2];
-        float m = -1.0f;
+        for (int j = 0; j < G2; j++) { A[j] = src[f + 4 * j]; B[j] = src[f + 4 * j + 1]; VA[j] = src[f + 4 * j + 2]; VB[j] = src[f + 4 * j + 3]; }
+        float2 nb[R][G2], nd[R][G2];
+        float m = 1.0f;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float2 tm = rz_f2(ray[r].time, ray[r].time);
 #pragma unroll
             for (int j = 0; j < G2; j++) {
-                // centre(t) = center.origin + center.dir * ray.time (geom.zig:40)
-                // oc = (c0 - o) + v * time: each instruction reads ONE register pair that came from
-                // shared memory (two "cold" 64-bit sources cost an FFMA2 ~3.3 cycles instead of 2)
-                const float2 ocx = __ffma2_rn(rz_f2(VA[j].x, VA[j].y), tm, __fadd2_rn(rz_f2(A[j].x, A[j].y), rz_f2(nox[r], nox[r])));
-                const float2 ocy = __ffma2_rn(rz_f2(VA[j].z, VA[j].w), tm, __fadd2_rn(rz_f2(A[j].z, A[j].w), rz_f2(noy[r], noy[r])));
-                const float2 ocz = __ffma2_rn(rz_f2(VB[j].x, VB[j].y), tm, __fadd2_rn(rz_f2(B[j].x, B[j].y), rz_f2(noz[r], noz[r])));
-                b[r][j] = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
-                                     __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
-                const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B[j].z, B[j].w))));
-                disc[r][j] = rz_f2(fmaf(b[r][j].x, b[r][j].x, -c.x), fmaf(b[r][j].y, b[r][j].y, -c.y));
-                m = fmaxf(m, fmaxf(disc[r][j].x, disc[r][j].y));
+                rz_test2_moving(A[j], B[j], VA[j], VB[j], q[r], nb[r][j], nd[r][j]);
+                m = fminf(m, fminf(nd[r][j].x, nd[r][j].y));
             }
         }
-        if (RZ_TRIGGER(m > 0.0f)) {
+        if (RZ_TRIGGER(m < 0.0f)) {
 #pragma unroll
             for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int j = 0; j < G2; j++) {
-                    if (disc[r][j].x > 0.0f) rz_consider(k + 2 * j, b[r][j].x, disc[r][j].x, ray[r].self_k, t_min, bt[r], bk[r]);
-                    if (disc[r][j].y > 0.0f) rz_consider(k + 2 * j + 1, b[r][j].y, disc[r][j].y, ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (nd[r][j].x < 0.0f) rz_consider(k + 2 * j, nb[r][j].x, nd[r][j].x, ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (nd[r][j].y < 0.0f) rz_consider(k + 2 * j + 1, nb[r][j].y, nd[r][j].y, ray[r].self_k, t_min, bt[r], bk[r]);
                 }
         }
     }
@@ -171,54 +168,91 @@ __device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk
 }
 
 // ------------------------------------------------------------------------------ K1 search over a culled list
-// Same packed arithmetic (and therefore the same (t, k), bit for bit) over a LIST of sphere pairs:
-// the primary-visibility kernel culls the set against the frustum of its 32-pixel tile first, so
-// camera rays test a handful of pairs instead of all of them.  ls / lm: pair indices into the
-// stationary / moving part of the pair-interleaved set (layout: RzSphereSet::pk).
+// The same packed arithmetic over a LIST of sphere pairs (the primary kernel culls the set against the frustum of its
+// 32-pixel tile, the sorted-stage kernel against the bounds of its unit's keys).  ls / lm: pair indices into the
+// stationary / moving part of the pair-interleaved set (layout: RzSphereSet::pk), ascending.
+//
+// The loop over the list is BRANCH-FREE.  A culled list is dense in hits (one ray in ~30 meets a given sphere of it; some lane
+// of the warp nearly always does), so a rare-path branch per sphere — four BSSY/BSYNC pairs per pair of spheres and rays —
+// was entered all the time: 16 % of the sorted-stage kernel's samples sat in it and its reconvergence points (round 1,
+// profiles/r01_sorted_stage_kernel_ncu.md).  Now the only thing kept per test is the SIGN of nd, shifted into a per-ray
+// mask by one funnel shift (SHF.L.W: mask = mask << 1 | sign); after every 16 pairs (32 tests) the lanes walk the set bits
+// of their masks in one loop — most significant first = ascending sphere index, the order of the brute-force search — redo
+// the test of that one sphere with the scalar rz_sphere_test (bit-identical per half) and apply the root rule.  The loop
+// runs max-over-lanes(candidates) times instead of once per sphere; a -0.0 or NaN sign is weeded out by the redone test.
+template <int R, bool MOVING>
+__device__ __forceinline__ void rz_resolve_masks(const float *__restrict__ base, const unsigned short *__restrict__ list, int cn, int k_base,
+                                                 unsigned (&m)[R], const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
+    unsigned any = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) any |= m[r];
+    while (any) {
+        any = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (m[r]) {
+                const int bit = 31 - __clz((int)m[r]);
+                m[r] &= ~(1u << bit);
+                const int pos = 2 * cn - 1 - bit;          // test number within the chunk: pair pos >> 1, half pos & 1
+                const int p = list[pos >> 1], h = pos & 1;
+                const float *s = base + (MOVING ? 16 : 8) * p + h;
+                float nb, nd;
+                rz_sphere_test(s[0], s[2], s[4], MOVING ? s[8] : 0.f, MOVING ? s[10] : 0.f, MOVING ? s[12] : 0.f, s[6], ray[r].o.x, ray[r].o.y,
+                               ray[r].o.z, ray[r].d.x, ray[r].d.y, ray[r].d.z, ray[r].time, nb, nd);
+                if (nd < 0.0f) rz_consider(k_base + 2 * p + h, nb, nd, ray[r].self_k, t_min, bt[r], bk[r]);
+            }
+            any |= m[r];
+        }
+    }
+}
+
 template <int R>
 __device__ __forceinline__ void rz_search_list2(const float4 *__restrict__ s_pk, const unsigned short *__restrict__ ls, int n_ls,
                                                 const unsigned short *__restrict__ lm, int n_lm, int n_static_pad,
                                                 const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
-    float nox[R], noy[R], noz[R];
+    RzRayOps q[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) { nox[r] = -ray[r].o.x; noy[r] = -ray[r].o.y; noz[r] = -ray[r].o.z; }
+    for (int r = 0; r < R; r++) q[r] = rz_ray_ops(ray[r]);
 #pragma unroll 1
-    for (int i = 0; i < n_ls; i++) {
-        const int p = ls[i];
-        const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
-        const int k = 2 * p;
+    for (int i0 = 0; i0 < n_ls; i0 += 16) {
+        const int cn = min(16, n_ls - i0);
+        unsigned m[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float2 ocx = __fadd2_rn(rz_f2(A.x, A.y), rz_f2(nox[r], nox[r]));
-            const float2 ocy = __fadd2_rn(rz_f2(A.z, A.w), rz_f2(noy[r], noy[r]));
-            const float2 ocz = __fadd2_rn(rz_f2(B.x, B.y), rz_f2(noz[r], noz[r]));
-            const float2 b = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
-                                        __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
-            const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B.z, B.w))));
-            const float dx = fmaf(b.x, b.x, -c.x), dy = fmaf(b.y, b.y, -c.y);
-            if (dx > 0.0f) rz_consider(k, b.x, dx, ray[r].self_k, t_min, bt[r], bk[r]);
-            if (dy > 0.0f) rz_consider(k + 1, b.y, dy, ray[r].self_k, t_min, bt[r], bk[r]);
+        for (int r = 0; r < R; r++) m[r] = 0u;
+#pragma unroll 2
+        for (int i = 0; i < cn; i++) {
+            const int p = ls[i0 + i];
+            const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                float2 nb, nd;
+                rz_test2_static(A, B, q[r], nb, nd);
+                m[r] = __funnelshift_l(__float_as_uint(nd.x), m[r], 1);
+                m[r] = __funnelshift_l(__float_as_uint(nd.y), m[r], 1);
+            }
         }
+        rz_resolve_masks<R, false>(reinterpret_cast<const float *>(s_pk), ls + i0, cn, 0, m, ray, t_min, bt, bk);
     }
     const float4 *__restrict__ mv = s_pk + n_static_pad;
 #pragma unroll 1
-    for (int i = 0; i < n_lm; i++) {
-        const int p = lm[i];
-        const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
-        const int k = n_static_pad + 2 * p;
+    for (int i0 = 0; i0 < n_lm; i0 += 16) {
+        const int cn = min(16, n_lm - i0);
+        unsigned m[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float2 tm = rz_f2(ray[r].time, ray[r].time);
-            const float2 ocx = __ffma2_rn(rz_f2(VA.x, VA.y), tm, __fadd2_rn(rz_f2(A.x, A.y), rz_f2(nox[r], nox[r])));
-            const float2 ocy = __ffma2_rn(rz_f2(VA.z, VA.w), tm, __fadd2_rn(rz_f2(A.z, A.w), rz_f2(noy[r], noy[r])));
-            const float2 ocz = __ffma2_rn(rz_f2(VB.x, VB.y), tm, __fadd2_rn(rz_f2(B.x, B.y), rz_f2(noz[r], noz[r])));
-            const float2 b = __ffma2_rn(ocz, rz_f2(ray[r].d.z, ray[r].d.z),
-                                        __ffma2_rn(ocy, rz_f2(ray[r].d.y, ray[r].d.y), __fmul2_rn(ocx, rz_f2(ray[r].d.x, ray[r].d.x))));
-            const float2 c = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __ffma2_rn(ocx, ocx, rz_f2(B.z, B.w))));
-            const float dx = fmaf(b.x, b.x, -c.x), dy = fmaf(b.y, b.y, -c.y);
-            if (dx > 0.0f) rz_consider(k, b.x, dx, ray[r].self_k, t_min, bt[r], bk[r]);
-            if (dy > 0.0f) rz_consider(k + 1, b.y, dy, ray[r].self_k, t_min, bt[r], bk[r]);
+        for (int r = 0; r < R; r++) m[r] = 0u;
+#pragma unroll 2
+        for (int i = 0; i < cn; i++) {
+            const int p = lm[i0 + i];
+            const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                float2 nb, nd;
+                rz_test2_moving(A, B, VA, VB, q[r], nb, nd);
+                m[r] = __funnelshift_l(__float_as_uint(nd.x), m[r], 1);
+                m[r] = __funnelshift_l(__float_as_uint(nd.y), m[r], 1);
+            }
         }
+        rz_resolve_masks<R, true>(reinterpret_cast<const float *>(mv), lm + i0, cn, n_static_pad, m, ray, t_min, bt, bk);
     }
 }
 
@@ -285,6 +319,7 @@ __device__ __forceinline__ void rz_queue_push(const RzPathArgs &a, bool cont, un
     if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     const unsigned e = base + __popc(m & lt_mask);
+    if (cont && e >= a.queue_cap) atomicOr(a.err, (unsigned)RZ_DEV_ERR_QUEUE_OVERFLOW);   // never silently: the render fails
     if (cont && e < a.queue_cap) {
         float4 *q = a.q_out + (size_t)e * 4u;
         __stcs(q + 0, make_float4(ray.o.x, ray.o.y, ray.o.z, ray.time));
@@ -309,6 +344,7 @@ __device__ __forceinline__ void rz_queue_push2(const RzPathArgs &a, const bool (
     const unsigned e2[2] = {base + (unsigned)__popc(m0 & lt_mask), base + n0 + (unsigned)__popc(m1 & lt_mask)};
 #pragma unroll
     for (int r = 0; r < 2; r++) {
+        if (cont[r] && e2[r] >= a.queue_cap) atomicOr(a.err, (unsigned)RZ_DEV_ERR_QUEUE_OVERFLOW);
         if (cont[r] && e2[r] < a.queue_cap) {
             float4 *q = a.q_out + (size_t)e2[r] * 4u;
             __stcs(q + 0, make_float4(ray[r].o.x, ray[r].o.y, ray[r].o.z, ray[r].time));

@@ -280,8 +280,7 @@ extern "C" cudaError_t rz_wavefront_render(const RzPathArgs *a, int sm_count, in
     cudaError_t e;
     const unsigned long long n_tiles = (a->n_local_px + 31u) / 32u;
     const unsigned long long total_paths = n_tiles * 32ull * a->spp;   // padding pixels are dead on arrival
-    const char *pool_env = getenv("RZ_WF_POOL_LOG2");   // tuning experiment
-    const int pool_log2 = pool_env ? std::min(26, std::max(16, atoi(pool_env))) : 21;
+    const int pool_log2 = 21;   // 2^21 slots: 2^21..2^25 measured within 10 % of each other
     const size_t M = (size_t)std::min<unsigned long long>(total_paths, 1ull << pool_log2);
     WfScratch *ws = reinterpret_cast<WfScratch *>(*scratch);
     if (!ws || ws->M < M) {
@@ -312,7 +311,9 @@ extern "C" cudaError_t rz_wavefront_render(const RzPathArgs *a, int sm_count, in
     const size_t smem = (size_t)(a->set.n_pad + (a->set.n_pad - a->set.n_static_pad)) * 16u;
     const int grid_i = sm_count * 8, grid_s = sm_count * 4;
     uint32_t n_launch = 0;
-    wf_init<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(ws->st, total_paths);
+    // the pool may be larger than this job needs (scratch reused after a bigger render): the free list is rebuilt over ALL
+    // of its ws->M slots, or the stale top of the stack would hand out slots the rewritten bottom also holds
+    wf_init<<<(unsigned)((ws->M + 255) / 256), 256, 0, stream>>>(ws->st, total_paths);
     n_launch++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 

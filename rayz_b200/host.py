@@ -240,8 +240,33 @@ class Backend:
     def set_stream(self, cuda_stream: int | None):
         abi.check(self.lib.rayz_cuda_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
-    def set_tuning(self, rays_per_thread: int = 0, chunk: int = 0):
-        abi.check(self.lib.rayz_cuda_set_tuning(self._h, rays_per_thread, chunk))
+    def get_tuning(self) -> dict:
+        t = abi.RzTuning()
+        abi.check(self.lib.rayz_cuda_get_tuning(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def set_tuning(self, rays_per_thread: int = 0, chunk: int = 0, **fields):
+        """rayz_cuda_get_tuning -> change -> rayz_cuda_set_tuning (include/rayz_cuda.h: RzTuning).  `chunk` sets the work-unit
+        size of the persistent kernels and of the primary kernel alike; other fields by name, e.g. second_stages=3."""
+        t = abi.RzTuning()
+        abi.check(self.lib.rayz_cuda_get_tuning(self._h, C.byref(t)))
+        if rays_per_thread:
+            t.rays_per_thread = rays_per_thread
+        if chunk:
+            t.chunk = t.chunk_primary = chunk
+        for k, v in fields.items():
+            if k not in dict(abi.RzTuning._fields_):
+                raise KeyError(k)
+            setattr(t, k, v)
+        abi.check(self.lib.rayz_cuda_set_tuning(self._h, C.byref(t)))
+
+    def debug_sort_keys(self, keys: np.ndarray):
+        """Test hook: the staged K1's key sort (rz_sort.cu) on caller-supplied 16-bit keys -> (keys in slot order, entry index in slot order)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint16)
+        ko = np.empty_like(keys)
+        io = np.empty(keys.shape, dtype=np.uint32)
+        abi.check(self.lib.rayz_cuda_debug_sort_keys(self._h, keys.ctypes.data, keys.size, ko.ctypes.data, io.ctypes.data))
+        return ko, io
 
     def upload_scene(self, arrays: dict):
         sc, keep = scene_struct(arrays)
@@ -416,4 +441,18 @@ def random_bouncing(img_w: int, seed: int = 42, grid_lo: int = -11, grid_hi: int
             else:
                 m = pool.add_dielectric(1.5)
             pool.add_sphere(center, 0.2, m, vel)
+    return tracer
+
+
+def penultimate_scene(img_w: int, devices=(0,)) -> Tracer:
+    """penultimateScene (rayz.zig:170-239) — dead code in the reference (it targets a removed MemPool API), restated with
+    today's calls in its insertion order: diffuse centre sphere, ground, a glass sphere with an air bubble inside it
+    (refractive index 1/1.5: hollow glass), and a fully fuzzy metal sphere.  Camera: vfov 20, focus 3.4, defocus 10 degrees."""
+    tracer = Tracer(img_w, 20.0, 3.4, 10.0, (-2, 2, 1), (0, 0, -1), (0, 1, 0), devices=devices)
+    pool = tracer.pool
+    pool.add_sphere((0, 0, -1.2), 0.5, pool.add_diffuse(pool.add_solid((0.1, 0.2, 0.5))))
+    pool.add_sphere((0, -100.5, -1), 100, pool.add_diffuse(pool.add_solid((0.8, 0.8, 0.0))))
+    pool.add_sphere((-1, 0, -1), 0.5, pool.add_dielectric(1.5))            # left outer
+    pool.add_sphere((-1, 0, -1), 0.4, pool.add_dielectric(1.0 / 1.5))      # left inner bubble
+    pool.add_sphere((1, 0, -1), 0.5, pool.add_metallic(pool.add_solid((0.8, 0.6, 0.2)), 1.0))
     return tracer

@@ -1,10 +1,12 @@
-// rz_search_variants.cuh — forms of the K1 search that were measured and NOT adopted; only scripts/searchbench.cu
+// rz_search_variants.cuh — (scripts only; round-1 forms with the textbook discriminant b^2 - c: since round 2 the product
+// uses the cancellation-free test rz_sphere_test, so these are no longer bit-identical to it, only rate comparisons)
+// forms of the K1 search that were measured and NOT adopted; only scripts/searchbench.cu
 // includes this header (profiles/r01_search_microbench.md holds the numbers).  All of them return bit-identical (t, k).
 //   rz_search_brute     scalar FFMA form of the first round-1 kernel (47 % of FP32 peak)
 //   RzSrcConst          packed search with the operands from the constant bank (LDCU -> UR.F32x2): LDCU-rate bound
 //   rz_search_brute_rp  packed by ray pairs instead of sphere pairs: same rate as the production form
 #pragma once
-#include "rz_search.cuh"
+#include "../rayz_b200/csrc/rz_search.cuh"
 
 // ------------------------------------------------------------------------------ K1 search
 // Brute force over the shared-memory sphere set for R rays at once.  Unit-length directions:
@@ -38,7 +40,7 @@ __device__ __forceinline__ void rz_search_brute(const float4 *__restrict__ s_cr,
             for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int j = 0; j < G; j++)
-                    if (disc[r][j] > 0.0f) rz_consider(i + j, b[r][j], disc[r][j], ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (disc[r][j] > 0.0f) rz_consider(i + j, -b[r][j], -disc[r][j], ray[r].self_k, t_min, bt[r], bk[r]);
         }
     }
 #pragma unroll 1
@@ -70,7 +72,7 @@ __device__ __forceinline__ void rz_search_brute(const float4 *__restrict__ s_cr,
             for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int j = 0; j < G; j++)
-                    if (disc[r][j] > 0.0f) rz_consider(i + j, b[r][j], disc[r][j], ray[r].self_k, t_min, bt[r], bk[r]);
+                    if (disc[r][j] > 0.0f) rz_consider(i + j, -b[r][j], -disc[r][j], ray[r].self_k, t_min, bt[r], bk[r]);
         }
     }
 }
@@ -141,8 +143,8 @@ __device__ __forceinline__ void rz_search_brute_rp(const float4 *__restrict__ s_
             for (int p = 0; p < P; p++)
 #pragma unroll
                 for (int j = 0; j < G; j++) {
-                    if (disc[p][j].x > 0.0f) rz_consider(k + j, b[p][j].x, disc[p][j].x, ray[2 * p].self_k, t_min, bt[2 * p], bk[2 * p]);
-                    if (disc[p][j].y > 0.0f) rz_consider(k + j, b[p][j].y, disc[p][j].y, ray[2 * p + 1].self_k, t_min, bt[2 * p + 1], bk[2 * p + 1]);
+                    if (disc[p][j].x > 0.0f) rz_consider(k + j, -b[p][j].x, -disc[p][j].x, ray[2 * p].self_k, t_min, bt[2 * p], bk[2 * p]);
+                    if (disc[p][j].y > 0.0f) rz_consider(k + j, -b[p][j].y, -disc[p][j].y, ray[2 * p + 1].self_k, t_min, bt[2 * p + 1], bk[2 * p + 1]);
                 }
         }
     }
@@ -172,8 +174,8 @@ __device__ __forceinline__ void rz_search_brute_rp(const float4 *__restrict__ s_
             for (int p = 0; p < P; p++)
 #pragma unroll
                 for (int j = 0; j < G; j++) {
-                    if (disc[p][j].x > 0.0f) rz_consider(k + j, b[p][j].x, disc[p][j].x, ray[2 * p].self_k, t_min, bt[2 * p], bk[2 * p]);
-                    if (disc[p][j].y > 0.0f) rz_consider(k + j, b[p][j].y, disc[p][j].y, ray[2 * p + 1].self_k, t_min, bt[2 * p + 1], bk[2 * p + 1]);
+                    if (disc[p][j].x > 0.0f) rz_consider(k + j, -b[p][j].x, -disc[p][j].x, ray[2 * p].self_k, t_min, bt[2 * p], bk[2 * p]);
+                    if (disc[p][j].y > 0.0f) rz_consider(k + j, -b[p][j].y, -disc[p][j].y, ray[2 * p + 1].self_k, t_min, bt[2 * p + 1], bk[2 * p + 1]);
                 }
         }
     }

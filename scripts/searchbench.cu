@@ -13,7 +13,7 @@
 #include <random>
 #include <algorithm>
 
-#include "../rayz_b200/csrc/rz_search_variants.cuh"
+#include "rz_search_variants.cuh"
 
 extern "C" cudaError_t rz_launch_ffma_peak(float *sink, int grid, int iters, int mode, cudaStream_t stream);
 

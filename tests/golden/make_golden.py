@@ -4,6 +4,8 @@
 
 ids_seed42_400x225.npz      primary-ray closest-hit sphere ids of the default scene (config 1 size)
 ids_seed42_1200x675.npz     same at config 2 size
+ids_config4_960x540.npz     same for BASELINE config 4's scene (randomBouncing with the grid loops widened to [-158, 158):
+                            99,856 spheres) at 960x540, through the reference's BVH (hit.zig:130-161,181-216)
 scene_seed42.npz            the flat scene arrays of randomBouncing(seed 42) (RzScene field names)
 config2_oracle_500spp.npz   (--full) 1200x675, 500 spp, depth 50 oracle render (row-stream mode,
                             seed 2024) reduced to 4x4 and 16x16 block means + global means
@@ -37,6 +39,12 @@ def main():
         assert ids.max() < 32767
         np.savez_compressed(os.path.join(HERE, f"ids_seed42_{w}x{h}.npz"), ids=ids.astype(np.int16))
         print(w, h, int((ids >= 0).sum()), "hits")
+    big = oracle.Scene.random_bouncing(42, -158, 158)
+    assert big.counts()[0] == 99856
+    cam, h = oracle.default_camera(960)
+    ids = big.primary_ids(cam, 960, h, use_bvh=True)
+    np.savez_compressed(os.path.join(HERE, f"ids_config4_960x{h}.npz"), ids=ids.astype(np.int32))
+    print("config 4:", 960, h, int((ids >= 0).sum()), "hits, max id", int(ids.max()))
     if "--full" in sys.argv:
         cam, h = oracle.default_camera(1200)
         t = time.time()

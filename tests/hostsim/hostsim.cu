@@ -16,16 +16,8 @@
 #include "../../include/rayz_cuda.h"
 #include "../../rayz_b200/csrc/rz_device.cuh"
 
-#define RZ_FAR_BIT 0x40000000
-
-static inline void consider(int k, float b, float disc, int self_k, float t_min, float &bt, int &bk) {
-    const float sq = sqrtf(disc);
-    float t = b - sq;
-    int tag = k;
-    if (k == self_k) { t = (b > 0.0f) ? b + sq : -1.0f; tag = k | RZ_FAR_BIT; }
-    else if (t < t_min) { t = b + sq; tag = k | RZ_FAR_BIT; }
-    if (t > t_min && t < bt) { bt = t; bk = tag; }
-}
+// the sphere test and the root rule are the product's own (rz_sphere_test / rz_consider, rz_device.cuh)
+static inline void consider(int k, float nb, float nd, int self_k, float t_min, float &bt, int &bk) { rz_consider(k, nb, nd, self_k, t_min, bt, bk); }
 
 extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth,
                               uint64_t seed, float t_min, uint32_t threads, double *out_rgb, uint64_t *counters) {
@@ -82,11 +74,9 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
                         float bt = 3.0e38f; int bk = -1;
                         for (uint32_t k = 0; k < n; k++) {
                             const float4 sp = cr[k], v = vel[k];
-                            const float ocx = fmaf(v.x, ray.time, sp.x - ray.o.x), ocy = fmaf(v.y, ray.time, sp.y - ray.o.y), ocz = fmaf(v.z, ray.time, sp.z - ray.o.z);
-                            const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
-                            const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, sp.w)));
-                            const float disc = fmaf(b, b, -c);
-                            if (disc > 0.0f) consider((int)k, b, disc, ray.self_k, t_min, bt, bk);
+                            float nb, nd;
+                            rz_sphere_test(sp.x, sp.y, sp.z, v.x, v.y, v.z, sp.w, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.time, nb, nd);
+                            if (nd < 0.0f) consider((int)k, nb, nd, ray.self_k, t_min, bt, bk);
                         }
                         ct[1]++;
                         if (bk < 0) {
@@ -402,11 +392,9 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
         for (uint32_t q = 0; q < cnt; q++) {
             const uint32_t k = list ? (*list)[q] : q;
             const float4 sp = cr[k], v = vel[k];
-            const float ocx = fmaf(v.x, ray.time, sp.x - ray.o.x), ocy = fmaf(v.y, ray.time, sp.y - ray.o.y), ocz = fmaf(v.z, ray.time, sp.z - ray.o.z);
-            const float b = fmaf(ocz, ray.d.z, fmaf(ocy, ray.d.y, ocx * ray.d.x));
-            const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, sp.w)));
-            const float disc = fmaf(b, b, -c);
-            if (disc > 0.0f) consider((int)k, b, disc, ray.self_k, t_min, bt, bk);
+            float nb, nd;
+            rz_sphere_test(sp.x, sp.y, sp.z, v.x, v.y, v.z, sp.w, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.time, nb, nd);
+            if (nd < 0.0f) consider((int)k, nb, nd, ray.self_k, t_min, bt, bk);
         }
     };
     struct Entry { uint32_t key; RzRay ray; };

@@ -20,7 +20,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(abi.SYMBOLS), (declared ^ set(abi.SYMBOLS))
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rayz_cuda_abi_version() == 2
+    assert lib.rayz_cuda_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
@@ -30,6 +30,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.RzStats) == 80
     assert C.sizeof(abi.RzTiming) == 48
     assert C.sizeof(abi.RzConfig) == 40
+    assert C.sizeof(abi.RzTuning) == 80
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
