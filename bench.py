@@ -12,9 +12,9 @@ A step is one full render of the workload (one pass of Tracer.render's pixel loo
 `value`  : whole-job Mpaths/s with scene and camera resident in HBM, results left in HBM on GPU0.
 `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
            (rayz_cuda_upload_scene + rayz_cuda_render: H2D of the scene, D2H of linear float4 + RGB8).
-`roofline`: FP32 (FFMA issue) bound — algorithmic flop of the brute-force search (SURVEY §8d /
-           DESIGN.md) over the CUDA-event duration of the path kernel, against the FFMA peak
-           measured live by the K6 microbenchmark.
+`roofline`: the dominant kernel against BOTH roofs — algorithmic flop (SURVEY §8d / DESIGN.md) over its CUDA-event
+           duration against the FFMA peak measured live by the K6 microbenchmark, and algorithmic HBM bytes over the same
+           duration against MEASURED_PEAKS.json's copy bandwidth; `bound` names the nearer roof.
 Only the cpu_baseline leg and --impl reference execute oracle/ (the CPU restatement of the Zig
 reference, which cannot be compiled in this image).
 """
@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mpaths/s"
+ENTRY_BYTES = 64   # one queue entry of the staged K1 (rz_search.cuh: rz_queue_push)
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45: SMs x lanes x 2 flop x max SM clock
 
 
@@ -134,7 +135,10 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"], "sample": sample},
+        "config": {"workload": w["name"], "width": w["width"], "height": h, "spp": w["spp"], "max_depth": w["depth"],
+                   "paths_per_step": paths, "sample": sample, "sample_spp": spp,
+                   "bounded_sample": "same scene, same resolution, same depth; each step renders sample_spp of the workload's spp "
+                                     "(Mpaths/s does not depend on spp: every sample costs the same)"},
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "oracle/ C++ restatement of the Zig reference (no zig toolchain in the image); rows "
                                  "over all host threads with per-row PRNG streams; the reference itself is single-threaded"},
@@ -162,16 +166,23 @@ def algorithmic_flops_per_path(stats: dict, n_static: int, n_moving: int) -> dic
             "f_secondary": max(0.0, S - 1.0) * f_isect}
 
 
-def ncu_traffic(variant: str, kernel: str, paths_per_launch: float):
-    """dram__bytes_read + dram__bytes_write of the roofline kernel per launch, scaled from the committed ncu --set full
-    captures (profiles/traffic.json: bytes per path of the pass, measured on a 40-spp config-2 render; the traffic is the
-    64-byte queue entries between the stages plus the first touch of the accumulators)."""
+def ncu_traffic_per_entry(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of a kernel, per queue entry (= ray segment) it processed, from the committed
+    `ncu --set full` capture of this round (profiles/traffic.json; the capture's launch is named there).  None if no capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            per_path = json.load(f).get(variant, {}).get(kernel.split(" ")[0].split("<")[0])
-        return None if per_path is None else per_path * paths_per_launch
+            return json.load(f).get("dram_bytes_per_segment", {}).get(kernel)
     except Exception:
         return None
+
+
+def measured_hbm_peak():
+    """(GB/s, source) — MEASURED_PEAKS.json (driver-written) or the profiling recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (torch copy, read+write bytes)"
+    except Exception:
+        return 6400.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to fd 1 when
@@ -205,6 +216,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -347,9 +359,81 @@ def main():
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     kern_ms, prim_ms, second_ms, sort_ms = (float(x) for x in kt.tolist())
     be.render_device(cam, p, sync=True)
+    tinfo_run = be.timing()
     launches_per_step = be.timing()["launches"]
     passes_per_step = be.timing()["passes"]
     variant_ran = {1: "mega", 2: "wavefront", 3: "bvh", 4: "mega_single"}.get(be.timing()["variant"], "?")
+
+    # ---- N > 1: (i) the gathered frame is checked, not just timed: at low spp the ranks' slabs, gathered over NCCL, must equal
+    # the same frame rendered by rank 0 alone, byte for byte (counter-based RNG + integer accumulation: sharding-invariant);
+    # (ii) rank 0 renders the FULL workload alone once, so that scaling can be read against the same work on one GPU.
+    frame_check = single_gpu = None
+    if world > 1:
+        chk_spp = 4
+        pc = Backend.params(W, H, chk_spp, DEPTH, seed=1, variant=resolved, shard_index=rank, shard_count=world, band_rows=band)
+        dl, d8, _ = be.render_device(cam, pc, sync=True)
+        lin = torch.as_tensor(DevArray(dl, (my_rows, W, 4), "<f4"), device=dev)
+        rgb = torch.as_tensor(DevArray(d8, (my_rows, W, 3), "|u1"), device=dev)
+        full_lin = gather_lin.run(lin)
+        full_rgb = gather_rgb.run(rgb)
+        barrier()
+        if rank == 0:
+            got_lin, got_rgb = full_lin.cpu().numpy().copy(), full_rgb.cpu().numpy().copy()
+            p1 = Backend.params(W, H, chk_spp, DEPTH, seed=1, variant=resolved)
+            ref_lin, ref_rgb, _ = be.render(cam, p1)
+            import zlib
+            frame_check = {"spp": chk_spp, "gathered_equals_single_gpu_render": bool(np.array_equal(got_lin, ref_lin) and np.array_equal(got_rgb, ref_rgb)),
+                           "crc32_rgb8_gathered": zlib.crc32(got_rgb.tobytes()), "crc32_rgb8_single_gpu": zlib.crc32(ref_rgb.tobytes()),
+                           "crc32_linear_gathered": zlib.crc32(got_lin.tobytes()), "crc32_linear_single_gpu": zlib.crc32(ref_lin.tobytes())}
+            assert frame_check["gathered_equals_single_gpu_render"], frame_check
+            p_full = Backend.params(W, H, SPP, DEPTH, seed=1, variant=resolved)
+            be.render_device(cam, p_full, sync=True)                     # warm-up (allocates this shape's buffers)
+            ms1 = []
+            for _ in range(2):
+                flush_buf.zero_()
+                a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_ev.record(stream)
+                be.render_device(cam, p_full, sync=False)
+                b_ev.record(stream)
+                b_ev.synchronize()
+                ms1.append(a_ev.elapsed_time(b_ev))
+            single_gpu = {"value": total_paths / (min(ms1) * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": min(ms1), "n_gpus": 1,
+                          "workload": w["name"], "note": "rank 0 alone, whole frame, same kernels, device-resident (best of 2); "
+                                                         "value / (n_gpus * this) is the strong-scaling efficiency on equal work"}
+        barrier()
+
+    # ---- the other BASELINE configs on one GPU (one warm-up + best of two timed renders each, device-resident; informational)
+    other_configs = None
+    if world == 1 and not args.no_other_configs:
+        other_configs = {}
+        for name, kw, ow, ospp in (("config4: 99,856 spheres (randomBouncing grid [-158,158)), device LBVH, 1920x1080, 256 spp, depth 50",
+                                    dict(grid_lo=-158, grid_hi=158), 1920, 256),
+                                   ("config5: glass-heavy (all-dielectric randomBouncing), 1200x675, 500 spp, depth 50", dict(glass_heavy=True), 1200, 500)):
+            t_o = rayz_b200.random_bouncing(ow, seed=42, **kw)
+            be_o = Backend((local_rank,))
+            be_o.set_stream(stream.cuda_stream)
+            be_o.upload_scene(t_o.pool.arrays())
+            po = Backend.params(ow, t_o.img.h, ospp, DEPTH, seed=1, variant="auto")
+            be_o.render_device(t_o.camera.rz, po, sync=True)
+            best, info = None, None
+            for _ in range(2):
+                flush_buf.zero_()
+                a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_ev.record(stream)
+                be_o.render_device(t_o.camera.rz, po, sync=False)
+                b_ev.record(stream)
+                b_ev.synchronize()
+                ms = a_ev.elapsed_time(b_ev)
+                if best is None or ms < best:
+                    best = ms
+            be_o.render_device(t_o.camera.rz, po, sync=True)
+            info = be_o.timing()
+            npaths = ow * t_o.img.h * ospp
+            other_configs[name.split(":")[0]] = {"workload": name, "value": npaths / (best * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": best,
+                                                 "paths_per_step": npaths, "spheres": len(t_o.pool.sphere_radius),
+                                                 "variant": {1: "mega", 2: "wavefront", 3: "bvh", 4: "mega_single"}.get(info["variant"]),
+                                                 "launches": info["launches"], "bvh_build_us": info["bvh_build_us"]}
+            be_o.close()
 
     # ---- e2e: reference-facing call with host buffers (rank 0 drives all N GPUs through the
     # library's own multi-device context: this is what the single-process Zig host would call)
@@ -394,64 +478,109 @@ def main():
 
     if rank == 0:
         fl = algorithmic_flops_per_path(stats, tinfo["n_static"], tinfo["n_moving"])
-        peak_tf, sms = be.fp32_peak(400)
+        # K6, the FP32 roof: three FFMA forms back to back, ~2 s each = 6 s of sustained FP32 load, SM clock sampled beside it
+        k6_sampler = ClockSampler(local_rank)
+        k6_sampler.start()
+        time.sleep(0.2)
+        k6_t0 = time.time()
+        peak_tf, sms = be.fp32_peak(4000)
+        k6_t1 = time.time()
+        k6_clocks = k6_sampler.stop(k6_t0, k6_t1)
+        hbm_peak, hbm_src = measured_hbm_peak()
         per_gpu_paths = total_paths / world
         two_stage = passes_per_step > 0
         stages = None
         if two_stage:
             # Staged K1: per-kernel durations from a render with serial passes (CUDA events around every launch, tails
             # included), algorithmic flop from each kernel's own sphere-test counter (16 per stationary, 22 per moving test;
-            # shading flop left out: an undercount of < 1 %).  The roofline kernel is the one with the largest share of the step.
-            scale = per_gpu_paths / max(1, stats["paths"])            # the stats pass ran fewer spp
+            # shading flop left out: an undercount of < 1 %), algorithmic HBM bytes from the queue entries each kernel reads and
+            # writes.  The roofline kernel is the one with the largest share of the step.
+            scale = per_gpu_paths / max(1, stats["paths"])            # the stats pass covers this rank's share
             n_sph = max(1, tinfo["n_static"] + tinfo["n_moving"])
             f_test = fl["f_isect"] / n_sph                            # mean flop per sphere test of this scene
             meg_ms = kern_ms - prim_ms - second_ms - sort_ms
-            # launches = passes * (primary + n_stage * k + tail) + resolve; k = 5 (selector, 3 cub kernels, stage kernel) or 4 (plain sort)
-            body = launches_per_step - 2 * passes_per_step - 1
-            n_stage = max(1, next((body // (k * passes_per_step) for k in (5, 4) if body % (k * passes_per_step) == 0), body // (5 * passes_per_step)))
-            def stage(name, st, ms, launches):
+            n_stage = max(1, tinfo_run["sorted_stages"])
+            ended = lambda st: st["ended_sky"] + st["ended_absorbed"] + st["ended_depth"]
+            E, KEY, IDX = ENTRY_BYTES, 2, 4
+            # queue entries written by a stage = its segments that did not end there; read by the next one
+            out0 = (stage_stats[0]["segments"] - ended(stage_stats[0])) * scale          # primary -> first sorted stage
+            in1 = stage_stats[1]["segments"] * scale                                      # all sorted stages, entries read
+            out1 = (stage_stats[1]["segments"] - ended(stage_stats[1])) * scale           # ... entries written (next stage or tail)
+            in2 = out1 - (in1 - out0) if n_stage else out0                                 # entries the tail kernel starts from
+            in2 = max(0.0, in2)
+            hbm = [out0 * (E + KEY) + 35 * W * H / world,                                 # primary: append entry + key (+ the frame, once)
+                   in1 * (E + KEY + IDX) + out1 * E + (out1 - in2) * KEY,                 # sorted stages: gather entry through key+index, append
+                   in2 * E,                                                               # tail: read its entries
+                   in1 * (2 * KEY + KEY + IDX)]                                           # sort: keys read twice (count, scatter), key + index written
+            def stage(name, st, ms, launches, hbm_bytes):
                 # a kernel that walked the BVH counted box tests too: 18 flop per box, 22 per (general) sphere test
-                flop = (st["sphere_tests"] * 22 + st["node_tests"] * 18) * scale if st["node_tests"] else st["sphere_tests"] * scale * f_test
-                return {"kernel": name, "ms_per_step": ms, "launches_per_step": launches, "share_of_step": ms / kern_ms,
-                        "segments": st["segments"] * scale, "sphere_tests": st["sphere_tests"] * scale,
-                        "node_tests": st["node_tests"] * scale, "flop": flop,
-                        "achieved_tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else None,
-                        "frac": flop / (ms * 1e-3) / 1e12 / peak_tf if ms > 0 and peak_tf else None}
-            stages = [stage("rz_primary_kernel (camera segments, tile-frustum cull)", stage_stats[0], prim_ms, passes_per_step),
-                      stage("rz_second_kernel (sorted segments 2.." + str(n_stage + 1) + ", per-unit cull)", stage_stats[1], second_ms, passes_per_step * n_stage),
+                flop = 0.0
+                if st is not None:
+                    flop = (st["sphere_tests"] * 22 + st["node_tests"] * 18) * scale if st["node_tests"] else st["sphere_tests"] * scale * f_test
+                d = {"kernel": name, "ms_per_step": ms, "launches_per_step": launches, "share_of_step": ms / kern_ms,
+                     "flop": flop, "achieved_tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else None,
+                     "frac": flop / (ms * 1e-3) / 1e12 / peak_tf if ms > 0 and peak_tf else None,
+                     "hbm_bytes_algorithmic": hbm_bytes, "hbm_gbs": hbm_bytes / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                     "hbm_frac": hbm_bytes / (ms * 1e-3) / 1e9 / hbm_peak if ms > 0 else None}
+                if st is not None:
+                    d.update({"segments": st["segments"] * scale, "sphere_tests": st["sphere_tests"] * scale, "node_tests": st["node_tests"] * scale})
+                return d
+            stages = [stage("rz_primary_kernel (camera segments, tile-frustum cull)", stage_stats[0], prim_ms, passes_per_step, hbm[0]),
+                      stage("rz_second_kernel (sorted segments 2.." + str(n_stage + 1) + ", per-unit cull)", stage_stats[1], second_ms, passes_per_step * n_stage, hbm[1]),
                       stage("rz_bvh_kernel<QUEUE> (persistent BVH kernel, later segments)" if stage_stats[2]["node_tests"] else
-                            "rz_path_kernel<QUEUE> (persistent brute-force megakernel, later segments)", stage_stats[2], meg_ms, passes_per_step),
-                      {"kernel": "cub::DeviceRadixSort (queue keys between the stages; library)", "ms_per_step": sort_ms, "share_of_step": sort_ms / kern_ms}]
+                            "rz_path_kernel<QUEUE> (persistent brute-force megakernel, later segments)", stage_stats[2], meg_ms, passes_per_step, hbm[2]),
+                      stage("rz_bin_kernel<count> + rz_bin_scan_kernel + rz_bin_kernel<scatter> (key sort between the stages, rz_sort.cu)", None, sort_ms,
+                            3 * passes_per_step * n_stage, hbm[3])]
             dom = max(stages[:3], key=lambda x: x["ms_per_step"])
-            dom_name, dom_ms, dom_flop, dom_launches = dom["kernel"], dom["ms_per_step"], dom["flop"], dom["launches_per_step"]
+            dom_name, dom_ms, dom_flop, dom_launches, dom_hbm = dom["kernel"], dom["ms_per_step"], dom["flop"], dom["launches_per_step"], dom["hbm_bytes_algorithmic"]
+            dom_segments = dom["segments"]
+            step_hbm = sum(hbm)
         else:
             dom_name = "rz_path_kernel (" + variant_ran + ")" if variant_ran != "bvh" else "rz_bvh_kernel"
             dom_ms = kern_ms
             dom_flop = per_gpu_paths * fl["f_path"]
             dom_launches = 1
+            dom_hbm = step_hbm = 35 * W * H / world
+            dom_segments = stats["segments"] * per_gpu_paths / max(1, stats["paths"])
         achieved = dom_flop / (dom_ms * 1e-3) / 1e12
         step_flops = per_gpu_paths * fl["f_path"] / (kern_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp32", "kernel": dom_name, "achieved": achieved, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                    "peak_source": "measured live: K6 FFMA/FFMA2 microbenchmark (MEASURED_PEAKS.json has no FP32 figure)",
-                    "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
+        fp32_frac = achieved / peak_tf if peak_tf else None
+        hbm_gbs = dom_hbm / (dom_ms * 1e-3) / 1e9
+        hbm_frac = hbm_gbs / hbm_peak
+        tpe = ncu_traffic_per_entry(dom_name.split(" ")[0].split("<")[0])
+        bound = "hbm" if hbm_frac > (fp32_frac or 0) else "fp32"
+        # achieved / peak / unit / frac describe the roof named by `bound`; both roofs are spelled out beside them, per launch
+        # (one launch = one kernel invocation; the dominant kernel is launched `launches_per_step` times per step)
+        roofline = {"bound": bound, "kernel": dom_name,
+                    "achieved": hbm_gbs if bound == "hbm" else achieved, "peak": hbm_peak if bound == "hbm" else peak_tf,
+                    "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": hbm_frac if bound == "hbm" else fp32_frac,
+                    "traffic": tpe * dom_segments / max(1, dom_launches) if tpe else None,
+                    "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled per ray segment from the committed "
+                                    "capture (profiles/traffic.json) — same unit and denominator as hbm.algorithmic_bytes_per_launch",
+                    "fp32": {"achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": fp32_frac,
+                             "flop_per_launch": dom_flop / max(1, dom_launches),
+                             "peak_source": "measured live: K6 FFMA/FFMA2 microbenchmark, 3 forms x ~2 s back to back (MEASURED_PEAKS.json has no FP32 figure)",
+                             "k6_clocks": k6_clocks, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS},
+                    "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac,
+                            "algorithmic_bytes_per_launch": dom_hbm / max(1, dom_launches), "algorithmic_bytes_per_step": dom_hbm,
+                            "entry_bytes": ENTRY_BYTES, "peak_source": hbm_src},
                     "kernel_ms_per_launch": dom_ms / max(1, dom_launches), "launches_per_step": dom_launches,
                     "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / kern_ms,
                     "stages": stages,
                     "all_kernels_ms_per_step_serial": kern_ms,
-                    "whole_step_achieved": step_flops, "whole_step_frac": step_flops / peak_tf if peak_tf else None,
+                    "whole_step": {"fp32_achieved": step_flops, "fp32_frac": step_flops / peak_tf if peak_tf else None,
+                                   "hbm_bytes_algorithmic": step_hbm, "hbm_gbs": step_hbm / (kern_ms * 1e-3) / 1e9,
+                                   "hbm_frac": step_hbm / (kern_ms * 1e-3) / 1e9 / hbm_peak},
                     "flop_per_path": fl["f_path"], "flop_per_path_dominant_kernel": dom_flop / per_gpu_paths,
                     "segments_per_path": fl["segments_per_path"], "sphere_tests_per_path": fl["tests_per_path"],
-                    "flop_per_segment_search": fl["f_isect"], "traffic": ncu_traffic(variant_ran, dom_name, per_gpu_paths / max(1, dom_launches)),
-                    "hbm_bytes_algorithmic": int(35 * W * H / world + (136 * (stage_stats[1]["segments"] + stage_stats[2]["paths"] + stats["paths"]) * per_gpu_paths / max(1, stats["paths"]) if two_stage else 0)),
+                    "flop_per_segment_search": fl["f_isect"],
                     "note": "The default (staged K1) wins by NOT doing arithmetic: tile-frustum and sorted-unit culls, and a BVH walk for the "
                             f"tail of the paths, cut the sphere tests per path from segments*n_spheres ({fl['segments_per_path'] * (tinfo['n_static'] + tinfo['n_moving']):.0f}) "
                             f"to {fl['tests_per_path']:.0f}, so its FP32 fraction is below that of K1 run as one brute-force "
                             "kernel, which variants.mega_single reports (frac_of_fp32_peak, the north star's 40 % target). "
                             "flop = algorithmic count of SURVEY 8(d) (16 per stationary, 22 per moving sphere test, 18 per BVH box test) of the "
-                            "tests each kernel actually counted in a stats render of the same workload; "
-                            "tensor cores unused by design; HBM traffic = 35 B/pixel of framebuffer once per render, plus, in the "
-                            "staged form, 64 B written + 64 B read (+ 8 B of sort key/index) per path and queue hop (upper bound)"}
+                            "tests each kernel actually counted in a stats render of the same workload; tensor cores unused by design; "
+                            "HBM bytes = the queue entries, keys and indices each kernel reads and writes (+ 35 B/pixel of framebuffer once per render)"}
         out = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -464,6 +593,13 @@ def main():
         }
         if e2e:
             out["e2e"] = e2e
+        if frame_check:
+            out["frame_check"] = frame_check
+        if single_gpu:
+            out["single_gpu_same_workload"] = single_gpu
+            out["strong_scaling_efficiency_same_workload"] = value / (world * single_gpu["value"])
+        if other_configs:
+            out["other_configs"] = other_configs
         if variants:
             if "mega_single" in variants and peak_tf:
                 variants["mega_single"]["frac_of_fp32_peak"] = variants["mega_single"]["algorithmic_tflops"] / peak_tf

@@ -176,6 +176,8 @@ typedef struct RzTiming {
     uint32_t passes;       /* staged K1: passes (primary / sort + sorted stages / tail kernel) of the render, else 0 */
     float second_ms;       /* staged K1: sum of the sorted-segment kernels' durations (clean with serial passes) */
     float sort_ms;         /* staged K1: sum of the key sorts' durations (clean with serial passes)             */
+    uint32_t sorted_stages; /* staged K1: sorted stages per pass of the render                                  */
+    uint32_t queue_entries; /* staged K1: entries each queue buffer holds (= paths per pass)                    */
 } RzTiming;
 
 typedef struct RzContext RzContext;

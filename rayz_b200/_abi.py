@@ -57,7 +57,8 @@ class RzStats(C.Structure):
 
 class RzTiming(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("resolve_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32),
-                ("n_static", C.c_uint32), ("n_moving", C.c_uint32), ("variant", C.c_uint32), ("bvh_build_us", C.c_uint32), ("primary_ms", C.c_float), ("passes", C.c_uint32), ("second_ms", C.c_float), ("sort_ms", C.c_float)]
+                ("n_static", C.c_uint32), ("n_moving", C.c_uint32), ("variant", C.c_uint32), ("bvh_build_us", C.c_uint32), ("primary_ms", C.c_float), ("passes", C.c_uint32), ("second_ms", C.c_float), ("sort_ms", C.c_float),
+                ("sorted_stages", C.c_uint32), ("queue_entries", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved0"}

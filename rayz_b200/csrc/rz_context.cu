@@ -149,6 +149,7 @@ struct Dev {
     std::vector<cudaEvent_t> pass_ev;   // staged K1: [3i] after the primary kernel of pass i, [3i+1] after the sorted stages, [3i+2] after the tail kernel
     std::vector<cudaEvent_t> stage_ev;  // staged K1: per pass and sorted stage, [2k] after the sort, [2k+1] after the kernel
     uint32_t n_second = 0;              // sorted stages per pass of the last render
+    uint32_t queue_entries = 0;         // entries per queue buffer of the last render (0 = not the staged form)
     uint32_t passes = 0;                // passes of the last render (0 = not the staged form)
     bool serial_passes = false;
 };
@@ -849,6 +850,8 @@ static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
     ctx->timing.second_ms = smax;
     ctx->timing.sort_ms = somax;
     ctx->timing.passes = passes;
+    ctx->timing.sorted_stages = ctx->devs[0].n_second;
+    ctx->timing.queue_entries = ctx->devs[0].queue_entries;
     if (collect_stats) {
         RzStats tot, stage[3];
         memset(&tot, 0, sizeof tot);
@@ -955,6 +958,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
         D.passes = 0;
         D.n_second = 0;
+        D.queue_entries = 0;
         if (n_local > 0) {
             if (variant == RZ_VARIANT_WAVEFRONT) {
                 uint32_t l = 0;
@@ -1013,6 +1017,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     }
                     D.passes = n_pass;
                     D.n_second = (uint32_t)n_second;
+                    D.queue_entries = (uint32_t)cap;
                     D.serial_passes = serial;
                     // Passes alternate between two streams and two sets of buffers: the persistent kernel ends with a tail of a
                     // few long paths (measured ~2 ms per pass), which the next pass's kernels fill.

@@ -743,9 +743,17 @@ def test_config4_image_parity_100k_spheres_device_lbvh(scene100k, orc):
     assert got["block_mae"] <= floor["block_mae"] * 1.15 + 1e-4
     sigma = (0.027 * 2 / (spp * w * h)) ** 0.5 * 3.0
     assert max(abs(x) for x in got["mean_diff"]) <= max(5e-4, 4 * sigma)
-    gs, os_ = gst["segments"] / gst["paths"], ost["segments"] / ost["paths"]
+    # Segments per path within 1 % — of the paths that are not trapped.  The reference's tmin = 1e-10 (renderer.zig:107) lets
+    # ~0.15 % of this scene's paths re-hit the sphere they just left at t ~ 2e-10, end up inside it and bounce there until
+    # depth 50 (oracle ended_depth 22,279 of 14.7 M; DESIGN.md "known deviation"); the backend excludes self-hits analytically
+    # (ended_depth 995).  Those trapped paths carry 50 segments each — 2.2 % of all segments — and nothing else differs:
+    trapped = lambda st: (st["segments"] - 50 * st["ended_depth"]) / st["paths"]
+    gs, os_ = trapped(gst), trapped(ost)
+    print("segments per untrapped path: gpu", gs, "oracle", os_, "| raw", gst["segments"] / n, ost["segments"] / n)
     assert abs(gs - os_) / os_ < 0.01, (gs, os_)
     assert abs(gst["ended_sky"] / n - ost["ended_sky"] / n) < 2e-3
+    assert abs(gst["hits_metallic"] - ost["hits_metallic"]) / ost["hits_metallic"] < 0.01
+    assert abs(gst["hits_dielectric"] - ost["hits_dielectric"]) / ost["hits_dielectric"] < 0.015
     # AUTO on this scene is the same kernel (the set does not fit shared memory), staged or not by job size
     lin2, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=1, variant="auto"))
     assert be.timing()["variant"] == 3 and np.array_equal(lin, lin2)

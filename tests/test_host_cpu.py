@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.RzRenderParams) == 56
     assert C.sizeof(abi.RzScene) == 16 + 14 * 8
     assert C.sizeof(abi.RzStats) == 80
-    assert C.sizeof(abi.RzTiming) == 48
+    assert C.sizeof(abi.RzTiming) == 56
     assert C.sizeof(abi.RzConfig) == 40
     assert C.sizeof(abi.RzTuning) == 80
 
