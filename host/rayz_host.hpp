@@ -180,24 +180,44 @@ struct Image {
     std::vector<V3> pixels;        // linear radiance, pixels[j*w+i]  (image.zig:7)
     std::vector<uint8_t> rgb8;     // device-side sqrt/clamp/trunc of image.zig:35-38
     static Image initEmpty(size_t h, size_t w) { Image i; i.h = h; i.w = w; i.pixels.resize(h * w); return i; }
-    // writePPM (image.zig:29-41): ASCII P3.  Same bytes as the reference's writer, produced with a
-    // table-driven itoa: at GPU speed the text dump is the slowest step after the render.
-    void writePPM(FILE *f) const {
-        std::fprintf(f, "P3\n%zu %zu\n%d\n", w, h, 255);
-        static char lut[256][4];
-        static int len[256];
+    // writePPM (image.zig:29-41): ASCII P3, "{r} {g} {b}\n" per pixel — the same bytes as the reference's writer.  At GPU
+    // speed this text dump is the slowest step after the render (config 3: 8.3 M pixels, ~95 MB of text), so it is built for
+    // throughput: one pre-sized buffer (at most 12 bytes per pixel), a table of the 256 possible "ddd " tokens copied as one
+    // 32-bit word each, and a single fwrite.  Returns the number of bytes written.
+    size_t formatPPM(std::vector<char> &buf) const {
+        struct Tok { uint32_t word; uint32_t len; };   // up to 3 digits + separator, little-endian in one word
+        static Tok sp[256], nl[256];
         static bool init = false;
-        if (!init) { for (int v = 0; v < 256; v++) len[v] = std::snprintf(lut[v], 4, "%d", v); init = true; }
-        std::vector<char> buf;
-        buf.reserve(h * w * 12 + 16);
-        for (size_t p = 0; p < h * w; p++) {
-            for (int c = 0; c < 3; c++) {
-                const uint8_t v = rgb8[p * 3 + c];
-                buf.insert(buf.end(), lut[v], lut[v] + len[v]);
-                buf.push_back(c == 2 ? '\n' : ' ');
+        if (!init) {
+            for (int v = 0; v < 256; v++) {
+                char t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                const int n = std::snprintf(t, sizeof t, "%d", v);
+                t[n] = ' ';
+                std::memcpy(&sp[v].word, t, 4); sp[v].len = (uint32_t)n + 1u;
+                t[n] = '\n';
+                std::memcpy(&nl[v].word, t, 4); nl[v].len = (uint32_t)n + 1u;
             }
+            init = true;
         }
-        std::fwrite(buf.data(), 1, buf.size(), f);
+        char head[64];
+        const int hn = std::snprintf(head, sizeof head, "P3\n%zu %zu\n%d\n", w, h, 255);
+        buf.resize((size_t)hn + h * w * 12 + 8);
+        char *o = buf.data();
+        std::memcpy(o, head, (size_t)hn);
+        o += hn;
+        const uint8_t *px = rgb8.data();
+        for (size_t p = 0, n = h * w; p < n; p++, px += 3) {
+            const Tok a = sp[px[0]], b = sp[px[1]], c = nl[px[2]];
+            std::memcpy(o, &a.word, 4); o += a.len;     // 4-byte stores that overlap by up to 2 bytes: no per-byte loop
+            std::memcpy(o, &b.word, 4); o += b.len;
+            std::memcpy(o, &c.word, 4); o += c.len;
+        }
+        return (size_t)(o - buf.data());
+    }
+    size_t writePPM(FILE *f) const {
+        std::vector<char> buf;
+        const size_t n = formatPPM(buf);
+        return std::fwrite(buf.data(), 1, n, f);
     }
 };
 
@@ -256,12 +276,17 @@ struct Tracer {
         return p;
     }
 
+    // The flattened MemPool (RzScene field order), kept alive here so that main can dump it (--dump-scene)
+    std::vector<double> sc, sv, sr, mf, mi, tcol, ts;
+    std::vector<uint32_t> sm, mk, mt, mm, tk, te, to;
+    std::vector<float> lin;   // linear float4 frame of the last render (--dump-linear)
+
     size_t render() {
         initBackend();
         // pool.initHittables + bvh.build (:76-78) -> flatten + upload
         const size_t ns = pool.spheres.size(), nm = pool.materials.size(), nt = pool.textures.size();
-        std::vector<double> sc(3 * ns), sv(3 * ns), sr(ns), mf(nm), mi(nm), tcol(3 * nt), ts(nt);
-        std::vector<uint32_t> sm(ns), mk(nm), mt(nm), mm(nm), tk(nt), te(nt), to(nt);
+        sc.assign(3 * ns, 0); sv.assign(3 * ns, 0); sr.assign(ns, 0); mf.assign(nm, 0); mi.assign(nm, 0); tcol.assign(3 * nt, 0); ts.assign(nt, 0);
+        sm.assign(ns, 0); mk.assign(nm, 0); mt.assign(nm, 0); mm.assign(nm, 0); tk.assign(nt, 0); te.assign(nt, 0); to.assign(nt, 0);
         for (size_t i = 0; i < ns; i++) {
             const Sphere &s = pool.spheres[i];
             sc[3 * i] = s.center.origin.x; sc[3 * i + 1] = s.center.origin.y; sc[3 * i + 2] = s.center.origin.z;
@@ -287,7 +312,7 @@ struct Tracer {
 
         const RzRenderParams p = renderParams();
         const RzCamera cam = camera.flat();
-        std::vector<float> lin(img.w * img.h * 4);
+        lin.assign(img.w * img.h * 4, 0.f);
         img.rgb8.resize(img.w * img.h * 3);
         uint64_t rays = 0;
         check(rayz_cuda_render(ctx, &cam, &p, lin.data(), img.rgb8.data(), &rays));
@@ -296,6 +321,30 @@ struct Tracer {
         return (size_t)rays;
     }
 };
+
+// --dump-scene: the flattened scene as raw little-endian arrays in RzScene field order, each preceded by nothing — sizes
+// follow from the three counts in the 16-byte header (n_spheres, n_materials, n_textures, 0).  Read by tests/test_host_gpu.py.
+inline bool dumpScene(const Tracer &t, const char *path) {
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return false;
+    const uint32_t head[4] = {(uint32_t)t.sr.size(), (uint32_t)t.mk.size(), (uint32_t)t.tk.size(), 0u};
+    std::fwrite(head, sizeof head, 1, f);
+    auto d = [&](const std::vector<double> &v) { if (!v.empty()) std::fwrite(v.data(), sizeof(double), v.size(), f); };
+    auto u = [&](const std::vector<uint32_t> &v) { if (!v.empty()) std::fwrite(v.data(), sizeof(uint32_t), v.size(), f); };
+    d(t.sc); d(t.sv); d(t.sr); u(t.sm); u(t.mk); d(t.mf); d(t.mi); u(t.mt); u(t.mm); u(t.tk); d(t.tcol); d(t.ts); u(t.te); u(t.to);
+    std::fclose(f);
+    return true;
+}
+
+// rayz.zig:170-239 (dead code in the reference: it targets a removed MemPool API), in its insertion order
+inline void penultimateScene(Tracer &tracer) {
+    MemPool &pool = tracer.pool;
+    pool.add(Sphere::stationary({0, 0, -1.2}, 0.5, pool.addAndReturnHandle(Material::Diffuse(pool.addAndReturnHandle(Texture::Solid({0.1, 0.2, 0.5}))))));
+    pool.add(Sphere::stationary({0, -100.5, -1}, 100, pool.addAndReturnHandle(Material::Diffuse(pool.addAndReturnHandle(Texture::Solid({0.8, 0.8, 0.0}))))));
+    pool.add(Sphere::stationary({-1, 0, -1}, 0.5, pool.addAndReturnHandle(Material::Dielectric(1.5))));         // left outer
+    pool.add(Sphere::stationary({-1, 0, -1}, 0.4, pool.addAndReturnHandle(Material::Dielectric(1.0 / 1.5))));   // left inner bubble
+    pool.add(Sphere::stationary({1, 0, -1}, 0.5, pool.addAndReturnHandle(Material::Metallic(pool.addAndReturnHandle(Texture::Solid({0.8, 0.6, 0.2})), 1.0))));
+}
 
 // rayz.zig:45-168
 inline void randomBouncing(Tracer &tracer, int grid_lo = -11, int grid_hi = 11) {

@@ -588,6 +588,12 @@ RZ_HD void rz_unit_bounds_init(RzUnitBounds &U) {
     U.T = 0.f; U.all_pos = 7u; U.all_neg = 7u;
 }
 
+// Upper edge of reach class c (what rz_key_bounds returns as T), with the margin for the FP32 evaluation of the exits that
+// rz_unit_bounds_finish applies.  Class 15 is open-ended.
+RZ_HD float rz_class_T(const RzPathArgs &a, int c) {
+    return c >= 15 ? 3.0e38f : fminf(a.reach_unit * exp2f(0.5f * (float)(c - 3)) * 1.0001f, 1.0e30f) * 1.001f;
+}
+
 RZ_HD void rz_unit_bounds_add_key(RzUnitBounds &U, const RzPathArgs &a, uint32_t key) {
     float lo[3], hi[3], Tk;
     uint32_t oct;
@@ -604,13 +610,17 @@ RZ_HD void rz_unit_bounds_add_key(RzUnitBounds &U, const RzPathArgs &a, uint32_t
 // after the merge over the unit: +inf-safe, with margin for the FP32 evaluation of the exits
 RZ_HD void rz_unit_bounds_finish(RzUnitBounds &U) { U.T = fminf(U.T, 1.0e30f) * 1.001f; }
 
-RZ_HD bool rz_unit_keep(const RzUnitBounds &U, float huge_radius, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
+// Can a ray of the unit reach the sphere at all, whatever its reach?  false: behind the cell box on an axis along which every
+// ray of the unit moves the other way (or a padding entry).  d2 = squared distance from the box of the origins to the sphere's
+// centre (at mid shutter), re = its radius swept over the shutter interval, with margins.  Huge spheres: d2 = 0.
+RZ_HD bool rz_unit_reachable(const RzUnitBounds &U, float huge_radius, float cx, float cy, float cz, float vx, float vy, float vz, float w,
+                             float &d2, float &re) {
+    d2 = 0.f; re = 0.f;
     if (!(w < 0.f)) return false;                                  // padding entry
     const float r = sqrtf(-w);
     if (r > huge_radius) return true;                              // outside the sphere box: never culled
-    const float re = (r + 0.5f * sqrtf(vx * vx + vy * vy + vz * vz)) * 1.02f + 0.02f;   // swept over the shutter + margin
+    re = (r + 0.5f * sqrtf(vx * vx + vy * vy + vz * vz)) * 1.02f + 0.02f;   // swept over the shutter + margin
     const float c[3] = {fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)};
-    float d2 = 0.f;
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
         if (((U.all_pos >> ax) & 1u) && c[ax] + re < U.lo[ax]) return false;   // every ray moves up this axis: sphere is behind
@@ -618,6 +628,47 @@ RZ_HD bool rz_unit_keep(const RzUnitBounds &U, float huge_radius, float cx, floa
         const float dd = fmaxf(0.f, fmaxf(U.lo[ax] - c[ax], c[ax] - U.hi[ax]));
         d2 = fmaf(dd, dd, d2);
     }
+    return true;
+}
+
+RZ_HD bool rz_unit_keep(const RzUnitBounds &U, float huge_radius, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
+    float d2, re;
+    if (!rz_unit_reachable(U, huge_radius, cx, cy, cz, vx, vy, vz, w, d2, re)) return false;
     const float rad = U.T + re;
     return d2 <= rad * rad;                                        // within reach of some ray of the unit
+}
+
+// The SMALLEST reach class whose rays can reach the sphere from the unit's box (16: none can).  A ray of class c stays inside
+// the sphere box for less than rz_class_T(c), so it needs exactly the spheres of classes <= c: the sorted-stage kernel orders
+// its sphere list by this number and gives every batch of rays the prefix that belongs to the batch's largest class.
+// Monotone in c by construction: the answer is found from a log2 estimate and then corrected with the predicate of
+// rz_unit_keep itself in both directions, so it never errs on the side of dropping a sphere.
+RZ_HD int rz_unit_class(const RzUnitBounds &U, const RzPathArgs &a, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
+    float d2, re;
+    if (!rz_unit_reachable(U, a.huge_radius, cx, cy, cz, vx, vy, vz, w, d2, re)) return 16;
+    auto within = [&](int c) { const float rad = rz_class_T(a, c) + re; return d2 <= rad * rad; };
+    const float dist = sqrtf(d2) - re;
+    if (!(dist > 0.f)) return 0;
+#ifdef __CUDA_ARCH__
+    const float l2 = __log2f(dist / a.reach_unit);
+#else
+    const float l2 = log2f(dist / a.reach_unit);
+#endif
+    int c = rz_clampi((int)(2.0f * l2 + 3.0f), 0, 15);
+    while (c > 0 && within(c - 1)) c--;
+    while (c < 15 && !within(c)) c++;
+    return c;
+}
+
+// the unit's box of origins and common direction signs from one key's cell and octant (the reach class is handled per ray)
+RZ_HD void rz_unit_bounds_add_cell(RzUnitBounds &U, const RzPathArgs &a, uint32_t key) {
+    float lo[3], hi[3], Tk;
+    uint32_t oct;
+    rz_key_bounds(a, key, lo, hi, oct, Tk);
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        U.lo[ax] = fminf(U.lo[ax], lo[ax]);
+        U.hi[ax] = fmaxf(U.hi[ax], hi[ax]);
+        if ((oct >> ax) & 1u) U.all_pos &= ~(1u << ax); else U.all_neg &= ~(1u << ax);
+    }
 }

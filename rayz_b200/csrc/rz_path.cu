@@ -44,6 +44,11 @@
 #define RZ_PRIMARY_BOUNDS __launch_bounds__(128)
 #endif
 
+// per-warp scratch of the sorted-stage kernel: tab[48] u32 | pair list u16[n_pairs] | entry order u16[ue] | pair classes u8[n_pairs]
+__host__ __device__ inline uint32_t rz_second_warp_bytes(uint32_t n_pairs, uint32_t ue) {
+    return (48u * 4u + 2u * n_pairs + 2u * ue + n_pairs + 15u) & ~15u;
+}
+
 // ------------------------------------------------------------------------------ the kernel
 struct RzStream {
     RzRay ray;
@@ -191,6 +196,109 @@ __global__ void __launch_bounds__(128, MB) rz_path_kernel(const RzPathArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------ staged kernels: shared pieces
+// Code size matters here: the L1.5 instruction cache of an SM holds 32 KB (2048 instructions), the round-1 kernels were
+// 40 KB each and ncu charged 3 stall cycles per issued instruction to `no_instruction`.  So everything outside the search
+// loop exists ONCE: the two rays a lane carries are shaded by one copy of the code (a two-trip loop that swaps the rays'
+// registers), the per-sphere cull is one loop over single spheres for stationary and moving alike, and the rare branches
+// (texture walk, unusual diffuse methods) are kept out of line.
+struct RzLaneRay {
+    RzRay ray;
+    float3 thr;
+    uint32_t seg, lp, gpix, smp;
+    int bk;
+    bool live, cont;
+    uint32_t key;    // sort key of the scattered ray (when it continues)
+};
+
+__device__ __forceinline__ void rz_swap_lane_rays(RzLaneRay &x, RzLaneRay &y) {
+    const RzLaneRay t = x;
+    x = y;
+    y = t;
+}
+
+struct RzSegCounters {
+    unsigned long long paths, segs, sph, hit[3], sky, abs_, depth;
+};
+
+// Shade the two rays of a lane after the search and append the survivors (with their sort keys) to the next queue.
+template <bool STATS>
+__device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRay (&L)[2], unsigned lane, unsigned lt_mask, RzSegCounters &C) {
+#pragma unroll 1
+    for (int trip = 0; trip < 2; trip++) {
+        RzLaneRay &Q = L[0];
+        Q.cont = false;
+        if (Q.live) {
+            if (STATS) C.segs++;
+            uint32_t kind;
+            const int res = rz_shade_segment(a, Q.ray, Q.thr, Q.seg, Q.lp, Q.gpix, Q.smp, Q.bk, kind);
+            if (STATS) {
+                if (kind < 3u) C.hit[kind]++;
+                if (res == RZ_END_SKY) C.sky++;
+                if (res == RZ_END_ABSORBED) C.abs_++;
+                if (res == RZ_END_DEPTH) C.depth++;
+            }
+            Q.cont = res == RZ_CONT;
+            if (Q.cont && a.q_out_keys) Q.key = rz_sort_key(a, Q.ray);
+        }
+        rz_swap_lane_rays(L[0], L[1]);
+    }
+    // ballot-compacted append: one atomic per warp for both rays
+    const unsigned m0 = __ballot_sync(0xffffffffu, L[0].cont), m1 = __ballot_sync(0xffffffffu, L[1].cont);
+    const unsigned n0 = (unsigned)__popc(m0), n1 = (unsigned)__popc(m1);
+    if (n0 + n1 == 0u) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.q_out_count, n0 + n1);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    unsigned e = base + (unsigned)__popc(m0 & lt_mask);
+#pragma unroll 1
+    for (int trip = 0; trip < 2; trip++) {
+        const RzLaneRay &Q = L[0];
+        if (Q.cont) {
+            if (e < a.queue_cap) {
+                float4 *q = a.q_out + (size_t)e * 4u;
+                __stcs(q + 0, make_float4(Q.ray.o.x, Q.ray.o.y, Q.ray.o.z, Q.ray.time));
+                __stcs(q + 1, make_float4(Q.ray.d.x, Q.ray.d.y, Q.ray.d.z, __int_as_float(Q.ray.self_k)));
+                __stcs(q + 2, make_float4(Q.thr.x, Q.thr.y, Q.thr.z, __uint_as_float(Q.seg)));
+                __stcs(q + 3, make_float4(__uint_as_float(Q.lp), __uint_as_float(Q.gpix), __uint_as_float(Q.smp), 0.f));
+                if (a.q_out_keys) a.q_out_keys[e] = (unsigned short)Q.key;
+            } else {
+                atomicOr(a.err, (unsigned)RZ_DEV_ERR_QUEUE_OVERFLOW);   // never silently: the render fails
+            }
+        }
+        rz_swap_lane_rays(L[0], L[1]);
+        e = base + n0 + (unsigned)__popc(m1 & lt_mask);
+    }
+}
+
+// One sphere of the pair-interleaved set as scalars: position k in the set -> (cx, cy, cz, vx, vy, vz, w = -r^2)
+__device__ __forceinline__ void rz_set_sphere(const float4 *__restrict__ s_pk, uint32_t k, uint32_t n_static_pad, float &cx, float &cy, float &cz,
+                                              float &vx, float &vy, float &vz, float &w) {
+    const float *f = reinterpret_cast<const float *>(s_pk);
+    if (k < n_static_pad) {
+        const float *s = f + 8u * (k >> 1) + (k & 1u);
+        cx = s[0]; cy = s[2]; cz = s[4]; w = s[6];
+        vx = vy = vz = 0.f;
+    } else {
+        const uint32_t m = k - n_static_pad;
+        const float *s = f + 4u * n_static_pad + 16u * (m >> 1) + (m & 1u);
+        cx = s[0]; cy = s[2]; cz = s[4]; w = s[6];
+        vx = s[8]; vy = s[10]; vz = s[12];
+    }
+}
+
+template <bool STATS>
+__device__ __forceinline__ void rz_flush_counters(const RzPathArgs &a, const RzSegCounters &C, unsigned lane) {
+    if (!STATS) return;
+    const unsigned long long v[10] = {C.paths, C.segs, C.sph, 0ull, C.hit[0], C.hit[1], C.hit[2], C.sky, C.abs_, C.depth};
+#pragma unroll 1
+    for (int i = 0; i < 10; i++) {
+        unsigned long long sum = v[i];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0 && sum) atomicAdd(&a.stats->v[i], sum);
+    }
+}
+
 // ------------------------------------------------------------------------------ primary kernel
 // Stage 1 of the staged K1: the camera segment of every path (Camera.getRay camera.zig:59-77 + the first
 // bounceRay level renderer.zig:103-126).  Camera rays of a 32-pixel tile are coherent, so the warp first
@@ -214,7 +322,7 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned long long c_paths = 0, c_segs = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
+    RzSegCounters C = {};
 
     while (true) {
         unsigned u = 0;
@@ -239,117 +347,95 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
         float cmin = valid ? rz_tile_corner_cos(a.cam, pc, ax) : 1.0f;
         for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
         const RzTileCone cone = rz_tile_cone(a.cam, ax, has_axis, cmin, a.focus_dist, a.lens_radius);
-        auto keep = [&](float cx, float cy, float cz, float vx, float vy, float vz, float w) -> bool {
-            return rz_tile_keep(cone, cx, cy, cz, vx, vy, vz, w);
-        };
+        // one lane per SPHERE (a pair is kept if either half is): 16 pairs per step, stationary and moving through the same code
         int n_ls = 0, n_lm = 0;
-        for (uint32_t p0 = 0; p0 < n_sp; p0 += 32u) {
-            const uint32_t p = p0 + lane;
-            bool k = false;
-            if (p < n_sp) {
-                const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
-                k = keep(A.x, A.z, B.x, 0.f, 0.f, 0.f, B.z) || keep(A.y, A.w, B.y, 0.f, 0.f, 0.f, B.w);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, k);
-            if (k) ls[n_ls + __popc(m & lt_mask)] = (unsigned short)p;
-            n_ls += __popc(m);
-        }
-        const float4 *mv = s_pk + a.set.n_static_pad;
-        for (uint32_t p0 = 0; p0 < n_mp; p0 += 32u) {
-            const uint32_t p = p0 + lane;
-            bool k = false;
-            if (p < n_mp) {
-                const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
-                k = keep(A.x, A.z, B.x, VA.x, VA.z, VB.x, B.z) || keep(A.y, A.w, B.y, VA.y, VA.w, VB.y, B.w);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, k);
-            if (k) lm[n_lm + __popc(m & lt_mask)] = (unsigned short)p;
-            n_lm += __popc(m);
+#pragma unroll 1
+        for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
+            const uint32_t k = k0 + lane;
+            float cx, cy, cz, vx, vy, vz, w;
+            rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // n_pad is a multiple of 4; lanes past it read padding
+            const bool keep = k < a.set.n_pad && rz_tile_keep(cone, cx, cy, cz, vx, vy, vz, w);
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            m = (m | (m >> 1)) & 0x55555555u;                       // bit 2j: pair j of this step is kept
+            const bool mine = ((m >> lane) & 1u) != 0u;             // even lanes speak for their pair
+            const bool st = k < a.set.n_static_pad;                 // n_static_pad is even: a pair never straddles the two parts
+            const unsigned ms = m & __ballot_sync(0xffffffffu, st);
+            if (mine && st) ls[n_ls + __popc(ms & lt_mask)] = (unsigned short)(k >> 1);
+            if (mine && !st) lm[n_lm + __popc((m & ~ms) & lt_mask)] = (unsigned short)((k - a.set.n_static_pad) >> 1);
+            n_ls += __popc(ms); n_lm += __popc(m & ~ms);
         }
         __syncwarp();
 
         // ---- the tile's samples of this chunk, two per lane and iteration
         const uint32_t s0 = chunk * a.chunk, ns = min(a.chunk, a.spp - s0);
+#pragma unroll 1
         for (uint32_t s = 0; s < ns; s += 2u) {
-            RzRay rays[2];
-            bool live[2];
-            uint32_t smp[2];
-            float bt[2];
-            int bk[2];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                smp[r] = a.sample_offset + s0 + s + (uint32_t)r;
-                const bool have = valid && (s + (uint32_t)r < ns);
-                live[r] = have && a.max_depth > 0u;
-                if (STATS && have) { c_paths++; if (!live[r]) c_depth++; }
-                if (live[r]) rays[r] = rz_camera_ray(a.cam, pi, pj, gpix, smp[r], a.seed_lo, a.seed_hi);
-                else { rays[r].o = f3(0.f, 0.f, 0.f); rays[r].d = f3(0.f, 1.f, 0.f); rays[r].time = 0.f; rays[r].self_k = -1; }
-                bt[r] = 3.0e38f; bk[r] = -1;
+            RzLaneRay L[2];
+#pragma unroll 1
+            for (int trip = 0; trip < 2; trip++) {                  // one copy of the camera-ray code for both rays
+                RzLaneRay &Q = L[0];
+                Q.smp = a.sample_offset + s0 + s + (uint32_t)trip;
+                const bool have = valid && (s + (uint32_t)trip < ns);
+                Q.live = have && a.max_depth > 0u;
+                if (STATS && have) { C.paths++; if (!Q.live) C.depth++; }
+                if (Q.live) Q.ray = rz_camera_ray(a.cam, pi, pj, gpix, Q.smp, a.seed_lo, a.seed_hi);
+                else { Q.ray.o = f3(0.f, 0.f, 0.f); Q.ray.d = f3(0.f, 1.f, 0.f); Q.ray.time = 0.f; Q.ray.self_k = -1; }
+                Q.thr = f3(1.f, 1.f, 1.f); Q.seg = 0u; Q.lp = lp; Q.gpix = gpix; Q.bk = -1; Q.cont = false; Q.key = 0u;
+                rz_swap_lane_rays(L[0], L[1]);
             }
-            rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
-            if (STATS) c_sph += (unsigned long long)(2 * (n_ls + n_lm)) * (live[0] ? 1u : 0u) + (unsigned long long)(2 * (n_ls + n_lm)) * (live[1] ? 1u : 0u);
-            bool cont[2] = {false, false};
-            float3 thr[2] = {f3(1.f, 1.f, 1.f), f3(1.f, 1.f, 1.f)};
-            uint32_t seg[2] = {0u, 0u};
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                uint32_t kind = 3u;
-                if (live[r]) {
-                    if (STATS) c_segs++;
-                    const int res = rz_shade_segment(a, rays[r], thr[r], seg[r], lp, gpix, smp[r], bk[r], kind);
-                    if (STATS) {
-                        if (kind < 3u) c_hit[kind]++;
-                        if (res == RZ_END_SKY) c_sky++;
-                        if (res == RZ_END_ABSORBED) c_abs++;
-                        if (res == RZ_END_DEPTH) c_depth++;
-                    }
-                    cont[r] = res == RZ_CONT;
-                }
+            {
+                const RzRay rays[2] = {L[0].ray, L[1].ray};
+                float bt[2] = {3.0e38f, 3.0e38f};
+                int bk[2] = {-1, -1};
+                rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
+                L[0].bk = bk[0]; L[1].bk = bk[1];
             }
-            const uint32_t lp2[2] = {lp, lp}, gpix2[2] = {gpix, gpix};
-            rz_queue_push2(a, cont, lane, lt_mask, rays, thr, seg, lp2, gpix2, smp);
+            if (STATS) C.sph += (unsigned long long)(2 * (n_ls + n_lm)) * ((L[0].live ? 1u : 0u) + (L[1].live ? 1u : 0u));
+            rz_shade_and_push2<STATS>(a, L, lane, lt_mask, C);
         }
         __syncwarp();   // the lists are rewritten for the next unit
     }
-
-    if (STATS) {
-        unsigned long long v[10] = {c_paths, c_segs, c_sph, 0ull, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
-#pragma unroll
-        for (int i = 0; i < 10; i++) {
-            unsigned long long sum = v[i];
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0 && sum) atomicAdd(&a.stats->v[i], sum);
-        }
-    }
+    rz_flush_counters<STATS>(a, C, lane);
 }
 
 // ------------------------------------------------------------------------------ sorted-segment kernel
 // The stages after the camera segment, one launch per segment (segments 2..6 by default).  Scattered rays are incoherent,
-// but their queue entries have been SORTED by (origin cell, direction octant, reach class) (rz_sort_key + cub radix sort),
-// so 512 consecutive entries start close together, head the same way and leave the sphere layer after a similar distance.
-// Per unit the warp merges the bounds its sorted KEYS stand for (rz_key_bounds: the cells of the origins, the axes on which
-// every ray moves the same way, the longest stay T inside the box around the non-huge spheres); a sphere can then only be
-// hit if it is not behind the cell box on such an axis and lies within T + r of it (rz_unit_keep).  The packed search runs
-// over that list (12 % of the spheres on the RTOW scene at 500 spp) with the same arithmetic per sphere, so (t, k) is
-// unchanged.  Both functions are host + device and property-tested on the CPU (tests/test_hostsim_cpu.py).
+// but their queue entries have been GROUPED by (origin cell, direction octant) — the top 12 bits of rz_sort_key, rz_sort.cu —
+// so the `unit_entries` consecutive entries of a work unit start close together and head the same way.  Per unit the warp
+//   1. merges the cells and octants of the unit's keys into a box of origins + the axes on which every ray moves the same way
+//      (rz_unit_bounds_add_cell), and orders the unit's entries by the key's low 4 bits, the reach class — how long a ray
+//      stays inside the box around the non-huge spheres (a counting sort over 16 classes in shared memory);
+//   2. gives every sphere the smallest reach class whose rays can get to it from that box (rz_unit_class; 16 = behind the
+//      box for every ray), and orders the sphere pairs by that class;
+//   3. takes the entries 64 at a time in class order: a batch whose largest class is c searches the pairs of classes <= c, a
+//      prefix of the ordered pair list (rz_search_list2: the same arithmetic per sphere, so (t, k) is unchanged).
+// Round 1 sorted on all 16 key bits (two radix passes) and culled each unit with its largest reach; ordering by reach
+// inside the unit costs one global pass less and culls every batch with its OWN reach.  The cull functions are host +
+// device and property-tested on the CPU (tests/test_hostsim_cpu.py).
 template <bool STATS>
 __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
     float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
-    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1;
+    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1, n_pairs = n_sp + n_mp;
     const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
-    unsigned short *ls = reinterpret_cast<unsigned short *>(s_pk + pk_f4) + (threadIdx.x >> 5) * (n_sp + n_mp);
+    const uint32_t ue = a.unit_entries;
+    // per-warp scratch: tab[48] | pair list [n_pairs] | entry order [ue] | pair classes [n_pairs] (layout: rz_second_smem_bytes)
+    const uint32_t warp_bytes = rz_second_warp_bytes(n_pairs, ue);
+    unsigned char *wb = reinterpret_cast<unsigned char *>(s_pk + pk_f4) + (threadIdx.x >> 5) * warp_bytes;
+    unsigned int *tab = reinterpret_cast<unsigned int *>(wb);             // [0,16) entries: end of class c; [16,32) stationary pairs of classes <= c; [32,48) moving
+    unsigned short *ls = reinterpret_cast<unsigned short *>(tab + 48);
     unsigned short *lm = ls + n_sp;
+    unsigned short *order = ls + n_pairs;
+    unsigned char *pcl = reinterpret_cast<unsigned char *>(order + ue);
 
     rz_stage_scene_pk(a.set, s_pk, &s_bar);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t n_in = min(*a.q_in_count, a.queue_cap);
-    const uint32_t ue = a.unit_entries;
     const uint32_t n_units = (n_in + ue - 1u) / ue;
-    unsigned long long c_segs = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
+    RzSegCounters C = {};
 
     while (true) {
         unsigned u = 0;
@@ -357,20 +443,20 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
         const uint32_t e0 = u * ue, ne = min(ue, n_in - e0);
+        const unsigned short *ukeys = a.q_in_keys + e0;
 
-        // ---- what the unit's rays have in common
+        // ---- 1. what the unit's rays have in common (cells + octants of the keys), and how many rays each reach class holds
+        tab[lane] = 0u;
+        if (lane < 16u) tab[32u + lane] = 0u;
+        __syncwarp();
         RzUnitBounds U;
         rz_unit_bounds_init(U);
-        // Bounds from the sorted KEYS, not from the entries: decoding 512 16-bit keys (1 KB, coalesced) replaces a gather of
-        // 512 x 32 B through the index that was 18 % of this kernel's warp-state samples.  The key gives conservative bounds:
-        // the origin lies in its cell (open-ended for the outermost cells, where out-of-box origins are clamped), the octant
-        // is exact, and the reach is below the upper edge of its class (the top class is unbounded).
-        uint32_t prev_key = 0xffffffffu;   // the keys are sorted: a lane mostly meets the key it has just decoded
+        uint32_t prev = 0xffffffffu;   // the groups are sorted: a lane mostly meets the (cell, octant) it has just decoded
+#pragma unroll 1
         for (uint32_t i = lane; i < ne; i += 32u) {
-            const uint32_t key = a.q_in_keys[e0 + i];
-            if (key == prev_key) continue;
-            prev_key = key;
-            rz_unit_bounds_add_key(U, a, key);
+            const uint32_t key = ukeys[i];
+            atomicAdd(&tab[key & 15u], 1u);
+            if ((key >> 4) != prev) { prev = key >> 4; rz_unit_bounds_add_cell(U, a, key); }
         }
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -378,97 +464,111 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
                 U.lo[ax] = fminf(U.lo[ax], __shfl_xor_sync(0xffffffffu, U.lo[ax], o));
                 U.hi[ax] = fmaxf(U.hi[ax], __shfl_xor_sync(0xffffffffu, U.hi[ax], o));
             }
-            U.T = fmaxf(U.T, __shfl_xor_sync(0xffffffffu, U.T, o));
             U.all_pos &= __shfl_xor_sync(0xffffffffu, U.all_pos, o);
             U.all_neg &= __shfl_xor_sync(0xffffffffu, U.all_neg, o);
         }
-        rz_unit_bounds_finish(U);
-        auto keep = [&](float cx, float cy, float cz, float vx, float vy, float vz, float w) -> bool {
-            return rz_unit_keep(U, a.huge_radius, cx, cy, cz, vx, vy, vz, w);
-        };
-        int n_ls = 0, n_lm = 0;
-        for (uint32_t p0 = 0; p0 < n_sp; p0 += 32u) {
-            const uint32_t p = p0 + lane;
-            bool k = false;
-            if (p < n_sp) {
-                const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
-                k = keep(A.x, A.z, B.x, 0.f, 0.f, 0.f, B.z) || keep(A.y, A.w, B.y, 0.f, 0.f, 0.f, B.w);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, k);
-            if (k) ls[n_ls + __popc(m & lt_mask)] = (unsigned short)p;
-            n_ls += __popc(m);
-        }
-        const float4 *mv = s_pk + a.set.n_static_pad;
-        for (uint32_t p0 = 0; p0 < n_mp; p0 += 32u) {
-            const uint32_t p = p0 + lane;
-            bool k = false;
-            if (p < n_mp) {
-                const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
-                k = keep(A.x, A.z, B.x, VA.x, VA.z, VB.x, B.z) || keep(A.y, A.w, B.y, VA.y, VA.w, VB.y, B.w);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, k);
-            if (k) lm[n_lm + __popc(m & lt_mask)] = (unsigned short)p;
-            n_lm += __popc(m);
+        __syncwarp();
+        {   // exclusive prefix over the 16 classes -> running cursors
+            const uint32_t cnt = lane < 16u ? tab[lane] : 0u;
+            uint32_t inc = cnt;
+            for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += t; }
+            __syncwarp();
+            if (lane < 16u) tab[lane] = inc - cnt;
         }
         __syncwarp();
+        // entries in class order: order[slot] = position in the unit.  Lanes with the same class take consecutive slots.
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < ne; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            const uint32_t c = i < ne ? ((uint32_t)ukeys[i] & 15u) : 16u + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t base = 0u;
+            if ((int)lane == leader && c < 16u) { base = tab[c]; tab[c] = base + (uint32_t)__popc(peers); }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (c < 16u) order[base + (uint32_t)__popc(peers & lt_mask)] = (unsigned short)i;
+            __syncwarp();
+        }
+        // now tab[c] = end of class c in `order`
 
-        // ---- the unit's rays, two per lane and iteration
+        // ---- 2. smallest class that reaches each sphere -> pairs ordered by class (one lane per sphere, one copy of the code)
+#pragma unroll 1
+        for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
+            const uint32_t k = k0 + lane;
+            float cx, cy, cz, vx, vy, vz, w;
+            rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);
+            int c = k < a.set.n_pad ? rz_unit_class(U, a, cx, cy, cz, vx, vy, vz, w) : 16;
+            c = min(c, __shfl_xor_sync(0xffffffffu, c, 1));                    // the pair's class
+            if (!(lane & 1u) && k < a.set.n_pad) {
+                pcl[k >> 1] = (unsigned char)c;
+                if (c < 16) atomicAdd(&tab[(k < a.set.n_static_pad ? 16u : 32u) + (uint32_t)c], 1u);
+            }
+        }
+        __syncwarp();
+        {   // exclusive prefixes of the two pair histograms
+            const uint32_t cnt = tab[16u + (lane & 15u) + (lane & 16u)];      // lanes 0-15: stationary, 16-31: moving
+            uint32_t inc = cnt;
+            for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)(lane & 15u) >= o) inc += t; }
+            __syncwarp();
+            tab[16u + lane] = inc - cnt;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t p0 = 0; p0 < n_pairs; p0 += 32u) {
+            const uint32_t p = p0 + lane;
+            const bool st = p < n_sp;
+            const uint32_t c = p < n_pairs ? (uint32_t)pcl[p] : 16u;
+            const uint32_t tag = c < 16u ? (c | (st ? 0u : 16u)) : 32u + lane;   // (part, class); unique for pairs that are dropped
+            const unsigned peers = __match_any_sync(0xffffffffu, tag);
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t base = 0u;
+            if ((int)lane == leader && c < 16u) { base = tab[16u + tag]; tab[16u + tag] = base + (uint32_t)__popc(peers); }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (c < 16u) (st ? ls : lm)[base + (uint32_t)__popc(peers & lt_mask)] = (unsigned short)(st ? p : p - n_sp);
+            __syncwarp();
+        }
+        // now tab[16 + c] / tab[32 + c] = stationary / moving pairs of classes <= c
+
+        // ---- 3. the unit's rays in class order, two per lane and iteration
+#pragma unroll 1
         for (uint32_t b0 = 0; b0 < ne; b0 += 64u) {
-            RzRay rays[2];
-            float3 thr[2];
-            uint32_t seg[2], lp[2], gpix[2], smp[2];
-            bool live[2];
-            float bt[2];
-            int bk[2];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const uint32_t i = b0 + lane + 32u * (uint32_t)r;
-                live[r] = i < ne;
-                if (live[r]) {
-                    const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + i] * 4u;
+            // the batch's largest class: that of its last entry = number of classes that end at or before it
+            const uint32_t last = min(b0 + 63u, ne - 1u);
+            const int cmax = min(15, __popc(__ballot_sync(0xffffffffu, lane < 16u && tab[lane] <= last)));
+            const int n_ls = (int)tab[16 + cmax], n_lm = (int)tab[32 + cmax];
+            RzLaneRay L[2];
+#pragma unroll 1
+            for (int trip = 0; trip < 2; trip++) {                  // one copy of the gather for both rays
+                RzLaneRay &Q = L[0];
+                const uint32_t j = b0 + lane + 32u * (uint32_t)trip;
+                Q.live = j < ne;
+                if (Q.live) {
+                    const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + order[j]] * 4u;
                     const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
-                    rays[r].o = f3(qa.x, qa.y, qa.z); rays[r].time = qa.w;
-                    rays[r].d = f3(qb.x, qb.y, qb.z); rays[r].self_k = __float_as_int(qb.w);
-                    thr[r] = f3(qc.x, qc.y, qc.z); seg[r] = __float_as_uint(qc.w);
-                    lp[r] = __float_as_uint(qd.x); gpix[r] = __float_as_uint(qd.y); smp[r] = __float_as_uint(qd.z);
+                    Q.ray.o = f3(qa.x, qa.y, qa.z); Q.ray.time = qa.w;
+                    Q.ray.d = f3(qb.x, qb.y, qb.z); Q.ray.self_k = __float_as_int(qb.w);
+                    Q.thr = f3(qc.x, qc.y, qc.z); Q.seg = __float_as_uint(qc.w);
+                    Q.lp = __float_as_uint(qd.x); Q.gpix = __float_as_uint(qd.y); Q.smp = __float_as_uint(qd.z);
                 } else {
-                    rays[r].o = f3(0.f, 0.f, 0.f); rays[r].d = f3(0.f, 1.f, 0.f); rays[r].time = 0.f; rays[r].self_k = -1;
-                    thr[r] = f3(0.f, 0.f, 0.f); seg[r] = 0; lp[r] = 0; gpix[r] = 0; smp[r] = 0;
+                    Q.ray.o = f3(0.f, 0.f, 0.f); Q.ray.d = f3(0.f, 1.f, 0.f); Q.ray.time = 0.f; Q.ray.self_k = -1;
+                    Q.thr = f3(0.f, 0.f, 0.f); Q.seg = 0; Q.lp = 0; Q.gpix = 0; Q.smp = 0;
                 }
-                bt[r] = 3.0e38f; bk[r] = -1;
+                Q.bk = -1; Q.cont = false; Q.key = 0u;
+                rz_swap_lane_rays(L[0], L[1]);
             }
-            rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
-            if (STATS) c_sph += (unsigned long long)(2 * (n_ls + n_lm)) * ((live[0] ? 1u : 0u) + (live[1] ? 1u : 0u));
-            bool cont[2] = {false, false};
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                if (live[r]) {
-                    if (STATS) c_segs++;
-                    uint32_t kind;
-                    const int res = rz_shade_segment(a, rays[r], thr[r], seg[r], lp[r], gpix[r], smp[r], bk[r], kind);
-                    if (STATS) {
-                        if (kind < 3u) c_hit[kind]++;
-                        if (res == RZ_END_SKY) c_sky++;
-                        if (res == RZ_END_ABSORBED) c_abs++;
-                        if (res == RZ_END_DEPTH) c_depth++;
-                    }
-                    cont[r] = res == RZ_CONT;
-                }
+            {
+                const RzRay rays[2] = {L[0].ray, L[1].ray};
+                float bt[2] = {3.0e38f, 3.0e38f};
+                int bk[2] = {-1, -1};
+                rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
+                L[0].bk = bk[0]; L[1].bk = bk[1];
             }
-            rz_queue_push2(a, cont, lane, lt_mask, rays, thr, seg, lp, gpix, smp);
+            if (STATS) C.sph += (unsigned long long)(2 * (n_ls + n_lm)) * ((L[0].live ? 1u : 0u) + (L[1].live ? 1u : 0u));
+            rz_shade_and_push2<STATS>(a, L, lane, lt_mask, C);
         }
         __syncwarp();
     }
-
-    if (STATS) {
-        unsigned long long v[10] = {0ull, c_segs, c_sph, 0ull, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
-#pragma unroll
-        for (int i = 0; i < 10; i++) {
-            unsigned long long sum = v[i];
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0 && sum) atomicAdd(&a.stats->v[i], sum);
-        }
-    }
+    rz_flush_counters<STATS>(a, C, lane);
 }
 
 // ------------------------------------------------------------------------------ launchers
@@ -499,6 +599,11 @@ extern "C" cudaError_t rz_path_warm(void) {
     return e;
 }
 
+// Shared memory the sorted-stage kernel needs: the set + per-warp scratch (rz_second_warp_bytes).
+extern "C" size_t rz_second_smem_bytes(const RzPathArgs *a) {
+    return rz_pk_bytes(*a) + 4u * (size_t)rz_second_warp_bytes(a->set.n_pad / 2u, a->unit_entries);
+}
+
 // Shared memory the primary kernel needs: the pair-interleaved set + one pair list per warp.
 extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a) {
     const size_t pairs = a->set.n_pad / 2u;
@@ -525,7 +630,7 @@ extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats,
 
 // Stage 2: second segments of the sorted queue (q_in through q_in_idx) -> q_out.
 extern "C" cudaError_t rz_launch_second(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
-    const size_t smem = rz_primary_smem_bytes(a);
+    const size_t smem = rz_second_smem_bytes(a);
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -1,21 +1,20 @@
-// rz_sort.cu — puts the staged K1's queue entries in the order of their 16-bit sort keys: a one-pass counting sort
-// ("binning") written for this job.  Round 1 called cub::DeviceRadixSort here (two 8-bit onesweep passes over key + index
-// pairs, ~26 B of HBM traffic per entry, wrapped in a CUDA graph with a SWITCH node because cub wants its item count on the
-// host); that was 12 % of the render step.
+// rz_sort.cu — groups the staged K1's queue entries by the top 12 bits of their sort key (origin cell + direction octant):
+// a one-pass counting sort written for this job.  Round 1 called cub::DeviceRadixSort here (two 8-bit onesweep passes over
+// key + index pairs, ~26 B of HBM traffic per entry, wrapped in a CUDA graph with a SWITCH node because cub wants its item
+// count on the host): 12 % of the render step, and a library kernel on the hot path.
 //
-// What the consumer (rz_second_kernel) needs is weaker than a sort: entries with EQUAL KEYS must be contiguous and the keys
-// ascending — the order inside a key's range is irrelevant (every entry of it yields the same cull bounds, and radiance is
-// accumulated in integers, so the image does not depend on which 512 entries share a work unit).  Without the stability a
-// multi-pass radix sort needs, one pass over the 65,536 possible keys is enough:
-//   rz_bin_kernel<false>  count   keys -> bins[key]                              (reads 2 B per entry)
-//   rz_bin_scan_kernel    scan    bins -> exclusive prefix = first slot of each key's range     (256 KB)
-//   rz_bin_kernel<true>   scatter entry i -> slot atomicAdd(bins[key]) : idx_out[slot] = i, keys_out[slot] = key
-//                                                                                (reads 2 B, writes 6 B per entry)
-// i.e. ~10 B of traffic per entry and no temporary buffers.  A global atomic per entry would serialise on the popular keys
-// (measured in round 1: +7 ms), so each CTA first aggregates a tile of 2048 keys in a shared-memory hash table (4096 slots,
-// linear probing, warp-level __match_any_sync pre-aggregation so that a hot key costs one shared atomic per warp row): one
-// global atomic per DISTINCT key of the tile.  The count pass keeps its table across tiles and flushes it only when it
-// fills up.  The scattered 2- and 4-byte stores land on ~65 k slowly advancing frontiers (4 MB) that stay in the 126 MB L2
+// What the consumer (rz_second_kernel) needs is weaker than a sort: entries that share (cell, octant) must be contiguous and
+// those groups ascending.  The order INSIDE a group is irrelevant — the kernel orders each work unit's entries by the key's
+// low 4 bits (the reach class) itself, in shared memory, and radiance is accumulated in integers, so the image does not
+// depend on which entries share a work unit.  Without the stability a multi-pass radix sort needs, ONE pass over 4096 bins
+// is enough, and 4096 counters fit shared memory:
+//   rz_bin_count_kernel    keys -> bins[key >> 4]          per-CTA histogram in shared memory, flushed once   (reads 2 B / entry)
+//   rz_bin_scan_kernel     bins -> exclusive prefix = first slot of each group                                (16 KB)
+//   rz_bin_scatter_kernel  per tile of 4096 keys: shared-memory histogram gives every key its rank inside (tile, bin); one
+//                          global atomicAdd per occupied bin reserves the tile's slots in the group's range; then
+//                          idx_out[slot] = entry index, keys_out[slot] = key                         (reads 2 B, writes 6 B / entry)
+// ~10 B of traffic per entry, no temporary buffers, no global atomic per entry (measured in round 1: +7 ms — the popular
+// keys serialise).  The scattered 2- and 4-byte stores land on <= 4096 slowly advancing frontiers that stay in the 126 MB L2
 // until their sectors are full.  Every kernel takes the live entry count from device memory: no host round trip, no
 // conditional graph, no 0xffff padding keys.
 #include <cuda_runtime.h>
@@ -23,110 +22,54 @@
 
 namespace {
 
-constexpr int RZ_BINS = 65536;
+constexpr int RZ_BINS = 4096;                                // 12 bits: [origin cell 9][octant 3]
+constexpr int RZ_BIN_SHIFT = 4;                              // the key's low 4 bits (reach class) are not sorted on
 constexpr int RZ_BIN_THREADS = 256;
-constexpr int RZ_BIN_ITEMS = 8;                              // keys per thread and tile
-constexpr int RZ_BIN_TILE = RZ_BIN_THREADS * RZ_BIN_ITEMS;   // 2048
-constexpr int RZ_BIN_SLOTS = 4096;                           // hash slots: load <= 50 % (scatter), <= 75 % (count)
+constexpr int RZ_BIN_ITEMS = 16;                             // keys per thread and tile
+constexpr int RZ_BIN_TILE = RZ_BIN_THREADS * RZ_BIN_ITEMS;   // 4096
 
 struct RzBinArgs {
     const unsigned short *keys_in;   // [n] in producer order
     const unsigned int *count;       // live entries (device counter of the producing kernel)
     uint32_t cap;                    // slots of the buffers (the count is clamped to it)
-    unsigned int *bins;              // [65536] counts -> (after the scan) next free slot of each key
+    unsigned int *bins;              // [4096] counts -> (after the scan) next free slot of each group
     unsigned short *keys_out;        // [n] keys in slot order
     uint32_t *idx_out;               // [n] entry index in slot order
 };
 
-__device__ __forceinline__ uint32_t rz_bin_hash(uint32_t key) { return ((key * 40503u) >> 4) & (uint32_t)(RZ_BIN_SLOTS - 1); }
-
-template <bool SCATTER>
-__global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_kernel(const RzBinArgs a) {
-    __shared__ uint32_t t_key[RZ_BIN_SLOTS];   // key + 1; 0 = empty
-    __shared__ uint32_t t_cnt[RZ_BIN_SLOTS];   // entries of the key in this tile; after the flush: their first global slot
-    __shared__ uint32_t s_occ;                 // occupied slots (count pass: when to flush)
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+__global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_count_kernel(const RzBinArgs a) {
+    __shared__ unsigned int sh[RZ_BINS];
+    const uint32_t tid = threadIdx.x;
     const uint32_t n = min(*a.count, a.cap);
-    const uint32_t n_tiles = (n + RZ_BIN_TILE - 1) / RZ_BIN_TILE;
-    for (uint32_t s = tid; s < RZ_BIN_SLOTS; s += RZ_BIN_THREADS) { t_key[s] = 0u; t_cnt[s] = 0u; }
-    if (tid == 0) s_occ = 0u;
+    for (uint32_t b = tid; b < RZ_BINS; b += RZ_BIN_THREADS) sh[b] = 0u;
     __syncthreads();
-
-    // one global atomic per occupied slot; the slot then holds the first global slot of its entries (scatter) and is
-    // cleared for the next tile by `clear`
-    auto flush = [&](bool clear) {
-        for (uint32_t s = tid; s < RZ_BIN_SLOTS; s += RZ_BIN_THREADS) {
-            const uint32_t k1 = t_key[s];
-            if (k1) {
-                const uint32_t base = atomicAdd(a.bins + (k1 - 1u), t_cnt[s]);
-                if (clear) { t_key[s] = 0u; t_cnt[s] = 0u; } else t_cnt[s] = base;
-            }
-        }
-    };
-
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t i0 = tile * RZ_BIN_TILE + tid;
-        uint32_t key[RZ_BIN_ITEMS], slot[RZ_BIN_ITEMS], rank[RZ_BIN_ITEMS];
+    // 8 keys (one 16-byte load) per thread and step; the buffers are 256-byte aligned
+    const uint32_t n8 = n >> 3;
+    const uint4 *k8 = reinterpret_cast<const uint4 *>(a.keys_in);
+    for (uint32_t i = blockIdx.x * RZ_BIN_THREADS + tid; i < n8; i += gridDim.x * RZ_BIN_THREADS) {
+        const uint4 v = __ldcs(k8 + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < RZ_BIN_ITEMS; j++) {
-            const uint32_t i = i0 + (uint32_t)j * RZ_BIN_THREADS;
-            key[j] = i < n ? (uint32_t)a.keys_in[i] : 0x10000u;   // past the end: a value no key has
-        }
-#pragma unroll
-        for (int j = 0; j < RZ_BIN_ITEMS; j++) {
-            const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
-            const int leader = __ffs((int)peers) - 1;
-            uint32_t s = 0u, r0 = 0u;
-            if ((int)lane == leader && key[j] < 0x10000u) {
-                uint32_t h = rz_bin_hash(key[j]);
-                for (int probe = 0; probe < RZ_BIN_SLOTS; probe++) {   // the table is never full: ends at the key's slot or an empty one
-                    const uint32_t prev = atomicCAS(&t_key[h], 0u, key[j] + 1u);
-                    if (prev == 0u) { if (!SCATTER) atomicAdd(&s_occ, 1u); break; }
-                    if (prev == key[j] + 1u) break;
-                    h = (h + 1u) & (uint32_t)(RZ_BIN_SLOTS - 1);
-                }
-                r0 = atomicAdd(&t_cnt[h], (uint32_t)__popc(peers));
-                s = h;
-            }
-            slot[j] = __shfl_sync(0xffffffffu, s, leader);
-            rank[j] = __shfl_sync(0xffffffffu, r0, leader) + (uint32_t)__popc(peers & lt_mask);
-        }
-        __syncthreads();
-        if (SCATTER) {
-            flush(false);
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < RZ_BIN_ITEMS; j++) {
-                if (key[j] < 0x10000u) {
-                    const uint32_t pos = t_cnt[slot[j]] + rank[j];
-                    if (pos < a.cap) {   // always true: the ranges partition [0, n)
-                        a.idx_out[pos] = i0 + (uint32_t)j * RZ_BIN_THREADS;
-                        a.keys_out[pos] = (unsigned short)key[j];
-                    }
-                }
-            }
-            __syncthreads();
-            for (uint32_t s = tid; s < RZ_BIN_SLOTS; s += RZ_BIN_THREADS) { t_key[s] = 0u; t_cnt[s] = 0u; }
-            __syncthreads();
-        } else if (s_occ > (uint32_t)(RZ_BIN_SLOTS / 4)) {   // the next tile may add 2048 keys: keep the load below 75 %
-            flush(true);
-            __syncthreads();
-            if (tid == 0) s_occ = 0u;
-            __syncthreads();
+        for (int j = 0; j < 4; j++) {
+            atomicAdd(&sh[(w[j] & 0xffffu) >> RZ_BIN_SHIFT], 1u);
+            atomicAdd(&sh[w[j] >> (16 + RZ_BIN_SHIFT)], 1u);
         }
     }
-    if (!SCATTER) flush(true);
+    if (blockIdx.x == 0 && tid < (n & 7u)) atomicAdd(&sh[(uint32_t)a.keys_in[(n8 << 3) + tid] >> RZ_BIN_SHIFT], 1u);
+    __syncthreads();
+    for (uint32_t b = tid; b < RZ_BINS; b += RZ_BIN_THREADS) {
+        const unsigned int c = sh[b];
+        if (c) atomicAdd(a.bins + b, c);
+    }
 }
 
-// exclusive prefix over the 65,536 bins, in place: one CTA, 1024 threads x 64 consecutive bins
+// exclusive prefix over the 4096 bins, in place: one CTA, 1024 threads x 4 consecutive bins
 __global__ void __launch_bounds__(1024) rz_bin_scan_kernel(unsigned int *bins) {
     __shared__ uint32_t s_warp[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    uint4 *p = reinterpret_cast<uint4 *>(bins) + (size_t)tid * 16u;
-    uint4 v[16];
-    uint32_t sum = 0u;
-#pragma unroll
-    for (int i = 0; i < 16; i++) { v[i] = p[i]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+    uint4 *p = reinterpret_cast<uint4 *>(bins) + tid;
+    const uint4 v = *p;
+    const uint32_t sum = v.x + v.y + v.z + v.w;
     uint32_t inc = sum;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += t; }
     if (lane == 31u) s_warp[w] = inc;
@@ -138,14 +81,48 @@ __global__ void __launch_bounds__(1024) rz_bin_scan_kernel(unsigned int *bins) {
     }
     __syncthreads();
     uint32_t run = inc - sum + (w ? s_warp[w - 1u] : 0u);
+    uint4 o;
+    o.x = run; run += v.x;
+    o.y = run; run += v.y;
+    o.z = run; run += v.z;
+    o.w = run;
+    *p = o;
+}
+
+__global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_scatter_kernel(const RzBinArgs a) {
+    __shared__ unsigned int sh[RZ_BINS];   // entries of the bin in this tile; after the reservation: their first global slot
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n = min(*a.count, a.cap);
+    const uint32_t n_tiles = (n + RZ_BIN_TILE - 1) / RZ_BIN_TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t b = tid; b < RZ_BINS; b += RZ_BIN_THREADS) sh[b] = 0u;
+        __syncthreads();
+        const uint32_t i0 = tile * RZ_BIN_TILE + tid;
+        uint32_t key[RZ_BIN_ITEMS], rank[RZ_BIN_ITEMS];
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        uint4 o;
-        o.x = run; run += v[i].x;
-        o.y = run; run += v[i].y;
-        o.z = run; run += v[i].z;
-        o.w = run; run += v[i].w;
-        p[i] = o;
+        for (int j = 0; j < RZ_BIN_ITEMS; j++) {
+            const uint32_t i = i0 + (uint32_t)j * RZ_BIN_THREADS;
+            key[j] = i < n ? (uint32_t)a.keys_in[i] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int j = 0; j < RZ_BIN_ITEMS; j++) rank[j] = key[j] != 0xffffffffu ? atomicAdd(&sh[key[j] >> RZ_BIN_SHIFT], 1u) : 0u;
+        __syncthreads();
+        for (uint32_t b = tid; b < RZ_BINS; b += RZ_BIN_THREADS) {
+            const unsigned int c = sh[b];
+            if (c) sh[b] = atomicAdd(a.bins + b, c);   // the tile's slots in the group's range
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RZ_BIN_ITEMS; j++) {
+            if (key[j] != 0xffffffffu) {
+                const uint32_t pos = sh[key[j] >> RZ_BIN_SHIFT] + rank[j];
+                if (pos < a.cap) {   // always true: the ranges partition [0, n)
+                    a.idx_out[pos] = i0 + (uint32_t)j * RZ_BIN_THREADS;
+                    a.keys_out[pos] = (unsigned short)key[j];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -153,34 +130,34 @@ __global__ void __launch_bounds__(1024) rz_bin_scan_kernel(unsigned int *bins) {
 
 extern "C" size_t rz_bin_scratch_bytes(void) { return (size_t)RZ_BINS * sizeof(unsigned int); }
 
-// keys_in[0, *count) -> idx_out / keys_out: entry indices and keys grouped by ascending key.  bins: rz_bin_scratch_bytes().
+// keys_in[0, *count) -> idx_out / keys_out: entry indices and keys grouped by ascending (key >> 4).  bins: rz_bin_scratch_bytes().
 extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned int *count, uint32_t cap, unsigned int *bins,
                                    unsigned short *keys_out, uint32_t *idx_out, int sm_count, cudaStream_t stream) {
-    static int per_sm = 0;
-    if (per_sm == 0) {
+    static int per_sm_count = 0, per_sm_scatter = 0;
+    if (per_sm_count == 0) {
         int a = 0, b = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, rz_bin_kernel<false>, RZ_BIN_THREADS, 0);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rz_bin_kernel<true>, RZ_BIN_THREADS, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, rz_bin_count_kernel, RZ_BIN_THREADS, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rz_bin_scatter_kernel, RZ_BIN_THREADS, 0);
         if (e != cudaSuccess) return e;
-        per_sm = a < b ? a : b;
-        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        if (a < 1 || b < 1) return cudaErrorInvalidConfiguration;
+        per_sm_count = a; per_sm_scatter = b;
     }
     RzBinArgs a;
     a.keys_in = keys_in; a.count = count; a.cap = cap; a.bins = bins; a.keys_out = keys_out; a.idx_out = idx_out;
     const unsigned tiles = (cap + RZ_BIN_TILE - 1) / RZ_BIN_TILE;
-    const unsigned grid = tiles < (unsigned)(sm_count * per_sm) ? (tiles ? tiles : 1u) : (unsigned)(sm_count * per_sm);
+    auto grid_for = [&](int per_sm) { const unsigned g = (unsigned)(sm_count * per_sm); return tiles < g ? (tiles ? tiles : 1u) : g; };
     cudaError_t e = cudaMemsetAsync(bins, 0, (size_t)RZ_BINS * sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    rz_bin_kernel<false><<<grid, RZ_BIN_THREADS, 0, stream>>>(a);
+    rz_bin_count_kernel<<<grid_for(per_sm_count), RZ_BIN_THREADS, 0, stream>>>(a);
     rz_bin_scan_kernel<<<1, 1024, 0, stream>>>(bins);
-    rz_bin_kernel<true><<<grid, RZ_BIN_THREADS, 0, stream>>>(a);
+    rz_bin_scatter_kernel<<<grid_for(per_sm_scatter), RZ_BIN_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 extern "C" cudaError_t rz_sort_warm(void) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, rz_bin_kernel<false>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_bin_kernel<true>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, rz_bin_count_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_bin_scatter_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rz_bin_scan_kernel);
     return e;
 }

@@ -277,6 +277,7 @@ extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cel
         const float spread = g.u01() < 0.5f ? 0.05f : 0.6f, jitter = ext / 64.0f * g.u01();
         RzUnitBounds U;
         rz_unit_bounds_init(U);
+        int cls[16];
         for (int k = 0; k < 16; k++) {
             float d[3];
             for (int ax = 0; ax < 3; ax++) d[ax] = bd[ax] + spread * g.sym();
@@ -284,9 +285,10 @@ extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cel
             if (!(len > 1e-6f)) { d[0] = 0.f; d[1] = 1.f; d[2] = 0.f; } else { d[0] /= len; d[1] /= len; d[2] /= len; }
             rays[k].o = f3(bo[0] + jitter * g.sym(), bo[1] + jitter * g.sym(), bo[2] + jitter * g.sym());
             rays[k].d = f3(d[0], d[1], d[2]); rays[k].time = g.u01(); rays[k].self_k = -1;
-            rz_unit_bounds_add_key(U, a, rz_sort_key(a, rays[k]));
+            const uint32_t key = rz_sort_key(a, rays[k]);
+            rz_unit_bounds_add_cell(U, a, key);     // the unit's box and common signs come from the cells and octants ...
+            cls[k] = (int)(key & 15u);              // ... each ray keeps its own reach class
         }
-        rz_unit_bounds_finish(U);
         // ---- spheres around the rays: ordinary ones lie inside the sphere box over the whole shutter interval (that is
         // what the box is), huge ones anywhere
         for (int k = 0; k < 16; k++) {
@@ -304,7 +306,8 @@ extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cel
                 }
                 if (!inside) continue;
                 const bool hit = ray_hits(rays[k], c0, v, r, 1e-4f);
-                const bool kept = rz_unit_keep(U, a.huge_radius, c0[0], c0[1], c0[2], v[0], v[1], v[2], -(r * r));
+                // the sorted-stage kernel gives a ray of reach class c the spheres of classes <= c (rz_unit_class)
+                const bool kept = rz_unit_class(U, a, c0[0], c0[1], c0[2], v[0], v[1], v[2], -(r * r)) <= cls[k];
                 if (hit) { out[1]++; if (kept) out[2]++; else out[0]++; }
                 else if (!kept) out[3]++;
             }
@@ -447,19 +450,21 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
             }
         }
     }
-    // ---- sorted-stage kernel: stable sort by key, units of 512, bounds from the keys, cull, search
-    std::stable_sort(queue.begin(), queue.end(), [](const Entry &x, const Entry &y) { return x.key < y.key; });
+    // ---- sorted-stage kernel: entries grouped by (cell, octant) = key >> 4 (rz_sort.cu), units of 512, box + signs from the
+    // cells, every sphere's smallest reach class (rz_unit_class); a ray of class c searches the spheres of classes <= c
+    std::stable_sort(queue.begin(), queue.end(), [](const Entry &x, const Entry &y) { return (x.key >> 4) < (y.key >> 4); });
+    std::vector<int> scls(n);
     for (size_t e0 = 0; e0 < queue.size(); e0 += 512) {
         const size_t ne = std::min<size_t>(512, queue.size() - e0);
         RzUnitBounds U;
         rz_unit_bounds_init(U);
-        for (size_t i = 0; i < ne; i++) rz_unit_bounds_add_key(U, a, queue[e0 + i].key);
-        rz_unit_bounds_finish(U);
-        list.clear();
-        for (uint32_t k = 0; k < n; k++)
-            if (rz_unit_keep(U, a.huge_radius, cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w)) list.push_back(k);
+        for (size_t i = 0; i < ne; i++) rz_unit_bounds_add_cell(U, a, queue[e0 + i].key);
+        for (uint32_t k = 0; k < n; k++) scls[k] = rz_unit_class(U, a, cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w);
         out[6]++;
         for (size_t i = 0; i < ne; i++) {
+            const int c = (int)(queue[e0 + i].key & 15u);
+            list.clear();
+            for (uint32_t k = 0; k < n; k++) if (scls[k] <= c) list.push_back(k);
             float bt, bt2; int bk, bk2;
             search(queue[e0 + i].ray, nullptr, bt, bk);
             search(queue[e0 + i].ray, &list, bt2, bk2);

@@ -536,7 +536,7 @@ def test_staged_megakernel_equals_single_kernel_bitwise_and_stage_stats(scene42,
     assert s2["sphere_tests"] < 0.4 * s1["sphere_tests"]
     c, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="mega", serial_passes=True))
     assert np.array_equal(a, c)
-    for ue in (64, 1024, 4096):                     # entries per sorted-stage work unit: only the cull's grain changes
+    for ue in (64, 1024, 2048):                     # entries per sorted-stage work unit: only the cull's grain changes
         be.set_tuning(unit_entries=ue)
         d, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="mega"))
         assert np.array_equal(a, d), ue
@@ -569,21 +569,22 @@ def test_staged_megakernel_many_small_passes(be, scene42):
 @pytest.mark.parametrize("n,kind", [(1, "one"), (2047, "uniform"), (2048, "few"), (2049, "sorted"), (70001, "uniform"), (1 << 20, "hot"),
                                     (3_000_017, "uniform"), (3_000_017, "few")])
 def test_key_sort_groups_every_entry_by_key(be, n, kind):
-    """rz_sort.cu directly (test hook): keys come out ascending, the indices are a permutation of the entries, and each index
-    names an entry with the key stored beside it.  Order inside a key's range is free (the consumer does not depend on it)."""
+    """rz_sort.cu directly (test hook): the entries come out grouped by ascending (key >> 4) — origin cell + octant; the low 4
+    bits, the reach class, are ordered per work unit by the consumer — the indices are a permutation of the entries, and each
+    index names an entry with the key stored beside it.  Order inside a group is free (the consumer does not depend on it)."""
     rng = np.random.default_rng(n)
     if kind == "uniform":
         keys = rng.integers(0, 65536, n, dtype=np.uint16)
     elif kind == "few":
-        keys = rng.choice(np.array([0, 1, 255, 256, 40000, 65535], dtype=np.uint16), n)
-    elif kind == "hot":     # one key holds 60 % of the entries: the shared-memory aggregation's worst case
+        keys = rng.choice(np.array([0, 1, 15, 16, 255, 256, 40000, 65535], dtype=np.uint16), n)
+    elif kind == "hot":     # one group holds 60 % of the entries: the shared-memory histogram's worst case
         keys = np.where(rng.random(n) < 0.6, np.uint16(12345), rng.integers(0, 65536, n, dtype=np.uint16)).astype(np.uint16)
     elif kind == "sorted":
         keys = np.sort(rng.integers(0, 3000, n, dtype=np.uint16))
     else:
         keys = np.array([777], dtype=np.uint16)
     ko, io = be.debug_sort_keys(keys)
-    assert np.array_equal(ko, np.sort(keys))
+    assert np.array_equal(ko >> 4, np.sort(keys >> 4))
     assert np.array_equal(np.sort(io), np.arange(n, dtype=np.uint32))
     assert np.array_equal(keys[io], ko)
 
