@@ -142,6 +142,9 @@ struct Dev {
     DBuf<RzStatsDev> stats;
     DBuf<float4> out_linear;
     DBuf<uint8_t> out_rgb8;
+    DBuf<float4> loc_linear;          // multi-device render into HOST buffers: this device's own rows, copied out over its own PCIe link
+    DBuf<uint8_t> loc_rgb8;
+    uint32_t loc_rows = 0;            // rows of the last such render
     DBuf<int32_t> ids;
     DBuf<float> sink;
     void *wf_scratch = nullptr;
@@ -484,7 +487,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
         D.accum.release(); D.counter.release(); D.errword.release();
         for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.bins[sd].release(); }
-        D.stats.release(); D.out_linear.release(); D.out_rgb8.release();
+        D.stats.release(); D.out_linear.release(); D.out_rgb8.release(); D.loc_linear.release(); D.loc_rgb8.release();
         D.ids.release(); D.sink.release();
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
         for (auto &ev : D.ev) if (ev) cudaEventDestroy(ev);
@@ -876,7 +879,7 @@ static int collect_timing_and_stats(RzContext *ctx, bool collect_stats) {
     return RZ_OK;
 }
 
-static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams *p, bool sync) {
+static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams *p, bool sync, bool host_direct = false) {
     if (!ctx || !cam || !p) return rz_fail(RZ_ERR_INVALID_ARG, "render: NULL argument");
     if (!ctx->have_scene) return rz_fail(RZ_ERR_NO_SCENE, "render: rayz_cuda_upload_scene has not been called");
     if (p->width == 0 || p->height == 0 || p->spp == 0) return rz_fail(RZ_ERR_INVALID_ARG, "render: width, height and spp must be > 0");
@@ -910,7 +913,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
     const uint32_t rows_ctx = [&] { uint32_t r = 0; for (uint32_t d = 0; d < ND; d++) r += rayz_cuda_shard_rows(p->height, s * ND + d, S * ND, band); return r; }();
     Dev &D0 = ctx->devs[0];
     RZ_CUDA(cudaSetDevice(D0.id));
-    {
+    if (!host_direct) {
         int rc;
         if ((rc = D0.out_linear.alloc((size_t)rows_ctx * p->width))) return rc;
         if ((rc = D0.out_rgb8.alloc((size_t)rows_ctx * p->width * 3))) return rc;
@@ -1081,6 +1084,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         r.accum = D.accum.p; r.out_linear = D0.out_linear.p; r.out_rgb8 = D0.out_rgb8.p;
         r.n_local_px = n_local; r.width = p->width; r.spp = p->spp;
         r.dev_index = d; r.dev_count = ND; r.band_rows = band;
+        if (host_direct) {   // every device resolves into its OWN compact buffers; rayz_cuda_render copies them out in parallel
+            if ((rc = D.loc_linear.alloc((size_t)n_local)) || (rc = D.loc_rgb8.alloc((size_t)n_local * 3))) return rc;
+            r.out_linear = D.loc_linear.p; r.out_rgb8 = D.loc_rgb8.p; r.dev_index = 0; r.dev_count = 1;
+            D.loc_rows = rows;
+        }
         RZ_CUDA(rz_launch_resolve(&r, D.stream));
         if (n_local > 0) launches += 1;
         RZ_CUDA(cudaEventRecord(D.ev[3], D.stream));
@@ -1151,18 +1159,55 @@ extern "C" int rayz_cuda_render_device(RzContext *ctx, const RzCamera *cam, cons
     return RZ_OK;
 }
 
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)?  Only then do async copies from
+// several devices run concurrently; pageable memory is staged by the driver one copy at a time.
+static bool host_pinned(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int rayz_cuda_render(RzContext *ctx, const RzCamera *cam, const RzRenderParams *params, float *out_linear_rgba,
                                 uint8_t *out_rgb8, uint64_t *out_paths) {
     const auto t0 = std::chrono::steady_clock::now();
-    const int rc = render_impl(ctx, cam, params, false);
+    if (!ctx || !params) return rz_fail(RZ_ERR_INVALID_ARG, "render: NULL argument");
+    // Several devices and page-locked host buffers: no gather to device 0 at all.  Every device resolves its own rows and
+    // copies them straight into the caller's frame over its own PCIe link (round 1 funnelled the 157 MB config-3 frame
+    // through GPU0's link: 4 % of the step at 8 GPUs).  Rows are dealt in bands, so one strided 2-D copy per device and
+    // buffer does it: band lb of device d is rows [(lb * ND + d) * band, ...) of the frame.
+    const uint32_t ND = (uint32_t)ctx->devs.size();
+    const bool direct = ND > 1 && (out_linear_rgba || out_rgb8) && host_pinned(out_linear_rgba) && host_pinned(out_rgb8);
+    const int rc = render_impl(ctx, cam, params, false, direct);
     if (rc) return rc;
     DeviceGuard guard;
     Dev &D0 = ctx->devs[0];
     const uint32_t rows = rayz_cuda_context_rows(ctx, params->height, params->shard_index, params->shard_count, params->band_rows);
     const size_t npx = (size_t)rows * params->width;
-    RZ_CUDA(cudaSetDevice(D0.id));
-    if (out_linear_rgba) RZ_CUDA(cudaMemcpyAsync(out_linear_rgba, D0.out_linear.p, npx * sizeof(float4), cudaMemcpyDeviceToHost, D0.stream));
-    if (out_rgb8) RZ_CUDA(cudaMemcpyAsync(out_rgb8, D0.out_rgb8.p, npx * 3, cudaMemcpyDeviceToHost, D0.stream));
+    if (direct) {
+        const uint32_t band = params->band_rows ? params->band_rows : 4, W = params->width;
+        for (uint32_t d = 0; d < ND; d++) {
+            Dev &D = ctx->devs[d];
+            RZ_CUDA(cudaSetDevice(D.id));
+            const uint32_t full = D.loc_rows / band, tail = D.loc_rows - full * band;   // whole bands + a partial last one
+            auto copy = [&](void *dst0, const void *src0, size_t px_bytes) -> cudaError_t {
+                const size_t band_bytes = (size_t)band * W * px_bytes;
+                unsigned char *dst = (unsigned char *)dst0 + (size_t)d * band_bytes;
+                cudaError_t e = cudaSuccess;
+                if (full) e = cudaMemcpy2DAsync(dst, (size_t)ND * band_bytes, src0, band_bytes, band_bytes, full, cudaMemcpyDeviceToHost, D.stream);
+                if (e == cudaSuccess && tail)
+                    e = cudaMemcpyAsync(dst + (size_t)full * ND * band_bytes, (const unsigned char *)src0 + (size_t)full * band_bytes, (size_t)tail * W * px_bytes,
+                                        cudaMemcpyDeviceToHost, D.stream);
+                return e;
+            };
+            if (out_linear_rgba) RZ_CUDA(copy(out_linear_rgba, D.loc_linear.p, sizeof(float4)));
+            if (out_rgb8) RZ_CUDA(copy(out_rgb8, D.loc_rgb8.p, 3));
+        }
+    } else {
+        RZ_CUDA(cudaSetDevice(D0.id));
+        if (out_linear_rgba) RZ_CUDA(cudaMemcpyAsync(out_linear_rgba, D0.out_linear.p, npx * sizeof(float4), cudaMemcpyDeviceToHost, D0.stream));
+        if (out_rgb8) RZ_CUDA(cudaMemcpyAsync(out_rgb8, D0.out_rgb8.p, npx * 3, cudaMemcpyDeviceToHost, D0.stream));
+    }
     for (Dev &D : ctx->devs) {
         RZ_CUDA(cudaSetDevice(D.id));
         RZ_CUDA(cudaStreamSynchronize(D.stream));

@@ -352,8 +352,8 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
 #pragma unroll 1
         for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
             const uint32_t k = k0 + lane;
-            float cx, cy, cz, vx, vy, vz, w;
-            rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // n_pad is a multiple of 4; lanes past it read padding
+            float cx = 0.f, cy = 0.f, cz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, w = 1.f;
+            if (k < a.set.n_pad) rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // lanes past the set: a padding entry
             const bool keep = k < a.set.n_pad && rz_tile_keep(cone, cx, cy, cz, vx, vy, vz, w);
             unsigned m = __ballot_sync(0xffffffffu, keep);
             m = (m | (m >> 1)) & 0x55555555u;                       // bit 2j: pair j of this step is kept
@@ -495,8 +495,8 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
 #pragma unroll 1
         for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
             const uint32_t k = k0 + lane;
-            float cx, cy, cz, vx, vy, vz, w;
-            rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);
+            float cx = 0.f, cy = 0.f, cz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, w = 1.f;
+            if (k < a.set.n_pad) rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // lanes past the set: a padding entry
             int c = k < a.set.n_pad ? rz_unit_class(U, a, cx, cy, cz, vx, vy, vz, w) : 16;
             c = min(c, __shfl_xor_sync(0xffffffffu, c, 1));                    // the pair's class
             if (!(lane & 1u) && k < a.set.n_pad) {
@@ -537,24 +537,29 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
             const int cmax = min(15, __popc(__ballot_sync(0xffffffffu, lane < 16u && tab[lane] <= last)));
             const int n_ls = (int)tab[16 + cmax], n_lm = (int)tab[32 + cmax];
             RzLaneRay L[2];
-#pragma unroll 1
-            for (int trip = 0; trip < 2; trip++) {                  // one copy of the gather for both rays
-                RzLaneRay &Q = L[0];
-                const uint32_t j = b0 + lane + 32u * (uint32_t)trip;
-                Q.live = j < ne;
-                if (Q.live) {
-                    const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + order[j]] * 4u;
-                    const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
-                    Q.ray.o = f3(qa.x, qa.y, qa.z); Q.ray.time = qa.w;
-                    Q.ray.d = f3(qb.x, qb.y, qb.z); Q.ray.self_k = __float_as_int(qb.w);
-                    Q.thr = f3(qc.x, qc.y, qc.z); Q.seg = __float_as_uint(qc.w);
-                    Q.lp = __float_as_uint(qd.x); Q.gpix = __float_as_uint(qd.y); Q.smp = __float_as_uint(qd.z);
-                } else {
-                    Q.ray.o = f3(0.f, 0.f, 0.f); Q.ray.d = f3(0.f, 1.f, 0.f); Q.ray.time = 0.f; Q.ray.self_k = -1;
-                    Q.thr = f3(0.f, 0.f, 0.f); Q.seg = 0; Q.lp = 0; Q.gpix = 0; Q.smp = 0;
+            {   // both rays' entries are fetched together: eight 16-byte loads in flight per lane (random 64 B gathers from HBM)
+                const float4 *e[2];
+                float4 qa[2], qb[2], qc[2], qd[2];
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const uint32_t j = b0 + lane + 32u * (uint32_t)r;
+                    L[r].live = j < ne;
+                    e[r] = a.q_in + (size_t)(L[r].live ? a.q_in_idx[e0 + order[j]] : 0u) * 4u;
                 }
-                Q.bk = -1; Q.cont = false; Q.key = 0u;
-                rz_swap_lane_rays(L[0], L[1]);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    if (L[r].live) { qa[r] = __ldcs(e[r]); qb[r] = __ldcs(e[r] + 1); qc[r] = __ldcs(e[r] + 2); qd[r] = __ldcs(e[r] + 3); }
+                    else { qa[r] = make_float4(0.f, 0.f, 0.f, 0.f); qb[r] = make_float4(0.f, 1.f, 0.f, __int_as_float(-1)); qc[r] = qa[r]; qd[r] = qa[r]; }
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    RzLaneRay &Q = L[r];
+                    Q.ray.o = f3(qa[r].x, qa[r].y, qa[r].z); Q.ray.time = qa[r].w;
+                    Q.ray.d = f3(qb[r].x, qb[r].y, qb[r].z); Q.ray.self_k = __float_as_int(qb[r].w);
+                    Q.thr = f3(qc[r].x, qc[r].y, qc[r].z); Q.seg = __float_as_uint(qc[r].w);
+                    Q.lp = __float_as_uint(qd[r].x); Q.gpix = __float_as_uint(qd[r].y); Q.smp = __float_as_uint(qd[r].z);
+                    Q.bk = -1; Q.cont = false; Q.key = 0u;
+                }
             }
             {
                 const RzRay rays[2] = {L[0].ray, L[1].ray};

@@ -213,6 +213,36 @@ __device__ __forceinline__ void rz_search_list2(const float4 *__restrict__ s_pk,
     RzRayOps q[R];
 #pragma unroll
     for (int r = 0; r < R; r++) q[r] = rz_ray_ops(ray[r]);
+#ifdef RZ_LIST_BRANCHY   // experiment (scripts/exp_build.sh): the round-1 form, one rare-path branch per test
+#pragma unroll 1
+    for (int i = 0; i < n_ls; i++) {
+        const int p = ls[i];
+        const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            float2 nb, nd;
+            rz_test2_static(A, B, q[r], nb, nd);
+            if (nd.x < 0.0f) rz_consider(2 * p, nb.x, nd.x, ray[r].self_k, t_min, bt[r], bk[r]);
+            if (nd.y < 0.0f) rz_consider(2 * p + 1, nb.y, nd.y, ray[r].self_k, t_min, bt[r], bk[r]);
+        }
+    }
+    {
+        const float4 *__restrict__ mvb = s_pk + n_static_pad;
+#pragma unroll 1
+        for (int i = 0; i < n_lm; i++) {
+            const int p = lm[i];
+            const float4 A = mvb[4 * p], B = mvb[4 * p + 1], VA = mvb[4 * p + 2], VB = mvb[4 * p + 3];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                float2 nb, nd;
+                rz_test2_moving(A, B, VA, VB, q[r], nb, nd);
+                if (nd.x < 0.0f) rz_consider(n_static_pad + 2 * p, nb.x, nd.x, ray[r].self_k, t_min, bt[r], bk[r]);
+                if (nd.y < 0.0f) rz_consider(n_static_pad + 2 * p + 1, nb.y, nd.y, ray[r].self_k, t_min, bt[r], bk[r]);
+            }
+        }
+        return;
+    }
+#endif
 #pragma unroll 1
     for (int i0 = 0; i0 < n_ls; i0 += 16) {
         const int cn = min(16, n_ls - i0);

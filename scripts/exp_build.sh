@@ -1,22 +1,21 @@
 #!/bin/bash
 # Builds experimental variants of librayz_cuda.so that differ in compile-time knobs of rz_path.cu (scripts/_build/exp/<name>.so);
-# scripts/gpu_exp.sh swaps them into rayz_b200/lib/ on the GPU box one after the other.
+# scripts/exp_probe.py --so loads one of them instead of the product library.
+#   scripts/exp_build.sh name1 "-DFLAG=1 ..." [name2 "flags" ...]
 set -e
 cd "$(dirname "$0")/.."
 python -m rayz_b200.build > /dev/null
 mkdir -p scripts/_build/exp
+rm -f scripts/_build/exp/*.so
 OBJ=rayz_b200/lib/obj
 build() {   # name, flags...
   local name=$1; shift
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=default --use_fast_math "$@" \
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=default --use_fast_math $@ \
        -c rayz_b200/csrc/rz_path.cu -o scripts/_build/exp/$name.o
   local objs=""; for o in $OBJ/*.o; do [ "$(basename $o)" = rz_path.o ] || objs="$objs $o"; done
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o scripts/_build/exp/$name.so scripts/_build/exp/$name.o $objs -cudart static -Xlinker --no-undefined
   rm -f scripts/_build/exp/$name.o
 }
-build s8 -DRZ_SECOND_MINB=8 &
-build s7 -DRZ_SECOND_MINB=7 &
-build p6 -DRZ_PRIMARY_MINB=6 &
-build p8 -DRZ_PRIMARY_MINB=8 &
+while [ $# -ge 2 ]; do build "$1" $2 & shift 2; done
 wait
 ls -la scripts/_build/exp

@@ -1,12 +1,9 @@
 #!/bin/bash
-# One GPU call: the env-knob sweep on the in-tree library, then each experimental build of scripts/exp_build.sh swapped in.
+# Experiment run: stage timings of the staged K1 under tuning settings and alternative builds (scripts/exp_probe.py).
+set -x
 mkdir -p gpurun_out
-timeout 600 python scripts/exp_probe.py default > gpurun_out/x_default.log 2>&1
-cp rayz_b200/lib/librayz_cuda.so /tmp/librayz_keep.so
-for f in scripts/_build/exp/s7.so; do
-  n=$(basename $f .so)
-  cp $f rayz_b200/lib/librayz_cuda.so
-  timeout 300 python scripts/exp_probe.py $n --quick > gpurun_out/x_$n.log 2>&1
-done
-cp /tmp/librayz_keep.so rayz_b200/lib/librayz_cuda.so
-cat gpurun_out/x_*.log | cut -c1-250
+L=gpurun_out/${1:-exp}.log
+: > $L
+python scripts/exp_probe.py --set "" --set unit_entries=1024 --set unit_entries=256 --set queue_log2=28 --set queue_log2=28,unit_entries=1024 --set second_stages=4 --set second_stages=3 >> $L 2>&1
+for so in scripts/_build/exp/*.so; do python scripts/exp_probe.py --so $so --set "" >> $L 2>&1; done
+cat $L

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+top = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 static = collections.Counter()
@@ -42,5 +42,6 @@ for k, v in static.items():
     byfile[k[0]] += v
 print("by file:", dict(byfile))
 print(f"{'file:line':28s} {'static':>6s} {'exec %':>7s} {'samp %':>7s}  source")
-for k, v in static.most_common(top):
-    print(f"{k[0] + ':' + str(k[1]):28s} {v:6d} {100 * dyn[k] / tot_d:7.2f} {100 * samples[k] / tot_p:7.2f}  {text.get(k, '')}")
+order = samples.most_common(top) if "--by-samples" in sys.argv else dyn.most_common(top) if "--by-exec" in sys.argv else static.most_common(top)
+for k, _ in order:
+    print(f"{k[0] + ':' + str(k[1]):28s} {static[k]:6d} {100 * dyn[k] / tot_d:7.2f} {100 * samples[k] / tot_p:7.2f}  {text.get(k, '')}")
