@@ -264,7 +264,8 @@ typedef struct RzTuning {
     int32_t bvh_descend_min;  /* K3: a descend round ends below this many descending lanes (default 24)                 */
     int32_t sah_leaf;         /* host SAH builder: max spheres per leaf, 1..8 (default 4); applies at the next upload   */
     double sah_node_cost;     /* host SAH builder: cost of a node visit relative to a sphere test (default 0.5)         */
-    uint32_t unit_entries;    /* sorted-stage kernel: queue entries per work unit, 64..2048, multiple of 64 (default 512) */
+    uint32_t unit_entries;    /* sorted-stage kernel: queue entries per work unit (upper bound; small stages use
+                               * fewer), 64..2048, multiple of 64 (default 1024)                                        */
     uint32_t debug_queue_cap; /* tests: pretend the queues hold only this many entries (0 = off) -> RZ_ERR_INTERNAL     */
     uint32_t debug_stack_cap; /* tests: pretend the K3 traversal stack holds only this many entries (0 = off)           */
 } RzTuning;

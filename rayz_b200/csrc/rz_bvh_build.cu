@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) lbvh_gather_set(uint32_t n, const uint32_
     o_cr[k] = make_float4((float)c.x, (float)c.y, (float)c.z, -(float)(c.w * c.w));
     o_vel[k] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)c.w);
     o_c64[k] = c;
-    o_v64[k] = make_double4(v.x, v.y, v.z, 0.0);
+    o_v64[k] = make_double4(v.x, v.y, v.z, 1.0 / c.w);   // .w = 1 / radius for rz_refine_hit
     o_mat[k] = mat[s];
     o_orig[k] = (int32_t)s;
 }

@@ -4,7 +4,8 @@
 // Restates the role of BVH.findHit + AABB.hit (reference src/hit.zig:70-98, 181-216) inside the path
 // loop of renderer.zig:85-126.  The reference recurses per ray, left child first; here every lane of
 // a persistent warp walks its own ray through a flattened BVH2 (both child boxes in the parent, 64 B,
-// read through ld.global.nc), near child first, with an explicit per-lane stack.
+// read through ld.global.nc), near child first, with an explicit per-lane stack.  (A 4-wide tree was measured and
+// rejected: rz_bvh_round under RZ_BVH_WIDE below.)
 //
 // What shapes the kernel is SIMT divergence, not arithmetic: the first version (per-lane
 // `while (stack)` with the leaf tests nested inside, rays replaced only between segments) ran with
@@ -29,11 +30,81 @@
 namespace {
 
 constexpr int RZ_SENTINEL = 0x7fffffff;
+#ifdef RZ_BVH_WIDE
+constexpr int RZ_STACK = 144;  // binary LBVH depth <= 96 = 48 wide levels x 3 pushes
+#else
 constexpr int RZ_STACK = 96;   // LBVH depth bound: 63 Morton bits + 32 index tie-break bits
+#endif
 
 // leaf reference: ~((count - 1) << 28 | first); first < 2^28, count <= 8
 __device__ __forceinline__ int rz_leaf_ref(int child, uint32_t cnt) { return ~((int)((cnt - 1u) << 28) | ~child); }
 
+#ifdef RZ_BVH_WIDE
+// EXPERIMENT (build with -DRZ_BVH_WIDE, scripts/exp_build.sh): the 4-wide tree of rz_bvh_wide.cu.  Measured on B200 and NOT
+// adopted: config-2 scene 3158 vs 3584 Mpaths/s, 99,856 spheres 1556 vs 1716 — the same number of box tests per segment
+// (27.6 vs 25 / 48.7 vs 47) in half as many, twice as long node visits, plus a sorting network per visit; the tree is L1/L2
+// resident, so the traversal is issue-bound, not latency-bound, and wider nodes buy nothing.
+// One while-while round for this lane's ray through the 4-wide tree: descend through internal nodes to the next leaf (or
+// until the warp's round is cut short), then test that leaf.  Shared by the persistent kernel and the staged (sorted) kernels.
+template <bool STATS>
+__device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *__restrict__ nodes, const RzRay &ray, float ix, float iy,
+                                             float iz, int &cur, int &sp, int (&stack)[RZ_STACK], float &bt, int &bk, int descend_min,
+                                             unsigned long long &c_nodes, unsigned long long &c_sph) {
+    // (1) descend through internal nodes until this lane holds a leaf or runs dry; the round ends early
+    //     once fewer than `descend_min` lanes are still descending, so that lanes holding a leaf do not idle
+    //     behind a few long descents (those lanes simply resume in the next round)
+    while ((unsigned)cur < (unsigned)RZ_SENTINEL) {
+        // slab test of AABB.hit (hit.zig:70-98) with multiply-by-inverse on the FOUR child boxes of the node (128 B, eight
+        // 16-byte loads through the read-only path); boxes are padded outward at build time
+        if (STATS) c_nodes += 4;
+        const float4 *n = nodes + (size_t)cur * 8u;
+        const float4 lx = __ldg(n + 0), hx = __ldg(n + 1), ly = __ldg(n + 2), hy = __ldg(n + 3), lz = __ldg(n + 4), hz = __ldg(n + 5);
+        const int4 ch = __ldg(reinterpret_cast<const int4 *>(n + 6));
+        const uint4 cn = __ldg(reinterpret_cast<const uint4 *>(n + 7));
+        const float ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
+        float tn[4];
+        int ref[4];
+#define RZ_BOX4(c, LX, HX, LY, HY, LZ, HZ, CH, CN)                                                                          \
+        {                                                                                                                   \
+            const float a0 = ((LX) - ox) * ix, b0 = ((HX) - ox) * ix, a1 = ((LY) - oy) * iy, b1 = ((HY) - oy) * iy;          \
+            const float a2 = ((LZ) - oz) * iz, b2 = ((HZ) - oz) * iz;                                                       \
+            const float t0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), a.t_min));                     \
+            const float t1 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), bt));                          \
+            const bool h = (t0 <= t1 * 1.0000004f) && ((CH) >= 0 || (CN) != 0u);   /* an unused slot is a leaf of 0 spheres */ \
+            tn[c] = h ? t0 : 3.0e38f;                                                                                       \
+            ref[c] = (CH) >= 0 ? (CH) : rz_leaf_ref((CH), (CN));   /* internal index >= 0, or a leaf (negative, with its count) */ \
+        }
+        RZ_BOX4(0, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, ch.x, cn.x)
+        RZ_BOX4(1, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, ch.y, cn.y)
+        RZ_BOX4(2, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, ch.z, cn.z)
+        RZ_BOX4(3, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, ch.w, cn.w)
+#undef RZ_BOX4
+        // sort the four (entry distance, child) pairs, nearest first: a 5-comparator network; misses (3e38) sink to the end
+#define RZ_CSWAP(i, j)                                                                           \
+        {                                                                                        \
+            const bool sw = tn[j] < tn[i];                                                       \
+            const float tf = sw ? tn[j] : tn[i], tg = sw ? tn[i] : tn[j];                        \
+            const int rf = sw ? ref[j] : ref[i], rg = sw ? ref[i] : ref[j];                      \
+            tn[i] = tf; tn[j] = tg; ref[i] = rf; ref[j] = rg;                                    \
+        }
+        RZ_CSWAP(0, 1) RZ_CSWAP(2, 3) RZ_CSWAP(0, 2) RZ_CSWAP(1, 3) RZ_CSWAP(1, 2)
+#undef RZ_CSWAP
+        if (tn[0] < 3.0e38f) {
+            // the nearest child next; the others go on the stack, farthest first
+#pragma unroll
+            for (int c = 3; c >= 1; c--) {
+                if (tn[c] < 3.0e38f) {
+                    if (sp < (int)a.stack_cap) stack[sp++] = ref[c];
+                    else atomicOr(a.err, (unsigned)RZ_DEV_ERR_STACK_OVERFLOW);   // a dropped subtree would darken the image silently
+                }
+            }
+            cur = ref[0];
+        } else {
+            cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
+        }
+        if (__popc(__activemask()) < descend_min) break;
+    }
+#else
 // One while-while round for this lane's ray: descend through internal nodes to the next leaf (or until the warp's round
 // is cut short), then test that leaf.  Shared by the persistent kernel and the staged (sorted) kernels.
 template <bool STATS>
@@ -81,6 +152,7 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
         }
         if (__popc(__activemask()) < descend_min) break;
     }
+#endif
     // (2) leaf phase
     if (cur < 0) {
         const int code = ~cur;

@@ -43,6 +43,8 @@ extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n);
 extern "C" cudaError_t rz_lbvh_build(uint32_t n, const double4 *c64, const double4 *v64, const uint32_t *mat, void *scratch,
                                      size_t scratch_bytes, RzBvhNode *nodes, float4 *o_cr, float4 *o_vel, double4 *o_c64,
                                      double4 *o_v64, uint32_t *o_mat, int32_t *o_orig, cudaStream_t stream);
+extern "C" size_t rz_bvh_wide_scratch_bytes(uint32_t n_nodes);
+extern "C" cudaError_t rz_bvh_wide_collapse(const RzBvhNode *n2, uint32_t n_nodes, void *scratch, RzBvh4Node *out, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_ids(const RzIdsArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_resolve(const RzResolveArgs *a, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_ffma_peak(float *sink, int grid, int iters, int mode, cudaStream_t stream);
@@ -117,7 +119,9 @@ struct Dev {
     cudaEvent_t ev_s2 = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, path0, path1, resolve1, done
     SetBufs brute, bvhset;
-    DBuf<RzBvhNode> bvh;
+    DBuf<RzBvhNode> bvh;              // the builders' binary tree (host SAH or device LBVH): input of the collapse
+    DBuf<RzBvh4Node> bvh4;            // what K3 walks: every second level collapsed (rz_bvh_wide.cu)
+    DBuf<int> wide_scratch;
     uint32_t bvh_nodes = 0;
     DBuf<int32_t> brute_to_bvh;       // staged K1 with a BVH tail: position in `brute` -> position in `bvhset` (empty: no such tail)
     DBuf<RzRefNode> refnodes;
@@ -377,7 +381,7 @@ struct HostSet {
         cr.push_back(make_float4((float)c[0], (float)c[1], (float)c[2], -(float)(r * r)));
         vel.push_back(make_float4((float)v[0], (float)v[1], (float)v[2], (float)r));
         c64.push_back(make_double4(c[0], c[1], c[2], r));
-        v64.push_back(make_double4(v[0], v[1], v[2], 0.0));
+        v64.push_back(make_double4(v[0], v[1], v[2], 1.0 / r));   // .w = 1 / radius for rz_refine_hit
         mat.push_back(sc.sphere_material[i]);
         orig.push_back((int32_t)i);
     }
@@ -481,7 +485,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
     for (Dev &D : ctx->devs) {
         if (cudaSetDevice(D.id) != cudaSuccess) continue;
         if (D.own_stream) cudaStreamSynchronize(D.own_stream);
-        D.brute.release(); D.bvhset.release(); D.bvh.release(); D.brute_to_bvh.release(); D.refnodes.release(); D.reforder.release();
+        D.brute.release(); D.bvhset.release(); D.bvh.release(); D.bvh4.release(); D.wide_scratch.release(); D.brute_to_bvh.release(); D.refnodes.release(); D.reforder.release();
         D.c64_orig.release(); D.v64_orig.release(); D.mat_orig.release(); D.lbvh_scratch.release();
         D.m_rec.release(); D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
@@ -525,7 +529,7 @@ static RzTuning default_tuning() {
     t.bvh_descend_min = 24;
     t.sah_leaf = 4;
     t.sah_node_cost = 0.5;
-    t.unit_entries = 512;
+    t.unit_entries = 1024;
     return t;
 }
 
@@ -586,7 +590,7 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
     bs.pad_to(bs.n_static_pad);
     // c64/v64/mat/orig are indexed by set position too: keep them aligned with the padding
     auto pad_aux = [](HostSet &h) {
-        while (h.c64.size() < h.cr.size()) { h.c64.push_back(make_double4(0, 0, 0, 1)); h.v64.push_back(make_double4(0, 0, 0, 0)); h.mat.push_back(0); h.orig.push_back(-1); }
+        while (h.c64.size() < h.cr.size()) { h.c64.push_back(make_double4(0, 0, 0, 1)); h.v64.push_back(make_double4(0, 0, 0, 1)); h.mat.push_back(0); h.orig.push_back(-1); }
     };
     pad_aux(bs);
     for (uint32_t i = 0; i < n; i++) {
@@ -718,8 +722,12 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
             RZ_CUDA(cudaEventRecord(D.ev[0], D.stream));
             RZ_CUDA(rz_lbvh_build(n, D.c64_orig.p, D.v64_orig.p, D.mat_orig.p, D.lbvh_scratch.p, D.lbvh_scratch.n, D.bvh.p, V.cr.p, V.vel.p,
                                   V.c64.p, V.v64.p, V.mat.p, V.orig.p, D.stream));
-            RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
         }
+#ifdef RZ_BVH_WIDE   // experiment: K3 walks the 4-wide collapse of the builders' binary tree (three small kernels, no host round trip)
+        if ((rc = D.bvh4.alloc(D.bvh_nodes)) || (rc = D.wide_scratch.alloc(rz_bvh_wide_scratch_bytes(D.bvh_nodes) / sizeof(int)))) return rc;
+        RZ_CUDA(rz_bvh_wide_collapse(D.bvh.p, D.bvh_nodes, D.wide_scratch.p, D.bvh4.p, D.stream));
+#endif
+        if (device_build) RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
         if ((rc = D.m_rec.upload(mrec, D.stream)) || (rc = D.m_kind.upload(mk, D.stream)) || (rc = D.m_tex.upload(mt, D.stream)) || (rc = D.m_method.upload(mm, D.stream)) ||
             (rc = D.m_fuzz.upload(mf, D.stream)) || (rc = D.m_ior.upload(mi, D.stream)) || (rc = D.t_kind.upload(tk, D.stream)) ||
             (rc = D.t_even.upload(te, D.stream)) || (rc = D.t_odd.upload(to, D.stream)) || (rc = D.t_color.upload(tc, D.stream)) ||
@@ -941,7 +949,11 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
         a.set = (variant == RZ_VARIANT_BVH) ? D.bvhset.view() : D.brute.view();
         a.mats.kind = D.m_kind.p; a.mats.fuzz = D.m_fuzz.p; a.mats.ior = D.m_ior.p; a.mats.tex = D.m_tex.p; a.mats.method = D.m_method.p; a.mats.rec = D.m_rec.p;
         a.texs.kind = D.t_kind.p; a.texs.color = D.t_color.p; a.texs.inv_scale = D.t_inv_scale.p; a.texs.even = D.t_even.p; a.texs.odd = D.t_odd.p;
+#ifdef RZ_BVH_WIDE
+        a.bvh = D.bvh4.p; a.bvh_nodes = D.bvh_nodes;
+#else
         a.bvh = D.bvh.p; a.bvh_nodes = D.bvh_nodes;
+#endif
         a.cam = cam_to_f32(cam);
         a.accum = D.accum.p; a.unit_counter = D.counter.p; a.stats = D.stats.p;
         a.width = p->width; a.height = p->height; a.n_local_px = n_local;

@@ -19,6 +19,13 @@
 #include <stdint.h>
 
 #define RZ_HD __host__ __device__ __forceinline__
+// Rare branches of the shading code are kept OUT of line on the device: the staged kernels are 35-45 KB against a 32 KB L1.5
+// instruction cache, and ncu charged up to 3 stall cycles per issued instruction to `no_instruction` (profiles/).
+#ifdef __CUDA_ARCH__
+#define RZ_COLD __device__ __noinline__
+#else
+#define RZ_COLD inline
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Device scene: structure-of-arrays, one "sphere set" per kernel family (the brute-force set is
@@ -32,7 +39,7 @@ struct RzSphereSet {
                            // (cx0,cx1,cy0,cy1)(cz0,cz1,w0,w1), w = -r^2; moving pairs follow, each with
                            // two more float4 (vx0,vx1,vy0,vy1)(vz0,vz1,0,0).  n_static_pad + 2*n_moving_pad float4.
     const double4 *c64;    // [n]     (cx, cy, cz, r)  f64, for the refinement of the winning hit
-    const double4 *v64;    // [n]     (vx, vy, vz, 0)  f64
+    const double4 *v64;    // [n]     (vx, vy, vz, 1 / r)  f64
     const uint32_t *mat;   // [n]     material index (MaterialHandle.idx)
     const int32_t *orig;   // [n]     index in the caller's sphere array (ids, stats)
     uint32_t n;            // real spheres
@@ -76,6 +83,14 @@ struct __align__(16) RzBvhNode {
     uint32_t cnt[2];
 };
 
+// BVH4 node (RZ_BVH_WIDE experiment, measured and not adopted): the four child boxes of a node in one 128-byte record, built by
+// collapsing every second level of the binary tree (rz_bvh_wide.cu).  Unused slots: empty box, child = ~0, cnt = 0.
+struct __align__(16) RzBvh4Node {
+    float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];
+    int32_t child[4];
+    uint32_t cnt[4];
+};
+
 struct RzCamF32 {
     float3 look_from, px_du, px_dv, px_origin, defocus_u, defocus_v;
     int defocus;
@@ -93,7 +108,7 @@ struct RzPathArgs {
     RzSphereSet set;
     RzMaterials mats;
     RzTextures texs;
-    const RzBvhNode *bvh;        // K3 only
+    const void *bvh;             // K3 only: RzBvhNode[] (or RzBvh4Node[] in the RZ_BVH_WIDE experiment)
     uint32_t bvh_nodes;
     RzCamF32 cam;
     unsigned long long *accum;   // [n_local_px_pad][4] u64 fixed point (2^-32), rgb + pad
@@ -300,7 +315,7 @@ RZ_HD float3 rz_sky(float3 d_unit) {
 // Texture.value (material.zig:44-50) with CheckerTexture's handle recursion (:32-38) unrolled
 // into a bounded loop.  The lattice test runs in f64 on the f64-refined hit point: on the
 // r=1000 ground sphere |y| is ~1e-8 near the origin, far below FP32 resolution at 1000.
-RZ_HD float3 rz_texture(const RzTextures &T, uint32_t tex, double px, double py, double pz) {
+RZ_COLD float3 rz_texture(const RzTextures T, uint32_t tex, double px, double py, double pz) {   // by value: a reference would force the caller's kernel parameters into local memory
 #pragma unroll 1
     for (int level = 0; level < 8; level++) {
         if (T.kind[tex] != 0u) break;  // solid
@@ -340,13 +355,16 @@ RZ_HD RzHit rz_refine_hit(const RzSphereSet &S, const RzRay &ray, int k, bool fa
     double disc = hb * hb - a * cc;
     if (!(disc > 0.0)) disc = 0.0;  // FP32 said "grazing hit"; f64 says tangent/miss: clamp
     const double rt = sqrt(disc);
-    const double inv_a = 1.0 / a;
+    // 1 / a without an f64 division (38 instructions): d is unit length to FP32 rounding, a = 1 + e with |e| ~ 1e-7, so
+    // x0 = 2 - a is off by e^2 ~ 1e-14 and one Newton step leaves e^4
+    const double x0 = 2.0 - a;
+    const double inv_a = x0 * (2.0 - a * x0);
     const double t = (far_root ? (hb + rt) : (hb - rt)) * inv_a;
     RzHit h;
     h.px = fma(dx, t, ox);
     h.py = fma(dy, t, oy);
     h.pz = fma(dz, t, oz);
-    const double inv_r = 1.0 / c.w;
+    const double inv_r = v.w;   // 1 / radius, divided once at upload (RzSphereSet::v64)
     double nx = (h.px - cx) * inv_r, ny = (h.py - cy) * inv_r, nz = (h.pz - cz) * inv_r;
     h.front = (nx * dx + ny * dy + nz * dz) < 0.0;
     if (!h.front) { nx = -nx; ny = -ny; nz = -nz; }
@@ -364,6 +382,15 @@ RZ_HD float rz_reflectance(float cosv, float ri) {
     return r0 + (1.0f - r0) * (m2 * m2 * m);
 }
 
+// DiffuseScatterMethod.UNIT_SPHERE: normal + point in ball; UNIT_SPHERE_SURFACE: normal + unit vector (material.zig:78-82).
+// No reference scene selects them (default HEMISPHERE, :74): out of line.
+RZ_COLD float3 rz_diffuse_other(uint32_t method, float3 s, float3 n, float uz) {
+    const float rad = (method == 0u) ? cbrtf(uz) : 1.0f;
+    float3 t = n + s * rad;
+    if (dot3(t, t) < 1e-12f) t = n;
+    return normalize3(t);
+}
+
 // Material.scatter (material.zig:167-176).  Returns false when the path is absorbed
 // (MetallicMaterial.scatter -> null, :116-117).  `ray` is replaced by the scattered ray,
 // `att` receives the attenuation.  u = four uniforms of this bounce's Philox block.
@@ -376,15 +403,8 @@ RZ_HD bool rz_scatter(const RzMatRec &M, const RzTextures &T, const RzHit &h, in
         // no cosine weighting, attenuation = albedo.
         const uint32_t method = M.method;
         const float3 s = rz_uniform_sphere(u.x, u.y);
-        if (method == 2u) {
-            nd = dot3(s, h.n) > 0.0f ? s : s * -1.0f;
-        } else {
-            // UNIT_SPHERE: normal + point in ball; UNIT_SPHERE_SURFACE: normal + unit vector (:78-82)
-            const float rad = (method == 0u) ? cbrtf(u.z) : 1.0f;
-            float3 t = h.n + s * rad;
-            if (dot3(t, t) < 1e-12f) t = h.n;
-            nd = normalize3(t);
-        }
+        if (method == 2u) nd = dot3(s, h.n) > 0.0f ? s : s * -1.0f;
+        else nd = rz_diffuse_other(method, s, h.n, u.z);
         att = M.solid ? M.color : rz_texture(T, M.tex, h.px, h.py, h.pz);
     } else if (kind == 1u) {
         // MetallicMaterial.scatter (:108-131): unit mirror direction + min(fuzz,1) * unit vector

@@ -35,8 +35,8 @@
 
 // Resident CTAs per SM the staged kernels are compiled for (register cap = 65536 / (128 * N)); undefined = ptxas decides.
 #ifndef RZ_SECOND_MINB
-#define RZ_SECOND_MINB 7   // 72 registers: the sorted-stage kernel waits on its gathers, a seventh CTA hides more of them (45.6 -> 44.3 ms)
-#endif
+#define RZ_SECOND_MINB 6   // 85 registers.  Round 1 ran 7 CTAs at 72; with the single-copy shading loop that cap costs ~140 B of spills per
+#endif                     // thread in the hot loop, and 6 CTAs without spills measured 4.5 % faster (55.1 -> 52.6 ms, scripts/exp_probe.py)
 #define RZ_SECOND_BOUNDS __launch_bounds__(128, RZ_SECOND_MINB)
 #ifdef RZ_PRIMARY_MINB
 #define RZ_PRIMARY_BOUNDS __launch_bounds__(128, RZ_PRIMARY_MINB)
@@ -44,9 +44,9 @@
 #define RZ_PRIMARY_BOUNDS __launch_bounds__(128)
 #endif
 
-// per-warp scratch of the sorted-stage kernel: tab[48] u32 | pair list u16[n_pairs] | entry order u16[ue] | pair classes u8[n_pairs]
+// per-warp scratch of the sorted-stage kernel: tab[64] u32 | pair list u16[n_pairs] | entry order u16[ue] | pair classes u8[n_pairs]
 __host__ __device__ inline uint32_t rz_second_warp_bytes(uint32_t n_pairs, uint32_t ue) {
-    return (48u * 4u + 2u * n_pairs + 2u * ue + n_pairs + 15u) & ~15u;
+    return (64u * 4u + 2u * n_pairs + 2u * ue + n_pairs + 15u) & ~15u;
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -217,6 +217,10 @@ __device__ __forceinline__ void rz_swap_lane_rays(RzLaneRay &x, RzLaneRay &y) {
     y = t;
 }
 
+// float <-> int whose signed order is the float's order (for atomicMin / atomicMax on shared memory)
+__device__ __forceinline__ int rz_f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float rz_ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
 struct RzSegCounters {
     unsigned long long paths, segs, sph, hit[3], sky, abs_, depth;
 };
@@ -224,9 +228,15 @@ struct RzSegCounters {
 // Shade the two rays of a lane after the search and append the survivors (with their sort keys) to the next queue.
 template <bool STATS>
 __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRay (&L)[2], unsigned lane, unsigned lt_mask, RzSegCounters &C) {
+#ifdef RZ_SHADE_UNROLL   // experiment (scripts/exp_build.sh): two copies of the shading code, the two rays' dependency chains interleave
+#pragma unroll
+    for (int trip = 0; trip < 2; trip++) {
+        RzLaneRay &Q = L[trip];
+#else
 #pragma unroll 1
     for (int trip = 0; trip < 2; trip++) {
         RzLaneRay &Q = L[0];
+#endif
         Q.cont = false;
         if (Q.live) {
             if (STATS) C.segs++;
@@ -241,7 +251,9 @@ __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRa
             Q.cont = res == RZ_CONT;
             if (Q.cont && a.q_out_keys) Q.key = rz_sort_key(a, Q.ray);
         }
+#ifndef RZ_SHADE_UNROLL
         rz_swap_lane_rays(L[0], L[1]);
+#endif
     }
     // ballot-compacted append: one atomic per warp for both rays
     const unsigned m0 = __ballot_sync(0xffffffffu, L[0].cont), m1 = __ballot_sync(0xffffffffu, L[1].cont);
@@ -419,21 +431,25 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
     const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1, n_pairs = n_sp + n_mp;
     const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
-    const uint32_t ue = a.unit_entries;
-    // per-warp scratch: tab[48] | pair list [n_pairs] | entry order [ue] | pair classes [n_pairs] (layout: rz_second_smem_bytes)
-    const uint32_t warp_bytes = rz_second_warp_bytes(n_pairs, ue);
+    const uint32_t ue_max = a.unit_entries;
+    // per-warp scratch: tab[64] | pair list [n_pairs] | entry order [ue] | pair classes [n_pairs] (layout: rz_second_smem_bytes)
+    const uint32_t warp_bytes = rz_second_warp_bytes(n_pairs, ue_max);
     unsigned char *wb = reinterpret_cast<unsigned char *>(s_pk + pk_f4) + (threadIdx.x >> 5) * warp_bytes;
-    unsigned int *tab = reinterpret_cast<unsigned int *>(wb);             // [0,16) entries: end of class c; [16,32) stationary pairs of classes <= c; [32,48) moving
-    unsigned short *ls = reinterpret_cast<unsigned short *>(tab + 48);
+    unsigned int *tab = reinterpret_cast<unsigned int *>(wb);             // [0,16) entries: end of class c; [16,32) stationary pairs of classes <= c; [32,48) moving; [48,56) merged bounds
+    unsigned short *ls = reinterpret_cast<unsigned short *>(tab + 64);
     unsigned short *lm = ls + n_sp;
     unsigned short *order = ls + n_pairs;
-    unsigned char *pcl = reinterpret_cast<unsigned char *>(order + ue);
+    unsigned char *pcl = reinterpret_cast<unsigned char *>(order + ue_max);
 
     rz_stage_scene_pk(a.set, s_pk, &s_bar);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t n_in = min(*a.q_in_count, a.queue_cap);
+    // Entries per work unit: RzTuning::unit_entries (1024: the per-unit set-up is ~10 % of a 512-entry unit), but never so
+    // many that a warp gets fewer than ~4 units — the late stages hold a few million entries for 3552 warps
+    uint32_t ue = ue_max;
+    if (ue > 256u) ue = min(ue, max(256u, (n_in / (4u * 4u * gridDim.x)) & ~63u));
     const uint32_t n_units = (n_in + ue - 1u) / ue;
     RzSegCounters C = {};
 
@@ -448,6 +464,7 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         // ---- 1. what the unit's rays have in common (cells + octants of the keys), and how many rays each reach class holds
         tab[lane] = 0u;
         if (lane < 16u) tab[32u + lane] = 0u;
+        if (lane < 8u) tab[48u + lane] = lane < 3u ? 0x7fffffffu : lane < 6u ? 0x80000000u : 7u;   // lo = +max, hi = -max (ordered ints), all_pos = all_neg = 7
         __syncwarp();
         RzUnitBounds U;
         rz_unit_bounds_init(U);
@@ -458,16 +475,22 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
             atomicAdd(&tab[key & 15u], 1u);
             if ((key >> 4) != prev) { prev = key >> 4; rz_unit_bounds_add_cell(U, a, key); }
         }
-        for (int o = 16; o > 0; o >>= 1) {
+        // merge the lanes' bounds through shared memory (min / max on order-preserving integers): 8 atomics per lane instead of
+        // 40 shuffles, each of which costs a convergence sequence here
+        if (prev != 0xffffffffu) {
+            int *ib = reinterpret_cast<int *>(tab + 48);
 #pragma unroll
-            for (int ax = 0; ax < 3; ax++) {
-                U.lo[ax] = fminf(U.lo[ax], __shfl_xor_sync(0xffffffffu, U.lo[ax], o));
-                U.hi[ax] = fmaxf(U.hi[ax], __shfl_xor_sync(0xffffffffu, U.hi[ax], o));
-            }
-            U.all_pos &= __shfl_xor_sync(0xffffffffu, U.all_pos, o);
-            U.all_neg &= __shfl_xor_sync(0xffffffffu, U.all_neg, o);
+            for (int ax = 0; ax < 3; ax++) { atomicMin(ib + ax, rz_f2ord(U.lo[ax])); atomicMax(ib + 3 + ax, rz_f2ord(U.hi[ax])); }
+            atomicAnd(tab + 54, U.all_pos);
+            atomicAnd(tab + 55, U.all_neg);
         }
         __syncwarp();
+        {
+            const int *ib = reinterpret_cast<const int *>(tab + 48);
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++) { U.lo[ax] = rz_ord2f(ib[ax]); U.hi[ax] = rz_ord2f(ib[3 + ax]); }
+            U.all_pos = tab[54]; U.all_neg = tab[55];
+        }
         {   // exclusive prefix over the 16 classes -> running cursors
             const uint32_t cnt = lane < 16u ? tab[lane] : 0u;
             uint32_t inc = cnt;

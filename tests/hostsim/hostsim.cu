@@ -30,7 +30,7 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
         const double *c = sc->sphere_center + 3 * i, *v = sc->sphere_velocity + 3 * i; const double r = sc->sphere_radius[i];
         cr[i] = make_float4((float)c[0], (float)c[1], (float)c[2], -(float)(r * r));
         vel[i] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)r);
-        c64[i] = make_double4(c[0], c[1], c[2], r); v64[i] = make_double4(v[0], v[1], v[2], 0);
+        c64[i] = make_double4(c[0], c[1], c[2], r); v64[i] = make_double4(v[0], v[1], v[2], 1.0 / r);
         smat[i] = sc->sphere_material[i]; orig[i] = (int32_t)i;
     }
     const uint32_t nm = sc->n_materials, nt = sc->n_textures;
@@ -335,7 +335,7 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
         const double *c = sc->sphere_center + 3 * i, *v = sc->sphere_velocity + 3 * i; const double r = sc->sphere_radius[i];
         cr[i] = make_float4((float)c[0], (float)c[1], (float)c[2], -(float)(r * r));
         vel[i] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)r);
-        c64[i] = make_double4(c[0], c[1], c[2], r); v64[i] = make_double4(v[0], v[1], v[2], 0);
+        c64[i] = make_double4(c[0], c[1], c[2], r); v64[i] = make_double4(v[0], v[1], v[2], 1.0 / r);
         smat[i] = sc->sphere_material[i]; orig[i] = (int32_t)i;
     }
     const uint32_t nm = sc->n_materials, nt = sc->n_textures;
