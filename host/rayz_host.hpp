@@ -350,10 +350,13 @@ inline void penultimateScene(Tracer &tracer) {
 inline void randomBouncing(Tracer &tracer, int grid_lo = -11, int grid_hi = 11) {
     MemPool &pool = tracer.pool;
     DefaultPrng &rand = tracer.rng;
-    pool.add(Sphere::stationary({0, -1000, 0}, 1000,
-                                pool.addAndReturnHandle(Material::Diffuse(pool.addAndReturnHandle(Texture::Checker(
-                                    0.32, pool.addAndReturnHandle(Texture::Solid({0.2, 0.3, 0.1})),
-                                    pool.addAndReturnHandle(Texture::Solid(V3::of(0.9)))))))));
+    // rayz.zig:57-73: Zig evaluates the nested struct literals in source order — even, odd, then the checker.  (C++ leaves the
+    // order of function arguments unspecified, so the handles are taken one statement at a time: tests/test_host_gpu.py compares
+    // the flattened scene with the oracle's byte for byte.)
+    const TextureHandle even = pool.addAndReturnHandle(Texture::Solid({0.2, 0.3, 0.1}));
+    const TextureHandle odd = pool.addAndReturnHandle(Texture::Solid(V3::of(0.9)));
+    const TextureHandle checker = pool.addAndReturnHandle(Texture::Checker(0.32, even, odd));
+    pool.add(Sphere::stationary({0, -1000, 0}, 1000, pool.addAndReturnHandle(Material::Diffuse(checker))));
     pool.add(Sphere::stationary({0, 1, 0}, 1.0, pool.addAndReturnHandle(Material::Dielectric(1.5))));
     pool.add(Sphere::stationary({-4, 1, 0}, 1.0, pool.addAndReturnHandle(Material::Diffuse(pool.addAndReturnHandle(Texture::Solid({0.4, 0.2, 0.1}))))));
     pool.add(Sphere::stationary({4, 1, 0}, 1.0, pool.addAndReturnHandle(Material::Metallic(pool.addAndReturnHandle(Texture::Solid({0.7, 0.6, 0.5}))))));

@@ -426,7 +426,7 @@ def test_multi_device_context_matches_single_device_bitwise(scene42):
             p8 = torch.empty((rows, ww, 3), dtype=torch.uint8).pin_memory().numpy()
             pl[:] = -1; p8[:] = 7
             many.render(cam2, pp, out_linear=pl, out_rgb8=p8)
-            want = sorted(j for d in range(n) for j in range(hh) if sc == 1 or (j // 4) % (sc * n) == s_ * n + d)
+            want = list(range(hh)) if sc == 1 else sorted(j for d in range(n) for j in range(hh) if (j // 4) % (sc * n) == s_ * n + d)
             assert np.array_equal(pl, ref_l[want]) and np.array_equal(p8, ref_8[want]), (ww, sc, s_)
     one.close(); many.close()
 
