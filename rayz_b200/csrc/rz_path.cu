@@ -38,11 +38,10 @@
 #define RZ_SECOND_MINB 6   // 85 registers.  Round 1 ran 7 CTAs at 72; with the single-copy shading loop that cap costs ~140 B of spills per
 #endif                     // thread in the hot loop, and 6 CTAs without spills measured 4.5 % faster (55.1 -> 52.6 ms, scripts/exp_probe.py)
 #define RZ_SECOND_BOUNDS __launch_bounds__(128, RZ_SECOND_MINB)
-#ifdef RZ_PRIMARY_MINB
-#define RZ_PRIMARY_BOUNDS __launch_bounds__(128, RZ_PRIMARY_MINB)
-#else
-#define RZ_PRIMARY_BOUNDS __launch_bounds__(128)
+#ifndef RZ_PRIMARY_MINB
+#define RZ_PRIMARY_MINB 6   // 85 registers: unconstrained the kernel takes 115 and 4 CTAs (18.2 ms); 5 -> 17.3, 6 -> 16.75, 7 -> 17.0 ms at config 2
 #endif
+#define RZ_PRIMARY_BOUNDS __launch_bounds__(128, RZ_PRIMARY_MINB)
 
 // per-warp scratch of the sorted-stage kernel: tab[64] u32 | pair list u16[n_pairs] | entry order u16[ue] | pair classes u8[n_pairs]
 __host__ __device__ inline uint32_t rz_second_warp_bytes(uint32_t n_pairs, uint32_t ue) {
@@ -252,7 +251,7 @@ __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRa
             if (Q.cont && a.q_out_keys) Q.key = rz_sort_key(a, Q.ray);
         }
 #ifndef RZ_SHADE_UNROLL
-        rz_swap_lane_rays(L[0], L[1]);
+        if (trip == 0) rz_swap_lane_rays(L[0], L[1]);   // ONE exchange per loop: the slots stay swapped afterwards, and nothing below cares which is which
 #endif
     }
     // ballot-compacted append: one atomic per warp for both rays
@@ -278,7 +277,7 @@ __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRa
                 atomicOr(a.err, (unsigned)RZ_DEV_ERR_QUEUE_OVERFLOW);   // never silently: the render fails
             }
         }
-        rz_swap_lane_rays(L[0], L[1]);
+        if (trip == 0) L[0] = L[1];   // the first ray is stored: only the second one still matters
         e = base + n0 + (unsigned)__popc(m1 & lt_mask);
     }
 }
@@ -393,7 +392,7 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
                 if (Q.live) Q.ray = rz_camera_ray(a.cam, pi, pj, gpix, Q.smp, a.seed_lo, a.seed_hi);
                 else { Q.ray.o = f3(0.f, 0.f, 0.f); Q.ray.d = f3(0.f, 1.f, 0.f); Q.ray.time = 0.f; Q.ray.self_k = -1; }
                 Q.thr = f3(1.f, 1.f, 1.f); Q.seg = 0u; Q.lp = lp; Q.gpix = gpix; Q.bk = -1; Q.cont = false; Q.key = 0u;
-                rz_swap_lane_rays(L[0], L[1]);
+                if (trip == 0) L[1] = L[0];   // slot 0 is rewritten by the second trip
             }
             {
                 const RzRay rays[2] = {L[0].ray, L[1].ray};

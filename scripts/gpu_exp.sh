@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 L=gpurun_out/${1:-exp}.log
 : > $L
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "sort or staged or hostile or capacity or sharding" >> $L 2>&1
-python scripts/exp_probe.py --set "" --set unit_entries=1024 --set unit_entries=256 --set queue_log2=28 --set second_stages=4 >> $L 2>&1
+python scripts/exp_probe.py --set "" --set queue_log2=28 >> $L 2>&1
 python scripts/exp_probe.py --glass --set "" >> $L 2>&1
-for so in scripts/_build/exp/*.so; do python scripts/exp_probe.py --so $so --set "" >> $L 2>&1; done
+for so in scripts/_build/exp/*.so; do [ -f $so ] && python scripts/exp_probe.py --so $so --set "" >> $L 2>&1; done
 grep -v "^+" $L | tail -40
