@@ -133,15 +133,12 @@ extern "C" size_t rz_bin_scratch_bytes(void) { return (size_t)RZ_BINS * sizeof(u
 // keys_in[0, *count) -> idx_out / keys_out: entry indices and keys grouped by ascending (key >> 4).  bins: rz_bin_scratch_bytes().
 extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned int *count, uint32_t cap, unsigned int *bins,
                                    unsigned short *keys_out, uint32_t *idx_out, int sm_count, cudaStream_t stream) {
-    static int per_sm_count = 0, per_sm_scatter = 0;
-    if (per_sm_count == 0) {
-        int a = 0, b = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, rz_bin_count_kernel, RZ_BIN_THREADS, 0);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rz_bin_scatter_kernel, RZ_BIN_THREADS, 0);
-        if (e != cudaSuccess) return e;
-        if (a < 1 || b < 1) return cudaErrorInvalidConfiguration;
-        per_sm_count = a; per_sm_scatter = b;
-    }
+    // resident CTAs per SM of the two kernels (called from one host thread per device: no shared mutable state here)
+    int per_sm_count = 0, per_sm_scatter = 0;
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, rz_bin_count_kernel, RZ_BIN_THREADS, 0);
+    if (eo == cudaSuccess) eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_scatter, rz_bin_scatter_kernel, RZ_BIN_THREADS, 0);
+    if (eo != cudaSuccess) return eo;
+    if (per_sm_count < 1 || per_sm_scatter < 1) return cudaErrorInvalidConfiguration;
     RzBinArgs a;
     a.keys_in = keys_in; a.count = count; a.cap = cap; a.bins = bins; a.keys_out = keys_out; a.idx_out = idx_out;
     const unsigned tiles = (cap + RZ_BIN_TILE - 1) / RZ_BIN_TILE;
