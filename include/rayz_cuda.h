@@ -53,8 +53,9 @@ enum { RZ_DIFFUSE_UNIT_SPHERE = 0, RZ_DIFFUSE_UNIT_SPHERE_SURFACE = 1, RZ_DIFFUS
 
 /* Kernel variants (RzRenderParams.variant). */
 enum {
-    RZ_VARIANT_AUTO = 0,      /* staged K1 when the scene fits shared memory and the job has
-                               * >= 2^26 paths per device, else the BVH kernel (same image either way) */
+    RZ_VARIANT_AUTO = 0,      /* staged K1 when the scene fits shared memory and the frame (width x height x spp)
+                               * has >= 2^26 paths, else the BVH kernel (the two agree up to a pixel or two:
+                               * FP32 sphere test against exact boxes)                                 */
     RZ_VARIANT_MEGA = 1,      /* K1: scene staged in shared memory; primary kernel -> sorted stages (culled
                                * brute force) -> persistent kernel for the tail of the paths: the BVH
                                * kernel, or the brute-force megakernel without a host-built tree
@@ -62,7 +63,7 @@ enum {
     RZ_VARIANT_WAVEFRONT = 2, /* K2: staged wavefront with warp-ballot compaction             */
     RZ_VARIANT_BVH = 3,       /* K3: persistent megakernel traversing the device BVH          */
     RZ_VARIANT_MEGA_SINGLE = 4 /* K1 as ONE persistent kernel (every segment brute force, paths
-                               * regenerated in place): the pure FP32-bound form, 59 % of FP32 peak */
+                               * regenerated in place): the pure FP32-bound form, 52 % of FP32 peak */
 };
 
 /*
@@ -111,7 +112,8 @@ typedef struct RzCamera {
  * that drives shard s of S with D devices behaves as shards s*D..s*D+D-1 of S*D.
  * Results of a shard are COMPACT (its rows only, in increasing j).  shard_count <= 1 means the
  * whole image.  The random stream is keyed by the GLOBAL pixel index, sample and bounce, so
- * any sharding reproduces the full-frame render bit for bit.
+ * any sharding reproduces the full-frame render bit for bit: which kernels run (AUTO's choice, the number of sorted stages)
+ * depends on the scene and the whole frame only, never on the shard, the device count or the memory that was free.
  */
 typedef struct RzRenderParams {
     uint32_t width;

@@ -24,7 +24,9 @@
 // planes by ray-direction sign (six 8-byte loads instead of three 16-byte loads and twelve min/max) was
 // 9 % SLOWER and is not used.
 // Sphere tests, hit refinement, shading, RNG keys and accumulation are the shared device functions of
-// rz_search.cuh / rz_device.cuh: images equal the brute-force kernel's bit for bit.
+// rz_search.cuh / rz_device.cuh: two trees give bit-identical images; against a brute-force search a pixel or two may
+// differ (the FP32 sphere test has a fuzzy surface, the boxes are exact: a grazing ray can "hit" a sphere a hair outside
+// its box, which brute force tests and the tree prunes — tests/test_gpu_parity.py bounds it at <= 3 pixels).
 #include "rz_search.cuh"
 
 namespace {
