@@ -270,6 +270,8 @@ typedef struct RzTuning {
                                * fewer), 64..2048, multiple of 64 (default 1024)                                        */
     uint32_t debug_queue_cap; /* tests: pretend the queues hold only this many entries (0 = off) -> RZ_ERR_INTERNAL     */
     uint32_t debug_stack_cap; /* tests: pretend the K3 traversal stack holds only this many entries (0 = off)           */
+    int32_t key_sectors;      /* sort key direction field: 0 = octant, 1 = 45-degree sector in the plane of the sphere
+                               * box's two long axes, -1 = sectors when that box is flat (default)                      */
 } RzTuning;
 int rayz_cuda_get_tuning(RzContext *ctx, RzTuning *out);
 int rayz_cuda_set_tuning(RzContext *ctx, const RzTuning *tuning);

@@ -69,7 +69,8 @@ class RzTuning(C.Structure):
                 ("queue_log2", C.c_int32), ("second_stages", C.c_int32), ("bvh_stages", C.c_int32), ("tail_brute", C.c_int32),
                 ("bvh_staged", C.c_int32), ("cell_bits", C.c_int32), ("bvh_active_min", C.c_int32), ("bvh_descend_min", C.c_int32),
                 ("sah_leaf", C.c_int32), ("sah_node_cost", C.c_double), ("unit_entries", C.c_uint32), ("debug_queue_cap", C.c_uint32),
-                ("debug_stack_cap", C.c_uint32)]
+                ("debug_stack_cap", C.c_uint32),
+                ("key_sectors", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

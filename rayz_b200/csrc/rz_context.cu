@@ -33,8 +33,10 @@ extern "C" cudaError_t rz_path_warm(void);
 extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a);
 extern "C" cudaError_t rz_launch_second(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" size_t rz_bin_scratch_bytes(void);
+extern "C" cudaError_t rz_launch_bin_lists(const RzPathArgs *a, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t rz_second_grid(const RzPathArgs *a, int collect_stats, int sm_count, int *grid);
 extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned int *count, uint32_t cap, unsigned int *bins,
-                                   unsigned short *keys_out, uint32_t *idx_out, int sm_count, cudaStream_t stream);
+                                   unsigned short *keys_out, uint32_t *idx_out, uint32_t ue_max, uint32_t ue_div, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_sort_warm(void);
 extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_bvh_warm(void);
@@ -117,7 +119,7 @@ struct Dev {
     int id = 0, sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t stream2 = nullptr;   // staged K1: odd passes run here so that a pass fills the tail of the previous one
-    cudaEvent_t ev_s2 = nullptr;
+    cudaEvent_t ev_s2 = nullptr, ev_tab = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, path0, path1, resolve1, done
     SetBufs brute, bvhset;
     DBuf<RzBvhNode> bvh;              // the builders' binary tree (host SAH or device LBVH): input of the collapse
@@ -141,7 +143,8 @@ struct Dev {
     DBuf<float4> q1[2], q2[2];
     DBuf<unsigned short> keys[2], keys_sorted[2];
     DBuf<uint32_t> idx_sorted[2];
-    DBuf<unsigned int> bins[2];       // rz_sort.cu: per-key counts / cursors of the side's sort
+    DBuf<unsigned int> bins[2];       // rz_sort.cu: per-key counts / cursors of the side's sort (RZ_BIN_* layout)
+    DBuf<unsigned char> bin_lists;    // per sort group: the reachable sphere pairs in reach-class order (rz_bin_lists_kernel)
     DBuf<unsigned int> counter;
     DBuf<unsigned int> errword;       // device error word (RZ_DEV_ERR_*), cleared at the start of every render / ids call
     DBuf<RzStatsDev> stats;
@@ -462,7 +465,8 @@ extern "C" int rayz_cuda_create(const RzConfig *cfg, RzContext **out) {
         D.sms = prop.multiProcessorCount;
         if ((e = cudaStreamCreateWithFlags(&D.own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         D.stream = D.own_stream;
-        if ((e = cudaStreamCreateWithFlags(&D.stream2, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreateWithFlags(&D.ev_s2, cudaEventDisableTiming)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        if ((e = cudaStreamCreateWithFlags(&D.stream2, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreateWithFlags(&D.ev_s2, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&D.ev_tab, cudaEventDisableTiming)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         for (auto &ev : D.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
         if ((e = rz_path_warm()) != cudaSuccess || (e = rz_bvh_warm()) != cudaSuccess || (e = rz_sort_warm()) != cudaSuccess) { rayz_cuda_destroy(ctx); return rz_fail(RZ_ERR_CUDA, "loading the path kernels: %s", cudaGetErrorString(e)); }
@@ -492,6 +496,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
         D.accum.release(); D.counter.release(); D.errword.release();
         for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.bins[sd].release(); }
+        D.bin_lists.release();
         D.stats.release(); D.out_linear.release(); D.out_rgb8.release(); D.loc_linear.release(); D.loc_rgb8.release();
         D.ids.release(); D.sink.release();
         if (D.wf_scratch) rz_wavefront_free(D.wf_scratch);
@@ -499,6 +504,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         for (auto &ev : D.pass_ev) if (ev) cudaEventDestroy(ev);
         for (auto &ev : D.stage_ev) if (ev) cudaEventDestroy(ev);
         if (D.ev_s2) cudaEventDestroy(D.ev_s2);
+        if (D.ev_tab) cudaEventDestroy(D.ev_tab);
         if (D.stream2) { cudaStreamSynchronize(D.stream2); cudaStreamDestroy(D.stream2); }
         if (D.own_stream) cudaStreamDestroy(D.own_stream);
     }
@@ -531,6 +537,7 @@ static RzTuning default_tuning() {
     t.sah_leaf = 4;
     t.sah_node_cost = 0.5;
     t.unit_entries = 1024;
+    t.key_sectors = -1;
     return t;
 }
 
@@ -550,6 +557,7 @@ extern "C" int rayz_cuda_set_tuning(RzContext *ctx, const RzTuning *t) {
     if (t->cell_bits < 0 || t->cell_bits > 9) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: cell_bits out of [0, 9]");
     if (t->bvh_active_min < 1 || t->bvh_active_min > 32 || t->bvh_descend_min < 1 || t->bvh_descend_min > 32) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: BVH lane thresholds out of [1, 32]");
     if (t->sah_leaf < 1 || t->sah_leaf > 8 || !(t->sah_node_cost >= 0)) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: SAH parameters out of range");
+    if (t->key_sectors < -1 || t->key_sectors > 1) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: key_sectors must be -1, 0 or 1");
     if (t->unit_entries < 64 || t->unit_entries > 2048 || (t->unit_entries & 63u)) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: unit_entries must be a multiple of 64 in [64, 2048]");
     ctx->tun = *t;
     return RZ_OK;
@@ -1043,8 +1051,21 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     const double lv = std::sqrt(cam->defocus_v[0] * cam->defocus_v[0] + cam->defocus_v[1] * cam->defocus_v[1] + cam->defocus_v[2] * cam->defocus_v[2]);
                     a.lens_radius = cam->defocus ? (float)(std::max(lu, lv) * 1.001) : 0.f;
                     a.queue_cap = ctx->tun.debug_queue_cap ? std::min((uint32_t)cap, ctx->tun.debug_queue_cap) : (uint32_t)cap;
-                    rz_key_grid(a, ctx->sb_lo, ctx->sb_hi, ctx->tun.cell_bits);
+                    rz_key_grid(a, ctx->sb_lo, ctx->sb_hi, ctx->tun.cell_bits, ctx->tun.key_sectors);
                     a.huge_radius = ctx->huge_radius;
+                    uint32_t ue_div = 0;
+                    if (second_stage && !bvh_family) {
+                        // the sorted-segment kernel's pair lists, one row per sort group: a function of the set and the key grid
+                        a.bin_row = rz_bin_row_bytes(a.set.n_pad / 2u);
+                        if (int rc = D.bin_lists.alloc((size_t)RZ_SORT_BINS * a.bin_row)) return rc;
+                        a.bin_lists = D.bin_lists.p;
+                        RZ_CUDA(rz_launch_bin_lists(&a, D.sms, D.stream));
+                        launches += 1;
+                        int grid2 = 0;
+                        RZ_CUDA(rz_second_grid(&a, (int)p->collect_stats, D.sms, &grid2));
+                        ue_div = 16u * (uint32_t)grid2;
+                    }
+                    RZ_CUDA(cudaEventRecord(D.ev_tab, D.stream));
                     while (D.pass_ev.size() < 3 * (size_t)n_pass) {
                         cudaEvent_t e = nullptr;
                         RZ_CUDA(cudaEventCreate(&e));
@@ -1061,7 +1082,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     D.serial_passes = serial;
                     // Passes alternate between two streams and two sets of buffers: the persistent kernel ends with a tail of a
                     // few long paths (measured ~2 ms per pass), which the next pass's kernels fill.
-                    if (n_sides > 1) RZ_CUDA(cudaStreamWaitEvent(D.stream2, D.ev[1], 0));
+                    if (n_sides > 1) RZ_CUDA(cudaStreamWaitEvent(D.stream2, D.ev_tab, 0));   // (recorded after ev[1] on the same stream)
                     uint32_t pass = 0;
                     for (uint32_t u0 = 0; u0 < total_units; u0 += units_per_pass, pass++) {
                         const int side = n_sides > 1 ? (int)(pass & 1u) : 0;
@@ -1084,12 +1105,12 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         for (int stg = 0; stg < n_second; stg++) {
                             const bool more = stg + 1 < n_second;
                             // group the entries by key (rz_sort.cu: count / scan / scatter, sized on the device from the live count)
-                            RZ_CUDA(rz_bin_sort(D.keys[side].p, ca, a.queue_cap, D.bins[side].p, D.keys_sorted[side].p, D.idx_sorted[side].p, D.sms, st));
+                            RZ_CUDA(rz_bin_sort(D.keys[side].p, ca, a.queue_cap, D.bins[side].p, D.keys_sorted[side].p, D.idx_sorted[side].p, a.unit_entries, ue_div, D.sms, st));
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg)], st));
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(cb, 0, sizeof(unsigned int), st));           // recycled output counter
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned int), st));      // the stage's unit counter
                             RzPathArgs a2 = a;
-                            a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p; a2.q_in_keys = D.keys_sorted[side].p;
+                            a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p; a2.q_in_keys = D.keys_sorted[side].p; a2.q_in_bins = D.bins[side].p;
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
                             a2.stats = D.stats.p + 1;
                             if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a2, (int)p->collect_stats, D.sms, st));
@@ -1334,7 +1355,7 @@ extern "C" int rayz_cuda_debug_sort_keys(RzContext *ctx, const unsigned short *k
     }
     cudaError_t e = cudaMemcpyAsync(ki.p, keys, (size_t)n * sizeof(unsigned short), cudaMemcpyHostToDevice, D.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.p, &n, sizeof n, cudaMemcpyHostToDevice, D.stream);
-    if (e == cudaSuccess) e = rz_bin_sort(ki.p, cnt.p, n, bins.p, ko.p, io.p, D.sms, D.stream);
+    if (e == cudaSuccess) e = rz_bin_sort(ki.p, cnt.p, n, bins.p, ko.p, io.p, 1024u, 0u, D.sms, D.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(keys_out, ko.p, (size_t)n * sizeof(unsigned short), cudaMemcpyDeviceToHost, D.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx_out, io.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);

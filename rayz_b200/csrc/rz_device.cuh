@@ -130,6 +130,9 @@ struct RzPathArgs {
     const unsigned int *q_in_count;   // entries in q_in (device counter written by the producing kernel)
     const uint32_t *q_in_idx;         // K1c: entry indices in key order
     const unsigned short *q_in_keys;  // K1c: the keys in the same order (the sort's key output)
+    const unsigned int *q_in_bins;    // K1c: the sort's scratch words: group ends | units before each group | unit size (RZ_BIN_*)
+    unsigned char *bin_lists;         // K1c: per group (cell, direction), the sphere pairs ordered by the smallest reach class that
+    uint32_t bin_row;                 //      gets to them (rz_bin_lists_kernel; rows of bin_row bytes, layout: rz_bin_row_bytes)
     float4 *q_out;
     unsigned int *q_out_count;
     unsigned short *q_out_keys;       // 16-bit sort key per appended entry (when a sorted stage follows)
@@ -140,6 +143,9 @@ struct RzPathArgs {
     float sb_inv_cell[3];             // cells per unit length along each axis (sort-key cells)
     uint32_t sb_cell_bits[3];         // 9 key bits shared out so that cells come out as cubic as possible
     float huge_radius;                // spheres above this radius are never culled (the r = 1000 ground)
+    uint32_t key_sectors;             // direction field of the sort key: 0 = octant (sign of d on each axis), 1 = one of eight 45-degree
+                                      // sectors in the plane of the sphere box's two longest axes (key_u, key_w): flat scenes
+    uint32_t key_u, key_w;            // those two axes
     float reach_unit;                 // max extent of the box / 32: classes of the sort key's reach field
     unsigned int *err;           // device error word (RZ_DEV_ERR_* bits): set instead of silently dropping work
     uint32_t unit_entries;       // sorted-stage kernels: queue entries per work unit (multiple of 64)
@@ -248,6 +254,16 @@ struct RzRay {
 // Every implementation follows THIS operation order per sphere (IEEE rn), so all searches return bit-identical (t, k).
 // ---------------------------------------------------------------------------------------------
 #define RZ_FAR_BIT 0x40000000
+
+// One row of the per-group pair lists: u16 end_s[16] | u16 end_m[16] | u16 ls[n_sp] | u16 lm[n_mp] — stationary / moving pairs in
+// class order; end_x[c] = pairs of classes <= c.  n_pairs = n_sp + n_mp.
+RZ_HD uint32_t rz_bin_row_bytes(uint32_t n_pairs) { return (64u + 2u * n_pairs + 15u) & ~15u; }
+
+// rz_sort.cu's scratch words (one set per side): bins | unit_first | ue
+#define RZ_SORT_BINS 4096
+#define RZ_BIN_UNIT_FIRST 4096                 /* [4097]: units before each group, then the total */
+#define RZ_BIN_UE (4096 + 4097)                /* entries per work unit of this launch */
+#define RZ_BIN_SCRATCH_WORDS (4096 + 4097 + 7)
 
 RZ_HD void rz_sphere_test(float cx, float cy, float cz, float vx, float vy, float vz, float w, float ox, float oy, float oz,
                           float dx, float dy, float dz, float time, float &nb, float &nd) {
@@ -471,7 +487,11 @@ RZ_HD int rz_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi :
 // Host side: the key's grid over the box [lo, hi] around the non-huge spheres.  `cell_bits` key bits (<= 9) are shared out
 // over the axes — each bit halves the cells of the axis whose cells are currently largest, so cells come out as cubic as
 // the extents allow; reach classes are measured in units of 1/32 of the longest extent.
-inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3], int cell_bits) {
+RZ_HD float rz_pick3(float x, float y, float z, uint32_t ax) { return ax == 0u ? x : ax == 1u ? y : z; }
+
+// key_mode: 0 = octant direction field, 1 = sectors, -1 = by the shape of the box (sectors when it is flat: the third
+// extent under 0.35 of the other two, so that almost every long ray travels near the plane of the two long axes).
+inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3], int cell_bits, int key_mode = -1) {
     float ext = 0.f, e3[3];
     uint32_t bits[3] = {0, 0, 0};
     for (int ax = 0; ax < 3; ax++) {
@@ -491,6 +511,13 @@ inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3
         a.sb_inv_cell[ax] = e3[ax] > 0.f ? (float)(1u << bits[ax]) / e3[ax] : 0.f;
     }
     a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;
+    int hax = 0;
+    for (int ax = 1; ax < 3; ax++) if (e3[ax] < e3[hax]) hax = ax;
+    a.key_u = (uint32_t)((hax + 1) % 3); a.key_w = (uint32_t)((hax + 2) % 3);
+    if (a.key_u > a.key_w) { const uint32_t t = a.key_u; a.key_u = a.key_w; a.key_w = t; }
+    const float e_min2 = e3[a.key_u] < e3[a.key_w] ? e3[a.key_u] : e3[a.key_w];
+    const bool flat = e_min2 > 0.f && e3[hax] < 0.35f * e_min2;
+    a.key_sectors = key_mode < 0 ? (flat ? 1u : 0u) : (uint32_t)(key_mode != 0);
 }
 
 // Sort key of a scattered ray: [origin cell 9 bits][direction octant 3 bits][reach class 4 bits] = 16 bits.  Rays with
@@ -502,7 +529,13 @@ RZ_HD uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
     const int cy = rz_clampi((int)((ray.o.y - a.sb_lo[1]) * a.sb_inv_cell[1]), 0, ny);
     const int cz = rz_clampi((int)((ray.o.z - a.sb_lo[2]) * a.sb_inv_cell[2]), 0, nz);
     const uint32_t cell = (uint32_t)(((cx << a.sb_cell_bits[1]) | cy) << a.sb_cell_bits[2]) | (uint32_t)cz;   // 9 bits
-    const uint32_t oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
+    uint32_t oct;
+    if (a.key_sectors) {   // sector of the direction's projection on the (u, w) plane: signs of d_u, d_w and which of the two is larger
+        const float du = rz_pick3(ray.d.x, ray.d.y, ray.d.z, a.key_u), dw = rz_pick3(ray.d.x, ray.d.y, ray.d.z, a.key_w);
+        oct = (du < 0.f ? 1u : 0u) | (dw < 0.f ? 2u : 0u) | (fabsf(du) < fabsf(dw) ? 4u : 0u);
+    } else {
+        oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
+    }
     const float te = rz_box_exit(a, ray);
     // 16 reach classes, two per octave of te / reach_unit from 1/4 up
 #ifdef __CUDA_ARCH__
@@ -600,12 +633,13 @@ RZ_HD bool rz_tile_keep(const RzTileCone &C, float cx, float cy, float cz, float
 struct RzUnitBounds {
     float lo[3], hi[3];          // box of the origins
     float T;                     // longest stay inside the sphere box
-    unsigned all_pos, all_neg;   // bit ax set: every ray has d[ax] >= 0 / d[ax] < 0
+    unsigned all_pos, all_neg;   // octant keys: bit ax set: every ray has d[ax] >= 0 / d[ax] < 0
+    unsigned sectors;            // sector keys: bit s set: some ray's direction lies in sector s
 };
 
 RZ_HD void rz_unit_bounds_init(RzUnitBounds &U) {
     for (int ax = 0; ax < 3; ax++) { U.lo[ax] = 3.0e38f; U.hi[ax] = -3.0e38f; }
-    U.T = 0.f; U.all_pos = 7u; U.all_neg = 7u;
+    U.T = 0.f; U.all_pos = 7u; U.all_neg = 7u; U.sectors = 0u;
 }
 
 // Upper edge of reach class c (what rz_key_bounds returns as T), with the margin for the FP32 evaluation of the exits that
@@ -624,6 +658,7 @@ RZ_HD void rz_unit_bounds_add_key(RzUnitBounds &U, const RzPathArgs &a, uint32_t
         U.hi[ax] = fmaxf(U.hi[ax], hi[ax]);
         if ((oct >> ax) & 1u) U.all_pos &= ~(1u << ax); else U.all_neg &= ~(1u << ax);   // key bit set <=> d < 0
     }
+    U.sectors |= 1u << oct;
     U.T = fmaxf(U.T, Tk);
 }
 
@@ -633,27 +668,62 @@ RZ_HD void rz_unit_bounds_finish(RzUnitBounds &U) { U.T = fminf(U.T, 1.0e30f) * 
 // Can a ray of the unit reach the sphere at all, whatever its reach?  false: behind the cell box on an axis along which every
 // ray of the unit moves the other way (or a padding entry).  d2 = squared distance from the box of the origins to the sphere's
 // centre (at mid shutter), re = its radius swept over the shutter interval, with margins.  Huge spheres: d2 = 0.
-RZ_HD bool rz_unit_reachable(const RzUnitBounds &U, float huge_radius, float cx, float cy, float cz, float vx, float vy, float vz, float w,
+// Sector keys: can a ray whose direction projects into sector s of the (u, w) plane get from the box of origins to the sphere?
+// Sector s = (d_u < 0, d_w < 0, |d_u| < |d_w|) is the wedge {n1.d >= 0, n2.d >= 0}: n1 along one axis, n2 a diagonal.  A point
+// p is reached from an origin o with such a direction only if n.(p - o) >= 0 for both; for a sphere, >= -|n| re; over the box,
+// n.o is replaced by its minimum (each half-plane with its own best corner: conservative).
+RZ_HD bool rz_sector_reaches(float lo_u, float hi_u, float lo_w, float hi_w, uint32_t s, float cu, float cw, float re) {
+    const float au = (s & 1u) ? -1.f : 1.f, aw = (s & 2u) ? -1.f : 1.f;   // |d_u| = au d_u, |d_w| = aw d_w
+    const bool w_larger = (s & 4u) != 0u;
+    // n1: the smaller component is still >= 0 in its own sign; n2: larger minus smaller >= 0
+    const float n1u = w_larger ? au : 0.f, n1w = w_larger ? 0.f : aw;
+    const float n2u = w_larger ? -au : au, n2w = w_larger ? aw : -aw;
+    auto box_min = [&](float nu, float nw) {   // min over the box of n.o (the box may be open-ended: +-3e38 times 0 stays 0)
+        return (nu > 0.f ? lo_u : hi_u) * nu + (nw > 0.f ? lo_w : hi_w) * nw;
+    };
+    if (n1u * cu + n1w * cw + re < box_min(n1u, n1w)) return false;
+    if (n2u * cu + n2w * cw + 1.4143f * re < box_min(n2u, n2w)) return false;
+    return true;
+}
+
+RZ_HD bool rz_unit_reachable(const RzUnitBounds &U, const RzPathArgs &a, float cx, float cy, float cz, float vx, float vy, float vz, float w,
                              float &d2, float &re) {
     d2 = 0.f; re = 0.f;
     if (!(w < 0.f)) return false;                                  // padding entry
     const float r = sqrtf(-w);
-    if (r > huge_radius) return true;                              // outside the sphere box: never culled
+    if (r > a.huge_radius) return true;                            // outside the sphere box: never culled
     re = (r + 0.5f * sqrtf(vx * vx + vy * vy + vz * vz)) * 1.02f + 0.02f;   // swept over the shutter + margin
     const float c[3] = {fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)};
+    if (a.key_sectors) {
+        bool any = false;
+        const float lo_u = rz_pick3(U.lo[0], U.lo[1], U.lo[2], a.key_u), hi_u = rz_pick3(U.hi[0], U.hi[1], U.hi[2], a.key_u);
+        const float lo_w = rz_pick3(U.lo[0], U.lo[1], U.lo[2], a.key_w), hi_w = rz_pick3(U.hi[0], U.hi[1], U.hi[2], a.key_w);
+        const float cu = rz_pick3(c[0], c[1], c[2], a.key_u), cw = rz_pick3(c[0], c[1], c[2], a.key_w);
+        for (unsigned m = U.sectors; m && !any; m &= m - 1u) {
+#ifdef __CUDA_ARCH__
+            const uint32_t s = (uint32_t)__ffs((int)m) - 1u;
+#else
+            uint32_t s = 0; while (!((m >> s) & 1u)) s++;
+#endif
+            any = rz_sector_reaches(lo_u, hi_u, lo_w, hi_w, s, cu, cw, re);
+        }
+        if (!any) return false;
+    }
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
-        if (((U.all_pos >> ax) & 1u) && c[ax] + re < U.lo[ax]) return false;   // every ray moves up this axis: sphere is behind
-        if (((U.all_neg >> ax) & 1u) && c[ax] - re > U.hi[ax]) return false;
+        if (!a.key_sectors) {
+            if (((U.all_pos >> ax) & 1u) && c[ax] + re < U.lo[ax]) return false;   // every ray moves up this axis: sphere is behind
+            if (((U.all_neg >> ax) & 1u) && c[ax] - re > U.hi[ax]) return false;
+        }
         const float dd = fmaxf(0.f, fmaxf(U.lo[ax] - c[ax], c[ax] - U.hi[ax]));
         d2 = fmaf(dd, dd, d2);
     }
     return true;
 }
 
-RZ_HD bool rz_unit_keep(const RzUnitBounds &U, float huge_radius, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
+RZ_HD bool rz_unit_keep(const RzUnitBounds &U, const RzPathArgs &a, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
     float d2, re;
-    if (!rz_unit_reachable(U, huge_radius, cx, cy, cz, vx, vy, vz, w, d2, re)) return false;
+    if (!rz_unit_reachable(U, a, cx, cy, cz, vx, vy, vz, w, d2, re)) return false;
     const float rad = U.T + re;
     return d2 <= rad * rad;                                        // within reach of some ray of the unit
 }
@@ -665,7 +735,7 @@ RZ_HD bool rz_unit_keep(const RzUnitBounds &U, float huge_radius, float cx, floa
 // rz_unit_keep itself in both directions, so it never errs on the side of dropping a sphere.
 RZ_HD int rz_unit_class(const RzUnitBounds &U, const RzPathArgs &a, float cx, float cy, float cz, float vx, float vy, float vz, float w) {
     float d2, re;
-    if (!rz_unit_reachable(U, a.huge_radius, cx, cy, cz, vx, vy, vz, w, d2, re)) return 16;
+    if (!rz_unit_reachable(U, a, cx, cy, cz, vx, vy, vz, w, d2, re)) return 16;
     auto within = [&](int c) { const float rad = rz_class_T(a, c) + re; return d2 <= rad * rad; };
     const float dist = sqrtf(d2) - re;
     if (!(dist > 0.f)) return 0;
@@ -691,4 +761,5 @@ RZ_HD void rz_unit_bounds_add_cell(RzUnitBounds &U, const RzPathArgs &a, uint32_
         U.hi[ax] = fmaxf(U.hi[ax], hi[ax]);
         if ((oct >> ax) & 1u) U.all_pos &= ~(1u << ax); else U.all_neg &= ~(1u << ax);
     }
+    U.sectors |= 1u << oct;
 }

@@ -43,9 +43,9 @@
 #endif
 #define RZ_PRIMARY_BOUNDS __launch_bounds__(128, RZ_PRIMARY_MINB)
 
-// per-warp scratch of the sorted-stage kernel: tab[64] u32 | pair list u16[n_pairs] | entry order u16[ue] | pair classes u8[n_pairs]
+// per-warp scratch of the sorted-stage kernel: tab[16] u32 | one row of the per-group pair lists | entry order u16[ue]
 __host__ __device__ inline uint32_t rz_second_warp_bytes(uint32_t n_pairs, uint32_t ue) {
-    return (64u * 4u + 2u * n_pairs + 2u * ue + n_pairs + 15u) & ~15u;
+    return (16u * 4u + rz_bin_row_bytes(n_pairs) + 2u * ue + 15u) & ~15u;
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -409,15 +409,85 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
     rz_flush_counters<STATS>(a, C, lane);
 }
 
+// ------------------------------------------------------------------------------ per-group pair lists
+// For every group of the sort — (origin cell, direction field) = the top 12 bits of rz_sort_key — the sphere pairs a ray of
+// that group can reach, ordered by the SMALLEST reach class that gets to them (rz_unit_class: class 16 = no ray of the group
+// can, the pair is left out).  Camera-independent: a function of the sphere set and the key grid only; one warp per group,
+// ~30 us for the 4096 groups, run at the start of every staged render.  The sorted-segment kernel copies a row per work unit
+// instead of classifying the set itself (round 2's first form did: ~15 % of its samples, and it had to merge the bounds of
+// every key in the unit, which is looser than one group's own).  Row layout: rz_bin_row_bytes.
+__global__ void __launch_bounds__(128) rz_bin_lists_kernel(const RzPathArgs a) {
+    extern __shared__ __align__(16) unsigned char rz_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
+    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1, n_pairs = n_sp + n_mp;
+    const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
+    // per-warp scratch: tab[32] (pairs per class: stationary, moving) | pair classes u8[n_pairs]
+    const uint32_t warp_bytes = (32u * 4u + n_pairs + 15u) & ~15u;
+    unsigned char *wb = reinterpret_cast<unsigned char *>(s_pk + pk_f4) + (threadIdx.x >> 5) * warp_bytes;
+    unsigned int *tab = reinterpret_cast<unsigned int *>(wb);
+    unsigned char *pcl = wb + 32u * 4u;
+    rz_stage_scene_pk(a.set, s_pk, &s_bar);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (uint32_t bin = blockIdx.x * 4u + (threadIdx.x >> 5); bin < (uint32_t)RZ_SORT_BINS; bin += gridDim.x * 4u) {
+        RzUnitBounds U;
+        rz_unit_bounds_init(U);
+        rz_unit_bounds_add_cell(U, a, bin << 4);
+        unsigned short *row = reinterpret_cast<unsigned short *>(a.bin_lists + (size_t)bin * a.bin_row);
+        unsigned short *ls = row + 32, *lm = ls + n_sp;
+        tab[lane] = 0u;
+        __syncwarp();
+        // smallest class that reaches each sphere -> class of the pair (one lane per sphere)
+#pragma unroll 1
+        for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
+            const uint32_t k = k0 + lane;
+            float cx = 0.f, cy = 0.f, cz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, w = 1.f;
+            if (k < a.set.n_pad) rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // lanes past the set: a padding entry
+            int c = k < a.set.n_pad ? rz_unit_class(U, a, cx, cy, cz, vx, vy, vz, w) : 16;
+            c = min(c, __shfl_xor_sync(0xffffffffu, c, 1));
+            if (!(lane & 1u) && k < a.set.n_pad) {
+                pcl[k >> 1] = (unsigned char)c;
+                if (c < 16) atomicAdd(&tab[(k < a.set.n_static_pad ? 0u : 16u) + (uint32_t)c], 1u);
+            }
+        }
+        __syncwarp();
+        {   // inclusive prefixes of the two histograms -> the row's end_s / end_m; exclusive ones -> running cursors
+            const uint32_t cnt = tab[lane];                                  // lanes 0-15: stationary, 16-31: moving
+            uint32_t inc = cnt;
+            for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)(lane & 15u) >= o) inc += t; }
+            __syncwarp();
+            tab[lane] = inc - cnt;
+            row[lane] = (unsigned short)inc;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t p0 = 0; p0 < n_pairs; p0 += 32u) {
+            const uint32_t p = p0 + lane;
+            const bool st = p < n_sp;
+            const uint32_t c = p < n_pairs ? (uint32_t)pcl[p] : 16u;
+            const uint32_t tag = c < 16u ? (c | (st ? 0u : 16u)) : 32u + lane;   // (part, class); unique for pairs that are dropped
+            const unsigned peers = __match_any_sync(0xffffffffu, tag);
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t base = 0u;
+            if ((int)lane == leader && c < 16u) { base = tab[tag]; tab[tag] = base + (uint32_t)__popc(peers); }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (c < 16u) (st ? ls : lm)[base + (uint32_t)__popc(peers & lt_mask)] = (unsigned short)(st ? p : p - n_sp);
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------ sorted-segment kernel
 // The stages after the camera segment, one launch per segment (segments 2..6 by default).  Scattered rays are incoherent,
-// but their queue entries have been GROUPED by (origin cell, direction octant) — the top 12 bits of rz_sort_key, rz_sort.cu —
-// so the `unit_entries` consecutive entries of a work unit start close together and head the same way.  Per unit the warp
-//   1. merges the cells and octants of the unit's keys into a box of origins + the axes on which every ray moves the same way
-//      (rz_unit_bounds_add_cell), and orders the unit's entries by the key's low 4 bits, the reach class — how long a ray
-//      stays inside the box around the non-huge spheres (a counting sort over 16 classes in shared memory);
-//   2. gives every sphere the smallest reach class whose rays can get to it from that box (rz_unit_class; 16 = behind the
-//      box for every ray), and orders the sphere pairs by that class;
+// but their queue entries have been GROUPED by (origin cell, direction field) — the top 12 bits of rz_sort_key, rz_sort.cu —
+// and the sort has cut every group into work units of at most `ue` entries, so the rays of a unit start in one cell and head
+// the same way.  Per unit the warp
+//   1. finds the unit's group (three warp-wide probes of the sort's unit prefix) and copies the group's row of pair lists
+//      (rz_bin_lists_kernel): the sphere pairs its rays can reach, ordered by the smallest reach class that gets to them;
+//   2. orders the unit's entries by the key's low 4 bits, the reach class — how long a ray stays inside the box around the
+//      non-huge spheres (a counting sort over 16 classes in shared memory);
 //   3. takes the entries 64 at a time in class order: a batch whose largest class is c searches the pairs of classes <= c, a
 //      prefix of the ordered pair list (rz_search_list2: the same arithmetic per sphere, so (t, k) is unchanged).
 // Round 1 sorted on all 16 key bits (two radix passes) and culled each unit with its largest reach; ordering by reach
@@ -431,25 +501,21 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1, n_pairs = n_sp + n_mp;
     const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
     const uint32_t ue_max = a.unit_entries;
-    // per-warp scratch: tab[64] | pair list [n_pairs] | entry order [ue] | pair classes [n_pairs] (layout: rz_second_smem_bytes)
+    // per-warp scratch: tab[16] | the group's row (end_s, end_m, ls, lm) | entry order [ue] (layout: rz_second_warp_bytes)
     const uint32_t warp_bytes = rz_second_warp_bytes(n_pairs, ue_max);
     unsigned char *wb = reinterpret_cast<unsigned char *>(s_pk + pk_f4) + (threadIdx.x >> 5) * warp_bytes;
-    unsigned int *tab = reinterpret_cast<unsigned int *>(wb);             // [0,16) entries: end of class c; [16,32) stationary pairs of classes <= c; [32,48) moving; [48,56) merged bounds
-    unsigned short *ls = reinterpret_cast<unsigned short *>(tab + 64);
+    unsigned int *tab = reinterpret_cast<unsigned int *>(wb);             // [0,16) entries: end of class c
+    unsigned short *row = reinterpret_cast<unsigned short *>(tab + 16);   // end_s[16] end_m[16]: pairs of classes <= c
+    unsigned short *ls = row + 32;
     unsigned short *lm = ls + n_sp;
-    unsigned short *order = ls + n_pairs;
-    unsigned char *pcl = reinterpret_cast<unsigned char *>(order + ue_max);
+    unsigned short *order = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(row) + a.bin_row);
 
     rz_stage_scene_pk(a.set, s_pk, &s_bar);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t n_in = min(*a.q_in_count, a.queue_cap);
-    // Entries per work unit: RzTuning::unit_entries (1024: the per-unit set-up is ~10 % of a 512-entry unit), but never so
-    // many that a warp gets fewer than ~4 units — the late stages hold a few million entries for 3552 warps
-    uint32_t ue = ue_max;
-    if (ue > 256u) ue = min(ue, max(256u, (n_in / (4u * 4u * gridDim.x)) & ~63u));
-    const uint32_t n_units = (n_in + ue - 1u) / ue;
+    const unsigned int *bin_end = a.q_in_bins, *unit_first = a.q_in_bins + RZ_BIN_UNIT_FIRST;
+    const uint32_t n_units = unit_first[RZ_SORT_BINS], ue = min(a.q_in_bins[RZ_BIN_UE], ue_max);
     RzSegCounters C = {};
 
     while (true) {
@@ -457,39 +523,28 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
-        const uint32_t e0 = u * ue, ne = min(ue, n_in - e0);
+        // ---- 1. the unit's group: the last b with unit_first[b] <= u (groups without entries share their successor's value)
+        uint32_t bin = 0u;
+#pragma unroll
+        for (uint32_t stride = 128u; stride; stride = stride == 128u ? 4u : stride == 4u ? 1u : 0u) {
+            const uint32_t i = bin + lane * stride;
+            const bool le = (stride > 1u || lane < 4u) && unit_first[i] <= u;       // unit_first[bin] <= u always: lane 0 votes yes
+            bin += ((uint32_t)__popc(__ballot_sync(0xffffffffu, le)) - 1u) * stride;
+        }
+        const uint32_t g0 = bin ? bin_end[bin - 1u] : 0u;                          // after the scatter: bins[b] = end of group b
+        const uint32_t e0 = g0 + (u - unit_first[bin]) * ue, ne = min(ue, bin_end[bin] - e0);
         const unsigned short *ukeys = a.q_in_keys + e0;
-
-        // ---- 1. what the unit's rays have in common (cells + octants of the keys), and how many rays each reach class holds
-        tab[lane] = 0u;
-        if (lane < 16u) tab[32u + lane] = 0u;
-        if (lane < 8u) tab[48u + lane] = lane < 3u ? 0x7fffffffu : lane < 6u ? 0x80000000u : 7u;   // lo = +max, hi = -max (ordered ints), all_pos = all_neg = 7
+        {   // the group's row -> shared memory (16-byte pieces; the table stays in L2)
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.bin_lists + (size_t)bin * a.bin_row);
+            uint4 *dst = reinterpret_cast<uint4 *>(row);
+            for (uint32_t i = lane; i < a.bin_row / 16u; i += 32u) dst[i] = __ldg(src + i);
+        }
+        // ---- 2. rays per reach class, then the entries in class order
+        if (lane < 16u) tab[lane] = 0u;
         __syncwarp();
-        RzUnitBounds U;
-        rz_unit_bounds_init(U);
-        uint32_t prev = 0xffffffffu;   // the groups are sorted: a lane mostly meets the (cell, octant) it has just decoded
 #pragma unroll 1
-        for (uint32_t i = lane; i < ne; i += 32u) {
-            const uint32_t key = ukeys[i];
-            atomicAdd(&tab[key & 15u], 1u);
-            if ((key >> 4) != prev) { prev = key >> 4; rz_unit_bounds_add_cell(U, a, key); }
-        }
-        // merge the lanes' bounds through shared memory (min / max on order-preserving integers): 8 atomics per lane instead of
-        // 40 shuffles, each of which costs a convergence sequence here
-        if (prev != 0xffffffffu) {
-            int *ib = reinterpret_cast<int *>(tab + 48);
-#pragma unroll
-            for (int ax = 0; ax < 3; ax++) { atomicMin(ib + ax, rz_f2ord(U.lo[ax])); atomicMax(ib + 3 + ax, rz_f2ord(U.hi[ax])); }
-            atomicAnd(tab + 54, U.all_pos);
-            atomicAnd(tab + 55, U.all_neg);
-        }
+        for (uint32_t i = lane; i < ne; i += 32u) atomicAdd(&tab[(uint32_t)ukeys[i] & 15u], 1u);
         __syncwarp();
-        {
-            const int *ib = reinterpret_cast<const int *>(tab + 48);
-#pragma unroll
-            for (int ax = 0; ax < 3; ax++) { U.lo[ax] = rz_ord2f(ib[ax]); U.hi[ax] = rz_ord2f(ib[3 + ax]); }
-            U.all_pos = tab[54]; U.all_neg = tab[55];
-        }
         {   // exclusive prefix over the 16 classes -> running cursors
             const uint32_t cnt = lane < 16u ? tab[lane] : 0u;
             uint32_t inc = cnt;
@@ -498,7 +553,7 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
             if (lane < 16u) tab[lane] = inc - cnt;
         }
         __syncwarp();
-        // entries in class order: order[slot] = position in the unit.  Lanes with the same class take consecutive slots.
+        // order[slot] = position in the unit.  Lanes with the same class take consecutive slots.
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < ne; i0 += 32u) {
             const uint32_t i = i0 + lane;
@@ -513,51 +568,13 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         }
         // now tab[c] = end of class c in `order`
 
-        // ---- 2. smallest class that reaches each sphere -> pairs ordered by class (one lane per sphere, one copy of the code)
-#pragma unroll 1
-        for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
-            const uint32_t k = k0 + lane;
-            float cx = 0.f, cy = 0.f, cz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, w = 1.f;
-            if (k < a.set.n_pad) rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // lanes past the set: a padding entry
-            int c = k < a.set.n_pad ? rz_unit_class(U, a, cx, cy, cz, vx, vy, vz, w) : 16;
-            c = min(c, __shfl_xor_sync(0xffffffffu, c, 1));                    // the pair's class
-            if (!(lane & 1u) && k < a.set.n_pad) {
-                pcl[k >> 1] = (unsigned char)c;
-                if (c < 16) atomicAdd(&tab[(k < a.set.n_static_pad ? 16u : 32u) + (uint32_t)c], 1u);
-            }
-        }
-        __syncwarp();
-        {   // exclusive prefixes of the two pair histograms
-            const uint32_t cnt = tab[16u + (lane & 15u) + (lane & 16u)];      // lanes 0-15: stationary, 16-31: moving
-            uint32_t inc = cnt;
-            for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)(lane & 15u) >= o) inc += t; }
-            __syncwarp();
-            tab[16u + lane] = inc - cnt;
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (uint32_t p0 = 0; p0 < n_pairs; p0 += 32u) {
-            const uint32_t p = p0 + lane;
-            const bool st = p < n_sp;
-            const uint32_t c = p < n_pairs ? (uint32_t)pcl[p] : 16u;
-            const uint32_t tag = c < 16u ? (c | (st ? 0u : 16u)) : 32u + lane;   // (part, class); unique for pairs that are dropped
-            const unsigned peers = __match_any_sync(0xffffffffu, tag);
-            const int leader = __ffs((int)peers) - 1;
-            uint32_t base = 0u;
-            if ((int)lane == leader && c < 16u) { base = tab[16u + tag]; tab[16u + tag] = base + (uint32_t)__popc(peers); }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (c < 16u) (st ? ls : lm)[base + (uint32_t)__popc(peers & lt_mask)] = (unsigned short)(st ? p : p - n_sp);
-            __syncwarp();
-        }
-        // now tab[16 + c] / tab[32 + c] = stationary / moving pairs of classes <= c
-
         // ---- 3. the unit's rays in class order, two per lane and iteration
 #pragma unroll 1
         for (uint32_t b0 = 0; b0 < ne; b0 += 64u) {
             // the batch's largest class: that of its last entry = number of classes that end at or before it
             const uint32_t last = min(b0 + 63u, ne - 1u);
             const int cmax = min(15, __popc(__ballot_sync(0xffffffffu, lane < 16u && tab[lane] <= last)));
-            const int n_ls = (int)tab[16 + cmax], n_lm = (int)tab[32 + cmax];
+            const int n_ls = (int)row[cmax], n_lm = (int)row[16 + cmax];
             RzLaneRay L[2];
             {   // both rays' entries are fetched together: eight 16-byte loads in flight per lane (random 64 B gathers from HBM)
                 const float4 *e[2];
@@ -653,6 +670,31 @@ extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats,
         return cudaGetLastError();
     };
     return collect_stats ? launch(rz_primary_kernel<true>) : launch(rz_primary_kernel<false>);
+}
+
+// Per-group pair lists of the sorted-segment kernel (a->bin_lists: RZ_SORT_BINS rows of a->bin_row bytes).
+extern "C" cudaError_t rz_launch_bin_lists(const RzPathArgs *a, int sm_count, cudaStream_t stream) {
+    const size_t smem = rz_pk_bytes(*a) + 4u * (size_t)((32u * 4u + a->set.n_pad / 2u + 15u) & ~15u);
+    cudaError_t e = cudaFuncSetAttribute(rz_bin_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rz_bin_lists_kernel<<<std::min(RZ_SORT_BINS / 4, sm_count * 4), 128, smem, stream>>>(*a);
+    return cudaGetLastError();
+}
+
+// Grid size of the sorted-segment kernel (the sort sizes the work units with it).
+extern "C" cudaError_t rz_second_grid(const RzPathArgs *a, int collect_stats, int sm_count, int *grid) {
+    const size_t smem = rz_second_smem_bytes(a);
+    auto query = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        *grid = sm_count * per_sm;
+        return cudaSuccess;
+    };
+    return collect_stats ? query(rz_second_kernel<true>) : query(rz_second_kernel<false>);
 }
 
 // Stage 2: second segments of the sorted queue (q_in through q_in_idx) -> q_out.

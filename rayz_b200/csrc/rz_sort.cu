@@ -17,12 +17,19 @@
 // keys serialise).  The scattered 2- and 4-byte stores land on <= 4096 slowly advancing frontiers that stay in the 126 MB L2
 // until their sectors are full.  Every kernel takes the live entry count from device memory: no host round trip, no
 // conditional graph, no 0xffff padding keys.
+//
+// The scan also cuts every group into the consumer's WORK UNITS (at most `ue` consecutive entries of ONE group) and leaves
+// their prefix beside the bins: unit_first[b] = units before group b, unit_first[4096] = all units.  A unit never straddles
+// two groups, so the consumer knows its rays' cell and direction sector exactly (rz_second_kernel, rz_bin_lists_kernel).
+// Scratch layout (unsigned int words, RZ_BIN_* in rz_device.cuh): [0, 4096) bins: counts -> first slot -> (after the
+// scatter) END of each group; [4096, 8193) unit_first; [8193] ue, the unit size chosen from the live count.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "rz_device.cuh"
 
 namespace {
 
-constexpr int RZ_BINS = 4096;                                // 12 bits: [origin cell 9][octant 3]
+constexpr int RZ_BINS = RZ_SORT_BINS;                        // 4096 = 12 bits: [origin cell 9][direction 3]
 constexpr int RZ_BIN_SHIFT = 4;                              // the key's low 4 bits (reach class) are not sorted on
 constexpr int RZ_BIN_THREADS = 256;
 constexpr int RZ_BIN_ITEMS = 16;                             // keys per thread and tile
@@ -63,15 +70,13 @@ __global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_count_kernel(const RzBi
     }
 }
 
-// exclusive prefix over the 4096 bins, in place: one CTA, 1024 threads x 4 consecutive bins
-__global__ void __launch_bounds__(1024) rz_bin_scan_kernel(unsigned int *bins) {
-    __shared__ uint32_t s_warp[32];
+// exclusive prefix of 1024 x 4 values held four per thread (one CTA of 1024 threads); returns the thread's own prefix and
+// leaves the grand total in *total
+__device__ __forceinline__ uint32_t rz_block_prefix(uint32_t sum, uint32_t *s_warp, uint32_t *total) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    uint4 *p = reinterpret_cast<uint4 *>(bins) + tid;
-    const uint4 v = *p;
-    const uint32_t sum = v.x + v.y + v.z + v.w;
     uint32_t inc = sum;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += t; }
+    __syncthreads();   // s_warp may still be read from the previous call
     if (lane == 31u) s_warp[w] = inc;
     __syncthreads();
     if (w == 0u) {
@@ -80,13 +85,37 @@ __global__ void __launch_bounds__(1024) rz_bin_scan_kernel(unsigned int *bins) {
         s_warp[lane] = x;
     }
     __syncthreads();
-    uint32_t run = inc - sum + (w ? s_warp[w - 1u] : 0u);
+    *total = s_warp[31];
+    return inc - sum + (w ? s_warp[w - 1u] : 0u);
+}
+
+// bins: counts -> first slot of each group (exclusive prefix, in place); unit_first: exclusive prefix of ceil(count / ue) and
+// its total; ue = ue_max, but never so many entries that the consumer's warps get fewer than ~4 units each (ue_div = 16 x its
+// grid size: the late stages hold a few million entries for 3552 warps).  One CTA, 1024 threads x 4 consecutive bins.
+__global__ void __launch_bounds__(1024) rz_bin_scan_kernel(unsigned int *scratch, const unsigned int *count, uint32_t cap, uint32_t ue_max, uint32_t ue_div) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n = min(*count, cap);
+    uint32_t ue = ue_max;
+    if (ue > 256u) ue = min(ue, max(256u, (n / max(ue_div, 1u)) & ~63u));
+    uint4 *p = reinterpret_cast<uint4 *>(scratch) + tid;
+    const uint4 v = *p;
+    uint32_t total;
+    uint32_t run = rz_block_prefix(v.x + v.y + v.z + v.w, s_warp, &total);
     uint4 o;
     o.x = run; run += v.x;
     o.y = run; run += v.y;
     o.z = run; run += v.z;
     o.w = run;
     *p = o;
+    const uint4 u = make_uint4((v.x + ue - 1u) / ue, (v.y + ue - 1u) / ue, (v.z + ue - 1u) / ue, (v.w + ue - 1u) / ue);
+    run = rz_block_prefix(u.x + u.y + u.z + u.w, s_warp, &total);
+    unsigned int *uf = scratch + RZ_BIN_UNIT_FIRST + 4u * tid;
+    uf[0] = run; run += u.x;
+    uf[1] = run; run += u.y;
+    uf[2] = run; run += u.z;
+    uf[3] = run;
+    if (tid == 0u) { scratch[RZ_BIN_UNIT_FIRST + RZ_SORT_BINS] = total; scratch[RZ_BIN_UE] = ue; }
 }
 
 __global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_scatter_kernel(const RzBinArgs a) {
@@ -128,11 +157,12 @@ __global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_scatter_kernel(const Rz
 
 }  // namespace
 
-extern "C" size_t rz_bin_scratch_bytes(void) { return (size_t)RZ_BINS * sizeof(unsigned int); }
+extern "C" size_t rz_bin_scratch_bytes(void) { return (size_t)RZ_BIN_SCRATCH_WORDS * sizeof(unsigned int); }
 
-// keys_in[0, *count) -> idx_out / keys_out: entry indices and keys grouped by ascending (key >> 4).  bins: rz_bin_scratch_bytes().
+// keys_in[0, *count) -> idx_out / keys_out: entry indices and keys grouped by ascending (key >> 4).  bins: rz_bin_scratch_bytes()
+// (layout above).  ue_max, ue_div: work-unit size of the consumer and 16 x its grid size.
 extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned int *count, uint32_t cap, unsigned int *bins,
-                                   unsigned short *keys_out, uint32_t *idx_out, int sm_count, cudaStream_t stream) {
+                                   unsigned short *keys_out, uint32_t *idx_out, uint32_t ue_max, uint32_t ue_div, int sm_count, cudaStream_t stream) {
     // resident CTAs per SM of the two kernels (called from one host thread per device: no shared mutable state here)
     int per_sm_count = 0, per_sm_scatter = 0;
     cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, rz_bin_count_kernel, RZ_BIN_THREADS, 0);
@@ -146,7 +176,7 @@ extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned
     cudaError_t e = cudaMemsetAsync(bins, 0, (size_t)RZ_BINS * sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
     rz_bin_count_kernel<<<grid_for(per_sm_count), RZ_BIN_THREADS, 0, stream>>>(a);
-    rz_bin_scan_kernel<<<1, 1024, 0, stream>>>(bins);
+    rz_bin_scan_kernel<<<1, 1024, 0, stream>>>(bins, count, cap, ue_max ? ue_max : 1024u, ue_div);
     rz_bin_scatter_kernel<<<grid_for(per_sm_scatter), RZ_BIN_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }

@@ -45,3 +45,15 @@ print(f"{'file:line':28s} {'static':>6s} {'exec %':>7s} {'samp %':>7s}  source")
 order = samples.most_common(top) if "--by-samples" in sys.argv else dyn.most_common(top) if "--by-exec" in sys.argv else static.most_common(top)
 for k, _ in order:
     print(f"{k[0] + ':' + str(k[1]):28s} {static[k]:6d} {100 * dyn[k] / tot_d:7.2f} {100 * samples[k] / tot_p:7.2f}  {text.get(k, '')}")
+# executed instructions / samples by file, and by 50-line bands of each file (which part of the kernel the time goes to)
+bands = collections.Counter()
+bands_p = collections.Counter()
+for k in static:
+    b = (k[0], k[1] // 50 * 50)
+    bands[b] += dyn[k]
+    bands_p[b] += samples[k]
+print("\nby 50-line band (exec % / samples %), bands above 0.5 % of either:")
+for b in sorted(bands):
+    e, p = 100 * bands[b] / tot_d, 100 * bands_p[b] / tot_p
+    if e >= 0.5 or p >= 0.5:
+        print(f"  {b[0]}:{b[1]}-{b[1] + 49}  {e:6.2f} {p:6.2f}")

@@ -124,11 +124,15 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
 // sorted-stage kernel culls spheres from exactly these bounds, so a violation here would be a missed hit there.
 // Returns the number of violations; counts[0..15] = rays per reach class, counts[16] = distinct keys seen.
 // ---------------------------------------------------------------------------------------------
+// direction field of the sort key in the checks below: -1 = chosen by the shape of the box (the product's default), 0 = octants, 1 = sectors
+static int g_key_mode = -1;
+extern "C" void hostsim_set_key_mode(int m) { g_key_mode = m; }
+
 extern "C" uint64_t hostsim_key_check(const float *lo, const float *hi, int cell_bits, uint64_t n_rays, uint64_t seed, uint64_t *counts) {
     RzPathArgs a;
     memset(&a, 0, sizeof a);
     const float l3[3] = {lo[0], lo[1], lo[2]}, h3[3] = {hi[0], hi[1], hi[2]};
-    rz_key_grid(a, l3, h3, cell_bits);
+    rz_key_grid(a, l3, h3, cell_bits, g_key_mode);
     std::vector<unsigned char> seen(65536, 0);
     uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
     auto u01 = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (float)((s >> 40) * (1.0 / 16777216.0)); };
@@ -155,7 +159,11 @@ extern "C" uint64_t hostsim_key_check(const float *lo, const float *hi, int cell
         bool ok = true;
         for (int ax = 0; ax < 3; ax++) {
             ok = ok && o[ax] >= blo[ax] && o[ax] <= bhi[ax];
-            ok = ok && (((oct >> ax) & 1u) != 0u) == (d[ax] < 0.f);
+            if (!a.key_sectors) ok = ok && (((oct >> ax) & 1u) != 0u) == (d[ax] < 0.f);
+        }
+        if (a.key_sectors) {   // sector of the projection on the (key_u, key_w) plane
+            const float du = d[a.key_u], dw = d[a.key_w];
+            ok = ok && ((oct & 1u) != 0u) == (du < 0.f) && ((oct & 2u) != 0u) == (dw < 0.f) && ((oct & 4u) != 0u) == (fabsf(du) < fabsf(dw));
         }
         ok = ok && rz_box_exit(a, ray) <= T;
         if (!ok) bad++;
@@ -264,7 +272,7 @@ extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cel
     RzPathArgs a;
     memset(&a, 0, sizeof a);
     const float l3[3] = {lo[0], lo[1], lo[2]}, h3[3] = {hi[0], hi[1], hi[2]};
-    rz_key_grid(a, l3, h3, cell_bits);
+    rz_key_grid(a, l3, h3, cell_bits, g_key_mode);
     a.huge_radius = huge_radius;
     Rng g(seed);
     for (int i = 0; i < 4; i++) out[i] = 0;
@@ -318,11 +326,11 @@ extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cel
 
 // ---------------------------------------------------------------------------------------------
 // The staged K1 on a real scene, stage by stage, on the CPU: camera rays searched over their tile's culled list, scattered
-// rays binned by sort key into units of 512 and searched over their unit's culled list — each against the brute-force
+// rays grouped by sort key and searched over their group's culled list — each against the brute-force
 // search over every sphere.  The closest hit (t and sphere) must be identical, which is the claim the staged form rests on
 // ("the culls only ever drop spheres a ray cannot reach").  Uses the functions the kernels call (rz_device.cuh).
 // out[0] = mismatches (primary), out[1] = primary rays, out[2] = sum of primary list sizes,
-// out[3] = mismatches (sorted units), out[4] = rays in units, out[5] = sum of unit list sizes (per ray), out[6] = units.
+// out[3] = mismatches (sorted units), out[4] = rays in units, out[5] = sum of list sizes (per ray), out[6] = groups.
 // ---------------------------------------------------------------------------------------------
 extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t tile_stride,
                                     uint64_t seed, uint64_t *out) {
@@ -383,7 +391,7 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
             const double pad = any ? 1e-3 * (hi[ax] - lo[ax]) + 1e-3 : 0.0;
             l3[ax] = any ? (float)(lo[ax] - pad) : -3.0e38f; h3[ax] = any ? (float)(hi[ax] + pad) : 3.0e38f;
         }
-        rz_key_grid(a, l3, h3, 9);
+        rz_key_grid(a, l3, h3, 9, g_key_mode);
         a.huge_radius = (float)huge;
     }
     const float t_min = 1e-4f;
@@ -450,27 +458,30 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
             }
         }
     }
-    // ---- sorted-stage kernel: entries grouped by (cell, octant) = key >> 4 (rz_sort.cu), units of 512, box + signs from the
-    // cells, every sphere's smallest reach class (rz_unit_class); a ray of class c searches the spheres of classes <= c
+    // ---- sorted-stage kernel: entries grouped by (cell, direction field) = key >> 4 (rz_sort.cu); a work unit never straddles
+    // two groups, so every ray searches its group's pair list (rz_bin_lists_kernel: every sphere's smallest reach class from
+    // the group's own cell and direction, rz_unit_class) up to its own class c: the spheres of classes <= c
     std::stable_sort(queue.begin(), queue.end(), [](const Entry &x, const Entry &y) { return (x.key >> 4) < (y.key >> 4); });
     std::vector<int> scls(n);
-    for (size_t e0 = 0; e0 < queue.size(); e0 += 512) {
-        const size_t ne = std::min<size_t>(512, queue.size() - e0);
+    for (size_t e0 = 0; e0 < queue.size();) {
+        size_t e1 = e0;
+        while (e1 < queue.size() && (queue[e1].key >> 4) == (queue[e0].key >> 4)) e1++;
         RzUnitBounds U;
         rz_unit_bounds_init(U);
-        for (size_t i = 0; i < ne; i++) rz_unit_bounds_add_cell(U, a, queue[e0 + i].key);
+        rz_unit_bounds_add_cell(U, a, queue[e0].key);
         for (uint32_t k = 0; k < n; k++) scls[k] = rz_unit_class(U, a, cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w);
         out[6]++;
-        for (size_t i = 0; i < ne; i++) {
-            const int c = (int)(queue[e0 + i].key & 15u);
+        for (size_t i = e0; i < e1; i++) {
+            const int c = (int)(queue[i].key & 15u);
             list.clear();
             for (uint32_t k = 0; k < n; k++) if (scls[k] <= c) list.push_back(k);
             float bt, bt2; int bk, bk2;
-            search(queue[e0 + i].ray, nullptr, bt, bk);
-            search(queue[e0 + i].ray, &list, bt2, bk2);
+            search(queue[i].ray, nullptr, bt, bk);
+            search(queue[i].ray, &list, bt2, bk2);
             out[4]++; out[5] += list.size();
             if (bk != bk2 || bt != bt2) out[3]++;
         }
+        e0 = e1;
     }
     return 0;
 }
