@@ -1056,7 +1056,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     uint32_t ue_div = 0;
                     if (second_stage && !bvh_family) {
                         // the sorted-segment kernel's pair lists, one row per sort group: a function of the set and the key grid
-                        a.bin_row = rz_bin_row_bytes(a.set.n_pad / 2u);
+                        a.bin_row = rz_bin_row_bytes(a.set.n_pad);
                         if (int rc = D.bin_lists.alloc((size_t)RZ_SORT_BINS * a.bin_row)) return rc;
                         a.bin_lists = D.bin_lists.p;
                         RZ_CUDA(rz_launch_bin_lists(&a, D.sms, D.stream));

@@ -255,9 +255,9 @@ struct RzRay {
 // ---------------------------------------------------------------------------------------------
 #define RZ_FAR_BIT 0x40000000
 
-// One row of the per-group pair lists: u16 end_s[16] | u16 end_m[16] | u16 ls[n_sp] | u16 lm[n_mp] — stationary / moving pairs in
-// class order; end_x[c] = pairs of classes <= c.  n_pairs = n_sp + n_mp.
-RZ_HD uint32_t rz_bin_row_bytes(uint32_t n_pairs) { return (64u + 2u * n_pairs + 15u) & ~15u; }
+// One row of the per-group sphere lists: u16 end_s[16] | u16 end_m[16] | u16 ls[n_static_pad] | u16 lm[n_pad - n_static_pad] —
+// set positions of the stationary / moving spheres in class order; end_x[c] = spheres of classes <= c.
+RZ_HD uint32_t rz_bin_row_bytes(uint32_t n_pad) { return (64u + 2u * n_pad + 15u) & ~15u; }
 
 // rz_sort.cu's scratch words (one set per side): bins | unit_first | ue
 #define RZ_SORT_BINS 4096

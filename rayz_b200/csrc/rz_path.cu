@@ -43,9 +43,9 @@
 #endif
 #define RZ_PRIMARY_BOUNDS __launch_bounds__(128, RZ_PRIMARY_MINB)
 
-// per-warp scratch of the sorted-stage kernel: tab[16] u32 | one row of the per-group pair lists | entry order u16[ue]
-__host__ __device__ inline uint32_t rz_second_warp_bytes(uint32_t n_pairs, uint32_t ue) {
-    return (16u * 4u + rz_bin_row_bytes(n_pairs) + 2u * ue + 15u) & ~15u;
+// per-warp scratch of the sorted-stage kernel: tab[16] u32 | one row of the per-group sphere lists | entry order u16[ue]
+__host__ __device__ inline uint32_t rz_second_warp_bytes(uint32_t n_pad, uint32_t ue) {
+    return (16u * 4u + rz_bin_row_bytes(n_pad) + 2u * ue + 15u) & ~15u;
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -282,22 +282,6 @@ __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRa
     }
 }
 
-// One sphere of the pair-interleaved set as scalars: position k in the set -> (cx, cy, cz, vx, vy, vz, w = -r^2)
-__device__ __forceinline__ void rz_set_sphere(const float4 *__restrict__ s_pk, uint32_t k, uint32_t n_static_pad, float &cx, float &cy, float &cz,
-                                              float &vx, float &vy, float &vz, float &w) {
-    const float *f = reinterpret_cast<const float *>(s_pk);
-    if (k < n_static_pad) {
-        const float *s = f + 8u * (k >> 1) + (k & 1u);
-        cx = s[0]; cy = s[2]; cz = s[4]; w = s[6];
-        vx = vy = vz = 0.f;
-    } else {
-        const uint32_t m = k - n_static_pad;
-        const float *s = f + 4u * n_static_pad + 16u * (m >> 1) + (m & 1u);
-        cx = s[0]; cy = s[2]; cz = s[4]; w = s[6];
-        vx = s[8]; vy = s[10]; vz = s[12];
-    }
-}
-
 template <bool STATS>
 __device__ __forceinline__ void rz_flush_counters(const RzPathArgs &a, const RzSegCounters &C, unsigned lane) {
     if (!STATS) return;
@@ -315,7 +299,7 @@ __device__ __forceinline__ void rz_flush_counters(const RzPathArgs &a, const RzS
 // bounceRay level renderer.zig:103-126).  Camera rays of a 32-pixel tile are coherent, so the warp first
 // culls the sphere set against the tile's frustum — a cone around the tile's mean direction, widened by the
 // pixel footprint, the thin-lens blur and each sphere's motion — and the packed search then runs over the
-// surviving handful of sphere pairs instead of all of them (rz_search_list2: same arithmetic, same (t, k)).
+// surviving handful of spheres instead of all of them (rz_search_lists_r2: same arithmetic, same (t, k)).
 // Paths that scatter are appended, ballot-compacted, to the HBM queue the sorted stages start from; paths
 // that leave the scene or are absorbed accumulate here.  36 % of all segments are camera segments.  The cull
 // (rz_tile_cone / rz_tile_keep, rz_device.cuh) is host + device and property-tested on the CPU.
@@ -323,13 +307,12 @@ template <bool STATS>
 __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
-    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
-    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1;   // sphere pairs
-    const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
-    unsigned short *ls = reinterpret_cast<unsigned short *>(s_pk + pk_f4) + (threadIdx.x >> 5) * (n_sp + n_mp);
-    unsigned short *lm = ls + n_sp;
+    float4 *s_cr = reinterpret_cast<float4 *>(rz_smem);
+    const uint32_t cv_f4 = 2u * a.set.n_pad - a.set.n_static_pad;
+    unsigned short *ls = reinterpret_cast<unsigned short *>(s_cr + cv_f4) + (threadIdx.x >> 5) * a.set.n_pad;   // kept stationary spheres
+    unsigned short *lm = ls + a.set.n_static_pad;                                                               // kept moving spheres
 
-    rz_stage_scene_pk(a.set, s_pk, &s_bar);
+    const float4 *s_vel = rz_stage_scene_cv(a.set, s_cr, &s_bar);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -358,21 +341,19 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
         float cmin = valid ? rz_tile_corner_cos(a.cam, pc, ax) : 1.0f;
         for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
         const RzTileCone cone = rz_tile_cone(a.cam, ax, has_axis, cmin, a.focus_dist, a.lens_radius);
-        // one lane per SPHERE (a pair is kept if either half is): 16 pairs per step, stationary and moving through the same code
+        // one lane per sphere, stationary and moving through the same code; the lists keep set order (= search order)
         int n_ls = 0, n_lm = 0;
 #pragma unroll 1
         for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
             const uint32_t k = k0 + lane;
-            float cx = 0.f, cy = 0.f, cz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, w = 1.f;
-            if (k < a.set.n_pad) rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // lanes past the set: a padding entry
-            const bool keep = k < a.set.n_pad && rz_tile_keep(cone, cx, cy, cz, vx, vy, vz, w);
-            unsigned m = __ballot_sync(0xffffffffu, keep);
-            m = (m | (m >> 1)) & 0x55555555u;                       // bit 2j: pair j of this step is kept
-            const bool mine = ((m >> lane) & 1u) != 0u;             // even lanes speak for their pair
-            const bool st = k < a.set.n_static_pad;                 // n_static_pad is even: a pair never straddles the two parts
+            const bool st = k < a.set.n_static_pad;
+            float4 S = make_float4(0.f, 0.f, 0.f, 1.f), V = make_float4(0.f, 0.f, 0.f, 0.f);   // lanes past the set: a padding entry
+            if (k < a.set.n_pad) { S = s_cr[k]; if (!st) V = s_vel[k]; }
+            const bool keep = k < a.set.n_pad && rz_tile_keep(cone, S.x, S.y, S.z, V.x, V.y, V.z, S.w);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
             const unsigned ms = m & __ballot_sync(0xffffffffu, st);
-            if (mine && st) ls[n_ls + __popc(ms & lt_mask)] = (unsigned short)(k >> 1);
-            if (mine && !st) lm[n_lm + __popc((m & ~ms) & lt_mask)] = (unsigned short)((k - a.set.n_static_pad) >> 1);
+            if (keep && st) ls[n_ls + __popc(ms & lt_mask)] = (unsigned short)k;
+            if (keep && !st) lm[n_lm + __popc((m & ~ms) & lt_mask)] = (unsigned short)k;
             n_ls += __popc(ms); n_lm += __popc(m & ~ms);
         }
         __syncwarp();
@@ -395,13 +376,14 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
                 if (trip == 0) L[1] = L[0];   // slot 0 is rewritten by the second trip
             }
             {
-                const RzRay rays[2] = {L[0].ray, L[1].ray};
+                RzRay rays[2] = {L[0].ray, L[1].ray};
                 float bt[2] = {3.0e38f, 3.0e38f};
                 int bk[2] = {-1, -1};
-                rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
+                rz_search_lists_r2(s_cr, s_vel, ls, n_ls, lm, n_lm, rays, a.t_min, bt, bk);
+                L[0].ray = rays[0]; L[1].ray = rays[1];   // (the search holds o, d, time as packed pairs and hands them back)
                 L[0].bk = bk[0]; L[1].bk = bk[1];
             }
-            if (STATS) C.sph += (unsigned long long)(2 * (n_ls + n_lm)) * ((L[0].live ? 1u : 0u) + (L[1].live ? 1u : 0u));
+            if (STATS) C.sph += (unsigned long long)(n_ls + n_lm) * ((L[0].live ? 1u : 0u) + (L[1].live ? 1u : 0u));
             rz_shade_and_push2<STATS>(a, L, lane, lt_mask, C);
         }
         __syncwarp();   // the lists are rewritten for the next unit
@@ -409,25 +391,24 @@ __global__ void RZ_PRIMARY_BOUNDS rz_primary_kernel(const RzPathArgs a) {
     rz_flush_counters<STATS>(a, C, lane);
 }
 
-// ------------------------------------------------------------------------------ per-group pair lists
-// For every group of the sort — (origin cell, direction field) = the top 12 bits of rz_sort_key — the sphere pairs a ray of
-// that group can reach, ordered by the SMALLEST reach class that gets to them (rz_unit_class: class 16 = no ray of the group
-// can, the pair is left out).  Camera-independent: a function of the sphere set and the key grid only; one warp per group,
-// ~30 us for the 4096 groups, run at the start of every staged render.  The sorted-segment kernel copies a row per work unit
-// instead of classifying the set itself (round 2's first form did: ~15 % of its samples, and it had to merge the bounds of
-// every key in the unit, which is looser than one group's own).  Row layout: rz_bin_row_bytes.
+// ------------------------------------------------------------------------------ per-group sphere lists
+// For every group of the sort — (origin cell, direction field) = the top 12 bits of rz_sort_key — the spheres a ray of that
+// group can reach, ordered by the SMALLEST reach class that gets to them (rz_unit_class: class 16 = no ray of the group
+// can, the sphere is left out; inside a class, set order).  Camera-independent: a function of the sphere set and the key grid
+// only; one warp per group, ~30 us for the 4096 groups, run at the start of every staged render.  The sorted-segment kernel
+// copies a row per work unit instead of classifying the set itself (round 2's first form did: ~15 % of its samples, and it
+// had to merge the bounds of every key in the unit, which is looser than one group's own).  Row layout: rz_bin_row_bytes.
 __global__ void __launch_bounds__(128) rz_bin_lists_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
-    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
-    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1, n_pairs = n_sp + n_mp;
-    const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
-    // per-warp scratch: tab[32] (pairs per class: stationary, moving) | pair classes u8[n_pairs]
-    const uint32_t warp_bytes = (32u * 4u + n_pairs + 15u) & ~15u;
-    unsigned char *wb = reinterpret_cast<unsigned char *>(s_pk + pk_f4) + (threadIdx.x >> 5) * warp_bytes;
+    float4 *s_cr = reinterpret_cast<float4 *>(rz_smem);
+    const uint32_t cv_f4 = 2u * a.set.n_pad - a.set.n_static_pad;
+    // per-warp scratch: tab[32] (spheres per class: stationary, moving) | sphere classes u8[n_pad]
+    const uint32_t warp_bytes = (32u * 4u + a.set.n_pad + 15u) & ~15u;
+    unsigned char *wb = reinterpret_cast<unsigned char *>(s_cr + cv_f4) + (threadIdx.x >> 5) * warp_bytes;
     unsigned int *tab = reinterpret_cast<unsigned int *>(wb);
-    unsigned char *pcl = wb + 32u * 4u;
-    rz_stage_scene_pk(a.set, s_pk, &s_bar);
+    unsigned char *scl = wb + 32u * 4u;
+    const float4 *s_vel = rz_stage_scene_cv(a.set, s_cr, &s_bar);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (uint32_t bin = blockIdx.x * 4u + (threadIdx.x >> 5); bin < (uint32_t)RZ_SORT_BINS; bin += gridDim.x * 4u) {
@@ -435,20 +416,21 @@ __global__ void __launch_bounds__(128) rz_bin_lists_kernel(const RzPathArgs a) {
         rz_unit_bounds_init(U);
         rz_unit_bounds_add_cell(U, a, bin << 4);
         unsigned short *row = reinterpret_cast<unsigned short *>(a.bin_lists + (size_t)bin * a.bin_row);
-        unsigned short *ls = row + 32, *lm = ls + n_sp;
+        unsigned short *ls = row + 32, *lm = ls + a.set.n_static_pad;
         tab[lane] = 0u;
         __syncwarp();
-        // smallest class that reaches each sphere -> class of the pair (one lane per sphere)
+        // smallest class that reaches each sphere (one lane per sphere)
 #pragma unroll 1
         for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
             const uint32_t k = k0 + lane;
-            float cx = 0.f, cy = 0.f, cz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, w = 1.f;
-            if (k < a.set.n_pad) rz_set_sphere(s_pk, k, a.set.n_static_pad, cx, cy, cz, vx, vy, vz, w);   // lanes past the set: a padding entry
-            int c = k < a.set.n_pad ? rz_unit_class(U, a, cx, cy, cz, vx, vy, vz, w) : 16;
-            c = min(c, __shfl_xor_sync(0xffffffffu, c, 1));
-            if (!(lane & 1u) && k < a.set.n_pad) {
-                pcl[k >> 1] = (unsigned char)c;
-                if (c < 16) atomicAdd(&tab[(k < a.set.n_static_pad ? 0u : 16u) + (uint32_t)c], 1u);
+            if (k < a.set.n_pad) {
+                const bool st = k < a.set.n_static_pad;
+                const float4 S = s_cr[k];
+                float4 V = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!st) V = s_vel[k];
+                const int c = rz_unit_class(U, a, S.x, S.y, S.z, V.x, V.y, V.z, S.w);
+                scl[k] = (unsigned char)c;
+                if (c < 16) atomicAdd(&tab[(st ? 0u : 16u) + (uint32_t)c], 1u);
             }
         }
         __syncwarp();
@@ -462,17 +444,17 @@ __global__ void __launch_bounds__(128) rz_bin_lists_kernel(const RzPathArgs a) {
         }
         __syncwarp();
 #pragma unroll 1
-        for (uint32_t p0 = 0; p0 < n_pairs; p0 += 32u) {
-            const uint32_t p = p0 + lane;
-            const bool st = p < n_sp;
-            const uint32_t c = p < n_pairs ? (uint32_t)pcl[p] : 16u;
-            const uint32_t tag = c < 16u ? (c | (st ? 0u : 16u)) : 32u + lane;   // (part, class); unique for pairs that are dropped
+        for (uint32_t k0 = 0; k0 < a.set.n_pad; k0 += 32u) {
+            const uint32_t k = k0 + lane;
+            const bool st = k < a.set.n_static_pad;
+            const uint32_t c = k < a.set.n_pad ? (uint32_t)scl[k] : 16u;
+            const uint32_t tag = c < 16u ? (c | (st ? 0u : 16u)) : 32u + lane;   // (part, class); unique for spheres that are dropped
             const unsigned peers = __match_any_sync(0xffffffffu, tag);
             const int leader = __ffs((int)peers) - 1;
             uint32_t base = 0u;
             if ((int)lane == leader && c < 16u) { base = tab[tag]; tab[tag] = base + (uint32_t)__popc(peers); }
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (c < 16u) (st ? ls : lm)[base + (uint32_t)__popc(peers & lt_mask)] = (unsigned short)(st ? p : p - n_sp);
+            if (c < 16u) (st ? ls : lm)[base + (uint32_t)__popc(peers & lt_mask)] = (unsigned short)k;
             __syncwarp();
         }
         __syncwarp();
@@ -497,20 +479,19 @@ template <bool STATS>
 __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     __shared__ __align__(8) uint64_t s_bar;
-    float4 *s_pk = reinterpret_cast<float4 *>(rz_smem);
-    const uint32_t n_sp = a.set.n_static_pad >> 1, n_mp = (a.set.n_pad - a.set.n_static_pad) >> 1, n_pairs = n_sp + n_mp;
-    const uint32_t pk_f4 = a.set.n_static_pad + 2u * (a.set.n_pad - a.set.n_static_pad);
+    float4 *s_cr = reinterpret_cast<float4 *>(rz_smem);
+    const uint32_t cv_f4 = 2u * a.set.n_pad - a.set.n_static_pad;
     const uint32_t ue_max = a.unit_entries;
     // per-warp scratch: tab[16] | the group's row (end_s, end_m, ls, lm) | entry order [ue] (layout: rz_second_warp_bytes)
-    const uint32_t warp_bytes = rz_second_warp_bytes(n_pairs, ue_max);
-    unsigned char *wb = reinterpret_cast<unsigned char *>(s_pk + pk_f4) + (threadIdx.x >> 5) * warp_bytes;
+    const uint32_t warp_bytes = rz_second_warp_bytes(a.set.n_pad, ue_max);
+    unsigned char *wb = reinterpret_cast<unsigned char *>(s_cr + cv_f4) + (threadIdx.x >> 5) * warp_bytes;
     unsigned int *tab = reinterpret_cast<unsigned int *>(wb);             // [0,16) entries: end of class c
-    unsigned short *row = reinterpret_cast<unsigned short *>(tab + 16);   // end_s[16] end_m[16]: pairs of classes <= c
+    unsigned short *row = reinterpret_cast<unsigned short *>(tab + 16);   // end_s[16] end_m[16]: spheres of classes <= c
     unsigned short *ls = row + 32;
-    unsigned short *lm = ls + n_sp;
+    unsigned short *lm = ls + a.set.n_static_pad;
     unsigned short *order = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(row) + a.bin_row);
 
-    rz_stage_scene_pk(a.set, s_pk, &s_bar);
+    const float4 *s_vel = rz_stage_scene_cv(a.set, s_cr, &s_bar);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -601,13 +582,14 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
                 }
             }
             {
-                const RzRay rays[2] = {L[0].ray, L[1].ray};
+                RzRay rays[2] = {L[0].ray, L[1].ray};
                 float bt[2] = {3.0e38f, 3.0e38f};
                 int bk[2] = {-1, -1};
-                rz_search_list2<2>(s_pk, ls, n_ls, lm, n_lm, (int)a.set.n_static_pad, rays, a.t_min, bt, bk);
+                rz_search_lists_r2(s_cr, s_vel, ls, n_ls, lm, n_lm, rays, a.t_min, bt, bk);
+                L[0].ray = rays[0]; L[1].ray = rays[1];   // (the search holds o, d, time as packed pairs and hands them back)
                 L[0].bk = bk[0]; L[1].bk = bk[1];
             }
-            if (STATS) C.sph += (unsigned long long)(2 * (n_ls + n_lm)) * ((L[0].live ? 1u : 0u) + (L[1].live ? 1u : 0u));
+            if (STATS) C.sph += (unsigned long long)(n_ls + n_lm) * ((L[0].live ? 1u : 0u) + (L[1].live ? 1u : 0u));
             rz_shade_and_push2<STATS>(a, L, lane, lt_mask, C);
         }
         __syncwarp();
@@ -645,13 +627,12 @@ extern "C" cudaError_t rz_path_warm(void) {
 
 // Shared memory the sorted-stage kernel needs: the set + per-warp scratch (rz_second_warp_bytes).
 extern "C" size_t rz_second_smem_bytes(const RzPathArgs *a) {
-    return rz_pk_bytes(*a) + 4u * (size_t)rz_second_warp_bytes(a->set.n_pad / 2u, a->unit_entries);
+    return rz_pk_bytes(*a) + 4u * (size_t)rz_second_warp_bytes(a->set.n_pad, a->unit_entries);
 }
 
 // Shared memory the primary kernel needs: the pair-interleaved set + one pair list per warp.
 extern "C" size_t rz_primary_smem_bytes(const RzPathArgs *a) {
-    const size_t pairs = a->set.n_pad / 2u;
-    return rz_pk_bytes(*a) + ((4u * pairs * sizeof(unsigned short) + 15u) & ~size_t(15));
+    return rz_pk_bytes(*a) + ((4u * (size_t)a->set.n_pad * sizeof(unsigned short) + 15u) & ~size_t(15));
 }
 
 // Stage 1: camera segments of the work units [unit_base, unit_base + n_units) -> queue.
@@ -674,7 +655,7 @@ extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats,
 
 // Per-group pair lists of the sorted-segment kernel (a->bin_lists: RZ_SORT_BINS rows of a->bin_row bytes).
 extern "C" cudaError_t rz_launch_bin_lists(const RzPathArgs *a, int sm_count, cudaStream_t stream) {
-    const size_t smem = rz_pk_bytes(*a) + 4u * (size_t)((32u * 4u + a->set.n_pad / 2u + 15u) & ~15u);
+    const size_t smem = rz_pk_bytes(*a) + 4u * (size_t)((32u * 4u + a->set.n_pad + 15u) & ~15u);
     cudaError_t e = cudaFuncSetAttribute(rz_bin_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     rz_bin_lists_kernel<<<std::min(RZ_SORT_BINS / 4, sm_count * 4), 128, smem, stream>>>(*a);

@@ -178,122 +178,143 @@ __device__ __forceinline__ void rz_search_brute2(const float4 *__restrict__ s_pk
 }
 
 // ------------------------------------------------------------------------------ K1 search over a culled list
-// The same packed arithmetic over a LIST of sphere pairs (the primary kernel culls the set against the frustum of its
-// 32-pixel tile, the sorted-stage kernel against the bounds of its unit's keys).  ls / lm: pair indices into the
-// stationary / moving part of the pair-interleaved set (layout: RzSphereSet::pk), ascending.
+// The staged kernels search a LIST of spheres (the primary kernel culls the set against the frustum of its 32-pixel tile, the
+// sorted-stage kernel takes the list of its rays' sort group).  Here the packed instructions work on the TWO RAYS of a lane
+// (the .x/.y halves hold ray 0 / ray 1) against ONE sphere, whose operands enter as broadcast registers: the same 12 (15)
+// issue slots per two tests as the pair form above, but the list has single-sphere granularity.  Round 2's first form kept
+// sphere PAIRS in the lists (a pair stays if either half does): 44 tests per ray where the per-sphere lists hold 33.
+// Each half follows the operation order of rz_sphere_test exactly (IEEE rn, FTZ): bit-identical (t, k) in every search.
 //
 // The loop over the list is BRANCH-FREE.  A culled list is dense in hits (one ray in ~30 meets a given sphere of it; some lane
-// of the warp nearly always does), so a rare-path branch per sphere — four BSSY/BSYNC pairs per pair of spheres and rays —
-// was entered all the time: 16 % of the sorted-stage kernel's samples sat in it and its reconvergence points (round 1,
-// profiles/r01_sorted_stage_kernel_ncu.md).  Now the only thing kept per test is the SIGN of nd, shifted into a per-ray
-// mask by one funnel shift (SHF.L.W: mask = mask << 1 | sign); after every 16 pairs (32 tests) the lanes walk the set bits
-// of their masks in one loop — most significant first = ascending sphere index, the order of the brute-force search — redo
-// the test of that one sphere with the scalar rz_sphere_test (bit-identical per half) and apply the root rule.  The loop
-// runs max-over-lanes(candidates) times instead of once per sphere; a -0.0 or NaN sign is weeded out by the redone test.
-template <int R, bool MOVING>
-__device__ __forceinline__ void rz_resolve_masks(const float *__restrict__ base, const unsigned short *__restrict__ list, int cn, int k_base,
-                                                 unsigned (&m)[R], const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
-    unsigned any = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++) any |= m[r];
+// of the warp nearly always does), so a rare-path branch per sphere was entered all the time: 16 % of the sorted-stage
+// kernel's samples sat in it and its reconvergence points (round 1, profiles/r01_sorted_stage_kernel_ncu.md).  Now the only
+// thing kept per test is the SIGN of nd, shifted into a per-ray mask by one funnel shift (SHF.L.W: mask = mask << 1 | sign);
+// after every 32 spheres the lanes walk the set bits of their masks in one loop — most significant first = list order —
+// redo the test of that one sphere with the scalar rz_sphere_test (bit-identical per half) and apply the root rule.  The
+// loop runs max-over-lanes(candidates) times instead of once per sphere; a -0.0 or NaN sign is weeded out by the redone test.
+// s_cr[k] = (cx, cy, cz, -r^2) of set position k; s_vel[k] = velocity, valid for k >= n_static_pad (the moving part).
+// The pairs are held as 64-bit registers through inline PTX (mov.b64 / add|mul|fma.rn.ftz.f32x2): written with the float2
+// intrinsics, the compiler kept the rays' scalar registers (they are needed again for shading) and rebuilt every pair with
+// two MOVs per use, six per sphere.  Here the pairs are the ONLY copy while the search runs — the scalars are re-read from
+// their halves afterwards — which also takes fewer registers than round 2's first form (o, -o, d, -d as scalars per ray).
+typedef unsigned long long rz_p2;   // (ray 0, ray 1) or a broadcast (s, s)
+__device__ __forceinline__ rz_p2 rz_pack(float x, float y) { rz_p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void rz_unpack(rz_p2 v, float &x, float &y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ float rz_half(rz_p2 v, int r) { float x, y; rz_unpack(v, x, y); return r ? y : x; }
+__device__ __forceinline__ rz_p2 rz_add2(rz_p2 a, rz_p2 b) { rz_p2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ rz_p2 rz_mul2(rz_p2 a, rz_p2 b) { rz_p2 r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ rz_p2 rz_fma2(rz_p2 a, rz_p2 b, rz_p2 c) { rz_p2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// sign flip of both halves as two plain neg.f32: ptxas folds them into the operand modifier of the consuming FFMA2 (-R.F32x2);
+// written with neg.ftz (what -x compiles to under --use_fast_math) it emits two FADDs instead.  The values negated here are
+// results of FTZ arithmetic, never denormal, so the two agree.
+__device__ __forceinline__ rz_p2 rz_neg2(rz_p2 v) {
+    float x, y, nx, ny;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+    asm("neg.f32 %0, %1;" : "=f"(nx) : "f"(x));
+    asm("neg.f32 %0, %1;" : "=f"(ny) : "f"(y));
+    rz_p2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(nx), "f"(ny));
+    return r;
+}
+
+// -o, -d, time of the lane's two rays: seven register pairs (+d enters as a negated operand)
+struct RzRay2Ops {
+    rz_p2 nox, noy, noz, ndx, ndy, ndz, ntime;   // all negated: a pair that merely copies two scalars is rebuilt by MOVs at every use
+};
+__device__ __forceinline__ RzRay2Ops rz_ray2_ops(const RzRay (&r)[2]) {
+    RzRay2Ops q;
+    q.nox = rz_pack(-r[0].o.x, -r[1].o.x); q.noy = rz_pack(-r[0].o.y, -r[1].o.y); q.noz = rz_pack(-r[0].o.z, -r[1].o.z);
+    q.ndx = rz_pack(-r[0].d.x, -r[1].d.x); q.ndy = rz_pack(-r[0].d.y, -r[1].d.y); q.ndz = rz_pack(-r[0].d.z, -r[1].d.z);
+    q.ntime = rz_pack(-r[0].time, -r[1].time);
+    return q;
+}
+// the rays' scalars back from the pairs (o = -(-o), d = -(-d): exact)
+__device__ __forceinline__ void rz_ray2_restore(const RzRay2Ops &q, RzRay (&r)[2]) {
+    float a, b;
+    rz_unpack(q.nox, a, b); r[0].o.x = -a; r[1].o.x = -b;
+    rz_unpack(q.noy, a, b); r[0].o.y = -a; r[1].o.y = -b;
+    rz_unpack(q.noz, a, b); r[0].o.z = -a; r[1].o.z = -b;
+    rz_unpack(q.ndx, a, b); r[0].d.x = -a; r[1].d.x = -b;
+    rz_unpack(q.ndy, a, b); r[0].d.y = -a; r[1].d.y = -b;
+    rz_unpack(q.ndz, a, b); r[0].d.z = -a; r[1].d.z = -b;
+    rz_unpack(q.ntime, a, b); r[0].time = -a; r[1].time = -b;
+}
+
+// sign bits of nd for the two rays against one sphere: the operation order of rz_sphere_test per half
+template <bool MOVING>
+__device__ __forceinline__ rz_p2 rz_test_r2(const float4 S, const float4 V, const RzRay2Ops &q) {
+    rz_p2 ocx = rz_add2(rz_pack(S.x, S.x), q.nox), ocy = rz_add2(rz_pack(S.y, S.y), q.noy), ocz = rz_add2(rz_pack(S.z, S.z), q.noz);
+    if (MOVING) {
+        ocx = rz_fma2(rz_neg2(rz_pack(V.x, V.x)), q.ntime, ocx);   // v t = (-v)(-t)
+        ocy = rz_fma2(rz_neg2(rz_pack(V.y, V.y)), q.ntime, ocy);
+        ocz = rz_fma2(rz_neg2(rz_pack(V.z, V.z)), q.ntime, ocz);
+    }
+    const rz_p2 nb = rz_fma2(ocz, q.ndz, rz_fma2(ocy, q.ndy, rz_mul2(ocx, q.ndx)));
+    const rz_p2 b = rz_neg2(nb);                                                               // l = oc + nb d = oc + (-nb)(-d)
+    const rz_p2 lx = rz_fma2(b, q.ndx, ocx), ly = rz_fma2(b, q.ndy, ocy), lz = rz_fma2(b, q.ndz, ocz);
+    return rz_fma2(lz, lz, rz_fma2(ly, ly, rz_fma2(lx, lx, rz_pack(S.w, S.w))));
+}
+
+template <bool MOVING>
+__device__ __forceinline__ void rz_resolve_masks(const float4 *__restrict__ s_cr, const float4 *__restrict__ s_vel,
+                                                 const unsigned short *__restrict__ list, int cn, unsigned (&m)[2], const RzRay2Ops &q,
+                                                 const int (&self_k)[2], float t_min, float (&bt)[2], int (&bk)[2]) {
+    unsigned any = m[0] | m[1];
     while (any) {
         any = 0;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
+        for (int r = 0; r < 2; r++) {
             if (m[r]) {
                 const int bit = 31 - __clz((int)m[r]);
                 m[r] &= ~(1u << bit);
-                const int pos = 2 * cn - 1 - bit;          // test number within the chunk: pair pos >> 1, half pos & 1
-                const int p = list[pos >> 1], h = pos & 1;
-                const float *s = base + (MOVING ? 16 : 8) * p + h;
+                const int k = list[cn - 1 - bit];           // test number within the chunk
+                const float4 S = s_cr[k];
+                float4 V = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MOVING) V = s_vel[k];
                 float nb, nd;
-                rz_sphere_test(s[0], s[2], s[4], MOVING ? s[8] : 0.f, MOVING ? s[10] : 0.f, MOVING ? s[12] : 0.f, s[6], ray[r].o.x, ray[r].o.y,
-                               ray[r].o.z, ray[r].d.x, ray[r].d.y, ray[r].d.z, ray[r].time, nb, nd);
-                if (nd < 0.0f) rz_consider(k_base + 2 * p + h, nb, nd, ray[r].self_k, t_min, bt[r], bk[r]);
+                rz_sphere_test(S.x, S.y, S.z, V.x, V.y, V.z, S.w, -rz_half(q.nox, r), -rz_half(q.noy, r), -rz_half(q.noz, r), -rz_half(q.ndx, r),
+                               -rz_half(q.ndy, r), -rz_half(q.ndz, r), -rz_half(q.ntime, r), nb, nd);
+                if (nd < 0.0f) rz_consider(k, nb, nd, self_k[r], t_min, bt[r], bk[r]);
             }
             any |= m[r];
         }
     }
 }
 
-template <int R>
-__device__ __forceinline__ void rz_search_list2(const float4 *__restrict__ s_pk, const unsigned short *__restrict__ ls, int n_ls,
-                                                const unsigned short *__restrict__ lm, int n_lm, int n_static_pad,
-                                                const RzRay (&ray)[R], float t_min, float (&bt)[R], int (&bk)[R]) {
-    RzRayOps q[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) q[r] = rz_ray_ops(ray[r]);
-#ifdef RZ_LIST_BRANCHY   // experiment (scripts/exp_build.sh): the round-1 form, one rare-path branch per test
+template <bool MOVING>
+__device__ __forceinline__ void rz_search_list_r2(const float4 *__restrict__ s_cr, const float4 *__restrict__ s_vel,
+                                                  const unsigned short *__restrict__ list, int n, const RzRay2Ops &q, const int (&self_k)[2],
+                                                  float t_min, float (&bt)[2], int (&bk)[2]) {
 #pragma unroll 1
-    for (int i = 0; i < n_ls; i++) {
-        const int p = ls[i];
-        const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            float2 nb, nd;
-            rz_test2_static(A, B, q[r], nb, nd);
-            if (nd.x < 0.0f) rz_consider(2 * p, nb.x, nd.x, ray[r].self_k, t_min, bt[r], bk[r]);
-            if (nd.y < 0.0f) rz_consider(2 * p + 1, nb.y, nd.y, ray[r].self_k, t_min, bt[r], bk[r]);
-        }
-    }
-    {
-        const float4 *__restrict__ mvb = s_pk + n_static_pad;
-#pragma unroll 1
-        for (int i = 0; i < n_lm; i++) {
-            const int p = lm[i];
-            const float4 A = mvb[4 * p], B = mvb[4 * p + 1], VA = mvb[4 * p + 2], VB = mvb[4 * p + 3];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                float2 nb, nd;
-                rz_test2_moving(A, B, VA, VB, q[r], nb, nd);
-                if (nd.x < 0.0f) rz_consider(n_static_pad + 2 * p, nb.x, nd.x, ray[r].self_k, t_min, bt[r], bk[r]);
-                if (nd.y < 0.0f) rz_consider(n_static_pad + 2 * p + 1, nb.y, nd.y, ray[r].self_k, t_min, bt[r], bk[r]);
-            }
-        }
-        return;
-    }
-#endif
-#pragma unroll 1
-    for (int i0 = 0; i0 < n_ls; i0 += 16) {
-        const int cn = min(16, n_ls - i0);
-        unsigned m[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) m[r] = 0u;
-#pragma unroll 2
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int cn = min(32, n - i0);
+        unsigned m[2] = {0u, 0u};
+#pragma unroll 4
         for (int i = 0; i < cn; i++) {
-            const int p = ls[i0 + i];
-            const float4 A = s_pk[2 * p], B = s_pk[2 * p + 1];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                float2 nb, nd;
-                rz_test2_static(A, B, q[r], nb, nd);
-                m[r] = __funnelshift_l(__float_as_uint(nd.x), m[r], 1);
-                m[r] = __funnelshift_l(__float_as_uint(nd.y), m[r], 1);
-            }
+            const int k = list[i0 + i];
+            const float4 S = s_cr[k];
+            float4 V = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MOVING) V = s_vel[k];
+            float n0, n1;
+            rz_unpack(rz_test_r2<MOVING>(S, V, q), n0, n1);
+            m[0] = __funnelshift_l(__float_as_uint(n0), m[0], 1);
+            m[1] = __funnelshift_l(__float_as_uint(n1), m[1], 1);
         }
-        rz_resolve_masks<R, false>(reinterpret_cast<const float *>(s_pk), ls + i0, cn, 0, m, ray, t_min, bt, bk);
+        rz_resolve_masks<MOVING>(s_cr, s_vel, list + i0, cn, m, q, self_k, t_min, bt, bk);
     }
-    const float4 *__restrict__ mv = s_pk + n_static_pad;
-#pragma unroll 1
-    for (int i0 = 0; i0 < n_lm; i0 += 16) {
-        const int cn = min(16, n_lm - i0);
-        unsigned m[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) m[r] = 0u;
-#pragma unroll 2
-        for (int i = 0; i < cn; i++) {
-            const int p = lm[i0 + i];
-            const float4 A = mv[4 * p], B = mv[4 * p + 1], VA = mv[4 * p + 2], VB = mv[4 * p + 3];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                float2 nb, nd;
-                rz_test2_moving(A, B, VA, VB, q[r], nb, nd);
-                m[r] = __funnelshift_l(__float_as_uint(nd.x), m[r], 1);
-                m[r] = __funnelshift_l(__float_as_uint(nd.y), m[r], 1);
-            }
-        }
-        rz_resolve_masks<R, true>(reinterpret_cast<const float *>(mv), lm + i0, cn, n_static_pad, m, ray, t_min, bt, bk);
-    }
+}
+
+// ls / lm: set positions of the stationary / moving spheres to test, in search order.  The rays' o, d and time live in the
+// packed pairs for the duration of the search and are written back from them at the end.
+__device__ __forceinline__ void rz_search_lists_r2(const float4 *__restrict__ s_cr, const float4 *__restrict__ s_vel,
+                                                   const unsigned short *__restrict__ ls, int n_ls, const unsigned short *__restrict__ lm, int n_lm,
+                                                   RzRay (&ray)[2], float t_min, float (&bt)[2], int (&bk)[2]) {
+    const RzRay2Ops q = rz_ray2_ops(ray);
+    const int self_k[2] = {ray[0].self_k, ray[1].self_k};
+    rz_search_list_r2<false>(s_cr, s_vel, ls, n_ls, q, self_k, t_min, bt, bk);
+    rz_search_list_r2<true>(s_cr, s_vel, lm, n_lm, q, self_k, t_min, bt, bk);
+    rz_ray2_restore(q, ray);
 }
 
 // ------------------------------------------------------------------------------ stage scene
@@ -308,6 +329,21 @@ __device__ __forceinline__ void rz_stage_scene_pk(const RzSphereSet &set, float4
         rz_bulk_g2s(s_pk, set.pk, bytes, bar);
     }
     rz_mbar_wait(bar, 0);
+}
+
+// The staged kernels' layout: s_cr[n_pad] = (cx, cy, cz, -r^2) by set position, then the velocities of the moving part
+// (s_cr + n_pad; returns the pointer biased so that s_vel[k] is the velocity of set position k >= n_static_pad).
+__device__ __forceinline__ const float4 *rz_stage_scene_cv(const RzSphereSet &set, float4 *s_cr, uint64_t *bar) {
+    const uint32_t bytes_cr = set.n_pad * 16u, bytes_vel = (set.n_pad - set.n_static_pad) * 16u;
+    if (threadIdx.x == 0) rz_mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rz_mbar_expect_tx(bar, bytes_cr + bytes_vel);
+        rz_bulk_g2s(s_cr, set.cr, bytes_cr, bar);
+        if (bytes_vel) rz_bulk_g2s(s_cr + set.n_pad, set.vel + set.n_static_pad, bytes_vel, bar);
+    }
+    rz_mbar_wait(bar, 0);
+    return s_cr + set.n_pad - set.n_static_pad;
 }
 
 // ------------------------------------------------------------------------------ shade

@@ -3,13 +3,14 @@
 #   gpurun -- 'bash scripts/gpu_ncu.sh <tag> [kernel-regex ...]'
 set -x
 T=${1:-ncu}; shift
+SPP=${SPP:-40}            # SPP=500: the launches of the benchmark configuration itself (four passes)
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --spp 40 --variant mega --no-cpu-baseline --no-e2e --no-variants --no-other-configs"
+CMD="python bench.py --steps 2 --warmup 3 --spp $SPP --variant mega --no-cpu-baseline --no-e2e --no-variants --no-other-configs"
 $CMD > gpurun_out/${T}_plain.log 2>&1 || exit 1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_launches.log 2>&1
 for K in "${@:-rz_second_kernel rz_primary_kernel}"; do
   for k in $K; do
-    S=2; [ "$k" == "rz_second_kernel" ] && S=10
+    S=2; [ "$k" == "rz_second_kernel" ] && S=${SKIP_SECOND:-10}
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $S -c 1 -o gpurun_out/${T}_prof_${k} $CMD > gpurun_out/${T}_full_${k}.log 2>&1
   done
 done
