@@ -162,6 +162,7 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
         const int cnt = (code >> 28) + 1;
         for (int e = 0; e < cnt; e++) {
             const int k = first + e;
+            if (k == (ray.self_k ^ RZ_SELF_OUT)) continue;   // left outward: cannot be hit again
             const float4 s = __ldg(a.set.cr + k);
             const float4 v = __ldg(a.set.vel + k);
             if (STATS) c_sph++;
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_kernel(const RzPathArgs a) {
                         const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
                         ray.o = f3(qa.x, qa.y, qa.z); ray.time = qa.w;
                         ray.d = f3(qb.x, qb.y, qb.z); ray.self_k = __float_as_int(qb.w);
-                        if (a.self_map && ray.self_k >= 0) ray.self_k = a.self_map[ray.self_k];   // entry written by a brute-force stage
+                        if (a.self_map && ray.self_k >= 0)                                          // entry written by a brute-force stage
+                            ray.self_k = a.self_map[ray.self_k & ~RZ_SELF_OUT] | (ray.self_k & RZ_SELF_OUT);
                         thr = f3(qc.x, qc.y, qc.z); seg = __float_as_uint(qc.w);
                         lp = __float_as_uint(qd.x); gpix = __float_as_uint(qd.y); sample = __float_as_uint(qd.z);
                         alive = true;

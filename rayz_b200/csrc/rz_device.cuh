@@ -156,7 +156,7 @@ struct RzPathArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11).  key = 64-bit seed; counter = (global pixel, sample,
+// Philox4x32 (Salmon et al., SC'11), seven rounds.  key = 64-bit seed; counter = (global pixel, sample,
 // bounce, lane) so the stream is a pure function of WHAT is sampled, never of where it runs:
 // any row sharding across GPUs reproduces the full-frame image bit for bit.
 // ---------------------------------------------------------------------------------------------
@@ -171,9 +171,13 @@ RZ_HD void rz_mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
 #endif
 }
 
+// Seven rounds: Philox4x32-7 is the variant Salmon et al. report as already Crush-resistant (BigCrush clean); -10 is their
+// default with a safety margin.  Two blocks per camera segment made the ten-round form 16 % of the primary kernel's
+// instructions (profiles/r02_primary_kernel_ncu.md).
+#define RZ_PHILOX_ROUNDS 7
 RZ_HD uint4 rz_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < RZ_PHILOX_ROUNDS; i++) {
         uint32_t h0, l0, h1, l1;
         rz_mulhilo(0xD2511F53u, c0, h0, l0);
         rz_mulhilo(0xCD9E8D57u, c2, h1, l1);
@@ -238,7 +242,11 @@ struct RzRay {
     int self_k;    // sphere (set index) the ray starts on, -1 for camera rays.  Self
                    // re-intersection is resolved analytically instead of by an epsilon:
                    // leaving outward -> cannot re-hit a convex sphere; inward -> far root.
+                   // | RZ_SELF_OUT when the scatter step already knows the ray leaves outward.
 };
+// Flag on RzRay::self_k: the ray leaves its sphere outward by a clear margin (rz_scatter), so the searches skip that sphere
+// without testing it.  Equivalent to the arithmetic rule in rz_consider (b < 0 -> rejected), which stays for grazing rays.
+#define RZ_SELF_OUT 0x20000000
 
 // ---------------------------------------------------------------------------------------------
 // The ray-sphere test every search of the backend uses (packed FP32x2 or scalar, brute force, culled list or BVH leaf):
@@ -283,8 +291,8 @@ RZ_HD void rz_consider(int k, float nb, float nd, int self_k, float t_min, float
     const float b = -nb;
     float t = b - sq;
     int tag = k;
-    if (k == self_k) {
-        t = (b > 0.0f) ? b + sq : -1.0f;
+    if (k == (self_k & ~RZ_SELF_OUT)) {
+        t = (b > 0.0f && !(self_k & RZ_SELF_OUT)) ? b + sq : -1.0f;
         tag = k | RZ_FAR_BIT;
     } else if (t < t_min) {
         t = b + sq;
@@ -450,7 +458,9 @@ RZ_HD bool rz_scatter(const RzMatRec &M, const RzTextures &T, const RzHit &h, in
     }
     ray.o = h.p;
     ray.d = nd;
-    ray.self_k = k;   // time is kept (material.zig:92,122,155)
+    // outward by a margin far above the FP32 error of b = (C - o).d (|C - o| 2^-22: r = 1000 -> 2e-4 r): b < 0 for certain
+    const float out = dot3(nd, h.n);
+    ray.self_k = ((h.front ? out : -out) > 1e-3f) ? (k | RZ_SELF_OUT) : k;   // time is kept (material.zig:92,122,155)
     return true;
 }
 
@@ -474,10 +484,10 @@ RZ_HD float rz_box_exit(const RzPathArgs &a, const RzRay &ray) {
     float t = 3.0e38f;
     const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
 #pragma unroll
-    for (int ax = 0; ax < 3; ax++) {
-        if (d[ax] > 0.f) t = fminf(t, (a.sb_hi[ax] - o[ax]) / d[ax]);
-        else if (d[ax] < 0.f) t = fminf(t, (a.sb_lo[ax] - o[ax]) / d[ax]);
-        else if (o[ax] < a.sb_lo[ax] || o[ax] > a.sb_hi[ax]) t = 0.f;
+    for (int ax = 0; ax < 3; ax++) {   // one division per axis, no branches: the face the ray heads for
+        float ta = ((d[ax] < 0.f ? a.sb_lo[ax] : a.sb_hi[ax]) - o[ax]) / d[ax];
+        if (d[ax] == 0.f) ta = (o[ax] < a.sb_lo[ax] || o[ax] > a.sb_hi[ax]) ? 0.f : 3.0e38f;   // parallel to the slab: outside for ever, or never leaves
+        t = fminf(t, ta);
     }
     return t;
 }

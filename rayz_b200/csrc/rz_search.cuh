@@ -269,13 +269,15 @@ __device__ __forceinline__ void rz_resolve_masks(const float4 *__restrict__ s_cr
                 const int bit = 31 - __clz((int)m[r]);
                 m[r] &= ~(1u << bit);
                 const int k = list[cn - 1 - bit];           // test number within the chunk
-                const float4 S = s_cr[k];
-                float4 V = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MOVING) V = s_vel[k];
-                float nb, nd;
-                rz_sphere_test(S.x, S.y, S.z, V.x, V.y, V.z, S.w, -rz_half(q.nox, r), -rz_half(q.noy, r), -rz_half(q.noz, r), -rz_half(q.ndx, r),
-                               -rz_half(q.ndy, r), -rz_half(q.ndz, r), -rz_half(q.ntime, r), nb, nd);
-                if (nd < 0.0f) rz_consider(k, nb, nd, self_k[r], t_min, bt[r], bk[r]);
+                if (k != (self_k[r] ^ RZ_SELF_OUT)) {       // not the sphere the ray has just left outward (one candidate of ~3 per ray)
+                    const float4 S = s_cr[k];
+                    float4 V = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MOVING) V = s_vel[k];
+                    float nb, nd;
+                    rz_sphere_test(S.x, S.y, S.z, V.x, V.y, V.z, S.w, -rz_half(q.nox, r), -rz_half(q.noy, r), -rz_half(q.noz, r), -rz_half(q.ndx, r),
+                                   -rz_half(q.ndy, r), -rz_half(q.ndz, r), -rz_half(q.ntime, r), nb, nd);
+                    if (nd < 0.0f) rz_consider(k, nb, nd, self_k[r], t_min, bt[r], bk[r]);
+                }
             }
             any |= m[r];
         }
