@@ -267,7 +267,8 @@ typedef struct RzTuning {
     int32_t sah_leaf;         /* host SAH builder: max spheres per leaf, 1..8 (default 4); applies at the next upload   */
     double sah_node_cost;     /* host SAH builder: cost of a node visit relative to a sphere test (default 0.5)         */
     uint32_t unit_entries;    /* sorted-stage kernel: queue entries per work unit (upper bound; small stages use
-                               * fewer), 64..2048, multiple of 64 (default 1024)                                        */
+                               * fewer), 64..2048, multiple of 64 (default 512: 4 bytes of shared memory per entry and
+                               * warp; 1024 costs a resident CTA)                                                       */
     uint32_t debug_queue_cap; /* tests: pretend the queues hold only this many entries (0 = off) -> RZ_ERR_INTERNAL     */
     uint32_t debug_stack_cap; /* tests: pretend the K3 traversal stack holds only this many entries (0 = off)           */
     int32_t key_sectors;      /* sort key direction field: 0 = octant, 1 = 45-degree sector in the plane of the sphere

@@ -536,7 +536,7 @@ static RzTuning default_tuning() {
     t.bvh_descend_min = 24;
     t.sah_leaf = 4;
     t.sah_node_cost = 0.5;
-    t.unit_entries = 1024;
+    t.unit_entries = 512;
     t.key_sectors = -1;
     return t;
 }

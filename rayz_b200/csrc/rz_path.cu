@@ -43,9 +43,9 @@
 #endif
 #define RZ_PRIMARY_BOUNDS __launch_bounds__(128, RZ_PRIMARY_MINB)
 
-// per-warp scratch of the sorted-stage kernel: tab[16] u32 | one row of the per-group sphere lists | entry order u16[ue]
+// per-warp scratch of the sorted-stage kernel: tab[16] u32 | one row of the per-group sphere lists | entry order u32[ue]
 __host__ __device__ inline uint32_t rz_second_warp_bytes(uint32_t n_pad, uint32_t ue) {
-    return (16u * 4u + rz_bin_row_bytes(n_pad) + 2u * ue + 15u) & ~15u;
+    return (16u * 4u + rz_bin_row_bytes(n_pad) + 4u * ue + 15u) & ~15u;
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -489,7 +489,7 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
     unsigned short *row = reinterpret_cast<unsigned short *>(tab + 16);   // end_s[16] end_m[16]: spheres of classes <= c
     unsigned short *ls = row + 32;
     unsigned short *lm = ls + a.set.n_static_pad;
-    unsigned short *order = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(row) + a.bin_row);
+    uint32_t *order = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(row) + a.bin_row);   // queue entry indices in class order
 
     const float4 *s_vel = rz_stage_scene_cv(a.set, s_cr, &s_bar);
 
@@ -524,7 +524,13 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         if (lane < 16u) tab[lane] = 0u;
         __syncwarp();
 #pragma unroll 1
-        for (uint32_t i = lane; i < ne; i += 32u) atomicAdd(&tab[(uint32_t)ukeys[i] & 15u], 1u);
+        for (uint32_t i0 = 0; i0 < ne; i0 += 128u) {   // four keys in flight per lane: the loop is pure load latency otherwise
+            uint32_t kc[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const uint32_t i = i0 + 32u * (uint32_t)j + lane; kc[j] = i < ne ? ((uint32_t)ukeys[i] & 15u) : 16u; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (kc[j] < 16u) atomicAdd(&tab[kc[j]], 1u);
+        }
         __syncwarp();
         {   // exclusive prefix over the 16 classes -> running cursors
             const uint32_t cnt = lane < 16u ? tab[lane] : 0u;
@@ -534,18 +540,28 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
             if (lane < 16u) tab[lane] = inc - cnt;
         }
         __syncwarp();
-        // order[slot] = position in the unit.  Lanes with the same class take consecutive slots.
+        // order[slot] = queue entry (read here, coalesced, so that the batches below go from shared memory straight to the
+        // entry).  Lanes with the same class take consecutive slots.
 #pragma unroll 1
-        for (uint32_t i0 = 0; i0 < ne; i0 += 32u) {
-            const uint32_t i = i0 + lane;
-            const uint32_t c = i < ne ? ((uint32_t)ukeys[i] & 15u) : 16u + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, c);
-            const int leader = __ffs((int)peers) - 1;
-            uint32_t base = 0u;
-            if ((int)lane == leader && c < 16u) { base = tab[c]; tab[c] = base + (uint32_t)__popc(peers); }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (c < 16u) order[base + (uint32_t)__popc(peers & lt_mask)] = (unsigned short)i;
-            __syncwarp();
+        for (uint32_t i0 = 0; i0 < ne; i0 += 128u) {
+            uint32_t kc[4], ke[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t i = i0 + 32u * (uint32_t)j + lane;
+                kc[j] = i < ne ? ((uint32_t)ukeys[i] & 15u) : 16u + lane;
+                ke[j] = i < ne ? __ldcs(a.q_in_idx + e0 + i) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t c = kc[j];
+                const unsigned peers = __match_any_sync(0xffffffffu, c);
+                const int leader = __ffs((int)peers) - 1;
+                uint32_t base = 0u;
+                if ((int)lane == leader && c < 16u) { base = tab[c]; tab[c] = base + (uint32_t)__popc(peers); }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (c < 16u) order[base + (uint32_t)__popc(peers & lt_mask)] = ke[j];
+                __syncwarp();
+            }
         }
         // now tab[c] = end of class c in `order`
 
@@ -564,7 +580,7 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
                 for (int r = 0; r < 2; r++) {
                     const uint32_t j = b0 + lane + 32u * (uint32_t)r;
                     L[r].live = j < ne;
-                    e[r] = a.q_in + (size_t)(L[r].live ? a.q_in_idx[e0 + order[j]] : 0u) * 4u;
+                    e[r] = a.q_in + (size_t)(L[r].live ? order[j] : 0u) * 4u;
                 }
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
