@@ -248,7 +248,6 @@ __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRa
                 if (res == RZ_END_DEPTH) C.depth++;
             }
             Q.cont = res == RZ_CONT;
-            if (Q.cont && a.q_out_keys) Q.key = rz_sort_key(a, Q.ray);
         }
 #ifndef RZ_SHADE_UNROLL
         if (trip == 0) rz_swap_lane_rays(L[0], L[1]);   // ONE exchange per loop: the slots stay swapped afterwards, and nothing below cares which is which
@@ -260,11 +259,15 @@ __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRa
     if (n0 + n1 == 0u) return;
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(a.q_out_count, n0 + n1);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    unsigned e = base + (unsigned)__popc(m0 & lt_mask);
+    unsigned e = (unsigned)__popc(m0 & lt_mask);
 #pragma unroll 1
     for (int trip = 0; trip < 2; trip++) {
-        const RzLaneRay &Q = L[0];
+        RzLaneRay &Q = L[0];
+        // the sort key is computed HERE, between the reservation and the first use of its result: ~100 instructions that hide
+        // the round trip of the atomic
+        if (Q.cont && a.q_out_keys) Q.key = rz_sort_key(a, Q.ray);
+        if (trip == 0) base = __shfl_sync(0xffffffffu, base, 0);
+        e += base;
         if (Q.cont) {
             if (e < a.queue_cap) {
                 float4 *q = a.q_out + (size_t)e * 4u;
@@ -278,7 +281,7 @@ __device__ __forceinline__ void rz_shade_and_push2(const RzPathArgs &a, RzLaneRa
             }
         }
         if (trip == 0) L[0] = L[1];   // the first ray is stored: only the second one still matters
-        e = base + n0 + (unsigned)__popc(m1 & lt_mask);
+        e = n0 + (unsigned)__popc(m1 & lt_mask);
     }
 }
 
