@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(128, 6) rz_bvh_stage_kernel(const RzPathArgs a
                 const uint32_t i = b * 32u + lane;
                 live = i < ne;
                 if (live) {
-                    const float4 *e = a.q_in + (size_t)a.q_in_idx[e0 + i] * 4u;
+                    const float4 *e = a.q_in + (size_t)(a.q_in_idx[e0 + i] & RZ_IDX_MASK) * 4u;
                     const float4 qa = __ldcs(e), qb = __ldcs(e + 1), qc = __ldcs(e + 2), qd = __ldcs(e + 3);
                     ray.o = f3(qa.x, qa.y, qa.z); ray.time = qa.w;
                     ray.d = f3(qb.x, qb.y, qb.z); ray.self_k = __float_as_int(qb.w);

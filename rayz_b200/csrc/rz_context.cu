@@ -141,7 +141,7 @@ struct Dev {
     DBuf<unsigned long long> accum;
     // staged K1, one set per side (passes alternate between two streams): q1 = after the camera segment, q2 = after the second
     DBuf<float4> q1[2], q2[2];
-    DBuf<unsigned short> keys[2], keys_sorted[2];
+    DBuf<unsigned short> keys[2];
     DBuf<uint32_t> idx_sorted[2];
     DBuf<unsigned int> bins[2];       // rz_sort.cu: per-key counts / cursors of the side's sort (RZ_BIN_* layout)
     DBuf<unsigned char> bin_lists;    // per sort group: the reachable sphere pairs in reach-class order (rz_bin_lists_kernel)
@@ -495,7 +495,7 @@ extern "C" void rayz_cuda_destroy(RzContext *ctx) {
         D.m_rec.release(); D.m_kind.release(); D.m_tex.release(); D.m_method.release(); D.t_kind.release(); D.t_even.release(); D.t_odd.release();
         D.m_fuzz.release(); D.m_ior.release(); D.t_color.release(); D.t_inv_scale.release();
         D.accum.release(); D.counter.release(); D.errword.release();
-        for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release(); D.bins[sd].release(); }
+        for (int sd = 0; sd < 2; sd++) { D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.idx_sorted[sd].release(); D.bins[sd].release(); }
         D.bin_lists.release();
         D.stats.release(); D.out_linear.release(); D.out_rgb8.release(); D.loc_linear.release(); D.loc_rgb8.release();
         D.ids.release(); D.sink.release();
@@ -828,7 +828,7 @@ static int alloc_queues(Dev &D, const QueuePlan &q) {
     for (int sd = 0; sd < q.n_sides; sd++) {
         if ((rc = D.q1[sd].alloc((size_t)q.cap * 4u))) return rc;
         if (q.second_stage) {
-            if ((rc = D.q2[sd].alloc((size_t)q.cap * 4u)) || (rc = D.keys[sd].alloc((size_t)q.cap)) || (rc = D.keys_sorted[sd].alloc((size_t)q.cap)) ||
+            if ((rc = D.q2[sd].alloc((size_t)q.cap * 4u)) || (rc = D.keys[sd].alloc((size_t)q.cap)) ||
                 (rc = D.idx_sorted[sd].alloc((size_t)q.cap)) || (rc = D.bins[sd].alloc(rz_bin_scratch_bytes() / sizeof(unsigned int))))
                 return rc;
         }
@@ -846,7 +846,7 @@ static int plan_and_alloc_queues(const RzTuning &tun, Dev &D, QueuePlan &qp, uin
         if (rc != RZ_ERR_OOM || qlog <= 22 || qp.cap < (1ull << qlog)) return rc;   // done, a real error, or nothing left to shrink
         cudaGetLastError();
         for (int sd = 0; sd < 2; sd++) {
-            D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.keys_sorted[sd].release(); D.idx_sorted[sd].release();
+            D.q1[sd].release(); D.q2[sd].release(); D.keys[sd].release(); D.idx_sorted[sd].release();
         }
     }
 }
@@ -1105,12 +1105,12 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                         for (int stg = 0; stg < n_second; stg++) {
                             const bool more = stg + 1 < n_second;
                             // group the entries by key (rz_sort.cu: count / scan / scatter, sized on the device from the live count)
-                            RZ_CUDA(rz_bin_sort(D.keys[side].p, ca, a.queue_cap, D.bins[side].p, D.keys_sorted[side].p, D.idx_sorted[side].p, a.unit_entries, ue_div, D.sms, st));
+                            RZ_CUDA(rz_bin_sort(D.keys[side].p, ca, a.queue_cap, D.bins[side].p, nullptr, D.idx_sorted[side].p, a.unit_entries, ue_div, D.sms, st));
                             RZ_CUDA(cudaEventRecord(D.stage_ev[2 * ((size_t)pass * n_second + stg)], st));
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(cb, 0, sizeof(unsigned int), st));           // recycled output counter
                             if (stg > 0) RZ_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned int), st));      // the stage's unit counter
                             RzPathArgs a2 = a;
-                            a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p; a2.q_in_keys = D.keys_sorted[side].p; a2.q_in_bins = D.bins[side].p;
+                            a2.q_in = qa; a2.q_in_count = ca; a2.q_in_idx = D.idx_sorted[side].p; a2.q_in_bins = D.bins[side].p;
                             a2.q_out = qb; a2.q_out_count = cb; a2.q_out_keys = more ? D.keys[side].p : nullptr; a2.unit_counter = ctr + 1;
                             a2.stats = D.stats.p + 1;
                             if (bvh_family) RZ_CUDA(rz_launch_bvh_stage(&a2, (int)p->collect_stats, D.sms, st));

@@ -128,8 +128,7 @@ struct RzPathArgs {
     //   K1b (megakern.): q_in -> every later segment, paths regenerated in place
     const float4 *q_in;
     const unsigned int *q_in_count;   // entries in q_in (device counter written by the producing kernel)
-    const uint32_t *q_in_idx;         // K1c: entry indices in key order
-    const unsigned short *q_in_keys;  // K1c: the keys in the same order (the sort's key output)
+    const uint32_t *q_in_idx;         // K1c: entry indices in key order, reach class in the top four bits (RZ_IDX_*)
     const unsigned int *q_in_bins;    // K1c: the sort's scratch words: group ends | units before each group | unit size (RZ_BIN_*)
     unsigned char *bin_lists;         // K1c: per group (cell, direction), the sphere pairs ordered by the smallest reach class that
     uint32_t bin_row;                 //      gets to them (rz_bin_lists_kernel; rows of bin_row bytes, layout: rz_bin_row_bytes)
@@ -266,6 +265,10 @@ struct RzRay {
 // One row of the per-group sphere lists: u16 end_s[16] | u16 end_m[16] | u16 ls[n_static_pad] | u16 lm[n_pad - n_static_pad] —
 // set positions of the stationary / moving spheres in class order; end_x[c] = spheres of classes <= c.
 RZ_HD uint32_t rz_bin_row_bytes(uint32_t n_pad) { return (64u + 2u * n_pad + 15u) & ~15u; }
+
+// The sort's output word per slot: queue entry index, with the key's reach class in the top four bits
+#define RZ_IDX_MASK 0x0fffffffu
+#define RZ_IDX_CLASS_SHIFT 28
 
 // rz_sort.cu's scratch words (one set per side): bins | unit_first | ue
 #define RZ_SORT_BINS 4096

@@ -517,7 +517,7 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         }
         const uint32_t g0 = bin ? bin_end[bin - 1u] : 0u;                          // after the scatter: bins[b] = end of group b
         const uint32_t e0 = g0 + (u - unit_first[bin]) * ue, ne = min(ue, bin_end[bin] - e0);
-        const unsigned short *ukeys = a.q_in_keys + e0;
+        const uint32_t *uidx = a.q_in_idx + e0;   // entry index | class << 28
         {   // the group's row -> shared memory (16-byte pieces; the table stays in L2)
             const uint4 *src = reinterpret_cast<const uint4 *>(a.bin_lists + (size_t)bin * a.bin_row);
             uint4 *dst = reinterpret_cast<uint4 *>(row);
@@ -530,7 +530,7 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         for (uint32_t i0 = 0; i0 < ne; i0 += 128u) {   // four keys in flight per lane: the loop is pure load latency otherwise
             uint32_t kc[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { const uint32_t i = i0 + 32u * (uint32_t)j + lane; kc[j] = i < ne ? ((uint32_t)ukeys[i] & 15u) : 16u; }
+            for (int j = 0; j < 4; j++) { const uint32_t i = i0 + 32u * (uint32_t)j + lane; kc[j] = i < ne ? (uidx[i] >> RZ_IDX_CLASS_SHIFT) : 16u; }
 #pragma unroll
             for (int j = 0; j < 4; j++) if (kc[j] < 16u) atomicAdd(&tab[kc[j]], 1u);
         }
@@ -547,22 +547,18 @@ __global__ void RZ_SECOND_BOUNDS rz_second_kernel(const RzPathArgs a) {
         // entry).  Lanes with the same class take consecutive slots.
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < ne; i0 += 128u) {
-            uint32_t kc[4], ke[4];
+            uint32_t ke[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const uint32_t i = i0 + 32u * (uint32_t)j + lane; ke[j] = i < ne ? uidx[i] : 0xffffffffu; }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t i = i0 + 32u * (uint32_t)j + lane;
-                kc[j] = i < ne ? ((uint32_t)ukeys[i] & 15u) : 16u + lane;
-                ke[j] = i < ne ? __ldcs(a.q_in_idx + e0 + i) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t c = kc[j];
+                const uint32_t c = ke[j] != 0xffffffffu ? (ke[j] >> RZ_IDX_CLASS_SHIFT) : 16u + lane;
                 const unsigned peers = __match_any_sync(0xffffffffu, c);
                 const int leader = __ffs((int)peers) - 1;
                 uint32_t base = 0u;
                 if ((int)lane == leader && c < 16u) { base = tab[c]; tab[c] = base + (uint32_t)__popc(peers); }
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (c < 16u) order[base + (uint32_t)__popc(peers & lt_mask)] = ke[j];
+                if (c < 16u) order[base + (uint32_t)__popc(peers & lt_mask)] = ke[j] & RZ_IDX_MASK;
                 __syncwarp();
             }
         }

@@ -12,8 +12,8 @@
 //   rz_bin_scan_kernel     bins -> exclusive prefix = first slot of each group                                (16 KB)
 //   rz_bin_scatter_kernel  per tile of 4096 keys: shared-memory histogram gives every key its rank inside (tile, bin); one
 //                          global atomicAdd per occupied bin reserves the tile's slots in the group's range; then
-//                          idx_out[slot] = entry index, keys_out[slot] = key                         (reads 2 B, writes 6 B / entry)
-// ~10 B of traffic per entry, no temporary buffers, no global atomic per entry (measured in round 1: +7 ms — the popular
+//                          idx_out[slot] = entry index | reach class << 28                          (reads 2 B, writes 4 B / entry)
+// ~8 B of traffic per entry, no temporary buffers, no global atomic per entry (measured in round 1: +7 ms — the popular
 // keys serialise).  The scattered 2- and 4-byte stores land on <= 4096 slowly advancing frontiers that stay in the 126 MB L2
 // until their sectors are full.  Every kernel takes the live entry count from device memory: no host round trip, no
 // conditional graph, no 0xffff padding keys.
@@ -40,8 +40,8 @@ struct RzBinArgs {
     const unsigned int *count;       // live entries (device counter of the producing kernel)
     uint32_t cap;                    // slots of the buffers (the count is clamped to it)
     unsigned int *bins;              // [4096] counts -> (after the scan) next free slot of each group
-    unsigned short *keys_out;        // [n] keys in slot order
-    uint32_t *idx_out;               // [n] entry index in slot order
+    unsigned short *keys_out;        // [n] keys in slot order (null in production: tests only)
+    uint32_t *idx_out;               // [n] entry index in slot order | reach class << 28 (RZ_IDX_* in rz_device.cuh)
 };
 
 __global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_count_kernel(const RzBinArgs a) {
@@ -146,8 +146,10 @@ __global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_scatter_kernel(const Rz
             if (key[j] != 0xffffffffu) {
                 const uint32_t pos = sh[key[j] >> RZ_BIN_SHIFT] + rank[j];
                 if (pos < a.cap) {   // always true: the ranges partition [0, n)
-                    a.idx_out[pos] = i0 + (uint32_t)j * RZ_BIN_THREADS;
-                    a.keys_out[pos] = (unsigned short)key[j];
+                    // entry index (< 2^28: RzTuning::queue_log2 <= 28) with the key's reach class in the top four bits: the
+                    // consumer needs nothing else of the key, and a second scattered 2-byte store per entry is the expensive kind
+                    a.idx_out[pos] = (i0 + (uint32_t)j * RZ_BIN_THREADS) | ((key[j] & 15u) << 28);
+                    if (a.keys_out) a.keys_out[pos] = (unsigned short)key[j];   // tests only
                 }
             }
         }
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(RZ_BIN_THREADS) rz_bin_scatter_kernel(const Rz
 
 extern "C" size_t rz_bin_scratch_bytes(void) { return (size_t)RZ_BIN_SCRATCH_WORDS * sizeof(unsigned int); }
 
-// keys_in[0, *count) -> idx_out / keys_out: entry indices and keys grouped by ascending (key >> 4).  bins: rz_bin_scratch_bytes()
+// keys_in[0, *count) -> idx_out (/ keys_out when not null): entry indices (+ class bits) and keys grouped by ascending (key >> 4).  bins: rz_bin_scratch_bytes()
 // (layout above).  ue_max, ue_div: work-unit size of the consumer and 16 x its grid size.
 extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned int *count, uint32_t cap, unsigned int *bins,
                                    unsigned short *keys_out, uint32_t *idx_out, uint32_t ue_max, uint32_t ue_div, int sm_count, cudaStream_t stream) {

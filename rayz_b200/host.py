@@ -261,7 +261,8 @@ class Backend:
         abi.check(self.lib.rayz_cuda_set_tuning(self._h, C.byref(t)))
 
     def debug_sort_keys(self, keys: np.ndarray):
-        """Test hook: the staged K1's key sort (rz_sort.cu) on caller-supplied 16-bit keys -> (keys in slot order, entry index in slot order)."""
+        """Test hook: the staged K1's key sort (rz_sort.cu) on caller-supplied 16-bit keys -> (keys in slot order, output word in slot order:
+        entry index | reach class << 28)."""
         keys = np.ascontiguousarray(keys, dtype=np.uint16)
         ko = np.empty_like(keys)
         io = np.empty(keys.shape, dtype=np.uint32)

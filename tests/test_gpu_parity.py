@@ -585,8 +585,9 @@ def test_staged_megakernel_many_small_passes(be, scene42):
                                     (3_000_017, "uniform"), (3_000_017, "few")])
 def test_key_sort_groups_every_entry_by_key(be, n, kind):
     """rz_sort.cu directly (test hook): the entries come out grouped by ascending (key >> 4) — origin cell + octant; the low 4
-    bits, the reach class, are ordered per work unit by the consumer — the indices are a permutation of the entries, and each
-    index names an entry with the key stored beside it.  Order inside a group is free (the consumer does not depend on it)."""
+    bits, the reach class, are ordered per work unit by the consumer — the indices (low 28 bits of the output word) are a
+    permutation of the entries, the word's top four bits repeat the entry's reach class, and each index names an entry with the
+    key stored beside it.  Order inside a group is free (the consumer does not depend on it)."""
     rng = np.random.default_rng(n)
     if kind == "uniform":
         keys = rng.integers(0, 65536, n, dtype=np.uint16)
@@ -598,10 +599,12 @@ def test_key_sort_groups_every_entry_by_key(be, n, kind):
         keys = np.sort(rng.integers(0, 3000, n, dtype=np.uint16))
     else:
         keys = np.array([777], dtype=np.uint16)
-    ko, io = be.debug_sort_keys(keys)
+    ko, word = be.debug_sort_keys(keys)
+    io = word & 0x0FFFFFFF
     assert np.array_equal(ko >> 4, np.sort(keys >> 4))
     assert np.array_equal(np.sort(io), np.arange(n, dtype=np.uint32))
     assert np.array_equal(keys[io], ko)
+    assert np.array_equal(word >> 28, ko & 15)
 
 
 @pytest.mark.gpu
