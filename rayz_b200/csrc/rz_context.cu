@@ -810,11 +810,12 @@ static QueuePlan plan_queues(const RzTuning &tun, uint32_t n_units, uint32_t chu
     // 3 -> 5426 / 4025, 4 -> 5510 / 4130, 5 -> 5549 / 4214, 6 -> 5547 / 4264; brute-force tail: 3 -> 3634 / 2635, 4 -> 3648 /
     // 2797, 5 -> 3576 / 2899.  BVH family: sorted stages measured as a loss (config-2 scene 3521 -> 3277 -> 3065 Mpaths/s for
     // 0, 1, 2 stages; 100k spheres 1582 -> 1427 -> 1327): batches without in-loop ray replacement cost more than coherence
-    // gains; only the coherent camera stage is kept.
+    // gains; only the coherent camera stage is kept.  Round 2, after the sorted-stage kernel got ~25 % cheaper per segment
+    // (profiles/r02_experiments.md, exp23; BVH tail): 4 -> 6439 / 4648, 5 -> 6575 / 4806, 6 -> 6667 / 4920, 7 -> 6713 / 4941.
     // NOTE: none of this depends on the job's size, shard count or on how much memory the device had left, so that a sharded
     // render runs exactly the kernels — and therefore computes exactly the pixels — of the full-frame one.
     if (bvh_family) q.n_second = enough_spheres ? tun.bvh_stages : 0;
-    else q.n_second = !enough_spheres ? 0 : tun.second_stages >= 0 ? tun.second_stages : !bvh_tail ? 4 : 5;
+    else q.n_second = !enough_spheres ? 0 : tun.second_stages >= 0 ? tun.second_stages : !bvh_tail ? 4 : 7;
     q.cap = std::max<uint64_t>(q.unit_paths, std::min<uint64_t>((uint64_t)n_units * q.unit_paths, 1ull << qlog));
     q.second_stage = q.n_second > 0;
     q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
