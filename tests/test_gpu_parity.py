@@ -555,6 +555,12 @@ def test_staged_megakernel_equals_single_kernel_bitwise_and_stage_stats(scene42,
         be.set_tuning(unit_entries=ue)
         d, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="mega"))
         assert np.array_equal(a, d), ue
+    be.set_tuning(unit_entries=512)
+    for sectors in (0, 1):                          # direction field of the sort key: octants or 45-degree sectors (default: by the box's shape)
+        for stages in (1, 3, 8):                    # and the number of sorted stages: the culls never change a closest hit
+            be.set_tuning(key_sectors=sectors, second_stages=stages)
+            d, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="mega"))
+            assert np.array_equal(a, d), (sectors, stages)
     be.close()
 
 
@@ -647,6 +653,11 @@ def test_staged_cull_is_conservative_on_hostile_scenes(seed):
     be.set_tuning(tail_brute=1)                        # culled lists + brute-force tail: the same FP32 test on fewer spheres
     out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega"))
     assert np.array_equal(ref, out)
+    for sectors in (0, 1):                             # both direction fields of the sort key (the default picks by the box's shape)
+        be.set_tuning(key_sectors=sectors, second_stages=8)
+        out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega"))
+        assert np.array_equal(ref, out), sectors
+    be.set_tuning(key_sectors=-1, second_stages=-1)
     be.set_tuning(tail_brute=0)                        # default: the tail of the paths walks the BVH (see below)
     out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega"))
     assert int((ref != out).any(axis=-1).sum()) <= 3 and float(np.abs(ref - out).mean()) < 1e-4
