@@ -531,9 +531,9 @@ def main():
             in2 = out1 - (in1 - out0) if n_stage else out0                                 # entries the tail kernel starts from
             in2 = max(0.0, in2)
             hbm = [out0 * (E + KEY) + 35 * W * H / world,                                 # primary: append entry + key (+ the frame, once)
-                   in1 * (E + KEY + IDX) + out1 * E + (out1 - in2) * KEY,                 # sorted stages: gather entry through key+index, append
+                   in1 * (E + IDX) + out1 * E + (out1 - in2) * KEY,                       # sorted stages: gather entry through the index word (class bits inside), append entry (+ key)
                    in2 * E,                                                               # tail: read its entries
-                   in1 * (2 * KEY + KEY + IDX)]                                           # sort: keys read twice (count, scatter), key + index written
+                   in1 * (2 * KEY + IDX)]                                                 # sort: keys read twice (count, scatter), index word written
             def stage(name, st, ms, launches, hbm_bytes):
                 # a kernel that walked the BVH counted box tests too: 18 flop per box, 22 per (general) sphere test
                 flop = 0.0
@@ -551,7 +551,7 @@ def main():
                       stage("rz_second_kernel (sorted segments 2.." + str(n_stage + 1) + ", per-unit cull)", stage_stats[1], second_ms, passes_per_step * n_stage, hbm[1]),
                       stage("rz_bvh_kernel<QUEUE> (persistent BVH kernel, later segments)" if stage_stats[2]["node_tests"] else
                             "rz_path_kernel<QUEUE> (persistent brute-force megakernel, later segments)", stage_stats[2], meg_ms, passes_per_step, hbm[2]),
-                      stage("rz_bin_kernel<count> + rz_bin_scan_kernel + rz_bin_kernel<scatter> (key sort between the stages, rz_sort.cu)", None, sort_ms,
+                      stage("rz_bin_count_kernel + rz_bin_scan_kernel + rz_bin_scatter_kernel (key sort between the stages, rz_sort.cu)", None, sort_ms,
                             3 * passes_per_step * n_stage, hbm[3])]
             dom = max(stages[:3], key=lambda x: x["ms_per_step"])
             dom_name, dom_ms, dom_flop, dom_launches, dom_hbm = dom["kernel"], dom["ms_per_step"], dom["flop"], dom["launches_per_step"], dom["hbm_bytes_algorithmic"]

@@ -12,7 +12,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 CMD="python bench.py --steps 2 --warmup 3 --spp 40 --variant mega --no-cpu-baseline --no-e2e --no-variants --no-other-configs"
 $CMD > gpurun_out/${T}_ncu_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rz_second_kernel -s 10 -c 1 -o gpurun_out/${T}_prof_second $CMD > gpurun_out/${T}_ncu_full1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rz_second_kernel -s 7 -c 1 -o gpurun_out/${T}_prof_second $CMD > gpurun_out/${T}_ncu_full1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rz_primary_kernel -s 2 -c 1 -o gpurun_out/${T}_prof_primary $CMD > gpurun_out/${T}_ncu_full2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:rz_bin_(count|scatter)_kernel" -s 20 -c 2 -o gpurun_out/${T}_prof_sort $CMD > gpurun_out/${T}_ncu_full3.log 2>&1
 fi
