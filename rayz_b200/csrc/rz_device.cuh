@@ -533,9 +533,10 @@ inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3
     a.key_sectors = key_mode < 0 ? (flat ? 1u : 0u) : (uint32_t)(key_mode != 0);
 }
 
-// Sort key of a scattered ray: [origin cell 9 bits][direction octant 3 bits][reach class 4 bits] = 16 bits.  Rays with
-// equal keys start in the same cell of the sphere box (the 9 bits are shared out over the axes by extent), head into the same
-// octant and stay inside the sphere box for a similar distance — which is what the sorted-segment kernel's per-unit cull feeds on.
+// Sort key of a scattered ray: [origin cell 9 bits][direction 3 bits][reach class 4 bits] = 16 bits.  Rays with equal keys
+// start in the same cell of the sphere box (the 9 bits are shared out over the axes by extent), head the same way — the same
+// octant, or for a flat sphere box the same 45-degree sector in the plane of its two long axes (rz_key_grid) — and stay
+// inside the sphere box for a similar distance: which is what the sorted-segment kernel's per-group lists feed on.
 RZ_HD uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
     const int nx = (1 << a.sb_cell_bits[0]) - 1, ny = (1 << a.sb_cell_bits[1]) - 1, nz = (1 << a.sb_cell_bits[2]) - 1;
     const int cx = rz_clampi((int)((ray.o.x - a.sb_lo[0]) * a.sb_inv_cell[0]), 0, nx);

@@ -1,17 +1,19 @@
-// rz_path.cu — K1: the brute-force FP32 path tracer for sm_100a, three kernels.
+// rz_path.cu — K1: the brute-force FP32 path tracer for sm_100a, three kernels and a table builder.
 //
 // Replaces the body of Tracer.render's pixel loop and everything under it
 // (reference src/renderer.zig:85-96, bounceRay :103-126, BVH.findHit hit.zig:181-216,
 // Sphere.hitInner geom.zig:38-66, Material.scatter material.zig:167-176).
 //
 //   rz_primary_kernel  (K1a)  camera segments; sphere set culled against each 32-pixel tile's frustum
-//   rz_second_kernel   (K1c)  the next few segments, one per launch, over queue entries sorted by
-//                             (origin cell, octant, reach); sphere set culled from each unit's actual rays
+//   rz_second_kernel   (K1c)  the next few segments, one per launch, over queue entries grouped by (origin cell, direction);
+//                             a work unit's rays share one group and search that group's precomputed sphere list
+//   rz_bin_lists_kernel       those lists: per group, the spheres its rays can reach, ordered by reach class
 //   rz_path_kernel     (K1b)  the whole path loop in one persistent kernel (RZ_VARIANT_MEGA_SINGLE), or (QUEUE) every
 //                             segment after the sorted stages when no host-built BVH is there for the tail
 // The host (rz_context.cu) runs them in passes sized by the HBM queues between them; by default the tail of the paths —
-// what survives the sorted stages — goes to the BVH kernel of rz_bvh_trace.cu instead of K1b.  All use the same packed
-// arithmetic per sphere (rz_search.cuh), the same shading and RNG keys: the image does not depend on the staging.
+// what survives the sorted stages — goes to the BVH kernel of rz_bvh_trace.cu instead of K1b.  All use the same
+// arithmetic per sphere (rz_sphere_test, packed two spheres per instruction in K1b and two rays per instruction in K1a /
+// K1c: rz_search.cuh), the same shading and RNG keys: the image does not depend on the staging.
 //
 // Execution model of rz_path_kernel
 //   * persistent CTAs, grid = SMs x resident CTAs; each WARP pulls work units
@@ -26,8 +28,8 @@
 //   * the whole sphere set is staged once per CTA into shared memory with a 1-D bulk
 //     async copy (cp.async.bulk + mbarrier, SASS UBLKCP) and searched by brute force with
 //     warp-uniform (broadcast) LDS.128 operands and Blackwell packed FP32x2 arithmetic
-//     (FFMA2/FADD2/FMUL2, two spheres per instruction): 11 issue slots per stationary
-//     sphere PAIR and ray, 14 per moving pair (rz_search_brute2);
+//     (FFMA2/FADD2/FMUL2, two spheres per instruction): 12 issue slots per stationary
+//     sphere PAIR and ray, 15 per moving pair (rz_search_brute2);
 //   * large scenes use the BVH kernels of rz_bvh_trace.cu (K3) instead.
 #include <algorithm>
 

@@ -1,9 +1,9 @@
-// rz_sort.cu — groups the staged K1's queue entries by the top 12 bits of their sort key (origin cell + direction octant):
+// rz_sort.cu — groups the staged K1's queue entries by the top 12 bits of their sort key (origin cell + direction field):
 // a one-pass counting sort written for this job.  Round 1 called cub::DeviceRadixSort here (two 8-bit onesweep passes over
 // key + index pairs, ~26 B of HBM traffic per entry, wrapped in a CUDA graph with a SWITCH node because cub wants its item
 // count on the host): 12 % of the render step, and a library kernel on the hot path.
 //
-// What the consumer (rz_second_kernel) needs is weaker than a sort: entries that share (cell, octant) must be contiguous and
+// What the consumer (rz_second_kernel) needs is weaker than a sort: entries that share (cell, direction) must be contiguous and
 // those groups ascending.  The order INSIDE a group is irrelevant — the kernel orders each work unit's entries by the key's
 // low 4 bits (the reach class) itself, in shared memory, and radiance is accumulated in integers, so the image does not
 // depend on which entries share a work unit.  Without the stability a multi-pass radix sort needs, ONE pass over 4096 bins
