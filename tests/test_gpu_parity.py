@@ -673,6 +673,42 @@ def test_staged_cull_is_conservative_on_hostile_scenes(seed):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["all_moving", "all_static_cube", "one_static", "no_ground_flat"])
+def test_staged_kernels_on_oddly_shaped_sphere_sets(kind):
+    """The staged kernels keep stationary and moving spheres in separate parts of shared memory and of every list, and pick
+    the sort key's direction field from the shape of the sphere box: sets with an empty part, a cubic box (octant keys) and a
+    flat one (sector keys), with and without a huge sphere, must give the single brute-force kernel's image bit for bit."""
+    rng = np.random.default_rng(11)
+    pool = rayz_b200.MemPool()
+    mats = [pool.add_diffuse(pool.add_solid((0.7, 0.4, 0.3))), pool.add_metallic(pool.add_solid((0.8, 0.8, 0.8)), 0.2), pool.add_dielectric(1.5)]
+    n = 70
+    for i in range(n):
+        if kind == "all_static_cube":
+            c, v = rng.uniform(-4, 4, 3), (0, 0, 0)
+        elif kind == "all_moving":
+            c, v = rng.uniform(-4, 4, 3) * (1, 0.2, 1), rng.uniform(-0.5, 0.5, 3)
+        elif kind == "one_static":
+            c, v = rng.uniform(-4, 4, 3) * (1, 0.2, 1), ((0, 0, 0) if i == 0 else rng.uniform(-0.5, 0.5, 3))
+        else:
+            c, v = rng.uniform(-5, 5, 3) * (1, 0.1, 1), ((0, 0, 0) if i % 2 else (0, 0.3, 0))
+        pool.add_sphere(c, float(rng.uniform(0.2, 0.5)), mats[i % 3], v)
+    if kind in ("all_static_cube", "one_static"):
+        pool.add_sphere((0, -1005, 0), 1000.0, mats[0], (0, 0, 0) if kind == "all_static_cube" else (0, 0.1, 0))   # a huge sphere (a moving one too)
+    w, h, spp = 192, 108, 8
+    cam = rayz_b200.Camera.init(40.0, 10.0, 0.5, (9, 3, 7), (0, 0, 0), (0, 1, 0), h, w).rz
+    be = Backend((0,))
+    be.upload_scene(pool.arrays())
+    ref, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=4, variant="mega_single"))
+    be.set_tuning(tail_brute=1)
+    for sectors in (-1, 0, 1):
+        be.set_tuning(key_sectors=sectors)
+        out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=4, variant="mega", collect_stats=True))
+        assert be.timing()["sorted_stages"] >= 1 and be.stage_stats(1)["segments"] > 0      # the sorted-stage kernel really ran
+        assert np.array_equal(ref, out), (kind, sectors)
+    be.close()
+
+
+@pytest.mark.gpu
 def test_reserve_then_render_and_auto_policy(scene42):
     """rayz_cuda_reserve pre-allocates the per-render buffers (before or after the scene upload) without changing results;
     RZ_VARIANT_AUTO resolves to the BVH kernel for small jobs and to the staged K1 for large ones (same image)."""
