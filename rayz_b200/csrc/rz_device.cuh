@@ -513,17 +513,6 @@ inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3
         if (!(e3[ax] > 0.f) || !(e3[ax] < 1.0e30f)) e3[ax] = 0.f;
         ext = e3[ax] > ext ? e3[ax] : ext;
     }
-    for (int b = 0; b < cell_bits; b++) {
-        int best = 0;
-        for (int ax = 1; ax < 3; ax++)
-            if (e3[ax] / (float)(1u << bits[ax]) > e3[best] / (float)(1u << bits[best])) best = ax;
-        bits[best]++;
-    }
-    for (int ax = 0; ax < 3; ax++) {
-        a.sb_cell_bits[ax] = bits[ax];
-        a.sb_inv_cell[ax] = e3[ax] > 0.f ? (float)(1u << bits[ax]) / e3[ax] : 0.f;
-    }
-    a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;
     int hax = 0;
     for (int ax = 1; ax < 3; ax++) if (e3[ax] < e3[hax]) hax = ax;
     a.key_u = (uint32_t)((hax + 1) % 3); a.key_w = (uint32_t)((hax + 2) % 3);
@@ -531,6 +520,21 @@ inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3
     const float e_min2 = e3[a.key_u] < e3[a.key_w] ? e3[a.key_u] : e3[a.key_w];
     const bool flat = e_min2 > 0.f && e3[hax] < 0.35f * e_min2;
     a.key_sectors = key_mode < 0 ? (flat ? 1u : 0u) : (uint32_t)(key_mode != 0);
+    // with sector keys every cell bit goes to the two long axes: the cull is a wedge in their plane, and a flat box has
+    // next to no origins in its upper half anyway
+    float w3[3] = {e3[0], e3[1], e3[2]};
+    if (a.key_sectors) w3[hax] = 0.f;
+    for (int b = 0; b < cell_bits; b++) {
+        int best = 0;
+        for (int ax = 1; ax < 3; ax++)
+            if (w3[ax] / (float)(1u << bits[ax]) > w3[best] / (float)(1u << bits[best])) best = ax;
+        bits[best]++;
+    }
+    for (int ax = 0; ax < 3; ax++) {
+        a.sb_cell_bits[ax] = bits[ax];
+        a.sb_inv_cell[ax] = e3[ax] > 0.f ? (float)(1u << bits[ax]) / e3[ax] : 0.f;
+    }
+    a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;
 }
 
 // Sort key of a scattered ray: [origin cell 9 bits][direction 3 bits][reach class 4 bits] = 16 bits.  Rays with equal keys
