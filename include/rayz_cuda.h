@@ -272,7 +272,13 @@ typedef struct RzTuning {
     uint32_t debug_queue_cap; /* tests: pretend the queues hold only this many entries (0 = off) -> RZ_ERR_INTERNAL     */
     uint32_t debug_stack_cap; /* tests: pretend the K3 traversal stack holds only this many entries (0 = off)           */
     int32_t key_sectors;      /* sort key direction field: 0 = octant, 1 = 45-degree sector in the plane of the sphere
-                               * box's two long axes, -1 = sectors when that box is flat (default)                      */
+                               * box's two long axes, 2 = 22.5-degree sector (and one cell bit less), -1 = 45-degree
+                               * sectors when that box is flat, octants otherwise (default)                              */
+    double huge_factor;       /* staged K1: spheres above huge_factor x the median radius (at most max(4, n/32) of them)
+                               * stay outside the box the sort key's cells and reach classes are measured in, and are
+                               * culled by direction only (default 4: the r = 1000 ground and the three r = 1 spheres of
+                               * the reference scenes; 8 keeps the latter inside: +40-60 % sphere tests per sorted
+                               * segment); applies at the next upload                                                    */
 } RzTuning;
 int rayz_cuda_get_tuning(RzContext *ctx, RzTuning *out);
 int rayz_cuda_set_tuning(RzContext *ctx, const RzTuning *tuning);

@@ -538,6 +538,7 @@ static RzTuning default_tuning() {
     t.sah_node_cost = 0.5;
     t.unit_entries = 512;
     t.key_sectors = -1;
+    t.huge_factor = 4.0;
     return t;
 }
 
@@ -557,7 +558,8 @@ extern "C" int rayz_cuda_set_tuning(RzContext *ctx, const RzTuning *t) {
     if (t->cell_bits < 0 || t->cell_bits > 9) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: cell_bits out of [0, 9]");
     if (t->bvh_active_min < 1 || t->bvh_active_min > 32 || t->bvh_descend_min < 1 || t->bvh_descend_min > 32) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: BVH lane thresholds out of [1, 32]");
     if (t->sah_leaf < 1 || t->sah_leaf > 8 || !(t->sah_node_cost >= 0)) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: SAH parameters out of range");
-    if (t->key_sectors < -1 || t->key_sectors > 1) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: key_sectors must be -1, 0 or 1");
+    if (t->key_sectors < -1 || t->key_sectors > 2) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: key_sectors must be -1, 0, 1 or 2");
+    if (!(t->huge_factor >= 1.0)) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: huge_factor must be >= 1");
     if (t->unit_entries < 64 || t->unit_entries > 2048 || (t->unit_entries & 63u)) return rz_fail(RZ_ERR_INVALID_ARG, "tuning: unit_entries must be a multiple of 64 in [64, 2048]");
     ctx->tun = *t;
     return RZ_OK;
@@ -625,11 +627,9 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
         for (int a = 0; a < 3; a++) { ctx->ref_lo[3 * (size_t)i + a] = bx.lo[a]; ctx->ref_hi[3 * (size_t)i + a] = bx.hi[a]; }
     }
 
-    // ---- box of the "non-huge" spheres (staged K1): a ray that has left it can only hit a huge sphere (the r = 1000 ground)
+    // ---- box of the "non-huge" spheres (staged K1): a ray that has left it can only hit a huge sphere (the r = 1000 ground, the three r = 1 spheres: rz_huge_threshold)
     {
-        std::vector<double> rad(sc->sphere_radius, sc->sphere_radius + n);
-        std::nth_element(rad.begin(), rad.begin() + n / 2, rad.end());
-        const double huge = 8.0 * rad[n / 2];
+        const double huge = rz_huge_threshold(sc->sphere_radius, n, ctx->tun.huge_factor);
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         bool any = false;
         for (uint32_t i = 0; i < n; i++) {

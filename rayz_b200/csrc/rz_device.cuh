@@ -18,6 +18,9 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <vector>
+
 #define RZ_HD __host__ __device__ __forceinline__
 // Rare branches of the shading code are kept OUT of line on the device: the staged kernels are 35-45 KB against a 32 KB L1.5
 // instruction cache, and ncu charged up to 3 stall cycles per issued instruction to `no_instruction` (profiles/).
@@ -502,6 +505,24 @@ RZ_HD int rz_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi :
 // the extents allow; reach classes are measured in units of 1/32 of the longest extent.
 RZ_HD float rz_pick3(float x, float y, float z, uint32_t ax) { return ax == 0u ? x : ax == 1u ? y : z; }
 
+// Which spheres stay OUTSIDE the sphere box ("huge": tested by every ray whose direction field can reach them, whatever its
+// reach class): those above 4 x the median radius — in the reference scenes the r = 1000 ground and the three r = 1 spheres,
+// which would otherwise make the box 2.0 high instead of 0.9 and more than double how long an upward ray counts as inside
+// it — but never more than max(4, n / 32) of them, largest first (each costs every list a test).  Returns the largest
+// radius that still belongs INSIDE the box.  Host only.
+inline double rz_huge_threshold(const double *radius, uint32_t n, double factor = 4.0) {
+    if (n == 0u) return 3.0e38;
+    std::vector<double> r(radius, radius + n);
+    std::nth_element(r.begin(), r.begin() + n / 2, r.end());
+    double thr = factor * r[n / 2];
+    const uint32_t cap = n / 32u > 4u ? n / 32u : 4u;
+    if (n > cap) {   // more than `cap` above the threshold: only the cap largest stay outside
+        std::nth_element(r.begin(), r.begin() + (n - 1u - cap), r.end());
+        if (r[n - 1u - cap] > thr) thr = r[n - 1u - cap];
+    }
+    return thr;
+}
+
 // key_mode: 0 = octant direction field, 1 = sectors, -1 = by the shape of the box (sectors when it is flat: the third
 // extent under 0.35 of the other two, so that almost every long ray travels near the plane of the two long axes).
 inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3], int cell_bits, int key_mode = -1) {
@@ -519,7 +540,8 @@ inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3
     if (a.key_u > a.key_w) { const uint32_t t = a.key_u; a.key_u = a.key_w; a.key_w = t; }
     const float e_min2 = e3[a.key_u] < e3[a.key_w] ? e3[a.key_u] : e3[a.key_w];
     const bool flat = e_min2 > 0.f && e3[hax] < 0.35f * e_min2;
-    a.key_sectors = key_mode < 0 ? (flat ? 1u : 0u) : (uint32_t)(key_mode != 0);
+    a.key_sectors = key_mode < 0 ? (flat ? 1u : 0u) : (uint32_t)(key_mode > 2 ? 1 : key_mode);
+    if (a.key_sectors == 2u && cell_bits > 8) cell_bits = 8;   // 16 sectors take a bit of the 12 the groups are made of
     // with sector keys every cell bit goes to the two long axes: the cull is a wedge in their plane, and a flat box has
     // next to no origins in its upper half anyway
     float w3[3] = {e3[0], e3[1], e3[2]};
@@ -537,7 +559,11 @@ inline void rz_key_grid(RzPathArgs &a, const float (&lo)[3], const float (&hi)[3
     a.reach_unit = ext > 0.f ? ext / 32.0f : 1.0f;
 }
 
-// Sort key of a scattered ray: [origin cell 9 bits][direction 3 bits][reach class 4 bits] = 16 bits.  Rays with equal keys
+#define RZ_TAN_22_5 0.41421356f
+// bits of the key's direction field: 3 (octants, eight 45-degree sectors) or 4 (sixteen 22.5-degree sectors)
+RZ_HD uint32_t rz_key_dir_bits(const RzPathArgs &a) { return a.key_sectors == 2u ? 4u : 3u; }
+
+// Sort key of a scattered ray: [origin cell 9 bits][direction 3 bits][reach class 4 bits] = 16 bits (or [8][4][4]).  Rays with equal keys
 // start in the same cell of the sphere box (the 9 bits are shared out over the axes by extent), head the same way — the same
 // octant, or for a flat sphere box the same 45-degree sector in the plane of its two long axes (rz_key_grid) — and stay
 // inside the sphere box for a similar distance: which is what the sorted-segment kernel's per-group lists feed on.
@@ -550,7 +576,10 @@ RZ_HD uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
     uint32_t oct;
     if (a.key_sectors) {   // sector of the direction's projection on the (u, w) plane: signs of d_u, d_w and which of the two is larger
         const float du = rz_pick3(ray.d.x, ray.d.y, ray.d.z, a.key_u), dw = rz_pick3(ray.d.x, ray.d.y, ray.d.z, a.key_w);
-        oct = (du < 0.f ? 1u : 0u) | (dw < 0.f ? 2u : 0u) | (fabsf(du) < fabsf(dw) ? 4u : 0u);
+        const float mu = fabsf(du), mw = fabsf(dw);
+        oct = (du < 0.f ? 1u : 0u) | (dw < 0.f ? 2u : 0u) | (mu < mw ? 4u : 0u);
+        // 16 sectors: + which half of the 45-degree wedge, the one next to the larger component's axis (bit set) or the diagonal's
+        if (a.key_sectors == 2u) oct |= fminf(mu, mw) < RZ_TAN_22_5 * fmaxf(mu, mw) ? 8u : 0u;
     } else {
         oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
     }
@@ -562,7 +591,7 @@ RZ_HD uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
     const float l2 = log2f(fmaxf(te / a.reach_unit, 0.25f));
 #endif
     const int reach = rz_clampi((int)(2.0f * l2 + 4.0f), 0, 15);
-    return (cell << 7) | (oct << 4) | (uint32_t)reach;
+    return (((cell << rz_key_dir_bits(a)) | oct) << 4) | (uint32_t)reach;
 }
 
 // What a key says about its rays, conservatively: the origin lies in [lo, hi] (the key's cell, open-ended for the outermost
@@ -571,8 +600,9 @@ RZ_HD uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
 RZ_HD void rz_key_bounds(const RzPathArgs &a, uint32_t key, float (&lo)[3], float (&hi)[3], uint32_t &oct, float &T) {
     const int nbx = (int)a.sb_cell_bits[0], nby = (int)a.sb_cell_bits[1], nbz = (int)a.sb_cell_bits[2];
     const int reach = (int)(key & 15u);
-    oct = (key >> 4) & 7u;
-    const uint32_t cell = key >> 7;
+    const uint32_t db = rz_key_dir_bits(a);
+    oct = (key >> 4) & ((1u << db) - 1u);
+    const uint32_t cell = key >> (4u + db);
     const int c3[3] = {(int)(cell >> (nby + nbz)), (int)((cell >> nbz) & ((1u << nby) - 1u)), (int)(cell & ((1u << nbz) - 1u))};
     const int n3[3] = {(1 << nbx) - 1, (1 << nby) - 1, (1 << nbz) - 1};
 #pragma unroll
@@ -690,17 +720,26 @@ RZ_HD void rz_unit_bounds_finish(RzUnitBounds &U) { U.T = fminf(U.T, 1.0e30f) * 
 // Sector s = (d_u < 0, d_w < 0, |d_u| < |d_w|) is the wedge {n1.d >= 0, n2.d >= 0}: n1 along one axis, n2 a diagonal.  A point
 // p is reached from an origin o with such a direction only if n.(p - o) >= 0 for both; for a sphere, >= -|n| re; over the box,
 // n.o is replaced by its minimum (each half-plane with its own best corner: conservative).
-RZ_HD bool rz_sector_reaches(float lo_u, float hi_u, float lo_w, float hi_w, uint32_t s, float cu, float cw, float re) {
+RZ_HD bool rz_sector_reaches(float lo_u, float hi_u, float lo_w, float hi_w, uint32_t s, float cu, float cw, float cu1, float cw1, float re,
+                             bool sixteen = false) {
     const float au = (s & 1u) ? -1.f : 1.f, aw = (s & 2u) ? -1.f : 1.f;   // |d_u| = au d_u, |d_w| = aw d_w
     const bool w_larger = (s & 4u) != 0u;
-    // n1: the smaller component is still >= 0 in its own sign; n2: larger minus smaller >= 0
-    const float n1u = w_larger ? au : 0.f, n1w = w_larger ? 0.f : aw;
-    const float n2u = w_larger ? -au : au, n2w = w_larger ? aw : -aw;
+    // In folded coordinates (M = the larger component's axis, m = the smaller's, both made positive) the sector is the wedge of
+    // polar angles [p_lo, p_hi]: 8 sectors: [0, 45]; 16 sectors: [0, 22.5] (bit 3 set) or [22.5, 45].  Inward unit normals:
+    // n_lo = (-sin p_lo, cos p_lo), n_hi = (sin p_hi, -cos p_hi).
+    const bool near_axis = !sixteen || (s & 8u) != 0u, near_diag = !sixteen || (s & 8u) == 0u;
+    const float loM = near_axis ? 0.f : -0.38268343f, lom = near_axis ? 1.f : 0.92387953f;
+    const float hiM = near_diag ? 0.70710678f : 0.38268343f, him = near_diag ? -0.70710678f : -0.92387953f;
+    // back to (u, w): M is w when w is the larger one; each axis with its sign
+    const float n1u = (w_larger ? lom : loM) * au, n1w = (w_larger ? loM : lom) * aw;
+    const float n2u = (w_larger ? him : hiM) * au, n2w = (w_larger ? hiM : him) * aw;
     auto box_min = [&](float nu, float nw) {   // min over the box of n.o (the box may be open-ended: +-3e38 times 0 stays 0)
         return (nu > 0.f ? lo_u : hi_u) * nu + (nw > 0.f ? lo_w : hi_w) * nw;
     };
-    if (n1u * cu + n1w * cw + re < box_min(n1u, n1w)) return false;
-    if (n2u * cu + n2w * cw + 1.4143f * re < box_min(n2u, n2w)) return false;
+    const float rem = re * 1.0001f + 1e-5f;   // the normals are unit length to FP32 rounding
+    // (cu, cw) -> (cu1, cw1): the segment the sphere's centre travels; a half-plane drops it only if it drops both ends
+    if (fmaxf(n1u * cu + n1w * cw, n1u * cu1 + n1w * cw1) + rem < box_min(n1u, n1w)) return false;
+    if (fmaxf(n2u * cu + n2w * cw, n2u * cu1 + n2w * cw1) + rem < box_min(n2u, n2w)) return false;
     return true;
 }
 
@@ -709,33 +748,39 @@ RZ_HD bool rz_unit_reachable(const RzUnitBounds &U, const RzPathArgs &a, float c
     d2 = 0.f; re = 0.f;
     if (!(w < 0.f)) return false;                                  // padding entry
     const float r = sqrtf(-w);
-    if (r > a.huge_radius) return true;                            // outside the sphere box: never culled
-    re = (r + 0.5f * sqrtf(vx * vx + vy * vy + vz * vz)) * 1.02f + 0.02f;   // swept over the shutter + margin
-    const float c[3] = {fmaf(0.5f, vx, cx), fmaf(0.5f, vy, cy), fmaf(0.5f, vz, cz)};
+    const bool huge = r > a.huge_radius;                           // outside the sphere box: never culled by distance, only by direction
+    re = r * 1.02f + 0.02f;                                        // radius + margin
+    // over the shutter interval the centre travels the segment c0 -> c0 + v (geom.zig:40, time in [0, 1)): every test below is
+    // made against the whole segment — its bounding interval per axis, its better end per half-plane — not against a sphere
+    // around the midpoint blown up by half the travel (the reference scenes' movers only bounce vertically: r + 0.25 -> r)
+    const float c0[3] = {cx, cy, cz}, c1[3] = {cx + vx, cy + vy, cz + vz};
     if (a.key_sectors) {
         bool any = false;
         const float lo_u = rz_pick3(U.lo[0], U.lo[1], U.lo[2], a.key_u), hi_u = rz_pick3(U.hi[0], U.hi[1], U.hi[2], a.key_u);
         const float lo_w = rz_pick3(U.lo[0], U.lo[1], U.lo[2], a.key_w), hi_w = rz_pick3(U.hi[0], U.hi[1], U.hi[2], a.key_w);
-        const float cu = rz_pick3(c[0], c[1], c[2], a.key_u), cw = rz_pick3(c[0], c[1], c[2], a.key_w);
+        const float cu0 = rz_pick3(c0[0], c0[1], c0[2], a.key_u), cw0 = rz_pick3(c0[0], c0[1], c0[2], a.key_w);
+        const float cu1 = rz_pick3(c1[0], c1[1], c1[2], a.key_u), cw1 = rz_pick3(c1[0], c1[1], c1[2], a.key_w);
         for (unsigned m = U.sectors; m && !any; m &= m - 1u) {
 #ifdef __CUDA_ARCH__
             const uint32_t s = (uint32_t)__ffs((int)m) - 1u;
 #else
             uint32_t s = 0; while (!((m >> s) & 1u)) s++;
 #endif
-            any = rz_sector_reaches(lo_u, hi_u, lo_w, hi_w, s, cu, cw, re);
+            any = rz_sector_reaches(lo_u, hi_u, lo_w, hi_w, s, cu0, cw0, cu1, cw1, re, a.key_sectors == 2u);
         }
         if (!any) return false;
     }
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
+        const float smin = fminf(c0[ax], c1[ax]), smax = fmaxf(c0[ax], c1[ax]);
         if (!a.key_sectors) {
-            if (((U.all_pos >> ax) & 1u) && c[ax] + re < U.lo[ax]) return false;   // every ray moves up this axis: sphere is behind
-            if (((U.all_neg >> ax) & 1u) && c[ax] - re > U.hi[ax]) return false;
+            if (((U.all_pos >> ax) & 1u) && smax + re < U.lo[ax]) return false;   // every ray moves up this axis: sphere is behind
+            if (((U.all_neg >> ax) & 1u) && smin - re > U.hi[ax]) return false;
         }
-        const float dd = fmaxf(0.f, fmaxf(U.lo[ax] - c[ax], c[ax] - U.hi[ax]));
+        const float dd = fmaxf(0.f, fmaxf(U.lo[ax] - smax, smin - U.hi[ax]));
         d2 = fmaf(dd, dd, d2);
     }
+    if (huge) { d2 = 0.f; re = 0.f; }                              // a ray can meet it after it has left the sphere box: every reach class
     return true;
 }
 

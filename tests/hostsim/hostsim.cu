@@ -5,6 +5,8 @@
 // restatement of the kernel's search/shade loop (rz_path.cu), so the FP32 algorithm's statistics
 // can be compared with the f64 oracle in a container without a GPU.  The GPU tests compare the
 // real kernels with the oracle; this only de-risks them.
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -127,6 +129,10 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
 // direction field of the sort key in the checks below: -1 = chosen by the shape of the box (the product's default), 0 = octants, 1 = sectors
 static int g_key_mode = -1;
 extern "C" void hostsim_set_key_mode(int m) { g_key_mode = m; }
+static double g_huge_factor = 4.0;   // experiment knob: spheres above this multiple of the median radius stay outside the sphere box
+extern "C" void hostsim_set_huge_factor(double f) { g_huge_factor = f; }
+static int g_cell_bits = 9;
+extern "C" void hostsim_set_cell_bits(int b) { g_cell_bits = b; }
 
 extern "C" uint64_t hostsim_key_check(const float *lo, const float *hi, int cell_bits, uint64_t n_rays, uint64_t seed, uint64_t *counts) {
     RzPathArgs a;
@@ -164,6 +170,9 @@ extern "C" uint64_t hostsim_key_check(const float *lo, const float *hi, int cell
         if (a.key_sectors) {   // sector of the projection on the (key_u, key_w) plane
             const float du = d[a.key_u], dw = d[a.key_w];
             ok = ok && ((oct & 1u) != 0u) == (du < 0.f) && ((oct & 2u) != 0u) == (dw < 0.f) && ((oct & 4u) != 0u) == (fabsf(du) < fabsf(dw));
+            if (a.key_sectors == 2u)   // sixteen sectors: + the half of the 45-degree wedge (next to the axis <=> bit 3)
+                ok = ok && ((oct & 8u) != 0u) == (fminf(fabsf(du), fabsf(dw)) < RZ_TAN_22_5 * fmaxf(fabsf(du), fabsf(dw)));
+            else ok = ok && oct < 8u;
         }
         ok = ok && rz_box_exit(a, ray) <= T;
         if (!ok) bad++;
@@ -368,14 +377,12 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
         f2 += pc * pc; lu += cam->defocus_u[ax] * cam->defocus_u[ax]; lv += cam->defocus_v[ax] * cam->defocus_v[ax];
     }
     const float focus_dist = (float)std::sqrt(f2), lens_radius = cam->defocus ? (float)(std::sqrt(std::max(lu, lv)) * 1.001) : 0.f;
-    // the sphere box as the library sets it up at upload (rz_context.cu: box of the spheres up to 8 x the median radius,
+    // the sphere box as the library sets it up at upload (rz_context.cu: box of the spheres rz_huge_threshold leaves inside,
     // motion over the shutter included, padded by 0.1 % + 1e-3)
     RzPathArgs a;
     memset(&a, 0, sizeof a);
     {
-        std::vector<double> rad(sc->sphere_radius, sc->sphere_radius + n);
-        std::nth_element(rad.begin(), rad.begin() + n / 2, rad.end());
-        const double huge = 8.0 * rad[n / 2];
+        const double huge = rz_huge_threshold(sc->sphere_radius, n, g_huge_factor);
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         bool any = false;
         for (uint32_t i = 0; i < n; i++) {
@@ -391,7 +398,7 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
             const double pad = any ? 1e-3 * (hi[ax] - lo[ax]) + 1e-3 : 0.0;
             l3[ax] = any ? (float)(lo[ax] - pad) : -3.0e38f; h3[ax] = any ? (float)(hi[ax] + pad) : 3.0e38f;
         }
-        rz_key_grid(a, l3, h3, 9, g_key_mode);
+        rz_key_grid(a, l3, h3, g_cell_bits, g_key_mode);
         a.huge_radius = (float)huge;
     }
     const float t_min = 1e-4f;
@@ -479,6 +486,7 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
             search(queue[i].ray, nullptr, bt, bk);
             search(queue[i].ray, &list, bt2, bk2);
             out[4]++; out[5] += list.size();
+            if (getenv("HS_DBG")) { static uint64_t hr[16], hl[16]; hr[c]++; hl[c] += list.size(); if (i + 1 == queue.size()) for (int q = 0; q < 16; q++) fprintf(stderr, "class %d rays %llu avg list %.1f T %.2f\n", q, (unsigned long long)hr[q], hr[q] ? (double)hl[q] / hr[q] : 0.0, rz_class_T(a, q)); }
             if (bk != bk2 || bt != bt2) out[3]++;
         }
         e0 = e1;
