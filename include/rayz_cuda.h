@@ -274,6 +274,8 @@ typedef struct RzTuning {
     int32_t key_sectors;      /* sort key direction field: 0 = octant, 1 = 45-degree sector in the plane of the sphere
                                * box's two long axes, 2 = 22.5-degree sector (and one cell bit less), -1 = 45-degree
                                * sectors when that box is flat, octants otherwise (default)                              */
+    int32_t lbvh_leaf;        /* device LBVH builder: subtrees of at most this many spheres become one leaf, 1..8
+                               * (default 1: 4 makes 6.5 sphere tests per segment instead of 1.5 for 6 fewer box tests); applies at the next upload                                */
     double huge_factor;       /* staged K1: spheres above huge_factor x the median radius (at most max(4, n/32) of them)
                                * stay outside the box the sort key's cells and reach classes are measured in, and are
                                * culled by direction only (default 4: the r = 1000 ground and the three r = 1 spheres of

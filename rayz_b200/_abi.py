@@ -70,7 +70,7 @@ class RzTuning(C.Structure):
                 ("bvh_staged", C.c_int32), ("cell_bits", C.c_int32), ("bvh_active_min", C.c_int32), ("bvh_descend_min", C.c_int32),
                 ("sah_leaf", C.c_int32), ("sah_node_cost", C.c_double), ("unit_entries", C.c_uint32), ("debug_queue_cap", C.c_uint32),
                 ("debug_stack_cap", C.c_uint32),
-                ("key_sectors", C.c_int32), ("huge_factor", C.c_double)]
+                ("key_sectors", C.c_int32), ("lbvh_leaf", C.c_int32), ("huge_factor", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -26,7 +26,6 @@
 
 namespace {
 
-constexpr int RZ_LBVH_LEAF = 4;
 
 struct LbvhTemp {
     float *lo, *hi;                 // [n][3] padded f32 sphere boxes
@@ -179,7 +178,7 @@ __global__ void __launch_bounds__(256) lbvh_refit(uint32_t n, LbvhTemp t) {
 
 // 6a. K3 node records.  One thread per internal node; nodes inside a collapsed subtree are never
 // referenced and are left as empty records.
-__global__ void __launch_bounds__(256) lbvh_emit(uint32_t n, LbvhTemp t, RzBvhNode *out) {
+__global__ void __launch_bounds__(256) lbvh_emit(uint32_t n, LbvhTemp t, RzBvhNode *out, int leaf_max) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = (int)n;
     if (i >= max(N - 1, 1)) return;
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(256) lbvh_emit(uint32_t n, LbvhTemp t, RzBvhNo
         } else {
             plo = t.nlo + 3 * ch[c]; phi = t.nhi + 3 * ch[c];
             const int count = t.last[ch[c]] - t.first[ch[c]] + 1;
-            if (count <= RZ_LBVH_LEAF) { child = ~t.first[ch[c]]; cnt = (uint32_t)count; }   // collapse the subtree
+            if (count <= leaf_max) { child = ~t.first[ch[c]]; cnt = (uint32_t)count; }   // collapse the subtree
             else { child = ch[c]; cnt = 0u; }
         }
         nd.child[c] = child; nd.cnt[c] = cnt;
@@ -260,7 +259,7 @@ extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n) {
 // Builds the K3 tree on `stream`.  Inputs: the scene's f64 spheres in caller order (c64: xyz + radius,
 // v64: velocity), material index per sphere.  Outputs: `nodes` (max(n-1,1) records, root = 0) and the
 // leaf-ordered sphere set arrays (n entries each).  Everything is device memory.
-extern "C" cudaError_t rz_lbvh_build(uint32_t n, const double4 *c64, const double4 *v64, const uint32_t *mat, void *scratch,
+extern "C" cudaError_t rz_lbvh_build(uint32_t n, int leaf_max, const double4 *c64, const double4 *v64, const uint32_t *mat, void *scratch,
                                      size_t scratch_bytes, RzBvhNode *nodes, float4 *o_cr, float4 *o_vel, double4 *o_c64,
                                      double4 *o_v64, uint32_t *o_mat, int32_t *o_orig, cudaStream_t stream) {
     if (n == 0) return cudaErrorInvalidValue;
@@ -290,7 +289,7 @@ extern "C" cudaError_t rz_lbvh_build(uint32_t n, const double4 *c64, const doubl
         lbvh_hierarchy<<<grid, 256, 0, stream>>>(n, t);
         lbvh_refit<<<grid, 256, 0, stream>>>(n, t);
     }
-    lbvh_emit<<<grid, 256, 0, stream>>>(n, t, nodes);
+    lbvh_emit<<<grid, 256, 0, stream>>>(n, t, nodes, leaf_max);
     lbvh_gather_set<<<grid, 256, 0, stream>>>(n, t.vals_out, c64, v64, mat, o_cr, o_vel, o_c64, o_v64, o_mat, o_orig);
     return cudaGetLastError();
 }

@@ -127,9 +127,23 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
             const float4 q1 = __ldg(nodes + cur * 4 + 1);  // loy0 loy1 hiy0 hiy1
             const float4 q2 = __ldg(nodes + cur * 4 + 2);  // loz0 loz1 hiz0 hiz1
             q3 = __ldg(reinterpret_cast<const int4 *>(nodes + cur * 4 + 3));
+#ifdef RZ_BVH_SCALAR_SLABS   // experiment (scripts/exp_build.sh): the 24 scalar FADD / FMUL of round 2's first form
             const float ax0 = (q0.x - ox) * ix, bx0 = (q0.z - ox) * ix, ax1 = (q0.y - ox) * ix, bx1 = (q0.w - ox) * ix;
             const float ay0 = (q1.x - oy) * iy, by0 = (q1.z - oy) * iy, ay1 = (q1.y - oy) * iy, by1 = (q1.w - oy) * iy;
             const float az0 = (q2.x - oz) * iz, bz0 = (q2.z - oz) * iz, az1 = (q2.y - oz) * iz, bz1 = (q2.w - oz) * iz;
+#else
+            // the two children's planes sit side by side in the node, so (plane - o) * inv_d is one FADD2 + one FMUL2 for both
+            // (packed FP32x2, the ray's operands as broadcasts): 12 issue slots instead of 24, the same IEEE operations per half
+            float ax0, ax1, bx0, bx1, ay0, ay1, by0, by1, az0, az1, bz0, bz1;
+            const rz_p2 nox = rz_pack(-ox, -ox), noy = rz_pack(-oy, -oy), noz = rz_pack(-oz, -oz);
+            const rz_p2 ix2 = rz_pack(ix, ix), iy2 = rz_pack(iy, iy), iz2 = rz_pack(iz, iz);
+            rz_unpack(rz_mul2(rz_add2(rz_pack(q0.x, q0.y), nox), ix2), ax0, ax1);
+            rz_unpack(rz_mul2(rz_add2(rz_pack(q0.z, q0.w), nox), ix2), bx0, bx1);
+            rz_unpack(rz_mul2(rz_add2(rz_pack(q1.x, q1.y), noy), iy2), ay0, ay1);
+            rz_unpack(rz_mul2(rz_add2(rz_pack(q1.z, q1.w), noy), iy2), by0, by1);
+            rz_unpack(rz_mul2(rz_add2(rz_pack(q2.x, q2.y), noz), iz2), az0, az1);
+            rz_unpack(rz_mul2(rz_add2(rz_pack(q2.z, q2.w), noz), iz2), bz0, bz1);
+#endif
             tn0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), a.t_min));
             tf0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), bt));
             tn1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), a.t_min));

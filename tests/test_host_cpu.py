@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.RzStats) == 80
     assert C.sizeof(abi.RzTiming) == 56
     assert C.sizeof(abi.RzConfig) == 40
-    assert C.sizeof(abi.RzTuning) == 88
+    assert C.sizeof(abi.RzTuning) == 96
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
