@@ -694,15 +694,22 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
         tc[i] = make_float4((float)sc->tex_color[3 * i], (float)sc->tex_color[3 * i + 1], (float)sc->tex_color[3 * i + 2], 0.f);
         ts[i] = sc->tex_kind[i] == RZ_TEX_CHECKER ? 1.0 / sc->tex_scale[i] : 0.0;
     }
-    // the same facts per material in one 32-byte record (RzMaterials::rec)
-    std::vector<float4> mrec(2 * (size_t)nm);
+    // the same facts per material in one 64-byte record (RzMaterials::rec)
+    std::vector<float4> mrec(4 * (size_t)nm);
     for (uint32_t i = 0; i < nm; i++) {
-        const bool solid = mk[i] != RZ_MAT_DIELECTRIC && nt > 0 && tk[mt[i]] != RZ_TEX_CHECKER;
-        const uint32_t bits = (mk[i] & 3u) | ((mm[i] & 3u) << 2) | (solid ? 16u : 0u);
+        const bool textured = mk[i] != RZ_MAT_DIELECTRIC && nt > 0;
+        const bool solid = textured && tk[mt[i]] != RZ_TEX_CHECKER;
+        const bool checker2 = textured && !solid && tk[te[mt[i]]] != RZ_TEX_CHECKER && tk[to[mt[i]]] != RZ_TEX_CHECKER;
+        const uint32_t bits = (mk[i] & 3u) | ((mm[i] & 3u) << 2) | (solid ? 16u : 0u) | (checker2 ? 32u : 0u);
         float fb, ft;
         memcpy(&fb, &bits, 4); memcpy(&ft, &mt[i], 4);
-        mrec[2 * (size_t)i] = make_float4(fb, mf[i], mi[i], ft);
-        mrec[2 * (size_t)i + 1] = solid ? tc[mt[i]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        mrec[4 * (size_t)i] = make_float4(fb, mf[i], mi[i], ft);
+        mrec[4 * (size_t)i + 1] = solid ? tc[mt[i]] : checker2 ? tc[te[mt[i]]] : zero;
+        mrec[4 * (size_t)i + 2] = checker2 ? tc[to[mt[i]]] : zero;
+        float4 sc4 = zero;
+        if (checker2) { const double inv = ts[mt[i]]; uint32_t w[2]; memcpy(w, &inv, 8); memcpy(&sc4.x, &w[0], 4); memcpy(&sc4.y, &w[1], 4); }   // low, high word
+        mrec[4 * (size_t)i + 3] = sc4;
     }
 
     DeviceGuard guard;

@@ -57,17 +57,22 @@ struct RzMaterials {
     const float *ior;
     const uint32_t *tex;
     const uint32_t *method; // RZ_DIFFUSE_* (material.zig:67-71)
-    const float4 *rec;      // [2 * n_materials] the same facts flattened for the shading step, one 32-byte record per material:
-                            //   (bits: kind | method << 2 | root-texture-is-solid << 4, fuzz, ior, bits: texture) (r, g, b, 0 of a solid root)
-                            // one load after set.mat[k] instead of a chain of four dependent ones (kind -> tex -> tex kind -> colour)
+    const float4 *rec;      // [4 * n_materials] the same facts flattened for the shading step, one 64-byte record per material:
+                            //   (bits: kind | method << 2 | root-texture-is-solid << 4 | root-is-a-checker-of-two-solids << 5, fuzz, ior, bits: texture)
+                            //   (r, g, b, 0 of a solid root, or of the checker's even texture) (r, g, b, 0 of its odd texture)
+                            //   (1 / scale of the checker as the two halves of an f64, 0, 0)
+                            // one load after set.mat[k] instead of a chain of dependent ones (kind -> tex -> tex kind -> 1/scale ->
+                            // even / odd -> its kind -> colour: the checker ground of the reference scenes is half of all hits)
 };
 
 // What the shading step needs to know about a material (decoded RzMaterials::rec).
 struct RzMatRec {
     uint32_t kind, method, tex;
     bool solid;      // the root texture is a solid colour: `color` is the attenuation, no texture walk
+    bool checker2;   // the root texture is a checker of two solid colours: `color` (even) / `odd` by the lattice cell, no walk either
     float fuzz, ior;
-    float3 color;
+    float3 color, odd;
+    double inv_scale;
 };
 
 struct RzTextures {
@@ -360,6 +365,12 @@ RZ_COLD float3 rz_texture(const RzTextures T, uint32_t tex, double px, double py
     return f3(c.x, c.y, c.z);
 }
 
+// The one-level case of rz_texture with its operands already in registers (RzMaterials::rec): the same f64 lattice test.
+RZ_HD float3 rz_checker2(const RzMatRec &M, double px, double py, double pz) {
+    const long long ix = (long long)floor(px * M.inv_scale), iy = (long long)floor(py * M.inv_scale), iz = (long long)floor(pz * M.inv_scale);
+    return ((ix + iy + iz) & 1ll) == 0 ? M.color : M.odd;
+}
+
 struct RzHit {
     double px, py, pz;  // hit point, f64
     float3 p;           // same, rounded: next ray origin
@@ -435,7 +446,7 @@ RZ_HD bool rz_scatter(const RzMatRec &M, const RzTextures &T, const RzHit &h, in
         const float3 s = rz_uniform_sphere(u.x, u.y);
         if (method == 2u) nd = dot3(s, h.n) > 0.0f ? s : s * -1.0f;
         else nd = rz_diffuse_other(method, s, h.n, u.z);
-        att = M.solid ? M.color : rz_texture(T, M.tex, h.px, h.py, h.pz);
+        att = M.solid ? M.color : M.checker2 ? rz_checker2(M, h.px, h.py, h.pz) : rz_texture(T, M.tex, h.px, h.py, h.pz);
     } else if (kind == 1u) {
         // MetallicMaterial.scatter (:108-131): unit mirror direction + min(fuzz,1) * unit vector
         const float dn = dot3(ray.d, h.n);
@@ -444,7 +455,7 @@ RZ_HD bool rz_scatter(const RzMatRec &M, const RzTextures &T, const RzHit &h, in
         if (fuzz > 0.0f) r = r + rz_uniform_sphere(u.x, u.y) * fminf(fuzz, 1.0f);
         if (!(dot3(r, h.n) > 0.0f)) return false;
         nd = normalize3(r);
-        att = M.solid ? M.color : rz_texture(T, M.tex, h.px, h.py, h.pz);
+        att = M.solid ? M.color : M.checker2 ? rz_checker2(M, h.px, h.py, h.pz) : rz_texture(T, M.tex, h.px, h.py, h.pz);
     } else {
         // DielectricMaterial.scatter (:137-159).  The reference leaves cos/sin/sqrt unclamped
         // (NaN on rounding, mapped to 0 at output by V3.sqrt); FP32 clamps to stay NaN-free.

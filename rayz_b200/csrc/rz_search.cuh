@@ -368,12 +368,21 @@ __device__ __forceinline__ int rz_shade_segment(const RzPathArgs &a, RzRay &ray,
     const int k = bk & ~RZ_FAR_BIT;
     const RzHit h = rz_refine_hit(a.set, ray, k, (bk & RZ_FAR_BIT) != 0);
     const uint32_t mat = a.set.mat[k];
-    const float4 m0 = __ldg(a.mats.rec + 2u * mat), m1 = __ldg(a.mats.rec + 2u * mat + 1u);
+    const float4 *mr = a.mats.rec + 4u * mat;
+#ifdef RZ_NO_CHECKER2   // experiment (scripts/exp_build.sh): checkers always through the texture walk
+    const float4 m0 = __ldg(mr), m1 = __ldg(mr + 1), m2 = make_float4(0.f, 0.f, 0.f, 0.f), m3 = m2;
+#else
+    const float4 m0 = __ldg(mr), m1 = __ldg(mr + 1), m2 = __ldg(mr + 2), m3 = __ldg(mr + 3);
+#endif
     const uint32_t mbits = __float_as_uint(m0.x);
     RzMatRec M;
-    M.kind = mbits & 3u; M.method = (mbits >> 2) & 3u; M.solid = ((mbits >> 4) & 1u) != 0u;
+    M.kind = mbits & 3u; M.method = (mbits >> 2) & 3u; M.solid = ((mbits >> 4) & 1u) != 0u; M.checker2 = ((mbits >> 5) & 1u) != 0u;
+#ifdef RZ_NO_CHECKER2
+    M.checker2 = false;
+#endif
     M.fuzz = m0.y; M.ior = m0.z; M.tex = __float_as_uint(m0.w);
-    M.color = f3(m1.x, m1.y, m1.z);
+    M.color = f3(m1.x, m1.y, m1.z); M.odd = f3(m2.x, m2.y, m2.z);
+    M.inv_scale = __hiloint2double(__float_as_int(m3.y), __float_as_int(m3.x));
     const uint32_t kind = M.kind;
     kind_out = kind < 3u ? kind : 0u;
     seg++;

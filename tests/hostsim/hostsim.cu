@@ -100,7 +100,7 @@ extern "C" int hostsim_render(const RzScene *sc, const RzCamera *cam, uint32_t w
                         // decoded from the SoA arrays, and always through the texture walk: an independent check of the
                         // flattened per-material records (and their solid-colour shortcut) the device kernels read
                         RzMatRec R;
-                        R.kind = kind; R.method = M.method[mat]; R.tex = M.tex[mat]; R.solid = false;
+                        R.kind = kind; R.method = M.method[mat]; R.tex = M.tex[mat]; R.solid = false; R.checker2 = false;
                         R.fuzz = M.fuzz[mat]; R.ior = M.ior[mat]; R.color = f3(0.f, 0.f, 0.f);
                         if (!rz_scatter(R, T, hit, k, u, ray, att)) { ct[8]++; break; }
                         thr = thr * att;
@@ -456,7 +456,7 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
                 const RzHit hit = rz_refine_hit(S, ray, k, (bk & RZ_FAR_BIT) != 0);
                 const uint32_t mat = smat[k];
                 RzMatRec R;
-                R.kind = mk[mat]; R.method = mm[mat]; R.tex = mt[mat]; R.solid = false; R.fuzz = mf[mat]; R.ior = mi[mat]; R.color = f3(0.f, 0.f, 0.f);
+                R.kind = mk[mat]; R.method = mm[mat]; R.tex = mt[mat]; R.solid = false; R.checker2 = false; R.fuzz = mf[mat]; R.ior = mi[mat]; R.color = f3(0.f, 0.f, 0.f);
                 const uint4 rb = rz_philox(gpix, s, 1u, 0u, k0, k1);
                 const float4 u = make_float4(rz_u01(rb.x >> 8), rz_u01(rb.y >> 8), rz_u01(rb.z >> 8), rz_u01(rb.w >> 8));
                 float3 att;
