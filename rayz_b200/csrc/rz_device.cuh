@@ -585,16 +585,20 @@ RZ_HD uint32_t rz_sort_key(const RzPathArgs &a, const RzRay &ray) {
     const int cz = rz_clampi((int)((ray.o.z - a.sb_lo[2]) * a.sb_inv_cell[2]), 0, nz);
     const uint32_t cell = (uint32_t)(((cx << a.sb_cell_bits[1]) | cy) << a.sb_cell_bits[2]) | (uint32_t)cz;   // 9 bits
     uint32_t oct;
+    float te = rz_box_exit(a, ray);
     if (a.key_sectors) {   // sector of the direction's projection on the (u, w) plane: signs of d_u, d_w and which of the two is larger
         const float du = rz_pick3(ray.d.x, ray.d.y, ray.d.z, a.key_u), dw = rz_pick3(ray.d.x, ray.d.y, ray.d.z, a.key_w);
         const float mu = fabsf(du), mw = fabsf(dw);
+        // sector keys put every cell bit into the (u, w) plane and cull in that plane only (the third axis of the box of origins is
+        // open-ended): what counts is how far the ray gets IN THE PLANE before it leaves the sphere box — a ray that climbs
+        // steeply out of a flat box leaves it after a short stretch of ground
+        te *= fminf(sqrtf(fmaf(du, du, dw * dw)) * 1.0001f, 1.0f);
         oct = (du < 0.f ? 1u : 0u) | (dw < 0.f ? 2u : 0u) | (mu < mw ? 4u : 0u);
         // 16 sectors: + which half of the 45-degree wedge, the one next to the larger component's axis (bit set) or the diagonal's
         if (a.key_sectors == 2u) oct |= fminf(mu, mw) < RZ_TAN_22_5 * fmaxf(mu, mw) ? 8u : 0u;
     } else {
         oct = (ray.d.x < 0.f ? 1u : 0u) | (ray.d.y < 0.f ? 2u : 0u) | (ray.d.z < 0.f ? 4u : 0u);
     }
-    const float te = rz_box_exit(a, ray);
     // 16 reach classes, two per octave of te / reach_unit from 1/4 up
 #ifdef __CUDA_ARCH__
     const float l2 = __log2f(fmaxf(te / a.reach_unit, 0.25f));

@@ -174,7 +174,11 @@ extern "C" uint64_t hostsim_key_check(const float *lo, const float *hi, int cell
                 ok = ok && ((oct & 8u) != 0u) == (fminf(fabsf(du), fabsf(dw)) < RZ_TAN_22_5 * fmaxf(fabsf(du), fabsf(dw)));
             else ok = ok && oct < 8u;
         }
-        ok = ok && rz_box_exit(a, ray) <= T;
+        {   // the reach the key stands for: the stay inside the sphere box — with sector keys, its projection on the (u, w) plane
+            float reach = rz_box_exit(a, ray);
+            if (a.key_sectors) reach *= sqrtf(d[a.key_u] * d[a.key_u] + d[a.key_w] * d[a.key_w]);
+            ok = ok && reach <= T;
+        }
         if (!ok) bad++;
         counts[key & 15u]++;
         if (!seen[key]) { seen[key] = 1; counts[16]++; }
