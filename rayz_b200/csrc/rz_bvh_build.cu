@@ -15,9 +15,11 @@
 //                  common-prefix length; ties between equal codes are broken by the index
 //   5. refit     : bottom-up, one thread per leaf, an atomic arrival counter per internal node; the
 //                  second arriver unions the two child boxes and continues upwards
-//   6. emit      : RzBvhNode records of K3 (both child boxes in the parent); subtrees of <= LEAF
-//                  spheres collapse into one leaf (their leaves are contiguous in sorted order);
-//                  the sphere set is gathered into leaf order
+//   6. emit      : RzBvhNode records of K3 (both child boxes in the parent); subtrees of <= leaf_max
+//                  spheres collapse into one leaf (their leaves are contiguous in sorted order) —
+//                  leaf_max = RzTuning::lbvh_leaf, default 1: a 4-sphere leaf saves 6 of 53 box tests
+//                  per ray segment and costs 5 more sphere tests, each divergent (config 4: 1735 vs
+//                  1872 Mpaths/s); the sphere set is gathered into leaf order
 //
 // One launch sequence on the caller's stream, no host round trip except the sort's temp-size query.
 #include <cub/device/device_radix_sort.cuh>

@@ -146,10 +146,11 @@ struct RzPathArgs {
     uint32_t queue_cap;               // entries each queue buffer holds
     uint32_t unit_base;               // first work unit of this pass (primary kernel)
     float focus_dist, lens_radius;    // thin-lens numbers for the tile-frustum cull (derived from the camera)
-    float sb_lo[3], sb_hi[3];         // box around every sphere that is not "huge" (radius <= huge_radius), motion included
+    float sb_lo[3], sb_hi[3];         // box around every sphere that is not "huge" (radius <= huge_radius: rz_huge_threshold), motion included
     float sb_inv_cell[3];             // cells per unit length along each axis (sort-key cells)
     uint32_t sb_cell_bits[3];         // 9 key bits shared out so that cells come out as cubic as possible
-    float huge_radius;                // spheres above this radius are never culled (the r = 1000 ground)
+    float huge_radius;                // spheres above this radius lie outside the sphere box: culled by direction only, never by reach
+                                      // (the r = 1000 ground, the three r = 1 spheres)
     uint32_t key_sectors;             // direction field of the sort key: 0 = octant (sign of d on each axis), 1 = one of eight 45-degree
                                       // sectors in the plane of the sphere box's two longest axes (key_u, key_w): flat scenes
     uint32_t key_u, key_w;            // those two axes
@@ -729,8 +730,9 @@ RZ_HD void rz_unit_bounds_add_key(RzUnitBounds &U, const RzPathArgs &a, uint32_t
 RZ_HD void rz_unit_bounds_finish(RzUnitBounds &U) { U.T = fminf(U.T, 1.0e30f) * 1.001f; }
 
 // Can a ray of the unit reach the sphere at all, whatever its reach?  false: behind the cell box on an axis along which every
-// ray of the unit moves the other way (or a padding entry).  d2 = squared distance from the box of the origins to the sphere's
-// centre (at mid shutter), re = its radius swept over the shutter interval, with margins.  Huge spheres: d2 = 0.
+// ray of the unit moves the other way, or outside the unit's direction wedge (or a padding entry).  d2 = squared distance from
+// the box of the origins to the segment the sphere's centre travels over the shutter interval (per axis: to its bounding
+// interval), re = its radius with margins.  Huge spheres: d2 = 0, re = 0 (every reach class).
 // Sector keys: can a ray whose direction projects into sector s of the (u, w) plane get from the box of origins to the sphere?
 // Sector s = (d_u < 0, d_w < 0, |d_u| < |d_w|) is the wedge {n1.d >= 0, n2.d >= 0}: n1 along one axis, n2 a diagonal.  A point
 // p is reached from an origin o with such a direction only if n.(p - o) >= 0 for both; for a sphere, >= -|n| re; over the box,

@@ -10,8 +10,10 @@ $CMD > gpurun_out/${T}_plain.log 2>&1 || exit 1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_launches.log 2>&1
 for K in "${@:-rz_second_kernel rz_primary_kernel}"; do
   for k in $K; do
-    S=2; [ "$k" == "rz_second_kernel" ] && S=${SKIP_SECOND:-10}
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $S -c 1 -o gpurun_out/${T}_prof_${k} $CMD > gpurun_out/${T}_full_${k}.log 2>&1
+    # the production instances only (template argument STATS = false; the bench's stats render launches the <true> ones);
+    # rz_second_kernel: seven launches per 40-spp render, so 14 skipped = the FIRST sorted stage of the third render
+    S=2; [ "$k" == "rz_second_kernel" ] && S=${SKIP_SECOND:-14}
+    timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:${k}<\(bool\)0" -s $S -c 1 -o gpurun_out/${T}_prof_${k} $CMD > gpurun_out/${T}_full_${k}.log 2>&1
   done
 done
 ls -la gpurun_out | grep ${T}_
