@@ -455,6 +455,17 @@ def test_device_lbvh_matches_host_sah_and_bruteforce_bitwise(scene42):
     ids_h = host.primary_ids(cam, w, h, use_bvh=True)
     ids_d = dev.primary_ids(cam, w, h, use_bvh=True)
     assert np.array_equal(ids_h, ids_d)
+    # the LBVH's leaf size (RzTuning::lbvh_leaf; default 1) shapes the tree, never the image: fewer, fuller leaves test more spheres
+    tests_per_leaf = {}
+    for leaf in (1, 4, 8):
+        dl = Backend((0,), bvh_build="device")
+        dl.set_tuning(lbvh_leaf=leaf)                            # (applies at the upload)
+        dl.upload_scene(scene42)
+        c, c8, _ = dl.render(cam, Backend.params(w, h, spp, 50, seed=9, variant="bvh", collect_stats=True))
+        assert np.array_equal(a, c) and np.array_equal(a8, c8), leaf
+        tests_per_leaf[leaf] = dl.stats()["sphere_tests"]
+        dl.close()
+    assert tests_per_leaf[1] < tests_per_leaf[4] < tests_per_leaf[8]
 
 
 @pytest.mark.gpu
@@ -556,7 +567,7 @@ def test_staged_megakernel_equals_single_kernel_bitwise_and_stage_stats(scene42,
         d, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="mega"))
         assert np.array_equal(a, d), ue
     be.set_tuning(unit_entries=512)
-    for sectors in (0, 1):                          # direction field of the sort key: octants or 45-degree sectors (default: by the box's shape)
+    for sectors in (0, 1, 2):                       # direction field of the sort key: octants, 45- or 22.5-degree sectors (default: by the box's shape)
         for stages in (1, 3, 8):                    # and the number of sorted stages: the culls never change a closest hit
             be.set_tuning(key_sectors=sectors, second_stages=stages)
             d, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="mega"))
@@ -653,7 +664,7 @@ def test_staged_cull_is_conservative_on_hostile_scenes(seed):
     be.set_tuning(tail_brute=1)                        # culled lists + brute-force tail: the same FP32 test on fewer spheres
     out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega"))
     assert np.array_equal(ref, out)
-    for sectors in (0, 1):                             # both direction fields of the sort key (the default picks by the box's shape)
+    for sectors in (0, 1, 2):                          # every direction field of the sort key (the default picks by the box's shape)
         be.set_tuning(key_sectors=sectors, second_stages=8)
         out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=seed, variant="mega"))
         assert np.array_equal(ref, out), sectors
@@ -700,12 +711,24 @@ def test_staged_kernels_on_oddly_shaped_sphere_sets(kind):
     be.upload_scene(pool.arrays())
     ref, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=4, variant="mega_single"))
     be.set_tuning(tail_brute=1)
-    for sectors in (-1, 0, 1):
+    for sectors in (-1, 0, 1, 2):
         be.set_tuning(key_sectors=sectors)
         out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=4, variant="mega", collect_stats=True))
         assert be.timing()["sorted_stages"] >= 1 and be.stage_stats(1)["segments"] > 0      # the sorted-stage kernel really ran
         assert np.array_equal(ref, out), (kind, sectors)
     be.close()
+    # which spheres stay outside the sphere box ("huge": culled by direction only) is a tuning matter, never an image matter:
+    # the largest few (factor 1: everything above the median radius, capped at max(4, n / 32)), the default, none but the ground
+    for factor in (1.0, 2.0, 1.0e6):
+        be = Backend((0,))
+        be.set_tuning(huge_factor=factor, tail_brute=1)    # (applies at the upload)
+        be.upload_scene(pool.arrays())
+        for sectors in (0, 1):
+            be.set_tuning(key_sectors=sectors)
+            out, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=4, variant="mega", collect_stats=True))
+            assert be.stage_stats(1)["segments"] > 0
+            assert np.array_equal(ref, out), (kind, factor, sectors)
+        be.close()
 
 
 @pytest.mark.gpu
