@@ -238,7 +238,38 @@ __global__ void __launch_bounds__(256) lbvh_gather_set(uint32_t n, const uint32_
     o_orig[k] = (int32_t)s;
 }
 
+// 7. finalize (both builders' trees): leaves get the reference the traversal follows (rz_leaf_ref), and an unused slot — only
+//    the root of a scene that is one leaf has one — becomes a copy of its sibling (visited twice at worst: the second visit
+//    finds nothing nearer), so that K3's node visit is slab tests and nothing else.
+__global__ void __launch_bounds__(256) bvh_finalize(RzBvhNode *nodes, uint32_t n_nodes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    RzBvhNode nd = nodes[i];
+    bool empty[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        empty[c] = nd.child[c] < 0 && nd.cnt[c] == 0u;
+        if (nd.child[c] < 0 && nd.cnt[c] != 0u) nd.child[c] = rz_leaf_ref(nd.child[c], nd.cnt[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        if (empty[c] && !empty[1 - c]) {
+            const int o = 1 - c;
+            nd.lox[c] = nd.lox[o]; nd.hix[c] = nd.hix[o]; nd.loy[c] = nd.loy[o]; nd.hiy[c] = nd.hiy[o]; nd.loz[c] = nd.loz[o]; nd.hiz[c] = nd.hiz[o];
+            nd.child[c] = nd.child[o]; nd.cnt[c] = nd.cnt[o];
+        }
+    }
+    nodes[i] = nd;
+}
+
 }  // namespace
+
+// Turns a freshly built tree (either builder's) into the form K3 traverses.  Once per tree: applying it twice would encode twice.
+extern "C" cudaError_t rz_bvh_finalize(RzBvhNode *nodes, uint32_t n_nodes, cudaStream_t stream) {
+    if (n_nodes == 0) return cudaSuccess;
+    bvh_finalize<<<(n_nodes + 255u) / 256u, 256, 0, stream>>>(nodes, n_nodes);
+    return cudaGetLastError();
+}
 
 // Bytes of scratch the build needs for n spheres (the caller allocates once and may reuse it).
 extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n) {

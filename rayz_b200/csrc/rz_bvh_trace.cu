@@ -40,8 +40,6 @@ constexpr int RZ_STACK = 144;  // binary LBVH depth <= 96 = 48 wide levels x 3 p
 constexpr int RZ_STACK = 96;   // LBVH depth bound: 63 Morton bits + 32 index tie-break bits
 #endif
 
-// leaf reference: ~((count - 1) << 28 | first); first < 2^28, count <= 8
-__device__ __forceinline__ int rz_leaf_ref(int child, uint32_t cnt) { return ~((int)((cnt - 1u) << 28) | ~child); }
 
 #ifdef RZ_BVH_WIDE
 // EXPERIMENT (build with -DRZ_BVH_WIDE, scripts/exp_build.sh): the 4-wide tree of rz_bvh_wide.cu.  Measured on B200 and NOT
@@ -151,11 +149,10 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
             tn1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), a.t_min));
             tf1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), bt));
         }
-        const bool h0 = (tn0 <= tf0 * 1.0000004f) && (q3.x >= 0 || q3.z != 0);   // an unused slot is a leaf of 0 spheres
-        const bool h1 = (tn1 <= tf1 * 1.0000004f) && (q3.y >= 0 || q3.w != 0);
-        // child references: internal index >= 0, or a leaf (encoded negative, carries its count)
-        const int c0 = q3.x >= 0 ? q3.x : rz_leaf_ref(q3.x, (uint32_t)q3.z);
-        const int c1 = q3.y >= 0 ? q3.y : rz_leaf_ref(q3.y, (uint32_t)q3.w);
+        const bool h0 = tn0 <= tf0 * 1.0000004f, h1 = tn1 <= tf1 * 1.0000004f;
+        // child references as rz_bvh_finalize left them in the node: internal index >= 0, or a leaf (rz_leaf_ref: negative, carries
+        // its count); there are no unused slots (round 2's first form decoded (child, count) here: 12 of ~63 instructions per visit)
+        const int c0 = q3.x, c1 = q3.y;
         if (h0 && h1) {
             const bool swap = tn1 < tn0;
             if (sp < (int)a.stack_cap) stack[sp++] = swap ? c0 : c1;

@@ -43,6 +43,7 @@ extern "C" cudaError_t rz_bvh_warm(void);
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_bvh_stage(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n);
+extern "C" cudaError_t rz_bvh_finalize(RzBvhNode *nodes, uint32_t n_nodes, cudaStream_t stream);
 extern "C" cudaError_t rz_lbvh_build(uint32_t n, int leaf_max, const double4 *c64, const double4 *v64, const uint32_t *mat, void *scratch,
                                      size_t scratch_bytes, RzBvhNode *nodes, float4 *o_cr, float4 *o_vel, double4 *o_c64,
                                      double4 *o_v64, uint32_t *o_mat, int32_t *o_orig, cudaStream_t stream);
@@ -745,6 +746,8 @@ extern "C" int rayz_cuda_upload_scene(RzContext *ctx, const RzScene *sc) {
 #ifdef RZ_BVH_WIDE   // experiment: K3 walks the 4-wide collapse of the builders' binary tree (three small kernels, no host round trip)
         if ((rc = D.bvh4.alloc(D.bvh_nodes)) || (rc = D.wide_scratch.alloc(rz_bvh_wide_scratch_bytes(D.bvh_nodes) / sizeof(int)))) return rc;
         RZ_CUDA(rz_bvh_wide_collapse(D.bvh.p, D.bvh_nodes, D.wide_scratch.p, D.bvh4.p, D.stream));
+#else
+        RZ_CUDA(rz_bvh_finalize(D.bvh.p, D.bvh_nodes, D.stream));   // leaves -> the references K3 follows; no unused slots
 #endif
         if (device_build) RZ_CUDA(cudaEventRecord(D.ev[1], D.stream));
         if ((rc = D.m_rec.upload(mrec, D.stream)) || (rc = D.m_kind.upload(mk, D.stream)) || (rc = D.m_tex.upload(mt, D.stream)) || (rc = D.m_method.upload(mm, D.stream)) ||

@@ -84,12 +84,19 @@ struct RzTextures {
 };
 
 // BVH2 node for the FP32 traversal kernel: both child boxes live in the parent so one 64-byte
-// fetch decides both children.  child < 0 => leaf: first = ~child, count in cnt.
+// fetch decides both children.  As built: child < 0 => leaf: first = ~child, count in cnt.  As traversed (after
+// rz_bvh_finalize): child = rz_leaf_ref(child, cnt) for leaves.
 struct __align__(16) RzBvhNode {
     float lox[2], hix[2], loy[2], hiy[2], loz[2], hiz[2];
     int32_t child[2];
     uint32_t cnt[2];
 };
+
+// What the traversal kernel follows: an internal node's index (>= 0), or a leaf — ~((count - 1) << 28 | first), first < 2^28,
+// count <= 8 — negative.  The builders write (child = ~first, cnt = count) for leaves; rz_bvh_finalize (rz_bvh_build.cu) turns
+// every leaf's `child` into this reference once, at upload, and fills an unused slot (the root of a tiny scene) with a copy of
+// its sibling, so that the node visit neither decodes nor checks anything.
+RZ_HD int rz_leaf_ref(int child, uint32_t cnt) { return ~((int)((cnt - 1u) << 28) | ~child); }
 
 // BVH4 node (RZ_BVH_WIDE experiment, measured and not adopted): the four child boxes of a node in one 128-byte record, built by
 // collapsing every second level of the binary tree (rz_bvh_wide.cu).  Unused slots: empty box, child = ~0, cnt = 0.
