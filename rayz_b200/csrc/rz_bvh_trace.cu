@@ -22,7 +22,8 @@
 // Measured on B200 (config-2 scene / 99,856 spheres, Mpaths/s): first version 2245 / 903; while-while +
 // replacement at ACTIVE_MIN = 8: 2640 / 1241; + DESCEND_MIN = 24: 3370 / 1547; + one sphere per LBVH leaf
 // (rz_bvh_build.cu) and the two children's slab arithmetic packed into FP32x2 (6 FADD2 + 6 FMUL2 per node
-// visit instead of 24 scalar instructions, bit-identical per half): 3774 / 1931.  Picking the near/far
+// visit instead of 24 scalar instructions, bit-identical per half): 3774 / 1931; + child references finalized
+// at upload (rz_bvh_finalize: nothing to decode or check per visit): 3974 / 2025.  Picking the near/far
 // planes by ray-direction sign (six 8-byte loads instead of three 16-byte loads and twelve min/max) was
 // 9 % SLOWER and is not used.
 // Sphere tests, hit refinement, shading, RNG keys and accumulation are the shared device functions of
