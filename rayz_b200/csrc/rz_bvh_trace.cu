@@ -43,6 +43,9 @@ constexpr int RZ_SENTINEL = 0x7fffffff;
 #ifndef RZ_BVH_MINB
 #define RZ_BVH_MINB 8
 #endif
+#ifndef RZ_BVH_UNIT_MIN
+#define RZ_BVH_UNIT_MIN 64   // smallest work unit of the queue-fed persistent kernel, in entries (512 = fixed units)
+#endif
 #ifdef RZ_BVH_WIDE
 constexpr int RZ_STACK = 144;  // binary LBVH depth <= 96 = 48 wide levels x 3 pushes
 #else
@@ -205,8 +208,17 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathAr
     // warp-uniform work-unit state (as in rz_path_kernel)
     bool have_unit = true;
     uint32_t unit_lp0 = 0, unit_s0 = 0, unit_paths = 0, k_next = 0;
-    const uint32_t n_entries = QUEUE ? min(*a.q_in_count, a.queue_cap) : 0u;   // QUEUE: paths start from queue entries (512 per unit)
-    const uint32_t n_units = QUEUE ? (n_entries + 511u) / 512u : a.n_units;
+    const uint32_t n_entries = QUEUE ? min(*a.q_in_count, a.queue_cap) : 0u;   // QUEUE: paths start from queue entries
+    // ... in units of 512, or fewer when the queue is short: as the tail of the staged K1 this kernel gets ~2 M entries per pass,
+    // less than one 512-entry unit per resident warp, and the launch then lasts as long as ONE warp needs for 512 paths while most
+    // warps hold nothing.  Units shrink (down to RZ_BVH_UNIT_MIN) until every warp can expect four; a unit boundary costs one
+    // atomic, the lanes refill across it.
+    uint32_t unit_size = 512u;
+    if (QUEUE) {
+        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+        while (unit_size > (uint32_t)RZ_BVH_UNIT_MIN && (uint64_t)n_entries < (uint64_t)warps * unit_size * 4u) unit_size >>= 1;
+    }
+    const uint32_t n_units = QUEUE ? (n_entries + unit_size - 1u) / unit_size : a.n_units;
 
     // per-lane path state
     RzRay ray;
@@ -254,8 +266,8 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathAr
                     u = __shfl_sync(0xffffffffu, u, 0);
                     if (u >= n_units) { have_unit = false; break; }
                     if (QUEUE) {
-                        unit_lp0 = u * 512u;                       // first queue entry of the unit
-                        unit_paths = min(512u, n_entries - unit_lp0);
+                        unit_lp0 = u * unit_size;                  // first queue entry of the unit
+                        unit_paths = min(unit_size, n_entries - unit_lp0);
                     } else {
                         const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
                         unit_lp0 = tile * 32u;
