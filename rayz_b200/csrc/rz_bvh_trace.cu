@@ -43,9 +43,6 @@ constexpr int RZ_SENTINEL = 0x7fffffff;
 #ifndef RZ_BVH_MINB
 #define RZ_BVH_MINB 8
 #endif
-#ifndef RZ_BVH_UNIT_MIN
-#define RZ_BVH_UNIT_MIN 64   // smallest work unit of the queue-fed persistent kernel, in entries (512 = fixed units)
-#endif
 #ifdef RZ_BVH_WIDE
 constexpr int RZ_STACK = 144;  // binary LBVH depth <= 96 = 48 wide levels x 3 pushes
 #else
@@ -199,7 +196,7 @@ __device__ __forceinline__ void rz_bvh_round(const RzPathArgs &a, const float4 *
     }
 }
 
-template <bool STATS, bool QUEUE>
+template <bool STATS, bool QUEUE, int UNIT = 512>
 __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -209,15 +206,12 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathAr
     bool have_unit = true;
     uint32_t unit_lp0 = 0, unit_s0 = 0, unit_paths = 0, k_next = 0;
     const uint32_t n_entries = QUEUE ? min(*a.q_in_count, a.queue_cap) : 0u;   // QUEUE: paths start from queue entries
-    // ... in units of 512, or fewer when the queue is short: as the tail of the staged K1 this kernel gets ~2 M entries per pass,
-    // less than one 512-entry unit per resident warp, and the launch then lasts as long as ONE warp needs for 512 paths while most
-    // warps hold nothing.  Units shrink (down to RZ_BVH_UNIT_MIN) until every warp can expect four; a unit boundary costs one
-    // atomic, the lanes refill across it.
-    uint32_t unit_size = 512u;
-    if (QUEUE) {
-        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-        while (unit_size > (uint32_t)RZ_BVH_UNIT_MIN && (uint64_t)n_entries < (uint64_t)warps * unit_size * 4u) unit_size >>= 1;
-    }
+    // ... in units of UNIT entries: 512 when the queue holds every path of a pass (a large scene's job after the camera stage), 64
+    // as the tail of the staged K1 — ~2 M entries per pass, less than one 512-entry unit per resident warp: the launch then lasts
+    // as long as ONE warp needs for 512 paths while most warps hold nothing (tail of a serial-pass config-2 render: 4.7 -> 3.5 ms).
+    // A unit boundary costs one atomic; the lanes refill across it.  (A unit size computed from the queue length on the device
+    // did the same for the tail but cost the large-scene case 1.4 %: one more live value at the 64-register cap.)
+    constexpr uint32_t unit_size = (uint32_t)UNIT;
     const uint32_t n_units = QUEUE ? (n_entries + unit_size - 1u) / unit_size : a.n_units;
 
     // per-lane path state
@@ -456,6 +450,8 @@ static void rz_bvh_tuning(RzPathArgs &b) {   // defaults are the measured optimu
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream) {
     RzPathArgs b = *a;
     rz_bvh_tuning(b);
+    if (b.q_in && b.self_map)   // the tail of the staged K1 (entries written by a brute-force stage): a short queue, small units
+        return collect_stats ? launch_kernel(rz_bvh_kernel<true, true, 64>, b, sm_count, stream) : launch_kernel(rz_bvh_kernel<false, true, 64>, b, sm_count, stream);
     if (b.q_in) return collect_stats ? launch_kernel(rz_bvh_kernel<true, true>, b, sm_count, stream) : launch_kernel(rz_bvh_kernel<false, true>, b, sm_count, stream);
     return collect_stats ? launch_kernel(rz_bvh_kernel<true, false>, b, sm_count, stream) : launch_kernel(rz_bvh_kernel<false, false>, b, sm_count, stream);
 }
