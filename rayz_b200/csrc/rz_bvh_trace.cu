@@ -43,6 +43,24 @@ constexpr int RZ_SENTINEL = 0x7fffffff;
 #ifndef RZ_BVH_MINB
 #define RZ_BVH_MINB 8
 #endif
+// Camera stage of a large scene: per 32-pixel tile, the tree is culled against the tile's cone of camera rays and the rays search the
+// surviving spheres as a list (rz_bvh_stage_kernel, CAMERA).  0 = every camera ray walks the tree on its own.
+#ifndef RZ_BVH_CAMERA_LISTS
+#define RZ_BVH_CAMERA_LISTS 1
+#endif
+#ifdef RZ_BVH_WIDE
+#undef RZ_BVH_CAMERA_LISTS
+#define RZ_BVH_CAMERA_LISTS 0
+#endif
+#ifndef RZ_BVH_CAMERA_MINB
+#define RZ_BVH_CAMERA_MINB 6   // resident CTAs of the camera stage with tile lists: cull + packed search + shading + the per-ray walk in one kernel
+#endif
+#ifndef RZ_CL_CAP
+#define RZ_CL_CAP 256          // spheres a tile's list can hold (more: the tile's rays walk the tree)
+#endif
+#ifndef RZ_CL_WL
+#define RZ_CL_WL 256           // nodes in flight during the cull (ring buffer; power of two)
+#endif
 #ifdef RZ_BVH_WIDE
 constexpr int RZ_STACK = 144;  // binary LBVH depth <= 96 = 48 wide levels x 3 pushes
 #else
@@ -333,7 +351,7 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathAr
 // a time.  Rays that start together and head the same way walk the same nodes, so the warp stays converged and the nodes stay
 // in L1; survivors go to the next queue, and the tail of the paths to the persistent kernel above (QUEUE).
 template <bool STATS, bool CAMERA>
-__global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_stage_kernel(const RzPathArgs a) {
+__global__ void __launch_bounds__(128, (CAMERA && RZ_BVH_CAMERA_LISTS) ? RZ_BVH_CAMERA_MINB : RZ_BVH_MINB) rz_bvh_stage_kernel(const RzPathArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float4 *__restrict__ nodes = reinterpret_cast<const float4 *>(a.bvh);
@@ -343,6 +361,17 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_stage_kernel(const Rz
     const int descend_min = (int)a.bvh_descend_min;
     int stack[RZ_STACK];
     unsigned long long c_paths = 0, c_segs = 0, c_nodes = 0, c_sph = 0, c_hit[3] = {0, 0, 0}, c_sky = 0, c_abs = 0, c_depth = 0;
+#if RZ_BVH_CAMERA_LISTS
+    // per-warp scratch of the camera stage's tile lists: candidate spheres (stationary ones from the front, moving ones from the
+    // back), their positions in the set, the cull's ring buffer of nodes; idl = 0, 1, 2, ... (the lists the packed search walks)
+    __shared__ float4 s_cl_cr[CAMERA ? 4 : 1][CAMERA ? RZ_CL_CAP : 1], s_cl_vel[CAMERA ? 4 : 1][CAMERA ? RZ_CL_CAP : 1];
+    __shared__ int s_cl_gid[CAMERA ? 4 : 1][CAMERA ? RZ_CL_CAP : 1], s_cl_wl[CAMERA ? 4 : 1][CAMERA ? RZ_CL_WL : 1];
+    __shared__ unsigned short s_cl_idl[CAMERA ? RZ_CL_CAP : 1];
+    if (CAMERA) {
+        for (unsigned i = threadIdx.x; i < (unsigned)RZ_CL_CAP; i += blockDim.x) s_cl_idl[i] = (unsigned short)i;
+        __syncthreads();
+    }
+#endif
 
     while (true) {
         unsigned u = 0;
@@ -354,8 +383,16 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_stage_kernel(const Rz
         if (CAMERA) {
             u += a.unit_base;
             const uint32_t tile = u / a.n_chunks, chunk = u - tile * a.n_chunks;
-            lp0 = tile * 32u + lane;
-            valid = lp0 < a.n_local_px;
+            if (a.tile_w) {   // 8 x 4 pixel blocks (rz_bvh_camera_tile_w: the host counts the units accordingly)
+                const uint32_t tiles_x = (a.width + 7u) >> 3;
+                const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                const uint32_t ti = tx * 8u + (lane & 7u), tr = ty * 4u + (lane >> 3);
+                lp0 = tr * a.width + ti;
+                valid = ti < a.width && lp0 < a.n_local_px;
+            } else {
+                lp0 = tile * 32u + lane;
+                valid = lp0 < a.n_local_px;
+            }
             if (valid) rz_local_to_global(lp0, a.width, a.shard_index, a.shard_count, a.band_rows, pi, pj);
             gpix0 = pj * a.width + pi;
             s0 = chunk * a.chunk;
@@ -364,6 +401,144 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_stage_kernel(const Rz
             e0 = u * ue; ne = min(ue, n_in - e0);
             n_batches = (ne + 31u) / 32u;
         }
+#if RZ_BVH_CAMERA_LISTS
+        if (CAMERA) {
+            // ---- Camera rays of a 32-pixel tile are coherent: instead of 32 x chunk separate walks, the warp culls the TREE once
+            // against the tile's cone (rz_tile_cone / rz_tile_keep of the primary kernel; a child box enters as its bounding
+            // sphere, which the per-sphere test cannot pass where the box's does not) and the tile's rays then search the
+            // surviving spheres as a list, two rays per lane packed into FP32x2 (rz_search_lists_r2: the arithmetic of every
+            // other search, the same (t, k)).  Breadth first, up to 32 nodes per step, one lane per node.  A tile whose list or
+            // frontier outgrows its scratch (the horizon band of a large scene) falls through to the per-ray walk below.
+            const unsigned warp = threadIdx.x >> 5;
+            float4 *w_cr = s_cl_cr[warp], *w_vel = s_cl_vel[warp];
+            int *w_gid = s_cl_gid[warp], *w_wl = s_cl_wl[warp];
+            int n_s = 0, n_m = 0;
+            bool lists_ok = true;
+            {
+                const float3 pc = rz_tile_pixel_dir(a.cam, pi, pj);
+                float3 ax = valid ? normalize3(pc) : f3(0.f, 0.f, 0.f);
+                for (int o = 16; o > 0; o >>= 1) {
+                    ax.x += __shfl_xor_sync(0xffffffffu, ax.x, o); ax.y += __shfl_xor_sync(0xffffffffu, ax.y, o); ax.z += __shfl_xor_sync(0xffffffffu, ax.z, o);
+                }
+                const bool has_axis = rz_tile_axis(ax);
+                float cmin = valid ? rz_tile_corner_cos(a.cam, pc, ax) : 1.0f;
+                for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+                const RzTileCone cone = rz_tile_cone(a.cam, ax, has_axis, cmin, a.focus_dist, a.lens_radius);
+                unsigned head = 0u, tail = 1u;
+                __syncwarp();
+                if (lane == 0) w_wl[0] = 0;   // the root
+                __syncwarp();
+                while (head < tail && lists_ok) {
+                    const unsigned take = min(32u, tail - head);
+                    bool keep[2] = {false, false};
+                    int ref[2] = {0, 0};
+                    if (lane < take) {
+                        const int node = w_wl[(head + lane) & (unsigned)(RZ_CL_WL - 1)];
+                        const float4 q0 = __ldg(nodes + node * 4 + 0), q1 = __ldg(nodes + node * 4 + 1), q2 = __ldg(nodes + node * 4 + 2);   // lo0 lo1 hi0 hi1 per axis
+                        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(nodes + node * 4 + 3));
+                        if (STATS) c_nodes += 2;
+                        {
+                            const float ex = q0.z - q0.x, ey = q1.z - q1.x, ez = q2.z - q2.x;
+                            const float r2 = 0.25f * (ex * ex + ey * ey + ez * ez) * 1.0002f + 1e-12f;
+                            keep[0] = rz_tile_keep(cone, 0.5f * (q0.x + q0.z), 0.5f * (q1.x + q1.z), 0.5f * (q2.x + q2.z), 0.f, 0.f, 0.f, -r2);
+                        }
+                        {
+                            const float ex = q0.w - q0.y, ey = q1.w - q1.y, ez = q2.w - q2.y;
+                            const float r2 = 0.25f * (ex * ex + ey * ey + ez * ez) * 1.0002f + 1e-12f;
+                            keep[1] = rz_tile_keep(cone, 0.5f * (q0.y + q0.w), 0.5f * (q1.y + q1.w), 0.5f * (q2.y + q2.w), 0.f, 0.f, 0.f, -r2);
+                        }
+                        ref[0] = q3.x; ref[1] = q3.y;
+                    }
+                    head += take;
+                    // internal children join the frontier
+                    const bool p0 = keep[0] && ref[0] >= 0, p1 = keep[1] && ref[1] >= 0;
+                    const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+                    const unsigned n0 = (unsigned)__popc(m0), n1 = (unsigned)__popc(m1);
+                    if (tail + n0 + n1 - head > (unsigned)RZ_CL_WL) { lists_ok = false; break; }
+                    if (p0) w_wl[(tail + (unsigned)__popc(m0 & lt_mask)) & (unsigned)(RZ_CL_WL - 1)] = ref[0];
+                    if (p1) w_wl[(tail + n0 + (unsigned)__popc(m1 & lt_mask)) & (unsigned)(RZ_CL_WL - 1)] = ref[1];
+                    tail += n0 + n1;
+                    // leaf children: their spheres, each against the cone with its own radius and motion
+#pragma unroll 1
+                    for (int c = 0; c < 2 && lists_ok; c++) {
+                        const bool leaf = keep[c] && ref[c] < 0;
+                        const int code = ~ref[c];
+                        const int first = code & 0x0fffffff;
+                        const int lc = leaf ? (code >> 28) + 1 : 0;
+#pragma unroll 1
+                        for (int e = 0; e < 8; e++) {
+                            const bool has = e < lc;
+                            if (!__any_sync(0xffffffffu, has)) break;
+                            const int k = first + e;
+                            float4 S = make_float4(0.f, 0.f, 0.f, 1.f), V = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (has) { S = __ldg(a.set.cr + k); V = __ldg(a.set.vel + k); }
+                            const bool kp = has && rz_tile_keep(cone, S.x, S.y, S.z, V.x, V.y, V.z, S.w);
+                            const bool still = V.x == 0.f && V.y == 0.f && V.z == 0.f;
+                            const unsigned ms = __ballot_sync(0xffffffffu, kp && still), mm = __ballot_sync(0xffffffffu, kp && !still);
+                            if (n_s + n_m + __popc(ms) + __popc(mm) > RZ_CL_CAP) { lists_ok = false; break; }
+                            if (kp && still) { const int i = n_s + __popc(ms & lt_mask); w_cr[i] = S; w_gid[i] = k; }
+                            if (kp && !still) { const int i = RZ_CL_CAP - 1 - (n_m + __popc(mm & lt_mask)); w_cr[i] = S; w_vel[i] = V; w_gid[i] = k; }
+                            n_s += __popc(ms); n_m += __popc(mm);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (lists_ok) {
+                const unsigned short *ls = s_cl_idl, *lm = s_cl_idl + (RZ_CL_CAP - n_m);
+#pragma unroll 1
+                for (uint32_t b = 0; b < n_batches; b += 2u) {
+                    RzRay rays[2];
+                    bool live[2];
+                    uint32_t smp[2];
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        smp[r] = a.sample_offset + s0 + b + (uint32_t)r;
+                        const bool have = valid && (b + (uint32_t)r < n_batches);
+                        live[r] = have && a.max_depth > 0u;
+                        if (STATS && have) { c_paths++; if (!live[r]) c_depth++; }
+                        if (live[r]) rays[r] = rz_camera_ray(a.cam, pi, pj, gpix0, smp[r], a.seed_lo, a.seed_hi);
+                        else { rays[r].o = f3(0.f, 0.f, 0.f); rays[r].d = f3(0.f, 1.f, 0.f); rays[r].time = 0.f; rays[r].self_k = -1; }
+                    }
+                    float bt[2] = {3.0e38f, 3.0e38f};
+                    int bk[2] = {-1, -1};
+                    rz_search_lists_r2(w_cr, w_vel, ls, n_s, lm, n_m, rays, a.t_min, bt, bk);
+                    if (STATS) c_sph += (unsigned long long)(n_s + n_m) * ((live[0] ? 1u : 0u) + (live[1] ? 1u : 0u));
+                    float3 thr[2] = {f3(1.f, 1.f, 1.f), f3(1.f, 1.f, 1.f)};
+                    uint32_t seg[2] = {0u, 0u};
+                    bool cont[2] = {false, false};
+                    // one copy of the shading code for both rays (code size: DESIGN.md section 3): shade slot 0, exchange, shade again, exchange back
+#pragma unroll 1
+                    for (int trip = 0; trip < 2; trip++) {
+                        if (live[0]) {
+                            const int hit = bk[0] < 0 ? -1 : (w_gid[bk[0] & ~RZ_FAR_BIT] | (bk[0] & RZ_FAR_BIT));   // list slot -> position in the set
+                            if (STATS) c_segs++;
+                            uint32_t kind;
+                            const int res = rz_shade_segment(a, rays[0], thr[0], seg[0], lp0, gpix0, smp[0], hit, kind);
+                            if (STATS) {
+                                if (kind < 3u) c_hit[kind]++;
+                                if (res == RZ_END_SKY) c_sky++;
+                                if (res == RZ_END_ABSORBED) c_abs++;
+                                if (res == RZ_END_DEPTH) c_depth++;
+                            }
+                            cont[0] = res == RZ_CONT;
+                        }
+                        { const RzRay t = rays[0]; rays[0] = rays[1]; rays[1] = t; }
+                        { const float3 t = thr[0]; thr[0] = thr[1]; thr[1] = t; }
+                        { const uint32_t t = seg[0]; seg[0] = seg[1]; seg[1] = t; }
+                        { const uint32_t t = smp[0]; smp[0] = smp[1]; smp[1] = t; }
+                        { const int t = bk[0]; bk[0] = bk[1]; bk[1] = t; }
+                        { const bool t = live[0]; live[0] = live[1]; live[1] = t; }
+                        { const bool t = cont[0]; cont[0] = cont[1]; cont[1] = t; }
+                    }
+                    const uint32_t lp2[2] = {lp0, lp0}, gp2[2] = {gpix0, gpix0};
+                    rz_queue_push2(a, cont, lane, lt_mask, rays, thr, seg, lp2, gp2, smp);
+                }
+                continue;   // next unit
+            }
+        }
+#endif
         for (uint32_t b = 0; b < n_batches; b++) {
             RzRay ray;
             float3 thr = f3(1.f, 1.f, 1.f);
@@ -431,6 +606,10 @@ cudaError_t launch_kernel(K kern, const RzPathArgs &a, int sm_count, cudaStream_
 }
 
 }  // namespace
+
+// Pixel layout of the camera stage's work units the host has to count with (RzPathArgs::tile_w): 8 x 4 blocks when the stage
+// builds tile lists — the cone around a compact block is a third as wide as around 32 pixels of a row —, else 0 (rows).
+extern "C" uint32_t rz_bvh_camera_tile_w(void) { return RZ_BVH_CAMERA_LISTS ? 8u : 0u; }
 
 extern "C" cudaError_t rz_bvh_warm(void) {
     cudaFuncAttributes fa;

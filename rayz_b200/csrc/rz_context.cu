@@ -40,6 +40,7 @@ extern "C" cudaError_t rz_bin_sort(const unsigned short *keys_in, const unsigned
 extern "C" cudaError_t rz_sort_warm(void);
 extern "C" cudaError_t rz_launch_primary(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_bvh_warm(void);
+extern "C" uint32_t rz_bvh_camera_tile_w(void);
 extern "C" cudaError_t rz_launch_bvh(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t rz_launch_bvh_stage(const RzPathArgs *a, int collect_stats, int sm_count, cudaStream_t stream);
 extern "C" size_t rz_lbvh_scratch_bytes(uint32_t n);
@@ -872,10 +873,16 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
                     // unit) -> queue] x n_second -> persistent tail kernel (BVH, or brute force).  Passes are sized by the queues
                     // (RzTuning::queue_log2, default 2^27 entries per buffer; two buffers per side, two sides).
                     const bool serial = (p->flags & RZ_RENDER_SERIAL_PASSES) != 0;
-                    if (!bvh_family) {   // the primary kernel's own work-unit size
+                    {   // the camera-stage kernels build a culled sphere list per unit: their own, larger work-unit size
                         a.chunk = std::min(ctx->tun.chunk_primary, p->spp);
                         a.n_chunks = (p->spp + a.chunk - 1) / a.chunk;
-                        a.n_units = n_tiles * a.n_chunks;
+                        uint64_t tiles = n_tiles;
+                        if (bvh_family && rz_bvh_camera_tile_w()) {   // K3's camera stage works on 8 x 4 pixel blocks
+                            a.tile_w = rz_bvh_camera_tile_w();
+                            tiles = (uint64_t)((p->width + 7u) / 8u) * ((n_local / p->width + 3u) / 4u);
+                        }
+                        if (tiles * a.n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "render: too many work units");
+                        a.n_units = (uint32_t)tiles * a.n_chunks;
                     }
                     // The tail of the paths (whatever survives the sorted stages: incoherent, few) goes to the BVH kernel when the
                     // host-built tree is there — ~28 node + sphere tests per segment instead of every sphere of the set
@@ -1053,10 +1060,11 @@ extern "C" int rayz_cuda_reserve(RzContext *ctx, const RzRenderParams *p) {
         const uint32_t n_tiles = (rows * p->width + 31u) / 32u;
         if ((rc = D.accum.alloc((size_t)n_tiles * 32u * 4u)) || (rc = D.counter.alloc(16)) || (rc = D.errword.alloc(4)) || (rc = D.stats.alloc(3))) return rc;
         if (p->variant == RZ_VARIANT_AUTO || p->variant == RZ_VARIANT_MEGA || (p->variant == RZ_VARIANT_BVH && (uint64_t)rows * p->width * p->spp >= (1ull << 26))) {
-            const uint32_t chunk = std::min(p->variant == RZ_VARIANT_BVH ? ctx->tun.chunk : ctx->tun.chunk_primary, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
-            if ((uint64_t)n_tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
+            const uint32_t chunk = std::min(ctx->tun.chunk_primary, p->spp), n_chunks = (p->spp + chunk - 1) / chunk;
+            const uint64_t tiles = std::max<uint64_t>(n_tiles, (uint64_t)((p->width + 7u) / 8u) * ((rows + 3u) / 4u));   // K3's camera stage: 8 x 4 blocks
+            if (tiles * n_chunks >= (1ull << 32)) return rz_fail(RZ_ERR_INVALID_ARG, "reserve: too many work units");
             QueuePlan qp;
-            if ((rc = plan_and_alloc_queues(ctx->tun, D, qp, n_tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0,
+            if ((rc = plan_and_alloc_queues(ctx->tun, D, qp, (uint32_t)tiles * n_chunks, chunk, (p->flags & RZ_RENDER_SERIAL_PASSES) != 0,
                                             !ctx->have_scene || ctx->n_spheres >= 64u, false, true)))
                 return rc;
         }

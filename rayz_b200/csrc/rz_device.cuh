@@ -168,6 +168,7 @@ struct RzPathArgs {
     const int32_t *self_map;     // K3 fed by a K1 queue: position in the brute-force set -> position in the BVH-ordered set (null: same set)
     uint32_t bvh_active_min;     // K3: lanes that must still be traversing for a burst to go on (ray replacement threshold)
     uint32_t bvh_descend_min;    // K3: a descend round ends once fewer lanes than this are still descending
+    uint32_t tile_w;             // K3 camera stage: 0 = a work unit's 32 pixels are consecutive in a row; 8 = an 8 x 4 block (tile lists: the narrower cone)
 };
 
 // ---------------------------------------------------------------------------------------------
