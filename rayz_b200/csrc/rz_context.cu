@@ -664,7 +664,11 @@ static QueuePlan plan_queues(const RzTuning &tun, uint32_t n_units, uint32_t chu
     q.second_stage = q.n_second > 0;
     q.units_per_pass = (uint32_t)std::max<uint64_t>(1, q.cap / q.unit_paths);
     q.n_pass = (n_units + q.units_per_pass - 1) / q.units_per_pass;
-    q.n_sides = (q.n_pass > 1 && !serial) ? 2 : 1;
+    // Passes alternate between two streams so that the next pass's first kernel fills the tail of the persistent one — except for
+    // K3 with tile lists: its camera stage holds 41 KB of shared memory per CTA, and running beside the traversal kernel of the
+    // previous pass it takes the L1 that kernel's node loads live in (config 4: 247.6 ms overlapped against 212.6 ms in series).
+    const bool overlap = !(bvh_family && rz_bvh_camera_tile_w() != 0u);
+    q.n_sides = (q.n_pass > 1 && !serial && overlap) ? 2 : 1;
     return q;
 }
 
