@@ -23,9 +23,12 @@
 // replacement at ACTIVE_MIN = 8: 2640 / 1241; + DESCEND_MIN = 24: 3370 / 1547; + one sphere per LBVH leaf
 // (rz_bvh_build.cu) and the two children's slab arithmetic packed into FP32x2 (6 FADD2 + 6 FMUL2 per node
 // visit instead of 24 scalar instructions, bit-identical per half): 3774 / 1931; + child references finalized
-// at upload (rz_bvh_finalize: nothing to decode or check per visit): 3974 / 2025.  Picking the near/far
-// planes by ray-direction sign (six 8-byte loads instead of three 16-byte loads and twelve min/max) was
-// 9 % SLOWER and is not used.
+// at upload (rz_bvh_finalize: nothing to decode or check per visit): 3974 / 2025; + 8 resident CTAs (RZ_BVH_MINB: the walk waits
+// on node loads from L2, warps pay more than registers): 4249 / 2139; + tile lists in the camera stage (rz_bvh_stage_kernel:
+// the tree culled once per 8 x 4-pixel block against the block's cone, the block's rays search the surviving spheres as a list):
+// 4813 / 2497.  Picking the near/far planes by ray-direction sign (six 8-byte loads instead of three 16-byte loads and twelve
+// min/max) was 9 % SLOWER and is not used; so were a branch-free node visit, a deferred leaf phase, a pending-leaf slot and an
+// L1 prefetch of the deferred child (profiles/r02_experiments.md expb7-expb10).
 // Sphere tests, hit refinement, shading, RNG keys and accumulation are the shared device functions of
 // rz_search.cuh / rz_device.cuh: two trees give bit-identical images; against a brute-force search a pixel or two may
 // differ (the FP32 sphere test has a fuzzy surface, the boxes are exact: a grazing ray can "hit" a sphere a hair outside
@@ -350,6 +353,9 @@ __global__ void __launch_bounds__(128, RZ_BVH_MINB) rz_bvh_kernel(const RzPathAr
 // rays tile by tile and scattered rays in SORTED order (key of rz_sort_key: origin cell, octant, reach), 32 rays per warp at
 // a time.  Rays that start together and head the same way walk the same nodes, so the warp stays converged and the nodes stay
 // in L1; survivors go to the next queue, and the tail of the paths to the persistent kernel above (QUEUE).
+// CAMERA with RZ_BVH_CAMERA_LISTS (the default): the camera rays of a work unit — an 8 x 4-pixel block x `chunk` samples — do
+// not walk the tree one by one; the warp culls the tree once against the block's cone and the rays search the surviving
+// spheres as a list (below).  The sorted stages (CAMERA = false) are off by default (RzTuning::bvh_stages = 0: measured as a loss).
 template <bool STATS, bool CAMERA>
 __global__ void __launch_bounds__(128, (CAMERA && RZ_BVH_CAMERA_LISTS) ? RZ_BVH_CAMERA_MINB : RZ_BVH_MINB) rz_bvh_stage_kernel(const RzPathArgs a) {
     const unsigned lane = threadIdx.x & 31u;
