@@ -864,7 +864,7 @@ static int render_impl(RzContext *ctx, const RzCamera *cam, const RzRenderParams
             } else {
                 // K3 on a big job: the same staged pipeline with BVH traversal instead of culled lists (sorted rays stay converged)
                 const bool bvh_family = variant == RZ_VARIANT_BVH;
-                const bool bvh_staged = bvh_family && ctx->tun.bvh_staged && (uint64_t)n_local * p->spp >= (1ull << 26);
+                const bool bvh_staged = bvh_family && ctx->tun.bvh_staged && (uint64_t)p->width * p->height * p->spp >= (1ull << 26);   // by the FRAME's size, never a shard's: every shard of a frame runs the same kernels (the staged camera stage searches block lists, the unstaged kernel walks the tree)
                 if (bvh_family && !bvh_staged) {
                     RZ_CUDA(rz_launch_bvh(&a, (int)p->collect_stats, D.sms, D.stream));
                     launches += 1;

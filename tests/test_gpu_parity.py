@@ -776,6 +776,35 @@ def test_big_job_staged_bvh_equals_staged_bruteforce(scene42):
     be.close()
 
 
+@pytest.mark.gpu
+def test_staged_bvh_block_lists_on_odd_sizes_and_shards(scene42):
+    """The staged K3's camera stage culls the tree once per 8 x 4-pixel block and searches the block's sphere list.  A frame
+    whose width is no multiple of 8 and whose height is no multiple of 4 (partial blocks on two edges), full and in three
+    shards of 3-row bands (blocks that straddle bands): the shards reproduce the full frame bit for bit, and the frame equals
+    the unstaged kernel's per-ray walks up to the documented FP32-test-vs-exact-box edge."""
+    w, spp = 1205, 84
+    cam, h = cam_for(w)
+    assert w % 8 and h % 4 and w * h * spp >= 1 << 26
+    be = Backend((0,))
+    be.upload_scene(scene42)
+    full, full8, n = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="bvh", collect_stats=True))
+    assert n == w * h * spp and be.timing()["variant"] == 3 and be.timing()["passes"] >= 1
+    st = be.stats()
+    assert st["paths"] == n and st["ended_sky"] + st["ended_absorbed"] + st["ended_depth"] == n
+    out, out8 = np.empty_like(full), np.empty_like(full8)
+    for s in range(3):
+        l, r, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="bvh", shard_index=s, shard_count=3, band_rows=3))
+        assert be.timing()["passes"] >= 1                      # staged by the frame's size, not the shard's
+        rows = [j for j in range(h) if (j // 3) % 3 == s]
+        out[rows] = l; out8[rows] = r
+    assert np.array_equal(out, full) and np.array_equal(out8, full8)
+    be.set_tuning(bvh_staged=0)
+    walk, _, _ = be.render(cam, Backend.params(w, h, spp, 50, seed=5, variant="bvh"))
+    assert be.timing()["passes"] == 0
+    assert int((walk != full).any(axis=-1).sum()) <= 3 and float(np.abs(walk - full).mean()) < 1e-5
+    be.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE config 4: 99,856 spheres (randomBouncing with the grid loops widened to [-158, 158)), device-built LBVH.
 # This is the code hit.zig:130-161,181-216 and geom.zig:38-66 are stressed by: rays travel hundreds of units, where the
