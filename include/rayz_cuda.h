@@ -260,7 +260,7 @@ typedef struct RzTuning {
     int32_t second_stages;    /* staged K1: sorted stages after the camera segment, 0..8; -1 = automatic (default)      */
     int32_t bvh_stages;       /* staged BVH kernel: sorted stages, 0..8 (default 0: measured as a loss)                 */
     int32_t tail_brute;       /* staged K1: 1 = the tail of the paths stays brute force (default 0: BVH kernel)         */
-    int32_t bvh_staged;       /* BVH variant: 1 = jobs of >= 2^26 paths run a camera stage + queue first (default 1)    */
+    int32_t bvh_staged;       /* BVH variant: 1 = FRAMES of >= 2^26 paths run a camera stage + queue first (default 1)  */
     int32_t cell_bits;        /* sort key: bits of the origin cell, 0..9 (default 9)                                    */
     int32_t bvh_active_min;   /* K3: lanes that must still traverse for a burst to go on, 1..32 (default 8)             */
     int32_t bvh_descend_min;  /* K3: a descend round ends below this many descending lanes (default 24)                 */
