@@ -443,16 +443,8 @@ __global__ void __launch_bounds__(128, (CAMERA && RZ_BVH_CAMERA_LISTS) ? RZ_BVH_
                         const float4 q0 = __ldg(nodes + node * 4 + 0), q1 = __ldg(nodes + node * 4 + 1), q2 = __ldg(nodes + node * 4 + 2);   // lo0 lo1 hi0 hi1 per axis
                         const int4 q3 = __ldg(reinterpret_cast<const int4 *>(nodes + node * 4 + 3));
                         if (STATS) c_nodes += 2;
-                        {
-                            const float ex = q0.z - q0.x, ey = q1.z - q1.x, ez = q2.z - q2.x;
-                            const float r2 = 0.25f * (ex * ex + ey * ey + ez * ez) * 1.0002f + 1e-12f;
-                            keep[0] = rz_tile_keep(cone, 0.5f * (q0.x + q0.z), 0.5f * (q1.x + q1.z), 0.5f * (q2.x + q2.z), 0.f, 0.f, 0.f, -r2);
-                        }
-                        {
-                            const float ex = q0.w - q0.y, ey = q1.w - q1.y, ez = q2.w - q2.y;
-                            const float r2 = 0.25f * (ex * ex + ey * ey + ez * ez) * 1.0002f + 1e-12f;
-                            keep[1] = rz_tile_keep(cone, 0.5f * (q0.y + q0.w), 0.5f * (q1.y + q1.w), 0.5f * (q2.y + q2.w), 0.f, 0.f, 0.f, -r2);
-                        }
+                        keep[0] = rz_tile_keep_box(cone, q0.x, q0.z, q1.x, q1.z, q2.x, q2.z);
+                        keep[1] = rz_tile_keep_box(cone, q0.y, q0.w, q1.y, q1.w, q2.y, q2.w);
                         ref[0] = q3.x; ref[1] = q3.y;
                     }
                     head += take;

@@ -701,6 +701,16 @@ RZ_HD bool rz_tile_keep(const RzTileCone &C, float cx, float cy, float cz, float
     return fmaxf(d2 - h * h, 0.f) <= rad * rad;
 }
 
+// K3's camera stage culls a TREE against the cone: a child box enters as its bounding sphere (centre, half diagonal with a margin
+// for the FP32 evaluation), stationary.  Every sphere inside the box — swept over the shutter: the builders' boxes cover both
+// ends — lies inside that bounding sphere, and rz_tile_keep only grows more permissive with the radius at a centre at most that
+// radius away, so a box is never dropped while a sphere inside it would be kept (tests/hostsim checks it on the CPU).
+RZ_HD bool rz_tile_keep_box(const RzTileCone &C, float lox, float hix, float loy, float hiy, float loz, float hiz) {
+    const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
+    const float r2 = 0.25f * (ex * ex + ey * ey + ez * ez) * 1.0002f + 1e-12f;
+    return rz_tile_keep(C, 0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz), 0.f, 0.f, 0.f, -r2);
+}
+
 // Sorted-stage kernel: what the rays of one unit have in common, merged from the bounds of their keys (rz_key_bounds).
 struct RzUnitBounds {
     float lo[3], hi[3];          // box of the origins

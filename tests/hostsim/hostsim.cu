@@ -280,6 +280,86 @@ extern "C" int hostsim_tile_cull_check(const RzCamera *cam, uint32_t w, uint32_t
     return 0;
 }
 
+// K3's camera stage (rz_bvh_stage_kernel with tile lists): work units are 8 x 4 pixel blocks and the TREE is culled against the
+// block's cone — a box as its bounding sphere (rz_tile_keep_box).  For camera rays of random blocks and spheres placed around
+// them: a sphere a ray hits must be kept, and so must every box that contains the sphere's sweep over the shutter — its own
+// FP32 box and ever larger ancestors (grown by random amounts on every side, up to thousands of units).
+// out: [0] hit spheres dropped, [1] hits, [2] boxes around hit spheres dropped, [3] boxes tested, [4] misses culled
+extern "C" int hostsim_block_cull_check(const RzCamera *cam, uint32_t w, uint32_t h, uint64_t n_blocks, uint64_t seed, uint64_t *out) {
+    RzCamF32 C;
+    C.look_from = make_float3((float)cam->look_from[0], (float)cam->look_from[1], (float)cam->look_from[2]);
+    C.px_du = make_float3((float)cam->px_du[0], (float)cam->px_du[1], (float)cam->px_du[2]);
+    C.px_dv = make_float3((float)cam->px_dv[0], (float)cam->px_dv[1], (float)cam->px_dv[2]);
+    C.px_origin = make_float3((float)cam->px_origin[0], (float)cam->px_origin[1], (float)cam->px_origin[2]);
+    C.defocus_u = make_float3((float)cam->defocus_u[0], (float)cam->defocus_u[1], (float)cam->defocus_u[2]);
+    C.defocus_v = make_float3((float)cam->defocus_v[0], (float)cam->defocus_v[1], (float)cam->defocus_v[2]);
+    C.defocus = cam->defocus;
+    double pcd[3], lu = 0, lv = 0, f2 = 0;
+    for (int ax = 0; ax < 3; ax++) {
+        pcd[ax] = cam->px_origin[ax] + 0.5 * (w - 1) * cam->px_du[ax] + 0.5 * (h - 1) * cam->px_dv[ax] - cam->look_from[ax];
+        f2 += pcd[ax] * pcd[ax]; lu += cam->defocus_u[ax] * cam->defocus_u[ax]; lv += cam->defocus_v[ax] * cam->defocus_v[ax];
+    }
+    const float focus_dist = (float)std::sqrt(f2);
+    const float lens_radius = cam->defocus ? (float)(std::sqrt(std::max(lu, lv)) * 1.001) : 0.f;
+    Rng g(seed);
+    for (int i = 0; i < 5; i++) out[i] = 0;
+    const uint32_t tiles_x = (w + 7u) / 8u, tiles_y = (h + 3u) / 4u, n_px = w * h;
+    for (uint64_t t = 0; t < n_blocks; t++) {
+        const uint32_t tile = (uint32_t)(g.u01() * (float)(tiles_x * tiles_y)) % (tiles_x * tiles_y);
+        // ---- the block's pixels as the kernel maps them (RzPathArgs::tile_w = 8), then the cone, lane by lane
+        float3 ax = f3(0.f, 0.f, 0.f), pcs[32];
+        uint32_t pis[32], pjs[32];
+        bool valid[32];
+        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            const uint32_t ti = tx * 8u + (lane & 7u), tr = ty * 4u + (lane >> 3);
+            const uint32_t lp = tr * w + ti;
+            valid[lane] = ti < w && lp < n_px;
+            pis[lane] = pjs[lane] = 0;
+            if (valid[lane]) rz_local_to_global(lp, w, 0, 1, 4, pis[lane], pjs[lane]);
+            pcs[lane] = rz_tile_pixel_dir(C, pis[lane], pjs[lane]);
+            if (valid[lane]) ax = ax + normalize3(pcs[lane]);
+        }
+        const bool has_axis = rz_tile_axis(ax);
+        float cmin = 1.0f;
+        for (uint32_t lane = 0; lane < 32; lane++)
+            if (valid[lane]) cmin = fminf(cmin, rz_tile_corner_cos(C, pcs[lane], ax));
+        const RzTileCone cone = rz_tile_cone(C, ax, has_axis, cmin, focus_dist, lens_radius);
+        for (int k = 0; k < 64; k++) {
+            const uint32_t lane = (uint32_t)(g.u01() * 32.f) & 31u;
+            if (!valid[lane]) continue;
+            const uint32_t gpix = pjs[lane] * w + pis[lane], sample = (uint32_t)(g.u01() * 4096.f);
+            const RzRay ray = rz_camera_ray(C, pis[lane], pjs[lane], gpix, sample, (uint32_t)seed, 77u);
+            for (int j = 0; j < 6; j++) {
+                const float tt = 0.05f + (j == 5 ? 400.0f : 40.0f) * g.u01() * g.u01();       // some far away: config 4's rays travel hundreds of units
+                const float r = j == 4 ? 1000.0f : 0.03f + 2.0f * g.u01() * g.u01();          // and a ground-sized sphere
+                float c0[3], v[3];
+                sphere_near(g, ray, tt, r, j < 2 ? 6.0f : 0.8f, c0, v);
+                const bool hit = ray_hits(ray, c0, v, r, 1e-4f);
+                const bool kept = rz_tile_keep(cone, c0[0], c0[1], c0[2], v[0], v[1], v[2], -(r * r));
+                if (!hit) { if (!kept) out[4]++; continue; }
+                out[1]++;
+                if (!kept) out[0]++;
+                // the sphere's box over the shutter (Sphere.boundingBox), rounded outward, then ever larger enclosing boxes
+                float lo[3], hi[3];
+                for (int a3 = 0; a3 < 3; a3++) {
+                    const float a0 = c0[a3], a1 = c0[a3] + v[a3];
+                    lo[a3] = nextafterf(fminf(a0, a1) - r, -INFINITY);
+                    hi[a3] = nextafterf(fmaxf(a0, a1) + r, INFINITY);
+                }
+                float grow = 0.0f;
+                for (int level = 0; level < 8; level++) {
+                    out[3]++;
+                    if (!rz_tile_keep_box(cone, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])) out[2]++;
+                    grow = level == 0 ? 0.05f : grow * 5.0f;                                   // 0.05 ... 3900 units
+                    for (int a3 = 0; a3 < 3; a3++) { lo[a3] -= grow * g.u01(); hi[a3] += grow * g.u01(); }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 extern "C" int hostsim_unit_cull_check(const float *lo, const float *hi, int cell_bits, float huge_radius, uint64_t n_units, uint64_t seed,
                                        uint64_t *out) {
     RzPathArgs a;

@@ -94,6 +94,28 @@ def _cam(width, defocus_angle, look_from=(13, 2, 3), look_at=(0, 0, 0), vfov=20.
 
 
 @pytest.mark.parametrize("width,defocus,look_from,vfov", [
+    (1920, 0.6, (13, 2, 3), 20.0),        # config 4's camera
+    (1205, 0.0, (13, 2, 3), 20.0),        # partial blocks on both edges, pinhole
+    (203, 2.0, (3, 3, 2), 60.0),          # wide blur, wide field
+])
+def test_block_cull_of_the_bvh_camera_stage_never_drops_a_box_or_a_sphere(hostsim, width, defocus, look_from, vfov):
+    """K3's camera stage culls the tree once per 8 x 4-pixel block against the block's cone (rz_tile_keep_box, the function the
+    kernel calls, on the block layout the kernel uses): whatever a camera ray of the block hits must be kept, and so must every
+    box around it — the sphere's own box over the shutter and enclosing boxes up to thousands of units — or the walk down the
+    tree would lose the sphere before its own test."""
+    hostsim.hostsim_block_cull_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+    h = int(width / rayz_b200.ASPECT_RATIO)
+    cam = rayz_b200.Camera.init(vfov, 10.0, defocus, look_from, (0, 0, 0), (0, 1, 0), h, width).rz
+    out = np.zeros(5, dtype=np.uint64)
+    assert hostsim.hostsim_block_cull_check(C.addressof(cam), width, h, 3000, 5, out.ctypes.data) == 0
+    dropped, hits, boxes_dropped, boxes, culled = (int(x) for x in out)
+    assert hits > 100_000 and boxes == 8 * hits
+    assert dropped == 0, f"{dropped} of {hits} hit spheres culled"
+    assert boxes_dropped == 0, f"{boxes_dropped} of {boxes} boxes around hit spheres culled"
+    assert culled > 1_000                 # and the cone does cull
+
+
+@pytest.mark.parametrize("width,defocus,look_from,vfov", [
     (1200, 0.6, (13, 2, 3), 20.0),        # the benchmark camera (rayz.zig:152-160)
     (400, 0.0, (13, 2, 3), 20.0),         # pinhole
     (160, 8.0, (0, 1.0, 8.0), 50.0),      # wide lens, wide field of view, coarse pixels
