@@ -254,7 +254,7 @@ typedef struct RzTuning {
     uint32_t struct_size;     /* sizeof(RzTuning) of the caller (checked)                                              */
     int32_t rays_per_thread;  /* K1b / wavefront: independent paths per lane, 1 or 2 (default 2)                        */
     uint32_t chunk;           /* samples per work unit (32 pixels x chunk) of the persistent kernels (default 16)       */
-    uint32_t chunk_primary;   /* ... of the staged K1's primary kernel, which builds one culled list per unit (64)      */
+    uint32_t chunk_primary;   /* ... of the camera-stage kernels (K1a, staged K3), which build a culled list per unit (64) */
     int32_t queue_log2;       /* staged K1: queue entries per pass = 2^queue_log2, 16..28 (default 27: 6.4 GB per queue
                                * buffer; 28 is ~2 % faster on 405 M-path renders and doubles the reservation)           */
     int32_t second_stages;    /* staged K1: sorted stages after the camera segment, 0..8; -1 = automatic (default)      */
