@@ -17,6 +17,7 @@
 
 #include "../../include/rayz_cuda.h"
 #include "../../rayz_b200/csrc/rz_device.cuh"
+#include "../../rayz_b200/csrc/rz_host_bvh.hpp"   // the host tree builders (K3's binned-SAH tree): hostsim_bvh_block_check
 
 // the sphere test and the root rule are the product's own (rz_sphere_test / rz_consider, rz_device.cuh)
 static inline void consider(int k, float nb, float nd, int self_k, float t_min, float &bt, int &bk) { rz_consider(k, nb, nd, self_k, t_min, bt, bk); }
@@ -574,6 +575,118 @@ extern "C" int hostsim_staged_check(const RzScene *sc, const RzCamera *cam, uint
             if (bk != bk2 || bt != bt2) out[3]++;
         }
         e0 = e1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3's camera stage on a real scene, on the CPU: the library's own binned-SAH tree (rz_host_bvh.hpp) is culled against the cone
+// of every `block_stride`-th 8 x 4 pixel block exactly as rz_bvh_stage_kernel does it (breadth first from the root, a child box
+// through rz_tile_keep_box, a leaf's spheres through rz_tile_keep), and `spp` camera rays per pixel of the block are searched
+// over the surviving spheres and over EVERY sphere with the kernels' sphere test and root rule: the closest hit (t and sphere)
+// must be the same.  out[0] = rays whose hit differs, out[1] = rays, out[2] = sum of list sizes over the blocks, out[3] = blocks,
+// out[4] = blocks whose list would outgrow `cap` (the kernel walks the tree per ray there), out[5] = largest frontier.
+// ---------------------------------------------------------------------------------------------
+extern "C" int hostsim_bvh_block_check(const RzScene *sc, const RzCamera *cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t block_stride,
+                                       uint32_t cap, uint64_t seed, uint64_t *out) {
+    const uint32_t n = sc->n_spheres;
+    SahBuilder sb;
+    sb.p.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        sb.p[i].b = sphere_box(*sc, i);
+        for (int a = 0; a < 3; a++) sb.p[i].c[a] = 0.5 * (sb.p[i].b.lo[a] + sb.p[i].b.hi[a]);
+        sb.p[i].s = i;
+    }
+    sb.run();
+    // the set in leaf order, as the library uploads it
+    std::vector<float4> cr(n), vel(n);
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t i = sb.order[k];
+        const double *c = sc->sphere_center + 3 * i, *v = sc->sphere_velocity + 3 * i; const double r = sc->sphere_radius[i];
+        cr[k] = make_float4((float)c[0], (float)c[1], (float)c[2], -(float)(r * r));
+        vel[k] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)r);
+    }
+    RzCamF32 C;
+    C.look_from = make_float3((float)cam->look_from[0], (float)cam->look_from[1], (float)cam->look_from[2]);
+    C.px_du = make_float3((float)cam->px_du[0], (float)cam->px_du[1], (float)cam->px_du[2]);
+    C.px_dv = make_float3((float)cam->px_dv[0], (float)cam->px_dv[1], (float)cam->px_dv[2]);
+    C.px_origin = make_float3((float)cam->px_origin[0], (float)cam->px_origin[1], (float)cam->px_origin[2]);
+    C.defocus_u = make_float3((float)cam->defocus_u[0], (float)cam->defocus_u[1], (float)cam->defocus_u[2]);
+    C.defocus_v = make_float3((float)cam->defocus_v[0], (float)cam->defocus_v[1], (float)cam->defocus_v[2]);
+    C.defocus = cam->defocus;
+    double f2 = 0, lu = 0, lv = 0;
+    for (int ax = 0; ax < 3; ax++) {
+        const double pc = cam->px_origin[ax] + 0.5 * (w - 1) * cam->px_du[ax] + 0.5 * (h - 1) * cam->px_dv[ax] - cam->look_from[ax];
+        f2 += pc * pc; lu += cam->defocus_u[ax] * cam->defocus_u[ax]; lv += cam->defocus_v[ax] * cam->defocus_v[ax];
+    }
+    const float focus_dist = (float)std::sqrt(f2), lens_radius = cam->defocus ? (float)(std::sqrt(std::max(lu, lv)) * 1.001) : 0.f;
+    for (int i = 0; i < 6; i++) out[i] = 0;
+    const uint32_t tiles_x = (w + 7u) / 8u, tiles_y = (h + 3u) / 4u, n_px = w * h;
+    std::vector<int> frontier, next, list;
+    for (uint32_t tile = 0; tile < tiles_x * tiles_y; tile += block_stride) {
+        float3 ax = f3(0.f, 0.f, 0.f), pcs[32];
+        uint32_t pis[32], pjs[32];
+        bool valid[32];
+        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            const uint32_t ti = tx * 8u + (lane & 7u), tr = ty * 4u + (lane >> 3);
+            const uint32_t lp = tr * w + ti;
+            valid[lane] = ti < w && lp < n_px;
+            pis[lane] = pjs[lane] = 0;
+            if (valid[lane]) rz_local_to_global(lp, w, 0, 1, 4, pis[lane], pjs[lane]);
+            pcs[lane] = rz_tile_pixel_dir(C, pis[lane], pjs[lane]);
+            if (valid[lane]) ax = ax + normalize3(pcs[lane]);
+        }
+        const bool has_axis = rz_tile_axis(ax);
+        float cmin = 1.0f;
+        for (uint32_t lane = 0; lane < 32; lane++)
+            if (valid[lane]) cmin = fminf(cmin, rz_tile_corner_cos(C, pcs[lane], ax));
+        const RzTileCone cone = rz_tile_cone(C, ax, has_axis, cmin, focus_dist, lens_radius);
+        // ---- the cull: breadth first from the root
+        frontier.assign(1, 0);
+        list.clear();
+        while (!frontier.empty()) {
+            out[5] = std::max<uint64_t>(out[5], frontier.size());
+            next.clear();
+            for (int node : frontier) {
+                const RzBvhNode &nd = sb.nodes[(size_t)node];
+                for (int c = 0; c < 2; c++) {
+                    if (nd.child[c] < 0 && nd.cnt[c] == 0u) continue;      // unused slot (the library fills it with the sibling: same spheres)
+                    if (!rz_tile_keep_box(cone, nd.lox[c], nd.hix[c], nd.loy[c], nd.hiy[c], nd.loz[c], nd.hiz[c])) continue;
+                    if (nd.child[c] >= 0) { next.push_back(nd.child[c]); continue; }
+                    const int first = ~nd.child[c];
+                    for (uint32_t e = 0; e < nd.cnt[c]; e++) {
+                        const int k = first + (int)e;
+                        if (rz_tile_keep(cone, cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w)) list.push_back(k);
+                    }
+                }
+            }
+            frontier.swap(next);
+        }
+        out[2] += list.size(); out[3]++;
+        if (list.size() > cap) out[4]++;
+        // ---- the block's camera rays: the list against every sphere
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            if (!valid[lane]) continue;
+            const uint32_t gpix = pjs[lane] * w + pis[lane];
+            for (uint32_t smp = 0; smp < spp; smp++) {
+                const RzRay ray = rz_camera_ray(C, pis[lane], pjs[lane], gpix, smp, (uint32_t)seed, (uint32_t)(seed >> 32));
+                float bt_l = 3.0e38f, bt_a = 3.0e38f;
+                int bk_l = -1, bk_a = -1;
+                for (int k : list) {
+                    float nb, nd2;
+                    rz_sphere_test(cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.time, nb, nd2);
+                    if (nd2 < 0.0f) rz_consider(k, nb, nd2, -1, 1e-4f, bt_l, bk_l);
+                }
+                for (int k = 0; k < (int)n; k++) {
+                    float nb, nd2;
+                    rz_sphere_test(cr[k].x, cr[k].y, cr[k].z, vel[k].x, vel[k].y, vel[k].z, cr[k].w, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.time, nb, nd2);
+                    if (nd2 < 0.0f) rz_consider(k, nb, nd2, -1, 1e-4f, bt_a, bk_a);
+                }
+                out[1]++;
+                if (bk_l != bk_a || bt_l != bt_a) out[0]++;
+            }
+        }
     }
     return 0;
 }

@@ -176,3 +176,24 @@ def test_staged_searches_equal_brute_force_on_the_benchmark_scene(hostsim, glass
     assert bad2 == 0, f"{bad2} of {rays2} scattered rays find a different hit over the unit list"
     assert list1 / rays1 < 0.15 * n          # the tile cull keeps a small part of the set ...
     assert list2 / rays2 < 0.12 * n          # ... and a sort group's list about 7 % of it (10 % on the GPU, which tests a whole batch up to its largest class)
+
+
+def test_bvh_camera_stage_block_lists_find_the_brute_force_hit(hostsim):
+    """K3's camera stage, on the CPU: the library's own binned-SAH tree culled against the cone of 8 x 4-pixel blocks the way
+    rz_bvh_stage_kernel does it, and the blocks' camera rays searched over the surviving spheres and over every sphere: same
+    closest hit (t and sphere), on the RTOW scene and on a 2,500-sphere version of config 4's scene."""
+    hostsim.hostsim_bvh_block_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                                C.c_void_p]
+    for grid, width, stride in ((11, 480, 37), (25, 960, 211)):
+        t = rayz_b200.random_bouncing(width, seed=42, grid_lo=-grid, grid_hi=grid)
+        arrays = t.pool.arrays()
+        sc, keep = scene_struct(arrays)
+        out = np.zeros(6, dtype=np.uint64)
+        assert hostsim.hostsim_bvh_block_check(C.addressof(sc), C.addressof(t.camera.rz), t.img.w, t.img.h, 6, stride, 256, 9, out.ctypes.data) == 0
+        bad, rays, list_sum, blocks, over, frontier = (int(x) for x in out)
+        n = len(arrays["sphere_radius"])
+        assert rays > 10_000 and blocks > 50, (rays, blocks)
+        assert bad == 0, f"{bad} of {rays} camera rays find a different hit over the block list ({n} spheres)"
+        assert list_sum / blocks < 0.1 * n        # the cull keeps a small part of the set ...
+        assert over <= 0.1 * blocks               # ... and few blocks outgrow the list (the kernel walks the tree there)
+        assert frontier <= 256                    # the kernel's ring buffer
